@@ -1,0 +1,54 @@
+// C-ABI glue: error reporting, launch accounting and the convolution dispatcher.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dmme {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool conv_tc_supported(const dmme_conv_desc& d);
+int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream);
+int conv_generic_forward(const dmme_conv_desc& d, cudaStream_t stream);
+
+}  // namespace dmme
+
+using namespace dmme;
+
+extern "C" int dmme_abi_version(void) { return DMME_ABI_VERSION; }
+extern "C" const char* dmme_last_error(void) { return g_err; }
+extern "C" long long dmme_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void dmme_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+extern "C" int dmme_conv2d_uses_tc(const dmme_conv_desc* d) {
+  if (!d) return 0;
+  if (d->kernel == DMME_CONV_GENERIC) return 0;
+  return conv_tc_supported(*d) ? 1 : 0;
+}
+
+extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
+  DMME_REQUIRE(d != nullptr, DMME_E_BADARG, "conv2d_fwd: null descriptor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (d->kernel) {
+    case DMME_CONV_TC:
+      return conv_tc_forward(*d, st);
+    case DMME_CONV_GENERIC:
+      return conv_generic_forward(*d, st);
+    case DMME_CONV_AUTO:
+      return conv_tc_supported(*d) ? conv_tc_forward(*d, st) : conv_generic_forward(*d, st);
+    default:
+      set_error("conv2d_fwd: unknown kernel selector %d", d->kernel);
+      return DMME_E_BADARG;
+  }
+}

@@ -1,0 +1,75 @@
+// Shared host/device helpers for the dmme_b200 kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dmme_b200.h"
+
+namespace dmme {
+
+// ---- host side: error reporting and launch accounting ------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define DMME_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) {                    \
+      ::dmme::set_error(__VA_ARGS__); \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  count_launch();
+  return 0;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- device side: storage-type access ----------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ld_act(const T* p);
+template <>
+__device__ __forceinline__ float ld_act<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_act<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void st_act(T* p, float v);
+template <>
+__device__ __forceinline__ void st_act<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_act<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xffff0000u);
+}
+
+__device__ __forceinline__ float silu_f(float y) { return y / (1.0f + __expf(-y)); }
+__device__ __forceinline__ float silu_precise(float y) { return y / (1.0f + expf(-y)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace dmme

@@ -1,0 +1,269 @@
+// GroupNorm (+ scale/shift) (+ SiLU) (+ channel-dropout mask) over NHWC activations.
+//
+// Fast path (bf16, C % 32 == 0, channels-per-group in {1,2,4,8,16,32}, HW <= 1024): one CTA owns one
+// (image, 32-channel slab) = 64 bytes per pixel.  The slab is read ONCE with 16-byte vector loads into
+// registers, mean and variance are computed in two register passes (fp32, same biased variance as
+// torch.native_group_norm), and the normalised/activated slab is written once: algorithmic traffic
+// = 2 B read + 2 B written per element.  The skip concat is two source pointers.
+// Generic path: any C / groups / HW / storage type; one CTA per (image, group), three global passes.
+#include "common.cuh"
+
+namespace dmme {
+
+struct GnParams {
+  const void* src0; const void* src1; int c0, c1;
+  int n, hw, groups; float eps;
+  const float* gamma; const float* beta;
+  const float* scale; const float* shift; int ss_rows, ss_ld;
+  const float* mask;  // [n][C] or null
+  int silu;
+  void* out;
+};
+
+// --------------------------------------------------------------------------------------------
+// fast path
+// --------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256, 2) gn_slab_kernel(const GnParams p) {
+  __shared__ float red[8][32];
+  __shared__ float chan_stat[32];
+  __shared__ float gmean[32], grstd[32];
+
+  const int C = p.c0 + p.c1;
+  const int slabs = C / 32;
+  const int n = blockIdx.x / slabs;
+  const int slab = blockIdx.x - n * slabs;
+  const int cbase = slab * 32;
+  const int cpg = C / p.groups;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int chunk = tid & 3;  // 8-channel vector inside the slab
+  const int nvec = p.hw * 4;  // 16-byte vectors in the slab
+
+  const __nv_bfloat16* src;
+  int csrc, coff;
+  if (cbase < p.c0) { src = static_cast<const __nv_bfloat16*>(p.src0); csrc = p.c0; coff = cbase; }
+  else { src = static_cast<const __nv_bfloat16*>(p.src1); csrc = p.c1; coff = cbase - p.c0; }
+  const __nv_bfloat16* base = src + static_cast<long long>(n) * p.hw * csrc + coff + chunk * 8;
+
+  uint4 v[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * blockDim.x;
+    if (vi < nvec) v[i] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(vi >> 2) * csrc));
+    else v[i] = make_uint4(0, 0, 0, 0);
+  }
+
+  // ---- pass 1: per-channel sums -> group means ----
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    float lo, hi;
+    unpack_bf16x2(v[i].x, lo, hi); s[0] += lo; s[1] += hi;
+    unpack_bf16x2(v[i].y, lo, hi); s[2] += lo; s[3] += hi;
+    unpack_bf16x2(v[i].z, lo, hi); s[4] += lo; s[5] += hi;
+    unpack_bf16x2(v[i].w, lo, hi); s[6] += lo; s[7] += hi;
+  }
+  // lanes with equal (lane & 3) hold the same channels
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 4);
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+  }
+  if (lane < 4) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = s[j];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += red[w][tid];
+    chan_stat[tid] = t;
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * cpg);
+  if (tid < 32) {
+    // group of channel tid inside the slab: channels [g0, g0 + cpg)
+    const int g0 = (tid / cpg) * cpg;
+    float t = 0.f;
+    for (int j = 0; j < cpg; ++j) t += chan_stat[g0 + j];
+    gmean[tid] = t * inv_cnt;
+  }
+  __syncthreads();
+  float mean[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mean[j] = gmean[chunk * 8 + j];
+
+  // ---- pass 2: centred second moment ----
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * blockDim.x;
+    if (vi < nvec) {
+      float lo, hi, d;
+      unpack_bf16x2(v[i].x, lo, hi); d = lo - mean[0]; s[0] += d * d; d = hi - mean[1]; s[1] += d * d;
+      unpack_bf16x2(v[i].y, lo, hi); d = lo - mean[2]; s[2] += d * d; d = hi - mean[3]; s[3] += d * d;
+      unpack_bf16x2(v[i].z, lo, hi); d = lo - mean[4]; s[4] += d * d; d = hi - mean[5]; s[5] += d * d;
+      unpack_bf16x2(v[i].w, lo, hi); d = lo - mean[6]; s[6] += d * d; d = hi - mean[7]; s[7] += d * d;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 4);
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+  }
+  if (lane < 4) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = s[j];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += red[w][tid];
+    chan_stat[tid] = t;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int g0 = (tid / cpg) * cpg;
+    float t = 0.f;
+    for (int j = 0; j < cpg; ++j) t += chan_stat[g0 + j];
+    grstd[tid] = rsqrtf(t * inv_cnt + p.eps);
+  }
+  __syncthreads();
+
+  // ---- per-channel affine folded into a*x + b ----
+  float a[8], b[8], m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cbase + chunk * 8 + j;
+    const float rs = grstd[chunk * 8 + j];
+    float ga = p.gamma ? p.gamma[c] : 1.f, be = p.beta ? p.beta[c] : 0.f;
+    float aa = rs * ga, bb = be - mean[j] * rs * ga;
+    if (p.scale) {
+      const long long r = static_cast<long long>(p.ss_rows == 1 ? 0 : n) * p.ss_ld;
+      const float sc = 1.f + p.scale[r + c], sh = p.shift[r + c];
+      aa *= sc;
+      bb = bb * sc + sh;
+    }
+    a[j] = aa; b[j] = bb;
+    m[j] = p.mask ? p.mask[static_cast<long long>(n) * C + c] : 1.f;
+  }
+
+  __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(n) * p.hw * C + cbase + chunk * 8;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * blockDim.x;
+    if (vi < nvec) {
+      float f[8];
+      unpack_bf16x2(v[i].x, f[0], f[1]);
+      unpack_bf16x2(v[i].y, f[2], f[3]);
+      unpack_bf16x2(v[i].z, f[4], f[5]);
+      unpack_bf16x2(v[i].w, f[6], f[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float yv = fmaf(f[j], a[j], b[j]);
+        if (p.silu) yv = silu_f(yv);
+        f[j] = yv * m[j];
+      }
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(obase + static_cast<long long>(vi >> 2) * C) = o;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// generic path: one CTA per (image, group)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) t += scratch[w];
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_generic_kernel(const GnParams p) {
+  __shared__ float scratch[8];
+  const int C = p.c0 + p.c1;
+  const int cpg = C / p.groups;
+  const int n = blockIdx.x / p.groups;
+  const int g = blockIdx.x - n * p.groups;
+  const int cnt = p.hw * cpg;
+  const T* s0 = static_cast<const T*>(p.src0);
+  const T* s1 = static_cast<const T*>(p.src1);
+
+  auto load = [&](int e) -> float {
+    const int l = e / cpg, c = g * cpg + (e - l * cpg);
+    if (c < p.c0) return ld_act<T>(s0 + (static_cast<long long>(n) * p.hw + l) * p.c0 + c);
+    return ld_act<T>(s1 + (static_cast<long long>(n) * p.hw + l) * p.c1 + (c - p.c0));
+  };
+
+  float s = 0.f;
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) s += load(e);
+  const float mean = block_sum(s, scratch) / cnt;
+  float q = 0.f;
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) { const float d = load(e) - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, scratch) / cnt + p.eps);
+
+  T* out = static_cast<T*>(p.out);
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+    const int l = e / cpg, c = g * cpg + (e - l * cpg);
+    float y = (load(e) - mean) * rstd;
+    if (p.gamma) y = y * p.gamma[c] + (p.beta ? p.beta[c] : 0.f);
+    if (p.scale) {
+      const long long r = static_cast<long long>(p.ss_rows == 1 ? 0 : n) * p.ss_ld;
+      y = y * (p.scale[r + c] + 1.f) + p.shift[r + c];
+    }
+    if (p.silu) y = silu_precise(y);
+    if (p.mask) y *= p.mask[static_cast<long long>(n) * C + c];
+    st_act<T>(out + (static_cast<long long>(n) * p.hw + l) * C + c, y);
+  }
+}
+
+}  // namespace dmme
+
+using namespace dmme;
+
+extern "C" int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, int c1, int n, int hw, int groups,
+                                  float eps, const float* gamma, const float* beta, const float* scale,
+                                  const float* shift, int ss_rows, int ss_ld, const float* chan_mask, int apply_silu,
+                                  void* out, int act_dtype, void* stream) {
+  DMME_REQUIRE(src0 && out, DMME_E_BADARG, "groupnorm: null src0/out");
+  DMME_REQUIRE(n > 0 && hw > 0 && c0 > 0 && c1 >= 0 && groups > 0, DMME_E_BADARG, "groupnorm: bad sizes");
+  DMME_REQUIRE(c1 == 0 || src1, DMME_E_BADARG, "groupnorm: c1 > 0 but src1 is null");
+  const int C = c0 + c1;
+  DMME_REQUIRE(C % groups == 0, DMME_E_SHAPE, "groupnorm: C=%d not divisible by groups=%d", C, groups);
+  DMME_REQUIRE((scale == nullptr) == (shift == nullptr), DMME_E_BADARG, "groupnorm: scale and shift come together");
+  GnParams p;
+  p.src0 = src0; p.src1 = src1; p.c0 = c0; p.c1 = c1; p.n = n; p.hw = hw; p.groups = groups; p.eps = eps;
+  p.gamma = gamma; p.beta = beta; p.scale = scale; p.shift = shift; p.ss_rows = ss_rows; p.ss_ld = ss_ld;
+  p.mask = chan_mask; p.silu = apply_silu; p.out = out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cpg = C / groups;
+  const bool fast = act_dtype == DMME_BF16 && C % 32 == 0 && c0 % 32 == 0 && (32 % cpg == 0) && hw <= 1024 &&
+                    (hw * 4) % 32 == 0;
+  if (fast) {
+    const int nvec = hw * 4;
+    const int threads = nvec < 256 ? nvec : 256;
+    const int maxv = ceil_div(nvec, threads);
+    const int blocks = n * (C / 32);
+    if (maxv <= 1) gn_slab_kernel<1><<<blocks, threads, 0, st>>>(p);
+    else if (maxv <= 4) gn_slab_kernel<4><<<blocks, threads, 0, st>>>(p);
+    else gn_slab_kernel<16><<<blocks, threads, 0, st>>>(p);
+    return check_launch("gn_slab_kernel");
+  }
+  if (act_dtype == DMME_BF16) gn_generic_kernel<__nv_bfloat16><<<n * groups, 256, 0, st>>>(p);
+  else gn_generic_kernel<float><<<n * groups, 256, 0, st>>>(p);
+  return check_launch("gn_generic_kernel");
+}

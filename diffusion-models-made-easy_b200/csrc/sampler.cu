@@ -1,0 +1,194 @@
+// Per-step sampler updates in image space (NCHW fp32), one elementwise pass each.
+// The arithmetic follows the reference operation by operation (separately rounded mul / sub / add,
+// IEEE sqrt and div) so that, given the same eps and the same noise, DDPM and DDIM updates are
+// bit-identical to torch on the CPU.  Schedule scalars are read from device tables at index *t_ptr,
+// so a captured CUDA graph of one step can be replayed for every t with no host work.
+#include "common.cuh"
+
+namespace dmme {
+
+// ---- Philox4x32-10 -----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x) + 0.5f) * 2.3283064365386963e-10f; }
+// four standard normals for element group g of stream sid
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long sid, unsigned long long g) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32),
+                                           static_cast<uint32_t>(sid), static_cast<uint32_t>(sid >> 32)),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  float4 z;
+  float s, c;
+  float rad = sqrtf(-2.0f * logf(u01(r.x)));
+  sincospif(2.0f * u01(r.y), &s, &c);
+  z.x = rad * c; z.y = rad * s;
+  rad = sqrtf(-2.0f * logf(u01(r.z)));
+  sincospif(2.0f * u01(r.w), &s, &c);
+  z.z = rad * c; z.w = rad * s;
+  return z;
+}
+
+__global__ void philox_normal_kernel(float* __restrict__ out, long long numel, unsigned long long seed,
+                                     unsigned long long sid) {
+  const long long groups = (numel + 3) / 4;
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 z = philox_normal4(seed, sid, g);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+    for (int j = 0; j < 4; ++j)
+      if (g * 4 + j < numel) out[g * 4 + j] = zz[j];
+  }
+}
+
+// ---- DDPM ancestral step ---------------------------------------------------------------------
+__global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                                 const float* __restrict__ beta, const float* __restrict__ alpha,
+                                 const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr,
+                                 long long numel, unsigned long long seed) {
+  const long long t = *t_ptr;
+  const float b = beta[t], a = alpha[t], ab = alpha_bar[t];
+  const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
+  const float c2 = __fdiv_rn(b, __fsqrt_rn(__fsub_rn(1.0f, ab)));
+  const float sd = __fsqrt_rn(b);
+  const bool last = (t == 1);
+  const long long groups = (numel + 3) / 4;
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!noise && !last) {
+      const float4 z = philox_normal4(seed, static_cast<unsigned long long>(t), g);
+      zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = g * 4 + j;
+      if (i < numel) {
+        const float mean = __fmul_rn(c1, __fsub_rn(x[i], __fmul_rn(c2, eps[i])));
+        const float z = noise ? noise[i] : zz[j];
+        x[i] = last ? mean : __fadd_rn(__fmul_rn(z, sd), mean);
+      }
+    }
+  }
+}
+
+// ---- DDIM step, as written in the reference --------------------------------------------------
+__global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                 const float* __restrict__ alpha_bar, const int64_t* __restrict__ tau,
+                                 const int64_t* __restrict__ i_ptr, long long numel) {
+  const long long i = *i_ptr;
+  const float ab_i = alpha_bar[tau[i]];
+  const float ab_p = alpha_bar[tau[i - 1]];
+  const float s1 = __fsqrt_rn(__fsub_rn(1.0f, ab_i));
+  const float sp = __fsqrt_rn(ab_p);
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < numel;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x0 = __fdiv_rn(__fsub_rn(x[e], __fmul_rn(s1, eps[e])), sp);
+    x[e] = __fmul_rn(sp, x0);
+  }
+}
+
+// ---- IDDPM learned-variance step -------------------------------------------------------------
+__global__ void iddpm_step_kernel(float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ noise,
+                                  const float* __restrict__ beta, const float* __restrict__ alpha,
+                                  const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr, int n, int c,
+                                  int hw, unsigned long long seed) {
+  const long long t = *t_ptr;
+  const float b = beta[t], a = alpha[t], ab = alpha_bar[t], abp = alpha_bar[t - 1];
+  const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
+  const float c2 = __fdiv_rn(b, __fsqrt_rn(__fsub_rn(1.0f, ab)));
+  const float bt = __fmul_rn(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)), b);
+  const float log_b = logf(b), log_bt = logf(fmaxf(bt, 1e-12f));
+  const bool last = (t == 1);
+  const long long numel = static_cast<long long>(n) * c * hw;
+  const long long groups = (numel + 3) / 4;
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!noise && !last) {
+      const float4 z = philox_normal4(seed, static_cast<unsigned long long>(t), g);
+      zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = g * 4 + j;
+      if (i < numel) {
+        const long long l = i % hw, nc = i / hw;
+        const long long ch = nc % c, ni = nc / c;
+        const float e = mo[(ni * 2 * c + ch) * hw + l];
+        const float v = mo[(ni * 2 * c + c + ch) * hw + l];
+        const float var = expf(__fadd_rn(__fmul_rn(v, log_b), __fmul_rn(__fsub_rn(1.0f, v), log_bt)));
+        const float mean = __fmul_rn(c1, __fsub_rn(x[i], __fmul_rn(c2, e)));
+        const float z = noise ? noise[i] : zz[j];
+        x[i] = last ? mean : __fadd_rn(__fmul_rn(z, __fsqrt_rn(var)), mean);
+      }
+    }
+  }
+}
+
+__global__ void gather_i64_kernel(const int64_t* table, const int64_t* idx, int64_t* out) { *out = table[*idx]; }
+__global__ void add_i64_kernel(int64_t* p, int64_t d) { *p += d; }
+
+static int ew_grid(long long work, int threads) {
+  long long b = ceil_div_ll(work, threads);
+  const long long cap = 148LL * 8;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace dmme
+
+using namespace dmme;
+
+extern "C" int dmme_ddpm_step(float* x, const float* eps, const float* noise, const float* beta, const float* alpha,
+                              const float* alpha_bar, const int64_t* t_ptr, long long numel, unsigned long long seed,
+                              void* stream) {
+  DMME_REQUIRE(x && eps && beta && alpha && alpha_bar && t_ptr && numel > 0, DMME_E_BADARG, "ddpm_step: bad arguments");
+  ddpm_step_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, eps, noise, beta, alpha, alpha_bar, t_ptr, numel, seed);
+  return check_launch("ddpm_step_kernel");
+}
+
+extern "C" int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar, const int64_t* tau,
+                              const int64_t* i_ptr, long long numel, void* stream) {
+  DMME_REQUIRE(x && eps && alpha_bar && tau && i_ptr && numel > 0, DMME_E_BADARG, "ddim_step: bad arguments");
+  ddim_step_kernel<<<ew_grid(numel, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, alpha_bar, tau, i_ptr, numel);
+  return check_launch("ddim_step_kernel");
+}
+
+extern "C" int dmme_iddpm_step(float* x, const float* model_out, const float* noise, const float* beta,
+                               const float* alpha, const float* alpha_bar, const int64_t* t_ptr, int n, int c, int hw,
+                               unsigned long long seed, void* stream) {
+  DMME_REQUIRE(x && model_out && beta && alpha && alpha_bar && t_ptr && n > 0 && c > 0 && hw > 0, DMME_E_BADARG,
+               "iddpm_step: bad arguments");
+  const long long numel = static_cast<long long>(n) * c * hw;
+  iddpm_step_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, model_out, noise, beta, alpha, alpha_bar, t_ptr, n, c, hw, seed);
+  return check_launch("iddpm_step_kernel");
+}
+
+extern "C" int dmme_gather_i64(const int64_t* table, const int64_t* idx_ptr, int64_t* out, void* stream) {
+  DMME_REQUIRE(table && idx_ptr && out, DMME_E_BADARG, "gather_i64: null pointer");
+  gather_i64_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(table, idx_ptr, out);
+  return check_launch("gather_i64_kernel");
+}
+
+extern "C" int dmme_add_i64(int64_t* value, int64_t delta, void* stream) {
+  DMME_REQUIRE(value, DMME_E_BADARG, "add_i64: null pointer");
+  add_i64_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(value, delta);
+  return check_launch("add_i64_kernel");
+}
+
+extern "C" int dmme_philox_normal(float* out, long long numel, unsigned long long seed, unsigned long long stream_id,
+                                  void* stream) {
+  DMME_REQUIRE(out && numel > 0, DMME_E_BADARG, "philox_normal: bad arguments");
+  philox_normal_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, numel, seed, stream_id);
+  return check_launch("philox_normal_kernel");
+}

@@ -1,0 +1,122 @@
+"""ctypes binding of the C-ABI library ``libdmme_b200.so`` (declared in ``include/dmme_b200.h``).
+
+The library is the product: there is no PyTorch or CPU fallback behind these calls.  Loading fails
+loudly when the shared object is missing, and every wrapper raises ``RuntimeError`` carrying
+``dmme_last_error()`` when a launch is refused, mirroring how the reference surfaces errors as
+Python exceptions (e.g. ``NotImplementedError`` in diffusion_models/ddim.py:50-51).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmme_b200.so")
+
+BF16, F32 = 0, 1
+IN_NHWC, IN_NCHW_F32 = 0, 1
+OUT_NHWC, OUT_NCHW_F32, OUT_QKV = 0, 1, 2
+CONV_AUTO, CONV_GENERIC, CONV_TC = 0, 1, 2
+
+# every symbol include/dmme_b200.h declares (checked by tests/test_abi.py without a GPU)
+EXPORTS = (
+    "dmme_abi_version", "dmme_last_error", "dmme_launch_count", "dmme_reset_launch_count",
+    "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
+    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_groupnorm_fwd", "dmme_attention_fwd",
+    "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
+    "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal",
+)
+
+
+class ConvDesc(C.Structure):
+    """Mirror of ``struct dmme_conv_desc``."""
+
+    _fields_ = [
+        ("src0", C.c_void_p), ("src1", C.c_void_p), ("c0", C.c_int), ("c1", C.c_int),
+        ("res0", C.c_void_p), ("res1", C.c_void_p), ("rc0", C.c_int), ("rc1", C.c_int),
+        ("n", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int),
+        ("ksize", C.c_int), ("stride", C.c_int), ("upsample", C.c_int), ("cout", C.c_int),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("temb", C.c_void_p),
+        ("temb_rows", C.c_int), ("temb_ld", C.c_int),
+        ("addend", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p), ("out3", C.c_void_p),
+        ("in_layout", C.c_int), ("out_layout", C.c_int), ("act_dtype", C.c_int), ("kernel", C.c_int),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"dmme_b200: {LIB_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C diffusion-models-made-easy_b200/csrc`). There is no fallback path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.dmme_last_error.restype = C.c_char_p
+    lib.dmme_launch_count.restype = C.c_longlong
+    lib.dmme_abi_version.restype = C.c_int
+    vp, i, ll, ull, f = C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_float
+    lib.dmme_pack_conv_weight.argtypes = [vp, i, i, i, vp, i, vp, i, vp]
+    lib.dmme_nchw_to_nhwc.argtypes = [vp, vp, i, i, i, i, i, vp]
+    lib.dmme_nhwc_to_nchw.argtypes = [vp, vp, i, i, i, i, i, vp]
+    lib.dmme_upsample2x_nhwc.argtypes = [vp, vp, i, i, i, i, i, vp]
+    lib.dmme_conv2d_fwd.argtypes = [C.POINTER(ConvDesc), vp]
+    lib.dmme_conv2d_uses_tc.argtypes = [C.POINTER(ConvDesc)]
+    lib.dmme_groupnorm_fwd.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, i, vp, i, vp]
+    lib.dmme_attention_fwd.argtypes = [vp, vp, vp, ll, i, i, i, ll, i, i, i, i, f, i, vp, i, vp]
+    lib.dmme_temb_mlp_fwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp]
+    lib.dmme_temb_proj_fwd.argtypes = [vp, i, i, vp, vp, i, vp, vp]
+    lib.dmme_ddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, ull, vp]
+    lib.dmme_ddim_step.argtypes = [vp, vp, vp, vp, vp, ll, vp]
+    lib.dmme_iddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, ull, vp]
+    lib.dmme_gather_i64.argtypes = [vp, vp, vp, vp]
+    lib.dmme_add_i64.argtypes = [vp, C.c_int64, vp]
+    lib.dmme_philox_normal.argtypes = [vp, ll, ull, ull, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("dmme_abi_version",):
+            pass
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().dmme_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"dmme_b200.{what} failed (code {rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Raw device pointer of a tensor (None stays a NULL pointer)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    """The CUDA stream every launch goes to: torch's current stream (see callbacks/ema.py:273-296)."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def act_code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return BF16
+    if dtype == torch.float32:
+        return F32
+    raise ValueError(f"activation dtype must be bfloat16 or float32, got {dtype}")
+
+
+def require_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dmme_b200 kernels need CUDA tensors; there is no CPU path")
+        if t is not None and not t.is_contiguous():
+            raise RuntimeError("dmme_b200 kernels need contiguous tensors")

@@ -1,0 +1,61 @@
+"""Deterministic DDIM sampling over a sub-sequence tau (drop-in for ``dmme.diffusion_models.DDIM``,
+src/dmme/diffusion_models/ddim.py:16-99).  The update is the reference's formula *as written*
+(equations/ddim/ddim.py:52-57): x <- sqrt(abar_prev) * ((x - sqrt(1 - abar_i) eps) / sqrt(abar_prev)),
+there is no eta and no noise term."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn, Tensor
+
+from .. import ops
+from ..equations import ddim as eq_ddim
+from .ddpm import DDPM
+
+
+class DDIM(DDPM):
+    r"""Denoising Diffusion Implicit Models
+
+    Args:
+        model: model passed to :code:`DDPM`
+        timesteps: total timesteps :math:`T`
+        sub_timesteps: sub-sequence length
+        tau_schedule: tau schedule to use, "linear" or "quadratic"
+    """
+
+    tau: Tensor
+
+    def __init__(self, model: nn.Module, timesteps: int = 1000, sub_timesteps: int = 50,
+                 tau_schedule: str = "quadratic") -> None:
+        super().__init__(model, timesteps)
+        self.sub_timesteps = sub_timesteps
+        kind = tau_schedule.lower()
+        if kind == "linear":
+            tau = eq_ddim.linear_tau(timesteps, sub_timesteps)
+        elif kind == "quadratic":
+            tau = eq_ddim.quadratic_tau(timesteps, sub_timesteps)
+        else:
+            raise NotImplementedError
+        self.register_buffer("tau", tau, persistent=False)
+
+    def sampling_step(self, x_tau_i: Tensor, i: Tensor, noise: Optional[Tensor] = None) -> Tensor:
+        r"""Mean of :math:`p_\theta(x_{\tau_{i-1}}|x_{\tau_i})`; ``i`` has shape (1,)."""
+        i = self._check_step_index(i)
+        x = x_tau_i.detach().float().contiguous().clone()
+        t_model = ops.gather_i64(self.tau, i, torch.empty(1, dtype=torch.int64, device=x.device))
+        eps = self.model.forward_raw(x, t_model)
+        return ops.ddim_step_(x, eps, self.alpha_bar, self.tau, i)
+
+    def _counter_start(self) -> int:
+        return self.sub_timesteps
+
+    def _num_steps(self) -> int:
+        return self.sub_timesteps
+
+    def _graph_step(self, x: Tensor, counter: Tensor, seed: int) -> None:
+        t_model = self.model.engine.ws.get("ddim.t", (1,), torch.int64, x.device)
+        ops.gather_i64(self.tau, counter, t_model)
+        eps = self.model.forward_raw(x, t_model)
+        ops.ddim_step_(x, eps, self.alpha_bar, self.tau, counter)
+        ops.add_i64_(counter, -1)

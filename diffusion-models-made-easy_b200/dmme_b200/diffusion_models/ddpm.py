@@ -1,0 +1,142 @@
+"""DDPM sampling (and, later, training) on the CUDA hot path.
+
+Drop-in for ``dmme.diffusion_models.DDPM`` (src/dmme/diffusion_models/ddpm.py:15-144): same
+constructor, same non-persistent buffers ``beta / alpha / alpha_bar`` of shape (T+1, 1, 1, 1), same
+``sampling_step / generate / forward`` entry points.  ``generate`` captures ONE denoising step
+(timestep embedding -> UNet -> fused sampler update -> step-counter decrement) in a CUDA graph whose
+kernels read ``t`` and the schedule scalars from device memory, and replays it T times: the
+reference's 1000-iteration host loop (ddpm.py:130-131) runs with no host work between steps.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+from torch import nn, Tensor
+
+from .. import ops
+from ..common.noise import gaussian
+from ..equations import ddpm as eq_ddpm
+
+
+class DDPM(nn.Module):
+    r"""Training and Sampling for DDPM
+
+    Args:
+        model: model predicting noise from data, :math:`\epsilon_\theta(x_t, t)`
+        timesteps: total timesteps :math:`T`
+        start: linear variance schedule start value
+        end: linear variance schedule end value
+    """
+
+    beta: Tensor
+    alpha: Tensor
+    alpha_bar: Tensor
+
+    def __init__(self, model: nn.Module, timesteps: int = 1000, start: float = 0.0001, end: float = 0.02) -> None:
+        super().__init__()
+        self.model = model
+        self.timesteps = timesteps
+        beta, alpha, alpha_bar = eq_ddpm.schedule_tables(eq_ddpm.linear_schedule(timesteps, start, end))
+        self._register_tables(beta, alpha, alpha_bar)
+
+    def _register_tables(self, beta: Tensor, alpha: Tensor, alpha_bar: Tensor) -> None:
+        for name, tab in (("beta", beta), ("alpha", alpha), ("alpha_bar", alpha_bar)):
+            self.register_buffer(name, tab.reshape(-1, 1, 1, 1).contiguous(), persistent=False)
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x: Tensor, t: Tensor) -> Tensor:
+        """Applies the internal model: :math:`\\epsilon_\\theta(x, t)`."""
+        return self.model(x, t)
+
+    def _check_step_index(self, t: Tensor) -> Tensor:
+        if t.numel() != 1:
+            # the reference itself fails here (torch.where broadcast, ddpm.py:110)
+            raise ValueError("sampling_step takes a step tensor of shape (1,), as DDPM.generate passes it")
+        return t.reshape(1).to(device=self.beta.device, dtype=torch.int64).contiguous()
+
+    def _update_(self, x: Tensor, model_out: Tensor, noise: Optional[Tensor], t: Tensor, seed: int) -> Tensor:
+        return ops.ddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed)
+
+    def sampling_step(self, x_t: Tensor, t: Tensor, noise: Optional[Tensor] = None) -> Tensor:
+        r"""Denoise by sampling from :math:`p_\theta(x_{t-1}|x_t)`.
+
+        Args:
+            x_t: image of shape (N, C, H, W)
+            t: the step, tensor of shape (1,)
+            noise: optional standard-normal tensor shaped like ``x_t`` (default: ``torch.randn_like``)
+        """
+        t = self._check_step_index(t)
+        x = x_t.detach().float().contiguous().clone()
+        out = self.model.forward_raw(x, t)
+        if noise is None:
+            noise = torch.randn_like(x)
+        return self._update_(x, out, noise.contiguous(), t, 0)
+
+    # ------------------------------------------------------------------------------------------
+    def _counter_start(self) -> int:
+        return self.timesteps
+
+    def _num_steps(self) -> int:
+        return self.timesteps
+
+    def _graph_step(self, x: Tensor, counter: Tensor, seed: int) -> None:
+        """One denoising step on device-resident state; everything launched here is graph-capturable."""
+        out = self.model.forward_raw(x, counter)
+        self._update_(x, out, None, counter, seed)
+        ops.add_i64_(counter, -1)
+
+    def _run_steps(self, x: Tensor, steps: int, seed: int, graph: bool,
+                   on_step: Optional[Callable[[int, Tensor], None]] = None) -> Tensor:
+        dev = x.device
+        counter = torch.full((1,), self._counter_start(), dtype=torch.int64, device=dev)
+        if not graph:
+            for k in range(steps):
+                self._graph_step(x, counter, seed)
+                if on_step is not None:
+                    on_step(k, x)
+            return x
+        # warm-up outside capture: packs weights, sizes the workspace, sets kernel attributes
+        x_saved = x.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._graph_step(x, counter, seed)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        x.copy_(x_saved)
+        counter.fill_(self._counter_start())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._graph_step(x, counter, seed)
+        # capture does not execute: state is still (x_T, T)
+        for k in range(steps):
+            g.replay()
+            if on_step is not None:
+                on_step(k, x)
+        return x
+
+    @torch.no_grad()
+    def generate(self, img_size: Tuple[int, int, int, int], *, x_T: Optional[Tensor] = None, seed: Optional[int] = None,
+                 graph: bool = True, on_step: Optional[Callable[[int, Tensor], None]] = None) -> Tensor:
+        """Generate images of shape (N, C, H, W) by running the full denoising chain.
+
+        Args:
+            img_size: (N, C, H, W)
+            x_T: optional starting noise (default ``dmme_b200.gaussian(img_size)`` like the reference)
+            seed: Philox seed of the per-step noise (default: drawn from torch's CPU generator)
+            graph: replay one captured CUDA graph per step (default) or launch eagerly
+            on_step: optional callback ``(k, x)`` after each step (k = 0 is t = T)
+        """
+        dev = self.beta.device
+        if dev.type != "cuda":
+            raise RuntimeError("dmme_b200 samplers run on CUDA only; move the module with .cuda()")
+        x = gaussian(tuple(img_size), device=dev) if x_T is None else x_T.detach().to(dev).float().clone()
+        x = x.contiguous()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return self._run_steps(x, self._num_steps(), seed, graph, on_step)
+
+    def training_step(self, x_0: Tensor) -> Tensor:
+        raise NotImplementedError(
+            "dmme_b200: the backward kernels (conv dgrad/wgrad, GroupNorm/attention backward) are not built yet; "
+            "training_step is the next row of the scope table (DESIGN.md)")

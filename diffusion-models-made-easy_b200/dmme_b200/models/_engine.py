@@ -1,0 +1,230 @@
+"""Forward executor shared by both UNet flavours.
+
+The ``nn.Module`` tree (see ``ddpm.py`` / ``iddpm.py``) only *holds* parameters under the reference's
+``state_dict`` names.  This executor walks that tree and issues the fused CUDA kernels:
+
+    ResBlock (models/ddpm.py:118-133)      ->  GN+SiLU | conv3x3(+temb) | GN+SiLU(+mask) | conv3x3 (+fused 1x1 residual | +x)
+    Attention (models/ddpm.py:54-75)       ->  GN | 1x1 qkv (Q, K, V^T) | attention core | 1x1 proj (+x)
+    torch.cat skip (models/ddpm.py:310)    ->  never materialised: two source pointers
+    UNet.condition + 22 block Linears      ->  temb_mlp + one batched temb_proj
+
+Packed weights (bf16 [cout][K] for the tcgen05 kernel, fp32 [K][cout] for the generic one) are cached per
+conv site and re-packed when a parameter's ``_version`` changes (optimizer step, load_state_dict).
+Activation buffers are cached per (site, shape) so a forward pass allocates nothing after the first call
+and can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import ops
+
+Tensor = torch.Tensor
+
+
+class Workspace:
+    """Named, shape-keyed device buffers (stable addresses across calls)."""
+
+    def __init__(self) -> None:
+        self._bufs: Dict[Tuple, Tensor] = {}
+
+    def get(self, name: str, shape, dtype, device) -> Tensor:
+        key = (name, tuple(shape), dtype, str(device))
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), dtype=dtype, device=device)
+            self._bufs[key] = t
+        return t
+
+    def clear(self) -> None:
+        self._bufs.clear()
+
+
+class Engine:
+    def __init__(self, unet: nn.Module, flavour: str) -> None:
+        self.unet = unet
+        self.flavour = flavour  # "ddpm" | "iddpm"
+        self.ws = Workspace()
+        self._packed: Dict[Tuple, Tuple[Tuple, Tensor]] = {}
+        self._blocks: Optional[List[Tuple[str, nn.Module]]] = None
+        self.force_generic = False  # debugging / fp32 mode: never take the tcgen05 path
+
+    # -- caches ------------------------------------------------------------------------------
+    def _cached(self, key: Tuple, versions: Tuple, build):
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == versions:
+            return hit[1]
+        val = build()
+        self._packed[key] = (versions, val)
+        return val
+
+    @staticmethod
+    def _ver(*params: Optional[Tensor]) -> Tuple:
+        return tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+
+    def packed_weight(self, conv: nn.Conv2d, res: Optional[nn.Conv2d], tc: bool) -> Tensor:
+        wr = res.weight if res is not None else None
+        return self._cached(("w", id(conv), tc), self._ver(conv.weight, wr),
+                            lambda: ops.pack_conv_weight(conv.weight, wr, tc))
+
+    def fused_bias(self, conv: nn.Conv2d, res: Optional[nn.Conv2d]) -> Tensor:
+        if res is None:
+            return conv.bias.detach()
+        return self._cached(("b", id(conv)), self._ver(conv.bias, res.bias),
+                            lambda: (conv.bias.detach() + res.bias.detach()).contiguous())
+
+    def resblocks(self) -> List[Tuple[str, nn.Module]]:
+        if self._blocks is None:
+            u = self.unet
+            out = []
+            for name, lst in (("down_layers", u.down_layers), ("middle_layers", u.middle_layers), ("up_layers", u.up_layers)):
+                for i, m in enumerate(lst):
+                    if hasattr(m, "conv1"):
+                        out.append((f"{name}.{i}", m))
+            self._blocks = out
+        return self._blocks
+
+    def temb_tables(self) -> Tuple[Tensor, Tensor, Dict[int, Tuple[int, int]]]:
+        """Concatenated [total][emb] weight / [total] bias of every ResBlock.condition Linear + column ranges."""
+        blocks = self.resblocks()
+        lins = [b.condition[0] for _, b in blocks]
+        vers = self._ver(*[l.weight for l in lins], *[l.bias for l in lins])
+
+        def build():
+            w = torch.cat([l.weight.detach().float() for l in lins], dim=0).contiguous()
+            b = torch.cat([l.bias.detach().float() for l in lins], dim=0).contiguous()
+            return w, b
+
+        w, b = self._cached(("temb",), vers, build)
+        offs, o = {}, 0
+        for (_, blk), l in zip(blocks, lins):
+            offs[id(blk)] = (o, l.weight.shape[0])
+            o += l.weight.shape[0]
+        return w, b, offs
+
+    # -- kernels -----------------------------------------------------------------------------
+    def conv(self, name: str, src0: Tensor, src1: Optional[Tensor], conv: nn.Conv2d, *, stride: int = 1,
+             upsample: bool = False, res: Optional[nn.Conv2d] = None, res0: Optional[Tensor] = None,
+             res1: Optional[Tensor] = None, temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
+             in_nchw: bool = False, out_layout: int = L.OUT_NHWC, act_dtype: Optional[torch.dtype] = None):
+        cout, ks = conv.weight.shape[0], conv.weight.shape[2]
+        act_dtype = act_dtype or src0.dtype
+        kernel = L.CONV_GENERIC if self.force_generic else L.CONV_AUTO
+        if upsample and not self.force_generic and act_dtype == torch.bfloat16 and src0.shape[3] % 64 == 0 and cout % 64 == 0:
+            # tensor-core path has no upsampling gather: materialise the x2 tensor once (memory-bound copy)
+            n, h, w, c = src0.shape
+            src0 = ops.upsample2x(src0, out=self.ws.get(name + ".up", (n, 2 * h, 2 * w, c), src0.dtype, src0.device))
+            upsample = False
+        d = ops.make_conv_desc(src0, src1, cout, ks, stride, upsample, res0, res1, in_nchw, out_layout, act_dtype, kernel)
+        tc = ops.conv_uses_tc(d)
+        w = self.packed_weight(conv, res, tc)
+        b = self.fused_bias(conv, res)
+        ho, wo = ops.conv_out_hw(d)
+        dev = src0.device
+        if out_layout == L.OUT_NCHW_F32:
+            out = self.ws.get(name, (d.n, cout, ho, wo), torch.float32, dev)
+            ops.conv2d_launch(d, w, b, out, temb, addend)
+            return out
+        if out_layout == L.OUT_QKV:
+            c = cout // 3
+            q = self.ws.get(name + ".q", (d.n, ho * wo, c), act_dtype, dev)
+            k = self.ws.get(name + ".k", (d.n, ho * wo, c), act_dtype, dev)
+            vt = self.ws.get(name + ".vt", (d.n, c, ho * wo), act_dtype, dev)
+            ops.conv2d_launch(d, w, b, q, temb, addend, k, vt)
+            return q, k, vt
+        out = self.ws.get(name, (d.n, ho, wo, cout), act_dtype, dev)
+        ops.conv2d_launch(d, w, b, out, temb, addend)
+        return out
+
+    def gn(self, name: str, norm: nn.GroupNorm, src0: Tensor, src1: Optional[Tensor], silu: bool,
+           scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, mask: Optional[Tensor] = None) -> Tensor:
+        n, h, w, c0 = src0.shape
+        c = c0 + (src1.shape[3] if src1 is not None else 0)
+        out = self.ws.get(name, (n, h, w, c), src0.dtype, src0.device)
+        return ops.groupnorm(src0, src1, norm.num_groups, norm.weight.detach(), norm.bias.detach(), silu, scale, shift,
+                             mask, norm.eps, out)
+
+    # -- blocks ------------------------------------------------------------------------------
+    def attention_block(self, name: str, att: nn.Module, x: Tensor) -> Tensor:
+        n, h, w, c = x.shape
+        seq = h * w
+        a = self.gn("scratch.attn_norm", att.norm, x, None, silu=False)
+        heads = getattr(att, "num_heads", None)
+        ao = self.ws.get("scratch.attn_out", (n, h, w, c), x.dtype, x.device)
+        if heads is None:
+            # single head; scale on K in the reference (models/ddpm.py:58) == scale on the scores
+            q, k, vt = self.conv("scratch.qkv", a, None, att.qkv_proj, out_layout=L.OUT_QKV)
+            ops.attention(q, k, vt, n, 1, seq, c, att.scale, seq * c, c, 0, True, c * seq, False, ao)
+        else:
+            # channels are [head][q | k | v][dh] (models/iddpm.py:38-39)
+            qkv = self.conv("scratch.qkv", a, None, att.qkv_proj)
+            dh = c // heads
+            flat = qkv.view(-1)
+            ops.attention(flat, flat[dh:], flat[2 * dh:], n, heads, seq, dh, att.scale, seq * 3 * c, 3 * c, 3 * dh,
+                          False, 0, True, ao)
+        return self.conv(name + ".attn", ao, None, att.proj, addend=x)
+
+    def resblock(self, name: str, blk: nn.Module, x0: Tensor, x1: Optional[Tensor], temb_all: Tensor,
+                 offs: Dict[int, Tuple[int, int]], masks: Optional[Dict[str, Tensor]]) -> Tensor:
+        o, width = offs[id(blk)]
+        cond = temb_all[:, o:o + width]
+        mask = masks.get(name) if masks else None
+        a1 = self.gn("scratch.a1", blk.conv1[0], x0, x1, silu=True)
+        conv2 = blk.conv2[-1]
+        if self.flavour == "ddpm":
+            h1 = self.conv("scratch.h1", a1, None, blk.conv1[2], temb=cond)
+            a2 = self.gn("scratch.a2", blk.conv2[0], h1, None, silu=True, mask=mask)
+        else:
+            h1 = self.conv("scratch.h1", a1, None, blk.conv1[2])
+            cout = width // 2
+            a2 = self.gn("scratch.a2", blk.norm, h1, None, silu=True, shift=cond[:, :cout], scale=cond[:, cout:], mask=mask)
+        has_attn = not isinstance(blk.attention, nn.Identity)
+        out_name = name + (".pre" if has_attn else "")
+        if isinstance(blk.residual, nn.Identity):
+            h2 = self.conv(out_name, a2, None, conv2, addend=x0)
+        else:
+            h2 = self.conv(out_name, a2, None, conv2, res=blk.residual, res0=x0, res1=x1)
+        if has_attn:
+            h2 = self.attention_block(name, blk.attention, h2)
+        return h2
+
+    # -- whole network -------------------------------------------------------------------------
+    def forward(self, x: Tensor, c: Tensor, act_dtype: torch.dtype, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+        u = self.unet
+        L.require_cuda(x, c)
+        if x.dtype != torch.float32:
+            x = x.float()
+        if c.dtype != torch.int64:
+            c = c.long()
+        if c.dim() != 1 or c.numel() not in (1, x.shape[0]):
+            raise ValueError(f"timestep tensor must have shape (1,) or (N,), got {tuple(c.shape)}")
+        dev = x.device
+        cond = u.condition
+        emb = ops.temb_mlp(c, cond[0].embeddings, cond[1].weight.detach(), cond[1].bias.detach(), cond[3].weight.detach(),
+                           cond[3].bias.detach(), out=self.ws.get("temb.emb", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev))
+        wcat, bcat, offs = self.temb_tables()
+        temb_all = ops.temb_proj(emb, wcat, bcat, out=self.ws.get("temb.all", (c.numel(), wcat.shape[0]), torch.float32, dev))
+
+        h = self.conv("input_conv", x, None, u.input_conv, in_nchw=True, act_dtype=act_dtype)
+        skips = [h]
+        for i, m in enumerate(u.down_layers):
+            name = f"down_layers.{i}"
+            if hasattr(m, "conv1"):
+                h = self.resblock(name, m, h, None, temb_all, offs, masks)
+            else:
+                h = self.conv(name, h, None, m, stride=2)
+            skips.append(h)
+        for i, m in enumerate(u.middle_layers):
+            h = self.resblock(f"middle_layers.{i}", m, h, None, temb_all, offs, masks)
+        for i, m in enumerate(u.up_layers):
+            name = f"up_layers.{i}"
+            if hasattr(m, "conv1"):
+                h = self.resblock(name, m, h, skips.pop(), temb_all, offs, masks)
+            else:
+                h = self.conv(name, h, None, m.conv, upsample=True)
+        a = self.gn("scratch.out_norm", u.output_conv[0], h, None, silu=True)
+        return self.conv("output_conv", a, None, u.output_conv[2], out_layout=L.OUT_NCHW_F32)

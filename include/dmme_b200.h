@@ -1,0 +1,178 @@
+/*
+ * dmme_b200.h -- C ABI of the B200-native hot path of diffusion-models-made-easy (dmme 0.5.2).
+ *
+ * The reference has no FFI layer: its hot path is a tree of torch.nn.Module calls.  Each entry
+ * point below replaces the ATen op sequence of one reference call site (cited per function,
+ * paths relative to the reference checkout).  All pointers are raw device pointers owned by
+ * the caller (torch owns the memory, kernels borrow it for the duration of the launch), all
+ * launches go to the given cudaStream_t (passed as void*), nothing synchronises, nothing
+ * allocates: every entry point is CUDA-graph capturable.
+ *
+ * Return value: 0 on success, a negative DMME_E_* code for an argument/shape error, or a
+ * positive cudaError_t.  dmme_last_error() returns a thread-local message for the last failure.
+ *
+ * Activation layout between kernels is NHWC ("pixel rows of channels"); activation storage
+ * type is selected per call by `act_dtype` (DMME_BF16 for the tensor-core path, DMME_F32 for
+ * the fp32 parity mode).  Image-space tensors (x_t, eps, noise) stay NCHW fp32 exactly as the
+ * reference holds them.
+ */
+#ifndef DMME_B200_H
+#define DMME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMME_ABI_VERSION 1
+
+enum { DMME_BF16 = 0, DMME_F32 = 1 };
+
+enum {
+  DMME_OK = 0,
+  DMME_E_BADARG = -1,      /* null pointer, non-positive size */
+  DMME_E_SHAPE = -2,       /* shape not supported by the requested kernel */
+  DMME_E_UNSUPPORTED = -3, /* feature combination not implemented */
+  DMME_E_DRIVER = -4       /* CUDA driver entry point unavailable (no tensor-map encoder) */
+};
+
+/* input / output layouts of a convolution call */
+enum { DMME_IN_NHWC = 0, DMME_IN_NCHW_F32 = 1 };
+enum {
+  DMME_OUT_NHWC = 0,     /* out[n][y][x][cout], act_dtype */
+  DMME_OUT_NCHW_F32 = 1, /* out[n][cout][y][x], fp32 (eps in image space) */
+  DMME_OUT_QKV = 2       /* cout = 3*C: q -> out[n][L][C], k -> out2[n][L][C], v -> out3[n][C][L] (V^T) */
+};
+
+/* which convolution kernel to run */
+enum {
+  DMME_CONV_AUTO = 0,    /* tcgen05 when the shape allows, generic otherwise */
+  DMME_CONV_GENERIC = 1, /* FFMA implicit GEMM, any shape, fp32 math */
+  DMME_CONV_TC = 2       /* tcgen05/TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate) */
+};
+
+/*
+ * One fused convolution:   out = conv_{k x k, stride, pad k/2}( cat(src0, src1) [nearest x2] )
+ *                                + conv_{1x1}( cat(res0, res1) )        (optional fused residual conv)
+ *                                + bias + temb[n or 0][:] + addend      (optional epilogue terms)
+ * Replaces: nn.Conv2d call sites models/ddpm.py:30,51,52,109,147,162,219,277 together with the
+ * in-place adds of ResBlock.forward models/ddpm.py:129,131, the skip torch.cat models/ddpm.py:310,
+ * nn.Upsample models/ddpm.py:161 and the attention residual models/ddpm.py:75.
+ */
+typedef struct dmme_conv_desc {
+  const void* src0; const void* src1; /* NHWC activations (or NCHW fp32 image when in_layout says so) */
+  int c0, c1;                         /* channels of src0 / src1 (c1 = 0: no concat) */
+  const void* res0; const void* res1; /* operands of the fused 1x1 residual conv, output resolution */
+  int rc0, rc1;                       /* channels of res0 / res1 (0: none) */
+  int n, h_in, w_in;                  /* batch and spatial size of src0/src1 */
+  int ksize;                          /* 1 or 3 */
+  int stride;                         /* 1 or 2 */
+  int upsample;                       /* 1: nearest-neighbour x2 of the source before the conv */
+  int cout;
+  const void* weight;                 /* packed by dmme_pack_conv_weight for the chosen kernel */
+  const float* bias;                  /* [cout] fp32, may be NULL */
+  const float* temb;                  /* optional [temb_rows][temb_ld] fp32, rows = 1 (broadcast) or n */
+  int temb_rows, temb_ld;
+  const void* addend;                 /* optional NHWC tensor of the output shape, act_dtype */
+  void* out; void* out2; void* out3;
+  int in_layout, out_layout;
+  int act_dtype;
+  int kernel;                         /* DMME_CONV_* */
+} dmme_conv_desc;
+
+/* library / device ------------------------------------------------------------------------- */
+int dmme_abi_version(void);
+const char* dmme_last_error(void);
+/* number of kernel launches issued through this library since the last reset (process-wide) */
+long long dmme_launch_count(void);
+void dmme_reset_launch_count(void);
+
+/* weights ---------------------------------------------------------------------------------- */
+/*
+ * Pack OIHW fp32 conv weights (state_dict layout, models/ddpm.py:30) and an optional fused
+ * 1x1 residual weight [cout][rc][1][1] (models/ddpm.py:109) into the GEMM-B layout:
+ *   kernel == DMME_CONV_TC      -> bf16 [cout][K]   (K-major rows, K = k*k*cin + rc, tap-major)
+ *   kernel == DMME_CONV_GENERIC -> fp32 [K][cout]
+ */
+int dmme_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, const float* w_res, int rc,
+                          void* packed, int kernel, void* stream);
+
+/* layout helpers --------------------------------------------------------------------------- */
+int dmme_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int act_dtype, void* stream);
+int dmme_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int act_dtype, void* stream);
+int dmme_upsample2x_nhwc(const void* src, void* dst, int n, int h, int w, int c, int act_dtype, void* stream);
+
+/* convolution ------------------------------------------------------------------------------ */
+int dmme_conv2d_fwd(const dmme_conv_desc* desc, void* stream);
+/* 1 when dmme_conv2d_fwd would take the tcgen05 path for this descriptor */
+int dmme_conv2d_uses_tc(const dmme_conv_desc* desc);
+
+/* GroupNorm (+ scale/shift) (+ SiLU) (+ channel dropout mask) -------------------------------- */
+/*
+ * y = [mask[n][c] *] [silu]( [ (1 + scale[n or 0][c]) * ] GN_{groups,eps}(cat(src0,src1)) * gamma + beta [+ shift] )
+ * Replaces: nn.GroupNorm -> nn.SiLU -> nn.Dropout2d of norm_act_drop_conv models/ddpm.py:25-35,
+ * Attention.norm models/ddpm.py:73 and the scale-shift norm of models/iddpm.py:119.
+ */
+int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, int c1, int n, int hw, int groups, float eps,
+                       const float* gamma, const float* beta, const float* scale, const float* shift,
+                       int ss_rows, int ss_ld, const float* chan_mask, int apply_silu, void* out,
+                       int act_dtype, void* stream);
+
+/* self-attention core ---------------------------------------------------------------------- */
+/*
+ * out[b'][l][h'*dh + c] = softmax_j( scale * <q[b][l][h], k[b][j][h]> ) v[b][j][h][c]
+ * q/k/v element (b, l, h, c) lives at ptr[b*batch_stride + l*row_stride + h*head_stride + c]
+ * (v_transposed = 1: v element at v[b*batch_stride_v + (h*dh + c)*L + l]).
+ * head_batch_swap = 1 reproduces the "(b head)" -> "(head b)" regrouping of
+ * MultiHeadAttention.forward_attention models/iddpm.py:38-46; 0 is Attention models/ddpm.py:54-63.
+ */
+int dmme_attention_fwd(const void* q, const void* k, const void* v, long long batch_stride, int row_stride,
+                       int head_stride, int v_transposed, long long v_batch_stride, int n, int heads, int L,
+                       int dh, float scale, int head_batch_swap, void* out, int act_dtype, void* stream);
+
+/* timestep embedding ----------------------------------------------------------------------- */
+/*
+ * emb = SiLU(W2 SiLU(W1 [sin(t f), cos(t f)] + b1) + b2)   (UNet.condition models/ddpm.py:211-217,338-349)
+ * t: int64 device pointer [rows]; freq: the persistent `condition.0.embeddings` buffer [half].
+ */
+int dmme_temb_mlp_fwd(const int64_t* t, int rows, const float* freq, int half, const float* w1, const float* b1,
+                      const float* w2, const float* b2, int emb_dim, float* emb_out, void* stream);
+/* out[rows][total] = emb[rows][emb_dim] Wcat[total][emb_dim]^T + bcat: all ResBlock.condition Linears
+ * (models/ddpm.py:101-104, models/iddpm.py:89-92) batched into one launch. */
+int dmme_temb_proj_fwd(const float* emb, int rows, int emb_dim, const float* wcat, const float* bcat, int total,
+                       float* out, void* stream);
+
+/* sampler updates (image space, NCHW fp32, elementwise) ------------------------------------- */
+/*
+ * tables: fp32 device arrays of length T+1 (beta, alpha, alpha_bar as registered by
+ * DDPM.__init__ diffusion_models/ddpm.py:41-51); t_ptr: int64 device scalar holding the current t.
+ * noise: fp32 tensor of standard normals (NULL: draw Philox4x32-10 normals from (seed, *t_ptr)).
+ * ddpm:  x <- where(t==1, mean, mean + sqrt(beta_t) z), mean = 1/sqrt(alpha_t) (x - beta_t/sqrt(1-abar_t) eps)
+ *        (diffusion_models/ddpm.py:83-111, equations/ddpm/ddpm.py:44-72)
+ */
+int dmme_ddpm_step(float* x, const float* eps, const float* noise, const float* beta, const float* alpha,
+                   const float* alpha_bar, const int64_t* t_ptr, long long numel, unsigned long long seed,
+                   void* stream);
+/* ddim (as written in equations/ddim/ddim.py:52-57): x0 = (x - sqrt(1-abar_i) eps)/sqrt(abar_prev); x <- sqrt(abar_prev) x0
+ * i_ptr: int64 device scalar with the sub-sequence index i; tau: int64 [S+1]. */
+int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar, const int64_t* tau, const int64_t* i_ptr,
+                   long long numel, void* stream);
+/* iddpm learned variance (diffusion_models/iddpm.py:118-164, equations/iddpm/losses.py:34-37):
+ * model_out NCHW fp32 [n][2*c][hw]: first c channels eps, last c channels v. */
+int dmme_iddpm_step(float* x, const float* model_out, const float* noise, const float* beta, const float* alpha,
+                    const float* alpha_bar, const int64_t* t_ptr, int n, int c, int hw, unsigned long long seed,
+                    void* stream);
+/* writes tau[*i_ptr] into *t_out (DDIM: the model is evaluated at tau_i) */
+int dmme_gather_i64(const int64_t* table, const int64_t* idx_ptr, int64_t* out, void* stream);
+/* *value += delta: advances the device-resident step counter between graph replays
+ * (the host loop `for t in range(T, 0, -1)` of DDPM.generate diffusion_models/ddpm.py:130) */
+int dmme_add_i64(int64_t* value, int64_t delta, void* stream);
+/* standard normals from Philox4x32-10 keyed by (seed, stream_id): used for x_T and per-step z */
+int dmme_philox_normal(float* out, long long numel, unsigned long long seed, unsigned long long stream_id,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMME_B200_H */

@@ -1,0 +1,411 @@
+"""Kernel-level parity: every C-ABI entry point against a plain torch fp32 computation of the same op
+on the CPU (the oracle's building blocks).  Tolerances: fp32 kernels 1e-5 rel-L2 (accumulation order),
+bf16-operand kernels 4e-3 rel-L2 against an fp32 computation on the SAME bf16-rounded operands
+(only the fp32 accumulation order and the bf16 output rounding differ), sampler updates bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import bf16_round, rel_l2, to_nchw, to_nhwc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from dmme_b200 import ops, _lib
+    return ops, _lib
+
+
+def run_conv(x, w, b, *, x1=None, stride=1, upsample=False, res=None, wres=None, bres=None, temb=None,
+             addend=None, dtype=torch.float32, kernel=None, in_nchw=False, out_layout=None):
+    """x, x1, res: NCHW fp32 CPU tensors.  Returns NCHW fp32 CPU output of the CUDA conv."""
+    ops, L = _ops()
+    kernel = L.CONV_AUTO if kernel is None else kernel
+    out_layout = L.OUT_NHWC if out_layout is None else out_layout
+    if in_nchw:
+        s0 = x.to(DEV).contiguous()
+        s1 = None
+    else:
+        s0 = to_nhwc(x, dtype).to(DEV)
+        s1 = to_nhwc(x1, dtype).to(DEV) if x1 is not None else None
+    r0 = to_nhwc(res, dtype).to(DEV) if res is not None else None
+    cout = w.shape[0]
+    d = ops.make_conv_desc(s0, s1, cout, w.shape[2], stride, upsample, r0, None, in_nchw, out_layout, dtype, kernel)
+    tc = ops.conv_uses_tc(d)
+    if kernel == L.CONV_TC:
+        assert tc, "shape must be eligible for the tcgen05 path"
+    wp = ops.pack_conv_weight(w.to(DEV), wres.to(DEV) if wres is not None else None, tc)
+    bias = b if bres is None else b + bres
+    ho, wo = ops.conv_out_hw(d)
+    n = x.shape[0]
+    ad = to_nhwc(addend, dtype).to(DEV) if addend is not None else None
+    tb = temb.to(DEV).contiguous() if temb is not None else None
+    if out_layout == L.OUT_NCHW_F32:
+        out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=DEV)
+        ops.conv2d_launch(d, wp, bias.to(DEV), out, tb, ad)
+        torch.cuda.synchronize()
+        return out.cpu(), tc
+    if out_layout == L.OUT_QKV:
+        c = cout // 3
+        q = torch.empty((n, ho * wo, c), dtype=dtype, device=DEV)
+        k = torch.empty_like(q)
+        vt = torch.empty((n, c, ho * wo), dtype=dtype, device=DEV)
+        ops.conv2d_launch(d, wp, bias.to(DEV), q, tb, ad, k, vt)
+        torch.cuda.synchronize()
+        return (q.float().cpu(), k.float().cpu(), vt.float().cpu()), tc
+    out = torch.empty((n, ho, wo, cout), dtype=dtype, device=DEV)
+    ops.conv2d_launch(d, wp, bias.to(DEV), out, tb, ad)
+    torch.cuda.synchronize()
+    return to_nchw(out.cpu()), tc
+
+
+def ref_conv(x, w, b, *, x1=None, stride=1, upsample=False, res=None, wres=None, bres=None, temb=None, addend=None):
+    xin = x if x1 is None else torch.cat([x, x1], dim=1)
+    if upsample:
+        xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+    y = F.conv2d(xin, w, b, stride=stride, padding=w.shape[2] // 2)
+    if res is not None:
+        y = y + F.conv2d(res, wres, bres)
+    if temb is not None:
+        rows = temb if temb.shape[0] == x.shape[0] else temb.expand(x.shape[0], -1)
+        y = y + rows[:, :, None, None]
+    if addend is not None:
+        y = y + addend
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# generic (FFMA) convolution: arbitrary shapes, fp32 storage
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(n=2, cin=3, cout=4, h=32, w=32, k=3),
+    dict(n=3, cin=8, cout=16, h=16, w=16, k=3, stride=2),
+    dict(n=2, cin=16, cout=8, h=8, w=8, k=3, upsample=True),
+    dict(n=2, cin=5, cout=7, h=6, w=10, k=1),
+    dict(n=1, cin=32, cout=32, h=4, w=4, k=3, cin1=32),
+    dict(n=2, cin=16, cout=24, h=8, w=8, k=3, res=40, temb="rows", addend=False),
+    dict(n=2, cin=16, cout=16, h=8, w=8, k=3, temb="bcast", addend=True),
+    dict(n=1, cin=70, cout=130, h=5, w=7, k=3),
+])
+def test_conv_generic_fp32(cfg):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(11)
+    n, cin, cout, h, w, k = (cfg[s] for s in ("n", "cin", "cout", "h", "w", "k"))
+    stride, up = cfg.get("stride", 1), cfg.get("upsample", False)
+    x = torch.randn(n, cin, h, w, generator=g)
+    x1 = torch.randn(n, cfg["cin1"], h, w, generator=g) if cfg.get("cin1") else None
+    ctot = cin + (cfg.get("cin1") or 0)
+    wt = torch.randn(cout, ctot, k, k, generator=g) / math.sqrt(ctot * k * k)
+    b = torch.randn(cout, generator=g)
+    ho, wo = (h * (2 if up else 1)) // stride, (w * (2 if up else 1)) // stride
+    kw = {}
+    if cfg.get("res"):
+        kw.update(res=torch.randn(n, cfg["res"], ho, wo, generator=g),
+                  wres=torch.randn(cout, cfg["res"], 1, 1, generator=g) / math.sqrt(cfg["res"]),
+                  bres=torch.randn(cout, generator=g))
+    if cfg.get("temb") == "rows":
+        kw["temb"] = torch.randn(n, cout, generator=g)
+    elif cfg.get("temb") == "bcast":
+        kw["temb"] = torch.randn(1, cout, generator=g)
+    if cfg.get("addend"):
+        kw["addend"] = torch.randn(n, cout, ho, wo, generator=g)
+    got, tc = run_conv(x, wt, b, x1=x1, stride=stride, upsample=up, kernel=L.CONV_GENERIC, **kw)
+    assert not tc
+    want = ref_conv(x, wt, b, x1=x1, stride=stride, upsample=up, **kw)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) < 1e-5
+
+
+def test_conv_generic_nchw_in_out():
+    _, L = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    w = torch.randn(16, 3, 3, 3, generator=g) / 5
+    b = torch.randn(16, generator=g)
+    got, _ = run_conv(x, w, b, kernel=L.CONV_GENERIC, in_nchw=True)
+    assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 1e-5
+    w2 = torch.randn(3, 16, 3, 3, generator=g) / 12
+    b2 = torch.randn(3, generator=g)
+    y = torch.randn(2, 16, 8, 8, generator=g)
+    got2, _ = run_conv(y, w2, b2, kernel=L.CONV_GENERIC, out_layout=L.OUT_NCHW_F32)
+    assert rel_l2(got2, F.conv2d(y, w2, b2, padding=1)) < 1e-5
+
+
+def test_conv_generic_bf16_storage():
+    _, L = _ops()
+    g = torch.Generator().manual_seed(6)
+    x = bf16_round(torch.randn(2, 24, 8, 8, generator=g))
+    w = torch.randn(40, 24, 3, 3, generator=g) / 15
+    b = torch.randn(40, generator=g)
+    got, _ = run_conv(x, w, b, dtype=torch.bfloat16, kernel=L.CONV_GENERIC)
+    assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 4e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 convolution
+# ---------------------------------------------------------------------------------------------
+TC_CASES = [
+    dict(n=2, cin=64, cout=64, h=32, w=32, k=3),                      # BN=64, smallest case
+    dict(n=4, cin=128, cout=128, h=32, w=32, k=3, temb="bcast"),       # the dominant shape
+    dict(n=2, cin=128, cout=256, h=16, w=16, k=3, temb="rows"),
+    dict(n=3, cin=256, cout=256, h=16, w=16, k=3, addend=True),
+    dict(n=5, cin=256, cout=256, h=8, w=8, k=3),                       # 2 images per tile, ragged batch
+    dict(n=11, cin=256, cout=256, h=4, w=4, k=3),                      # 8 images per tile, ragged batch
+    dict(n=2, cin=128, cout=128, h=32, w=32, k=3, stride=2),           # DownSample
+    dict(n=3, cin=256, cout=256, h=8, w=8, k=3, stride=2),
+    dict(n=2, cin=256, cout=128, h=32, w=32, k=3, cin1=128, res=True),  # concat + fused 1x1 residual
+    dict(n=2, cin=256, cout=256, h=16, w=16, k=3, cin1=256, res=True),
+    dict(n=2, cin=256, cout=256, h=16, w=16, k=1),                     # attention proj
+    dict(n=2, cin=128, cout=128, h=16, w=16, k=1, addend=True),
+    dict(n=40, cin=256, cout=256, h=16, w=16, k=3),                    # enough tiles to select BN=256
+]
+
+
+@pytest.mark.parametrize("cfg", TC_CASES)
+def test_conv_tc(cfg):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(21)
+    n, cin, cout, h, w, k = (cfg[s] for s in ("n", "cin", "cout", "h", "w", "k"))
+    stride = cfg.get("stride", 1)
+    c1 = cfg.get("cin1", 0)
+    c0 = cin - c1
+    xa = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    x, x1 = (xa[:, :c0].contiguous(), xa[:, c0:].contiguous()) if c1 else (xa, None)
+    wt = bf16_round(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    b = torch.randn(cout, generator=g)
+    ho, wo = h // stride, w // stride
+    kw = {}
+    if cfg.get("res"):
+        # the fused residual conv reads the same concat input
+        kw.update(res=xa, wres=bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin)),
+                  bres=torch.randn(cout, generator=g))
+    if cfg.get("temb") == "rows":
+        kw["temb"] = torch.randn(n, cout, generator=g)
+    elif cfg.get("temb") == "bcast":
+        kw["temb"] = torch.randn(1, cout, generator=g)
+    if cfg.get("addend"):
+        kw["addend"] = bf16_round(torch.randn(n, cout, ho, wo, generator=g))
+    got, tc = run_conv(x, wt, b, x1=x1, stride=stride, dtype=torch.bfloat16, kernel=L.CONV_TC, **kw)
+    assert tc
+    want = ref_conv(x, wt, b, x1=x1, stride=stride, **kw)
+    err = rel_l2(got, want)
+    assert err < 4e-3, f"rel-L2 {err}"
+
+
+def test_conv_tc_res_two_sources():
+    """fused residual conv whose operand is itself a two-source concat (the up-path ResBlocks)."""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(3)
+    n, c0, c1, cout, h = 2, 128, 128, 128, 16
+    a2 = bf16_round(torch.randn(n, cout, h, h, generator=g))
+    xa = bf16_round(torch.randn(n, c0 + c1, h, h, generator=g))
+    w2 = bf16_round(torch.randn(cout, cout, 3, 3, generator=g) / math.sqrt(9 * cout))
+    wr = bf16_round(torch.randn(cout, c0 + c1, 1, 1, generator=g) / math.sqrt(c0 + c1))
+    b = torch.randn(cout, generator=g)
+    s0 = to_nhwc(a2, torch.bfloat16).to(DEV)
+    r0 = to_nhwc(xa[:, :c0], torch.bfloat16).to(DEV)
+    r1 = to_nhwc(xa[:, c0:], torch.bfloat16).to(DEV)
+    d = ops.make_conv_desc(s0, None, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_TC)
+    wp = ops.pack_conv_weight(w2.to(DEV), wr.to(DEV), True)
+    out = torch.empty((n, h, h, cout), dtype=torch.bfloat16, device=DEV)
+    ops.conv2d_launch(d, wp, b.to(DEV), out)
+    torch.cuda.synchronize()
+    want = F.conv2d(a2, w2, b, padding=1) + F.conv2d(xa, wr)
+    assert rel_l2(to_nchw(out.cpu()), want) < 4e-3
+
+
+@pytest.mark.parametrize("kernel", ["tc", "generic"])
+@pytest.mark.parametrize("c,h", [(128, 16), (256, 16), (256, 4)])
+def test_conv_qkv_layout(kernel, c, h):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(8)
+    n = 3
+    x = bf16_round(torch.randn(n, c, h, h, generator=g))
+    w = bf16_round(torch.randn(3 * c, c, 1, 1, generator=g) / math.sqrt(c))
+    b = torch.randn(3 * c, generator=g)
+    (q, k, vt), tc = run_conv(x, w, b, dtype=torch.bfloat16, kernel=L.CONV_TC if kernel == "tc" else L.CONV_GENERIC,
+                              out_layout=L.OUT_QKV)
+    assert tc == (kernel == "tc")
+    y = F.conv2d(x, w, b).flatten(2)  # n, 3c, L
+    assert rel_l2(q, y[:, :c].transpose(1, 2)) < 4e-3
+    assert rel_l2(k, y[:, c:2 * c].transpose(1, 2)) < 4e-3
+    assert rel_l2(vt, y[:, 2 * c:]) < 4e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(n=3, c=128, hw=(32, 32), groups=32, dtype="bf16", silu=True),
+    dict(n=2, c=256, hw=(16, 16), groups=32, dtype="bf16", silu=True, c1=128),
+    dict(n=2, c=512, hw=(8, 8), groups=32, dtype="bf16", silu=False),
+    dict(n=5, c=256, hw=(4, 4), groups=32, dtype="bf16", silu=True, ss=True, mask=True),
+    dict(n=2, c=8, hw=(16, 16), groups=2, dtype="fp32", silu=True),
+    dict(n=2, c=12, hw=(5, 7), groups=3, dtype="fp32", silu=False, c1=4, ss=True, mask=True),
+    dict(n=2, c=64, hw=(64, 64), groups=32, dtype="bf16", silu=True),
+])
+def test_groupnorm(cfg):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(4)
+    n, c, (h, w), groups = cfg["n"], cfg["c"], cfg["hw"], cfg["groups"]
+    dtype = torch.bfloat16 if cfg["dtype"] == "bf16" else torch.float32
+    x = torch.randn(n, c, h, w, generator=g) * 2 + 0.5
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+    gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g)
+    c1 = cfg.get("c1", 0)
+    s0 = to_nhwc(x[:, :c - c1], dtype).to(DEV)
+    s1 = to_nhwc(x[:, c - c1:], dtype).to(DEV) if c1 else None
+    scale = shift = mask = None
+    want = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+    if cfg.get("ss"):
+        both = torch.randn(n, 2 * c, generator=g)
+        shift, scale = both[:, :c], both[:, c:]
+        want = want * (scale[:, :, None, None] + 1) + shift[:, :, None, None]
+        both = both.to(DEV)
+        shift, scale = both[:, :c], both[:, c:]
+    if cfg["silu"]:
+        want = F.silu(want)
+    if cfg.get("mask"):
+        mask = (torch.rand(n, c, generator=g) > 0.3).float() / 0.7
+        want = want * mask[:, :, None, None]
+        mask = mask.to(DEV)
+    got = ops.groupnorm(s0, s1, groups, gamma.to(DEV), beta.to(DEV), cfg["silu"], scale, shift, mask)
+    torch.cuda.synchronize()
+    tol = 4e-3 if dtype == torch.bfloat16 else 1e-5
+    assert rel_l2(to_nchw(got.cpu()), want) < tol
+
+
+# ---------------------------------------------------------------------------------------------
+# attention core
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,c,L_,dtype", [(2, 16, 64, "fp32"), (3, 128, 256, "bf16"), (2, 256, 16, "bf16"), (1, 8, 1024, "fp32")])
+def test_attention_single_head(n, c, L_, dtype):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(9)
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    q, k, v = (torch.randn(n, L_, c, generator=g) for _ in range(3))
+    if dt == torch.bfloat16:
+        q, k, v = bf16_round(q), bf16_round(k), bf16_round(v)
+    scale = c ** -0.5
+    want = torch.bmm(F.softmax(torch.bmm(q, k.transpose(1, 2) * scale), dim=2), v)
+    out = torch.empty(n, L_, c, dtype=dt, device=DEV)
+    vt = v.transpose(1, 2).contiguous().to(dt).to(DEV)
+    ops.attention(q.to(dt).to(DEV), k.to(dt).to(DEV), vt, n, 1, L_, c, scale, L_ * c, c, 0, True, c * L_, False, out)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().cpu(), want) < (4e-3 if dt == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("n,c,heads,L_", [(3, 32, 4, 64), (2, 128, 4, 256), (4, 16, 4, 16)])
+def test_attention_multi_head_iddpm_regrouping(n, c, heads, L_):
+    """models/iddpm.py:36-47 including the (b head) -> (head b) output regrouping."""
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(10)
+    qkv = torch.randn(n, L_, 3 * c, generator=g)  # NHWC view of the qkv conv output, channels [head][q|k|v][dh]
+    dh = c // heads
+    t = qkv.reshape(n, L_, heads, 3 * dh).permute(0, 2, 1, 3).reshape(n * heads, L_, 3 * dh)
+    q, k, v = t.chunk(3, dim=2)
+    scale = c ** -0.5
+    o = torch.bmm(F.softmax(torch.bmm(q, k.transpose(1, 2) * scale), dim=2), v)
+    want = o.reshape(heads, n, L_, dh).permute(1, 2, 0, 3).reshape(n, L_, c)
+    dev = qkv.to(DEV).contiguous()
+    flat = dev.view(-1)
+    out = torch.empty(n, L_, c, dtype=torch.float32, device=DEV)
+    ops.attention(flat, flat[dh:], flat[2 * dh:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, 3 * dh, False, 0, True, out)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), want) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# timestep embedding
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,pos,emb", [(1, 128, 512), (7, 128, 512), (3, 4, 8)])
+def test_temb(rows, pos, emb):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(12)
+    half = pos // 2
+    freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).unsqueeze(0)
+    t = torch.randint(0, 1001, (rows,), generator=g)
+    w1, b1 = torch.randn(emb, pos, generator=g) / math.sqrt(pos), torch.randn(emb, generator=g)
+    w2, b2 = torch.randn(emb, emb, generator=g) / math.sqrt(emb), torch.randn(emb, generator=g)
+    e = t.unsqueeze(1) * freq
+    e = torch.cat((e.sin(), e.cos()), dim=-1)
+    want = F.silu(F.linear(F.silu(F.linear(e, w1, b1)), w2, b2))
+    got = ops.temb_mlp(t.to(DEV), freq.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(got.cpu(), want) < 2e-5
+    wc, bc = torch.randn(300, emb, generator=g) / math.sqrt(emb), torch.randn(300, generator=g)
+    got2 = ops.temb_proj(got, wc.to(DEV), bc.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(got2.cpu(), F.linear(got.cpu(), wc, bc)) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler updates: bit-exact against the oracle given the same eps and z
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("t", [1000, 500, 2, 1])
+def test_ddpm_step_bit_exact(t):
+    import dmme_oracle as O
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(13)
+    tabs = O.linear_tables(1000)
+    x, eps, z = (torch.randn(5, 3, 32, 32, generator=g) for _ in range(3))
+    tt = torch.tensor([t])
+    want = O.ddpm_step(x, tt, eps, z, tabs)
+    xd = x.to(DEV).clone()
+    ops.ddpm_step_(xd, eps.to(DEV), z.to(DEV), *(tb.to(DEV) for tb in tabs), tt.to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(xd.cpu(), want)
+
+
+@pytest.mark.parametrize("i", [50, 25, 2, 1])
+def test_ddim_step_bit_exact(i):
+    import dmme_oracle as O
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(14)
+    _, _, ab = O.linear_tables(1000)
+    tau = O.tau_table(1000, 50)
+    x, eps = (torch.randn(4, 3, 32, 32, generator=g) for _ in range(2))
+    ii = torch.tensor([i])
+    want = O.ddim_step(x, ii, eps, ab, tau)
+    xd = x.to(DEV).clone()
+    ops.ddim_step_(xd, eps.to(DEV), ab.to(DEV), tau.to(DEV), ii.to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(xd.cpu(), want)
+
+
+@pytest.mark.parametrize("t", [1000, 400, 1])
+def test_iddpm_step(t):
+    import dmme_oracle as O
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(15)
+    tabs = O.cosine_tables(1000)
+    x, z = (torch.randn(4, 3, 32, 32, generator=g) for _ in range(2))
+    mo = torch.randn(4, 6, 32, 32, generator=g)
+    tt = torch.tensor([t])
+    want = O.iddpm_step(x, tt, mo, z, tabs)
+    xd = x.to(DEV).clone()
+    ops.iddpm_step_(xd, mo.to(DEV), z.to(DEV), *(tb.to(DEV) for tb in tabs), tt.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(xd.cpu(), want) < 1e-6  # expf/logf differ from the CPU's by an ulp
+
+
+def test_philox_normal_moments_and_step_counter():
+    ops, _ = _ops()
+    z = ops.philox_normal((1 << 20,), 1234, 7, DEV)
+    z2 = ops.philox_normal((1 << 20,), 1234, 8, DEV)
+    torch.cuda.synchronize()
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1) < 5e-3
+    assert abs(float((z * z2).mean())) < 5e-3
+    assert abs(float((z ** 4).mean()) - 3) < 5e-2
+    c = torch.full((1,), 10, dtype=torch.int64, device=DEV)
+    ops.add_i64_(c, -1)
+    tau = torch.arange(0, 40, 2, device=DEV)
+    out = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.gather_i64(tau, c, out)
+    torch.cuda.synchronize()
+    assert int(c) == 9 and int(out) == 18

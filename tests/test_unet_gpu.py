@@ -1,0 +1,173 @@
+"""Whole-path parity on the GPU: UNet forward, sampler steps and trajectories against the CPU oracle
+(oracle/dmme_oracle.py, itself pinned to the unmodified reference by tests/test_oracle.py).
+
+Tolerances are BASELINE.json's: per-call UNet output rel-L2 <= 1e-2 in bf16 mode and <= 1e-4 in fp32
+mode against the reference fp32; DDIM eta=0 trajectories from a fixed x_T within the same tolerance."""
+import pytest
+import torch
+
+import dmme_oracle as O
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TINY = dict(in_channels=3, pos_dim=4, emb_dim=8, num_groups=2, channels_per_depth=(4, 8, 16, 32), num_blocks=3)
+BF16_TOL = 1e-2
+FP32_TOL = 1e-4
+
+
+def _unet(flavour, seed=0, **kw):
+    from dmme_b200.models import ddpm, iddpm
+    torch.manual_seed(seed)
+    m = (ddpm.UNet if flavour == "ddpm" else iddpm.UNet)(**kw).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    return m.to(DEV), sd
+
+
+@pytest.mark.parametrize("flavour", ["ddpm", "iddpm"])
+@pytest.mark.parametrize("tshape", ["one", "per_sample"])
+def test_tiny_unet_fp32(flavour, tshape):
+    """the reference's own test fixture (tests/test_ddpm.py:8-15): odd channel counts, 2 groups."""
+    m, sd = _unet(flavour, precision="fp32", **TINY)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 3, 32, 32, generator=g)
+    t = torch.tensor([37]) if tshape == "one" else torch.tensor([1, 50, 99])
+    want = O.unet_forward(sd, x, t, groups=2, flavour=flavour)
+    got = m(x.to(DEV), t.to(DEV)).cpu()
+    assert got.shape == want.shape
+    assert rel_l2(got, want) < FP32_TOL
+
+
+def test_tiny_iddpm_unet_64x64_fp32():
+    """tests/test_iddpm.py:30 feeds 64x64 images: attention at L = 1024 and L = 256."""
+    m, sd = _unet("iddpm", precision="fp32", **TINY)
+    x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    t = torch.tensor([1, 1, 1, 1])
+    want = O.unet_forward(sd, x, t, groups=2, flavour="iddpm")
+    assert rel_l2(m(x.to(DEV), t.to(DEV)).cpu(), want) < FP32_TOL
+
+
+def test_tiny_unet_dropout_masks_fp32():
+    """training-mode channel dropout with injected masks (torch's Philox stream cannot be matched)."""
+    m, sd = _unet("ddpm", precision="fp32", **TINY)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    t = torch.tensor([5, 60])
+    masks = {}
+    for name, blk in m.engine.resblocks():
+        c = blk.conv2[-1].weight.shape[1]
+        masks[name] = (torch.rand(2, c, generator=g) > 0.1).float() / 0.9
+    want = O.unet_forward(sd, x, t, groups=2, dropout_masks=masks)
+    got = m.forward_raw(x.to(DEV), t.to(DEV), {k: v.to(DEV) for k, v in masks.items()}).cpu()
+    assert rel_l2(got, want) < FP32_TOL
+
+
+def _c1_inputs(n=16):
+    torch.manual_seed(1234)
+    return torch.randn(256, 3, 32, 32)[:n].contiguous(), torch.tensor([500])
+
+
+@pytest.mark.parametrize("t", [1, 500, 1000])
+def test_default_ddpm_unet_bf16(t):
+    """BASELINE config #1 inputs (batch 16, seed-0 weights, x from seed 1234) through the tcgen05 path."""
+    m, sd = _unet("ddpm")
+    x, _ = _c1_inputs(16)
+    tt = torch.tensor([t])
+    want = O.unet_forward(sd, x, tt)
+    got = m(x.to(DEV), tt.to(DEV)).cpu()
+    err = rel_l2(got, want)
+    print(f"default ddpm unet bf16 t={t}: rel-L2 {err:.3e}")
+    assert err < BF16_TOL
+
+
+def test_default_ddpm_unet_fp32_mode():
+    m, sd = _unet("ddpm", precision="fp32")
+    x, tt = _c1_inputs(4)
+    want = O.unet_forward(sd, x, tt)
+    err = rel_l2(m(x.to(DEV), tt.to(DEV)).cpu(), want)
+    print(f"default ddpm unet fp32 mode: rel-L2 {err:.3e}")
+    assert err < FP32_TOL
+
+
+def test_default_iddpm_unet_bf16_per_sample_t():
+    """IDDPM flavour, t of shape (N,): the attention regrouping couples samples, so the whole batch is compared."""
+    m, sd = _unet("iddpm")
+    x, _ = _c1_inputs(8)
+    t = torch.tensor([1, 17, 250, 500, 640, 800, 999, 3])
+    want = O.unet_forward(sd, x, t, flavour="iddpm")
+    err = rel_l2(m(x.to(DEV), t.to(DEV)).cpu(), want)
+    print(f"default iddpm unet bf16: rel-L2 {err:.3e}")
+    assert err < BF16_TOL
+
+
+def test_ddpm_sampling_step_injected_noise():
+    from dmme_b200 import DDPM
+    m, sd = _unet("ddpm", precision="fp32", **TINY)
+    d = DDPM(m, timesteps=100).to(DEV)
+    tabs = O.linear_tables(100)
+    g = torch.Generator().manual_seed(4)
+    x, z = torch.randn(3, 3, 32, 32, generator=g), torch.randn(3, 3, 32, 32, generator=g)
+    for t in (100, 1):
+        tt = torch.tensor([t])
+        want = O.ddpm_step(x, tt, O.unet_forward(sd, x, tt, groups=2), z, tabs)
+        got = d.sampling_step(x.to(DEV), tt.to(DEV), noise=z.to(DEV)).cpu()
+        assert rel_l2(got, want) < FP32_TOL
+    with pytest.raises(ValueError):
+        d.sampling_step(x.to(DEV), torch.tensor([3, 4, 5]).to(DEV))
+
+
+def test_iddpm_sampling_step_injected_noise():
+    from dmme_b200 import IDDPM
+    m, sd = _unet("iddpm", precision="fp32", **TINY)
+    d = IDDPM(m, timesteps=100).to(DEV)
+    tabs = O.cosine_tables(100)
+    g = torch.Generator().manual_seed(5)
+    x, z = torch.randn(3, 3, 32, 32, generator=g), torch.randn(3, 3, 32, 32, generator=g)
+    tt = torch.tensor([57])
+    want = O.iddpm_step(x, tt, O.unet_forward(sd, x, tt, groups=2, flavour="iddpm"), z, tabs)
+    got = d.sampling_step(x.to(DEV), tt.to(DEV), noise=z.to(DEV)).cpu()
+    assert rel_l2(got, want) < FP32_TOL
+
+
+def test_ddim_trajectory_tiny_fp32():
+    from dmme_b200 import DDIM
+    m, sd = _unet("ddpm", precision="fp32", **TINY)
+    d = DDIM(m, timesteps=100, sub_timesteps=5).to(DEV)
+    x_T = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(6))
+    _, _, ab = O.linear_tables(100)
+    want = O.ddim_generate(sd, x_T, ab, O.tau_table(100, 5), groups=2)
+    for graph in (False, True):
+        got = d.generate(x_T.shape, x_T=x_T.to(DEV), graph=graph).cpu()
+        assert rel_l2(got, want) < FP32_TOL
+
+
+def test_ddim_trajectory_default_bf16():
+    """BASELINE config #3: 50-step deterministic DDIM (quadratic tau) from a fixed x_T, whole trajectory."""
+    from dmme_b200 import DDIM
+    m, sd = _unet("ddpm")
+    d = DDIM(m).to(DEV)
+    x_T, _ = _c1_inputs(4)
+    _, _, ab = O.linear_tables(1000)
+    want, traj = O.ddim_generate(sd, x_T, ab, O.tau_table(1000, 50), return_trajectory=True)
+    seen = []
+    got = d.generate(x_T.shape, x_T=x_T.to(DEV), on_step=lambda k, x: seen.append(x.cpu().clone())).cpu()
+    errs = [rel_l2(a, b) for a, b in zip(seen, traj)]
+    print("ddim trajectory rel-L2: first %.3e  max %.3e  last %.3e" % (errs[0], max(errs), errs[-1]))
+    assert len(seen) == 50 and max(errs) < BF16_TOL
+    assert rel_l2(got, want) < BF16_TOL
+
+
+def test_ddpm_generate_graph_equals_eager_and_is_seeded():
+    from dmme_b200 import DDPM
+    m, _ = _unet("ddpm", **TINY)
+    d = DDPM(m, timesteps=20).to(DEV)
+    x_T = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(7)).to(DEV)
+    a = d.generate(x_T.shape, x_T=x_T, seed=99, graph=True)
+    b = d.generate(x_T.shape, x_T=x_T, seed=99, graph=False)
+    c = d.generate(x_T.shape, x_T=x_T, seed=100, graph=True)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    assert torch.isfinite(a).all()
+    out = d.generate((2, 3, 32, 32))  # reference smoke test: tests/test_ddpm.py:45-60
+    assert out.shape == (2, 3, 32, 32)
