@@ -158,7 +158,7 @@ TC_CASES = [
     dict(n=2, cin=128, cout=128, h=32, w=32, k=3, stride=2),           # DownSample
     dict(n=3, cin=256, cout=256, h=8, w=8, k=3, stride=2),
     dict(n=2, cin=256, cout=128, h=32, w=32, k=3, cin1=128, res=True),  # concat + fused 1x1 residual
-    dict(n=2, cin=256, cout=256, h=16, w=16, k=3, cin1=256, res=True),
+    dict(n=2, cin=512, cout=256, h=16, w=16, k=3, cin1=256, res=True),
     dict(n=2, cin=256, cout=256, h=16, w=16, k=1),                     # attention proj
     dict(n=2, cin=128, cout=128, h=16, w=16, k=1, addend=True),
     dict(n=40, cin=256, cout=256, h=16, w=16, k=3),                    # enough tiles to select BN=256
