@@ -21,6 +21,9 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool conv_tc_supported(const dmme_conv_desc& d);
 int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream);
 int conv_generic_forward(const dmme_conv_desc& d, cudaStream_t stream);
+bool conv_in_supported(const dmme_conv_desc& d);
+bool conv_out_supported(const dmme_conv_desc& d);
+int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream);
 
 }  // namespace dmme
 
@@ -46,7 +49,9 @@ extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
     case DMME_CONV_GENERIC:
       return conv_generic_forward(*d, st);
     case DMME_CONV_AUTO:
-      return conv_tc_supported(*d) ? conv_tc_forward(*d, st) : conv_generic_forward(*d, st);
+      if (conv_tc_supported(*d)) return conv_tc_forward(*d, st);
+      if (conv_in_supported(*d) || conv_out_supported(*d)) return conv_small_forward(*d, st);
+      return conv_generic_forward(*d, st);
     default:
       set_error("conv2d_fwd: unknown kernel selector %d", d->kernel);
       return DMME_E_BADARG;

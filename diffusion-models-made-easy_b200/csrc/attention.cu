@@ -116,16 +116,33 @@ __global__ void __launch_bounds__(256) attn_generic_kernel(const AttnParams p) {
   }
 }
 
+bool attn_tc_supported(int act_dtype, int heads, int L, int dh, int row_stride, long long batch_stride,
+                       int v_transposed, long long v_batch_stride, int swap);
+int attn_tc_forward(const void* q, const void* k, const void* vt, int n, int d, float scale, void* out,
+                    cudaStream_t stream);
+
 }  // namespace dmme
 
 using namespace dmme;
 
+extern "C" int dmme_attention_uses_tc(long long batch_stride, int row_stride, int v_transposed,
+                                      long long v_batch_stride, int heads, int L, int dh, int head_batch_swap,
+                                      int act_dtype) {
+  return attn_tc_supported(act_dtype, heads, L, dh, row_stride, batch_stride, v_transposed, v_batch_stride,
+                           head_batch_swap) ? 1 : 0;
+}
+
 extern "C" int dmme_attention_fwd(const void* q, const void* k, const void* v, long long batch_stride,
                                   int row_stride, int head_stride, int v_transposed, long long v_batch_stride, int n,
                                   int heads, int L, int dh, float scale, int head_batch_swap, void* out,
-                                  int act_dtype, void* stream) {
+                                  int act_dtype, int kernel, void* stream) {
   DMME_REQUIRE(q && k && v && out, DMME_E_BADARG, "attention: null pointer");
   DMME_REQUIRE(n > 0 && heads > 0 && L > 0 && dh > 0, DMME_E_BADARG, "attention: bad sizes");
+  const bool tc_ok = attn_tc_supported(act_dtype, heads, L, dh, row_stride, batch_stride, v_transposed,
+                                       v_batch_stride, head_batch_swap);
+  DMME_REQUIRE(kernel != DMME_CONV_TC || tc_ok, DMME_E_SHAPE, "attention: shape/layout not eligible for the tcgen05 kernel");
+  if (tc_ok && kernel != DMME_CONV_GENERIC)
+    return attn_tc_forward(q, k, v, n, dh, scale, out, static_cast<cudaStream_t>(stream));
   DMME_REQUIRE(dh <= 256, DMME_E_SHAPE, "attention: head dim %d > 256 not supported", dh);
   const size_t smem = sizeof(float) * (static_cast<size_t>(kAttnRows) * dh + kAttnTile * (dh + 1) +
                                         static_cast<size_t>(kAttnRows) * L);

@@ -1,0 +1,236 @@
+// Fused single-head self-attention core on tcgen05 for the 16x16-resolution blocks (L = 256 tokens):
+//
+//   S = Q K^T   (128 query rows x 256 keys, fp32 in TMEM columns [0,256))
+//   P = exp2((S - rowmax) * scale * log2e)      (fp32 row statistics, P rounded to bf16 into shared memory)
+//   O = P V     (128 x d, fp32 in TMEM columns [256, 256 + d)),   out = O / rowsum
+//
+// One CTA per (image, 128-query block).  Q/K chunks of 64 channels and V^T chunks of 64 keys stream through
+// a two-slot TMA ring; the score matrix never leaves the SM.  Operands are all K-major SWIZZLE_128B tiles:
+// Q,K from the [n][L][C] tensors and V from the transposed [n][C][L] tensor the qkv conv epilogue writes.
+// Replaces torch.bmm / F.softmax / torch.bmm of Attention.forward_attention (models/ddpm.py:58-61).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "tmap.cuh"
+
+namespace dmme {
+
+struct AttnTcParams {
+  CUtensorMap q, k, vt;
+  int n, d;
+  float scale_log2e;
+  __nv_bfloat16* out;  // [n][256][d]
+};
+
+constexpr int kSeq = 256;
+constexpr int kAttnThreads = 192;
+constexpr int kStageA = 128 * 128;        // 128 rows x 64 bf16
+constexpr int kStageB = 256 * 128;        // up to 256 rows x 64 bf16
+constexpr int kAttnStage = kStageA + kStageB;
+constexpr int kAttnStages = 2;
+constexpr int kPBytes = 128 * kSeq * 2;   // P: 4 chunks of [128][64] bf16
+constexpr int kAttnSmem = kAttnStages * kAttnStage + kPBytes + 1024;
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kAttnStages];
+  __shared__ __align__(8) uint64_t empty_bar[kAttnStages];
+  __shared__ __align__(8) uint64_t s_full, p_ready, o_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* ring = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* pbuf = ring + kAttnStages * kAttnStage;
+
+  const int q0 = blockIdx.x * 128;
+  const int img = blockIdx.y;
+  const int d = p.d;
+  const int kch = d / 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kAttnStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&s_full, 1);
+    mbar_init(&p_ready, 128);
+    mbar_init(&o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q);
+    tma_prefetch_desc(&p.k);
+    tma_prefetch_desc(&p.vt);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot;
+  const uint32_t tmem_o = tmem_slot + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int kc = 0; kc < kch; ++kc, ++it) {
+        const int s = it % kAttnStages;
+        mbar_wait(&empty_bar[s], ((it / kAttnStages) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], kStageA + kStageB);
+        tma_load_3d(ring + s * kAttnStage, &p.q, &full_bar[s], kc * 64, q0, img);
+        tma_load_3d(ring + s * kAttnStage + kStageA, &p.k, &full_bar[s], kc * 64, 0, img);
+      }
+      for (int jc = 0; jc < kSeq / 64; ++jc, ++it) {
+        const int s = it % kAttnStages;
+        mbar_wait(&empty_bar[s], ((it / kAttnStages) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], d * 128);
+        tma_load_3d(ring + s * kAttnStage + kStageA, &p.vt, &full_bar[s], jc * 64, 0, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, kSeq);
+      const uint32_t idesc_o = umma_idesc_bf16(128, d);
+      int it = 0;
+      for (int kc = 0; kc < kch; ++kc, ++it) {
+        const int s = it % kAttnStages;
+        mbar_wait(&full_bar[s], (it / kAttnStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + s * kAttnStage);
+        const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + kStageA);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, (kc | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&s_full);
+      mbar_wait(&p_ready, 0);
+      tc_fence_after();
+      for (int jc = 0; jc < kSeq / 64; ++jc, ++it) {
+        const int s = it % kAttnStages;
+        mbar_wait(&full_bar[s], (it / kAttnStages) & 1);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(pbuf + jc * kStageA));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + s * kAttnStage + kStageA));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_o, adesc + 2 * k, bdesc + 2 * k, idesc_o, (jc | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&o_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    mbar_wait(&s_full, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < kSeq; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_s + lane_off + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    float sum = 0.f;
+    const float sl = p.scale_log2e;
+    const float mxs = mx * sl;
+    uint8_t* prow = pbuf + row * 128;
+#pragma unroll 1
+    for (int c = 0; c < kSeq; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_s + lane_off + c, v);
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        e[j] = exp2f(fmaf(__uint_as_float(v[j]), sl, -mxs));
+        sum += e[j];
+      }
+      uint8_t* pc = prow + (c >> 6) * kStageA;
+      const int u0 = (c & 63) >> 3;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 o;
+        o.x = pack_bf16x2(e[8 * jj + 0], e[8 * jj + 1]);
+        o.y = pack_bf16x2(e[8 * jj + 2], e[8 * jj + 3]);
+        o.z = pack_bf16x2(e[8 * jj + 4], e[8 * jj + 5]);
+        o.w = pack_bf16x2(e[8 * jj + 6], e[8 * jj + 7]);
+        *reinterpret_cast<uint4*>(pc + (((u0 + jj) ^ (row & 7)) << 4)) = o;
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();  // P was written through the generic proxy; the MMA reads it through the async proxy
+    mbar_arrive(&p_ready);
+
+    mbar_wait(&o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(img) * kSeq + q0 + row) * d;
+#pragma unroll 1
+    for (int c = 0; c < d; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + lane_off + c, v);
+      tmem_ld_wait();
+      uint4* dp = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]) * inv, __uint_as_float(v[8 * jj + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv);
+        dp[jj] = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_slot, 512);
+  }
+}
+
+bool attn_tc_supported(int act_dtype, int heads, int L, int dh, int row_stride, long long batch_stride,
+                       int v_transposed, long long v_batch_stride, int swap) {
+  return act_dtype == DMME_BF16 && heads == 1 && L == kSeq && dh % 64 == 0 && dh >= 64 && dh <= 256 &&
+         row_stride == dh && batch_stride == static_cast<long long>(L) * dh && v_transposed &&
+         v_batch_stride == static_cast<long long>(L) * dh && !swap;
+}
+
+int attn_tc_forward(const void* q, const void* k, const void* vt, int n, int d, float scale, void* out,
+                    cudaStream_t stream) {
+  AttnTcParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)d, (uint64_t)kSeq, (uint64_t)n};
+    uint64_t strides[2] = {(uint64_t)d * 2, (uint64_t)kSeq * d * 2};
+    uint32_t boxq[3] = {64u, 128u, 1u}, boxk[3] = {64u, 256u, 1u};
+    if ((rc = encode_map(&p.q, q, 3, dims, strides, boxq))) return rc;
+    if ((rc = encode_map(&p.k, k, 3, dims, strides, boxk))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)kSeq, (uint64_t)d, (uint64_t)n};
+    uint64_t strides[2] = {(uint64_t)kSeq * 2, (uint64_t)kSeq * d * 2};
+    uint32_t box[3] = {64u, (uint32_t)d, 1u};
+    if ((rc = encode_map(&p.vt, vt, 3, dims, strides, box))) return rc;
+  }
+  p.n = n; p.d = d;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  dim3 grid(kSeq / 128, n);
+  attn_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(p);
+  return check_launch("attn_tc_kernel");
+}
+
+}  // namespace dmme

@@ -205,7 +205,8 @@ class Engine:
         dev = x.device
         cond = u.condition
         emb = ops.temb_mlp(c, cond[0].embeddings, cond[1].weight.detach(), cond[1].bias.detach(), cond[3].weight.detach(),
-                           cond[3].bias.detach(), out=self.ws.get("temb.emb", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev))
+                           cond[3].bias.detach(), out=self.ws.get("temb.emb", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev),
+                           scratch=self.ws.get("temb.hidden", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev))
         wcat, bcat, offs = self.temb_tables()
         temb_all = ops.temb_proj(emb, wcat, bcat, out=self.ws.get("temb.all", (c.numel(), wcat.shape[0]), torch.float32, dev))
 

@@ -152,23 +152,24 @@ def groupnorm(src0: Tensor, src1: Optional[Tensor], groups: int, gamma: Tensor, 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, n: int, heads: int, seq: int, dh: int, scale: float,
               batch_stride: int, row_stride: int, head_stride: int, v_transposed: bool, v_batch_stride: int,
-              head_batch_swap: bool, out: Tensor) -> Tensor:
+              head_batch_swap: bool, out: Tensor, kernel: int = L.CONV_AUTO) -> Tensor:
     L.check(L.load().dmme_attention_fwd(ptr(q), ptr(k), ptr(v), batch_stride, row_stride, head_stride,
                                         int(v_transposed), v_batch_stride, n, heads, seq, dh, scale,
-                                        int(head_batch_swap), ptr(out), L.act_code(out.dtype), L.stream_ptr()),
+                                        int(head_batch_swap), ptr(out), L.act_code(out.dtype), kernel, L.stream_ptr()),
             "attention_fwd")
     return out
 
 
 def temb_mlp(t: Tensor, freq: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor,
-             out: Optional[Tensor] = None) -> Tensor:
+             out: Optional[Tensor] = None, scratch: Optional[Tensor] = None) -> Tensor:
     L.require_cuda(t, freq, w1, b1, w2, b2)
     if t.dtype != torch.int64:
         t = t.long()
     rows, emb = t.numel(), w2.shape[0]
     y = _empty((rows, emb), torch.float32, t.device, out)
+    scratch = _empty((rows, emb), torch.float32, t.device, scratch)
     L.check(L.load().dmme_temb_mlp_fwd(ptr(t), rows, ptr(freq), freq.numel(), ptr(w1), ptr(b1), ptr(w2), ptr(b2), emb,
-                                       ptr(y), L.stream_ptr()), "temb_mlp_fwd")
+                                       ptr(scratch), ptr(y), L.stream_ptr()), "temb_mlp_fwd")
     return y
 
 

@@ -126,18 +126,25 @@ int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, int c1, int n
  * (v_transposed = 1: v element at v[b*batch_stride_v + (h*dh + c)*L + l]).
  * head_batch_swap = 1 reproduces the "(b head)" -> "(head b)" regrouping of
  * MultiHeadAttention.forward_attention models/iddpm.py:38-46; 0 is Attention models/ddpm.py:54-63.
+ * kernel: DMME_CONV_AUTO / DMME_CONV_GENERIC / DMME_CONV_TC (same selector values as the convolution).
  */
 int dmme_attention_fwd(const void* q, const void* k, const void* v, long long batch_stride, int row_stride,
                        int head_stride, int v_transposed, long long v_batch_stride, int n, int heads, int L,
-                       int dh, float scale, int head_batch_swap, void* out, int act_dtype, void* stream);
+                       int dh, float scale, int head_batch_swap, void* out, int act_dtype, int kernel,
+                       void* stream);
+/* 1 when DMME_CONV_AUTO would run the fused tcgen05 kernel (bf16, single head, L = 256, dh in {64,128,192,256},
+ * dense [n][L][dh] q/k and transposed v) instead of the generic CUDA-core kernel */
+int dmme_attention_uses_tc(long long batch_stride, int row_stride, int v_transposed, long long v_batch_stride,
+                           int heads, int L, int dh, int head_batch_swap, int act_dtype);
 
 /* timestep embedding ----------------------------------------------------------------------- */
 /*
  * emb = SiLU(W2 SiLU(W1 [sin(t f), cos(t f)] + b1) + b2)   (UNet.condition models/ddpm.py:211-217,338-349)
- * t: int64 device pointer [rows]; freq: the persistent `condition.0.embeddings` buffer [half].
+ * t: int64 device pointer [rows]; freq: the persistent `condition.0.embeddings` buffer [half];
+ * scratch: fp32 [rows][emb_dim] workspace for the hidden layer.
  */
 int dmme_temb_mlp_fwd(const int64_t* t, int rows, const float* freq, int half, const float* w1, const float* b1,
-                      const float* w2, const float* b2, int emb_dim, float* emb_out, void* stream);
+                      const float* w2, const float* b2, int emb_dim, float* scratch, float* emb_out, void* stream);
 /* out[rows][total] = emb[rows][emb_dim] Wcat[total][emb_dim]^T + bcat: all ResBlock.condition Linears
  * (models/ddpm.py:101-104, models/iddpm.py:89-92) batched into one launch. */
 int dmme_temb_proj_fwd(const float* emb, int rows, int emb_dim, const float* wcat, const float* bcat, int total,

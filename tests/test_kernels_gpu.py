@@ -145,6 +145,32 @@ def test_conv_generic_bf16_storage():
     assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 4e-3
 
 
+@pytest.mark.parametrize("n,h,cout", [(3, 32, 128), (2, 16, 64), (5, 8, 256)])
+def test_conv_in_image_to_nhwc_bf16(n, h, cout):
+    """input_conv fast path: NCHW fp32 image (3 channels) -> NHWC bf16"""
+    _, L = _ops()
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(n, 3, h, h, generator=g)
+    w = torch.randn(cout, 3, 3, 3, generator=g) / 5
+    b = torch.randn(cout, generator=g)
+    got, tc = run_conv(x, w, b, dtype=torch.bfloat16, in_nchw=True)
+    assert not tc
+    assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,cin,cout", [(3, 32, 128, 3), (2, 16, 128, 6), (5, 8, 64, 3), (1, 32, 256, 6)])
+def test_conv_out_nhwc_bf16_to_image(n, h, cin, cout):
+    """output_conv fast path: NHWC bf16 -> eps NCHW fp32 with 3 (DDPM) or 6 (IDDPM) channels"""
+    _, L = _ops()
+    g = torch.Generator().manual_seed(32)
+    x = bf16_round(torch.randn(n, cin, h, h, generator=g))
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+    b = torch.randn(cout, generator=g)
+    got, tc = run_conv(x, w, b, dtype=torch.bfloat16, out_layout=L.OUT_NCHW_F32)
+    assert not tc
+    assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # tcgen05 convolution
 # ---------------------------------------------------------------------------------------------
@@ -298,6 +324,30 @@ def test_attention_single_head(n, c, L_, dtype):
     ops.attention(q.to(dt).to(DEV), k.to(dt).to(DEV), vt, n, 1, L_, c, scale, L_ * c, c, 0, True, c * L_, False, out)
     torch.cuda.synchronize()
     assert rel_l2(out.float().cpu(), want) < (4e-3 if dt == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("n,c", [(3, 128), (2, 256), (5, 64), (300, 128)])
+def test_attention_tc(n, c):
+    """fused tcgen05 attention (L = 256) against fp32 softmax attention on the same bf16 operands"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(19)
+    seq = 256
+    q, k, v = (bf16_round(torch.randn(n, seq, c, generator=g)) for _ in range(3))
+    q = q * 2.0  # spread the logits so the softmax is far from uniform
+    scale = c ** -0.5
+    want = torch.bmm(F.softmax(torch.bmm(q, k.transpose(1, 2) * scale), dim=2), v)
+    out = torch.empty(n, seq, c, dtype=torch.bfloat16, device=DEV)
+    vt = v.transpose(1, 2).contiguous().to(torch.bfloat16).to(DEV)
+    args = (q.to(torch.bfloat16).to(DEV), k.to(torch.bfloat16).to(DEV), vt, n, 1, seq, c, scale, seq * c, c, 0, True,
+            c * seq, False)
+    ops.attention(*args, out, kernel=L.CONV_TC)
+    torch.cuda.synchronize()
+    err = rel_l2(out.float().cpu(), want)
+    assert err < 6e-3, err  # P is rounded to bf16 before the PV product
+    gen = torch.empty_like(out)
+    ops.attention(*args, gen, kernel=L.CONV_GENERIC)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().cpu(), gen.float().cpu()) < 6e-3
 
 
 @pytest.mark.parametrize("n,c,heads,L_", [(3, 32, 4, 64), (2, 128, 4, 256), (4, 16, 4, 16)])
