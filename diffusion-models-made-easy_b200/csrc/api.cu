@@ -40,6 +40,13 @@ extern "C" int dmme_conv2d_uses_tc(const dmme_conv_desc* d) {
   return conv_tc_supported(*d) ? 1 : 0;
 }
 
+extern "C" int dmme_conv2d_writes_stats(const dmme_conv_desc* d) {
+  if (!d || d->kernel == DMME_CONV_GENERIC || d->out_layout != DMME_OUT_NHWC || d->cout % 4) return 0;
+  if (conv_tc_supported(*d)) return 1;
+  if (d->kernel == DMME_CONV_AUTO && conv_in_supported(*d) && (static_cast<long long>(d->h_in) * d->w_in) % 64 == 0) return 1;
+  return 0;
+}
+
 extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
   DMME_REQUIRE(d != nullptr, DMME_E_BADARG, "conv2d_fwd: null descriptor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -11,52 +11,91 @@ struct ConvSmallParams {
   const void* src; void* out;
   const float* weight; const float* bias;
   int n, h, w, cin, cout;
+  long long* stats;  // conv_in only: GroupNorm micro-group sums of the stored output (see dmme_conv_desc.stats)
 };
 
-// ---- input conv: one thread = one pixel x 8 output channels --------------------------------------
+constexpr int kInPixPerBlock = 64;
+
+// ---- input conv: one thread = one pixel x 8 output channels; a CTA owns 64 consecutive pixels of one image ----
+template <int CIN>
 __global__ void __launch_bounds__(256) conv_in_kernel(const ConvSmallParams p) {
-  extern __shared__ float wsm[];  // [9*cin][cout] then bias [cout]
-  const int K = 9 * p.cin;
+  extern __shared__ float wsm[];  // [9*CIN][cout], bias [cout], reduction scratch
+  constexpr int K = 9 * CIN;
   for (int i = threadIdx.x; i < K * p.cout; i += blockDim.x) wsm[i] = p.weight[i];
   float* bsm = wsm + K * p.cout;
   for (int i = threadIdx.x; i < p.cout; i += blockDim.x) bsm[i] = p.bias ? p.bias[i] : 0.f;
+  float* red = bsm + p.cout;  // [pixels per iteration][cout/4][2]
   __syncthreads();
-  const int cg = p.cout / 8;
-  const long long total = static_cast<long long>(p.n) * p.h * p.w * cg;
+  const int cg = p.cout / 8;            // threads per pixel
+  const int ppi = blockDim.x / cg;      // pixels per iteration
+  const int g = threadIdx.x % cg, slot = threadIdx.x / cg;
   const float* x = static_cast<const float*>(p.src);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
   const long long plane = static_cast<long long>(p.h) * p.w;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % cg);
-    const long long pix = i / cg;
+  const long long npix = static_cast<long long>(p.n) * plane;
+  const long long base = static_cast<long long>(blockIdx.x) * kInPixPerBlock;
+  float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+  for (int it = 0; it < kInPixPerBlock; it += ppi) {
+    const long long pix = base + it + slot;
+    if (pix >= npix || slot >= ppi) continue;
     const int xx = static_cast<int>(pix % p.w);
     const int yy = static_cast<int>((pix / p.w) % p.h);
     const long long ni = pix / plane;
+    float in[K];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int iy = yy + r - 1, ix = xx + q - 1;
+        const bool ok = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+          in[(r * 3 + q) * CIN + ci] = ok ? __ldg(x + (ni * CIN + ci) * plane + static_cast<long long>(iy) * p.w + ix) : 0.f;
+      }
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = bsm[g * 8 + j];
-    for (int r = 0; r < 3; ++r) {
-      const int iy = yy + r - 1;
-      if (iy < 0 || iy >= p.h) continue;
-      for (int s = 0; s < 3; ++s) {
-        const int ix = xx + s - 1;
-        if (ix < 0 || ix >= p.w) continue;
-        for (int ci = 0; ci < p.cin; ++ci) {
-          const float v = __ldg(x + (ni * p.cin + ci) * plane + static_cast<long long>(iy) * p.w + ix);
-          const float4* wr = reinterpret_cast<const float4*>(wsm + ((r * 3 + s) * p.cin + ci) * p.cout + g * 8);
-          const float4 w0 = wr[0], w1 = wr[1];
-          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
-        }
-      }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float4* wr = reinterpret_cast<const float4*>(wsm + k * p.cout + g * 8);
+      const float4 w0 = wr[0], w1 = wr[1];
+      const float v = in[k];
+      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+      acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+      acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+      acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
     }
     uint4 o;
     o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
     o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
     *reinterpret_cast<uint4*>(out + pix * p.cout + g * 8) = o;
+    if (p.stats) {
+      unpack_bf16x2(o.x, acc[0], acc[1]); unpack_bf16x2(o.y, acc[2], acc[3]);
+      unpack_bf16x2(o.z, acc[4], acc[5]); unpack_bf16x2(o.w, acc[6], acc[7]);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        s1[m] += (acc[4 * m] + acc[4 * m + 1]) + (acc[4 * m + 2] + acc[4 * m + 3]);
+        s2[m] += (acc[4 * m] * acc[4 * m] + acc[4 * m + 1] * acc[4 * m + 1]) +
+                 (acc[4 * m + 2] * acc[4 * m + 2] + acc[4 * m + 3] * acc[4 * m + 3]);
+      }
+    }
+  }
+  if (p.stats) {  // the 64 pixels of a CTA belong to one image (host checks plane % 64 == 0)
+    const int mg = p.cout / 4;
+    if (slot < ppi) {
+      red[(slot * mg + g * 2) * 2 + 0] = s1[0]; red[(slot * mg + g * 2) * 2 + 1] = s2[0];
+      red[(slot * mg + g * 2 + 1) * 2 + 0] = s1[1]; red[(slot * mg + g * 2 + 1) * 2 + 1] = s2[1];
+    }
+    __syncthreads();
+    const long long ni = base / plane;
+    if (base < npix) {
+      for (int e = threadIdx.x; e < mg * 2; e += blockDim.x) {
+        float t = 0.f;
+        for (int sl = 0; sl < ppi; ++sl) t += red[sl * mg * 2 + e];
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.stats) + ni * mg * 2 + e,
+                  static_cast<unsigned long long>(__float2ll_rn(t * static_cast<float>(1 << DMME_STATS_FRAC_BITS))));
+      }
+    }
   }
 }
 
@@ -87,29 +126,29 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvSmallParams p) 
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-    for (int r = 0; r < 3; ++r) {
-      const int iy = yy + r - 1;
-      if (iy < 0 || iy >= p.h) continue;
-      for (int s = 0; s < 3; ++s) {
-        const int ix = xx + s - 1;
-        if (ix < 0 || ix >= p.w) continue;
-        const __nv_bfloat16* row = src + ((ni * p.h + iy) * p.w + ix) * p.cin;
-        const int kbase = (r * 3 + s) * p.cin;
-        for (int u = 0; u < units; ++u) {
-          const int ch = (u * 8 + lane8) * 8;
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + ch));
-          float f[8];
-          unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
-          unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+    for (int u = 0; u < units; ++u) {
+      const int ch = (u * 8 + lane8) * 8;
+      uint4 v[9];
 #pragma unroll
-          for (int c = 0; c < COUT; ++c) {
-            const float4* wr = reinterpret_cast<const float4*>(wsm + c * K + kbase + ch);
-            const float4 w0 = wr[0], w1 = wr[1];
-            acc[c] = fmaf(f[0], w0.x, acc[c]); acc[c] = fmaf(f[1], w0.y, acc[c]);
-            acc[c] = fmaf(f[2], w0.z, acc[c]); acc[c] = fmaf(f[3], w0.w, acc[c]);
-            acc[c] = fmaf(f[4], w1.x, acc[c]); acc[c] = fmaf(f[5], w1.y, acc[c]);
-            acc[c] = fmaf(f[6], w1.z, acc[c]); acc[c] = fmaf(f[7], w1.w, acc[c]);
-          }
+      for (int t = 0; t < 9; ++t) {  // nine independent 16-byte loads in flight
+        const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+        const bool in = ok && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+        v[t] = in ? __ldg(reinterpret_cast<const uint4*>(src + ((ni * p.h + iy) * p.w + ix) * p.cin + ch))
+                  : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float f[8];
+        unpack_bf16x2(v[t].x, f[0], f[1]); unpack_bf16x2(v[t].y, f[2], f[3]);
+        unpack_bf16x2(v[t].z, f[4], f[5]); unpack_bf16x2(v[t].w, f[6], f[7]);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          const float4* wr = reinterpret_cast<const float4*>(wsm + c * K + t * p.cin + ch);
+          const float4 w0 = wr[0], w1 = wr[1];
+          acc[c] = fmaf(f[0], w0.x, acc[c]); acc[c] = fmaf(f[1], w0.y, acc[c]);
+          acc[c] = fmaf(f[2], w0.z, acc[c]); acc[c] = fmaf(f[3], w0.w, acc[c]);
+          acc[c] = fmaf(f[4], w1.x, acc[c]); acc[c] = fmaf(f[5], w1.y, acc[c]);
+          acc[c] = fmaf(f[6], w1.z, acc[c]); acc[c] = fmaf(f[7], w1.w, acc[c]);
         }
       }
     }
@@ -120,12 +159,12 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvSmallParams p) 
       acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
     }
     if (ok && lane8 < COUT) {
-      float v = acc[0];
+      float v0 = acc[0];
 #pragma unroll
       for (int c = 1; c < COUT; ++c)
-        if (lane8 == c) v = acc[c];
-      v += p.bias ? p.bias[lane8] : 0.f;
-      out[(ni * COUT + lane8) * plane + static_cast<long long>(yy) * p.w + xx] = v;
+        if (lane8 == c) v0 = acc[c];
+      v0 += p.bias ? p.bias[lane8] : 0.f;
+      out[(ni * COUT + lane8) * plane + static_cast<long long>(yy) * p.w + xx] = v0;
     }
   }
 }
@@ -135,8 +174,8 @@ static bool plain(const dmme_conv_desc& d) {
          !d.addend && d.act_dtype == DMME_BF16;
 }
 bool conv_in_supported(const dmme_conv_desc& d) {
-  return plain(d) && d.in_layout == DMME_IN_NCHW_F32 && d.out_layout == DMME_OUT_NHWC && d.c0 <= 4 &&
-         d.cout % 8 == 0 && d.cout <= 512;
+  return plain(d) && d.in_layout == DMME_IN_NCHW_F32 && d.out_layout == DMME_OUT_NHWC && d.c0 == 3 &&
+         d.cout % 8 == 0 && d.cout <= 256 && 256 % (d.cout / 8) == 0;
 }
 bool conv_out_supported(const dmme_conv_desc& d) {
   return plain(d) && d.in_layout == DMME_IN_NHWC && d.out_layout == DMME_OUT_NCHW_F32 && d.c0 % 64 == 0 &&
@@ -148,18 +187,20 @@ int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   ConvSmallParams p;
   p.src = d.src0; p.out = d.out; p.weight = static_cast<const float*>(d.weight); p.bias = d.bias;
   p.n = d.n; p.h = d.h_in; p.w = d.w_in; p.cin = d.c0; p.cout = d.cout;
+  p.stats = nullptr;
   if (conv_in_supported(d)) {
-    const size_t smem = sizeof(float) * (static_cast<size_t>(9) * d.c0 * d.cout + d.cout);
+    const int cg = d.cout / 8, ppi = 256 / cg;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(27) * d.cout + d.cout + static_cast<size_t>(ppi) * (d.cout / 4) * 2);
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       if (e != cudaSuccess) { set_error("conv_in: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
       configured = true;
     }
-    const long long total = static_cast<long long>(d.n) * d.h_in * d.w_in * (d.cout / 8);
-    const long long blocks = ceil_div_ll(total, 256);
-    const int grid = static_cast<int>(blocks < 148 * 8 ? blocks : 148 * 8);
-    conv_in_kernel<<<grid, 256, smem, stream>>>(p);
+    const long long npix = static_cast<long long>(d.n) * d.h_in * d.w_in;
+    if ((static_cast<long long>(d.h_in) * d.w_in) % kInPixPerBlock == 0) p.stats = d.stats;
+    const int grid = static_cast<int>(ceil_div_ll(npix, kInPixPerBlock));
+    conv_in_kernel<3><<<grid, 256, smem, stream>>>(p);
     return check_launch("conv_in_kernel");
   }
   DMME_REQUIRE(conv_out_supported(d), DMME_E_SHAPE, "conv_small: unsupported shape");

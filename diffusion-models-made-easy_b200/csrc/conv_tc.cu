@@ -38,6 +38,7 @@ struct ConvTcParams {
   __nv_bfloat16* out2;
   __nv_bfloat16* out3;
   int out_mode;
+  long long* stats;  // [n][cout/4][2] fixed-point micro-group sums (GroupNorm statistics of the stored output)
 };
 
 constexpr int kTileM = 128;
@@ -185,16 +186,20 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     }
     const int L = p.ho * p.wo;
 
+    // lanes of one warp that belong to the same image (GroupNorm statistics are per image)
+    const int seg = L < 32 ? L : 32;
+    const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
+
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
       tmem_ld_wait();
-      if (valid) {
-        float f[32];
+      float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const int col = col0 + c;
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      const int col = col0 + c;
+      if (valid) {
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -242,6 +247,36 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
             o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
             o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
             dp[j] = o;
+            // keep the rounded values: the statistics below describe the tensor as stored
+            unpack_bf16x2(o.x, f[8 * j + 0], f[8 * j + 1]);
+            unpack_bf16x2(o.y, f[8 * j + 2], f[8 * j + 3]);
+            unpack_bf16x2(o.z, f[8 * j + 4], f[8 * j + 5]);
+            unpack_bf16x2(o.w, f[8 * j + 6], f[8 * j + 7]);
+          }
+        }
+      }
+      if (p.stats) {  // warp-uniform
+        float s1[8], s2[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float a = f[4 * g], b = f[4 * g + 1], cc = f[4 * g + 2], dd = f[4 * g + 3];
+          s1[g] = valid ? (a + b) + (cc + dd) : 0.f;
+          s2[g] = valid ? (a * a + b * b) + (cc * cc + dd * dd) : 0.f;
+        }
+        for (int off = seg >> 1; off > 0; off >>= 1) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], off);
+            s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], off);
+          }
+        }
+        if ((lane & (seg - 1)) == 0 && n < p.n) {
+          unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats) +
+                                   (static_cast<long long>(n) * (p.cout >> 2) + (col >> 2)) * 2;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            atomicAdd(st + 2 * g, static_cast<unsigned long long>(__float2ll_rn(s1[g] * kFix)));
+            atomicAdd(st + 2 * g + 1, static_cast<unsigned long long>(__float2ll_rn(s2[g] * kFix)));
           }
         }
       }
@@ -340,6 +375,7 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   p.out2 = static_cast<__nv_bfloat16*>(d.out2);
   p.out3 = static_cast<__nv_bfloat16*>(d.out3);
   p.out_mode = d.out_layout;
+  p.stats = d.out_layout == DMME_OUT_NHWC ? d.stats : nullptr;
   DMME_REQUIRE(d.src0 && d.weight && d.out, DMME_E_BADARG, "conv_tc: null src0/weight/out");
   DMME_REQUIRE(d.c1 == 0 || d.src1, DMME_E_BADARG, "conv_tc: c1 > 0 but src1 is null");
   DMME_REQUIRE(d.rc0 == 0 || d.res0, DMME_E_BADARG, "conv_tc: rc0 > 0 but res0 is null");

@@ -52,6 +52,11 @@ class Engine:
         self._packed: Dict[Tuple, Tuple[Tuple, Tensor]] = {}
         self._blocks: Optional[List[Tuple[str, nn.Module]]] = None
         self.force_generic = False  # debugging / fp32 mode: never take the tcgen05 path
+        # GroupNorm statistics written by conv epilogues: one zeroed int64 arena per forward pass
+        self._arena: Optional[Tensor] = None
+        self._arena_cursor = 0
+        self._arena_need = 0
+        self._stats: Dict[int, Tensor] = {}
 
     # -- caches ------------------------------------------------------------------------------
     def _cached(self, key: Tuple, versions: Tuple, build):
@@ -106,6 +111,26 @@ class Engine:
             o += l.weight.shape[0]
         return w, b, offs
 
+    # -- GroupNorm statistics arena ------------------------------------------------------------
+    def _begin_stats(self, device) -> None:
+        if self._arena is None or self._arena.device != device or self._arena.numel() < self._arena_need:
+            self._arena = torch.zeros(max(self._arena_need, 1 << 16), dtype=torch.int64, device=device)
+        else:
+            self._arena.zero_()
+        self._arena_cursor = 0
+        self._arena_need = 0
+        self._stats.clear()
+
+    def _stats_for(self, out: Tensor, n: int, cout: int) -> Optional[Tensor]:
+        size = n * (cout // 4) * 2
+        self._arena_need += size
+        if self._arena_cursor + size > self._arena.numel():
+            return None  # arena grows on the next forward; this tensor's consumer reduces its own statistics
+        st = self._arena[self._arena_cursor:self._arena_cursor + size]
+        self._arena_cursor += size
+        self._stats[out.data_ptr()] = st
+        return st
+
     # -- kernels -----------------------------------------------------------------------------
     def conv(self, name: str, src0: Tensor, src1: Optional[Tensor], conv: nn.Conv2d, *, stride: int = 1,
              upsample: bool = False, res: Optional[nn.Conv2d] = None, res0: Optional[Tensor] = None,
@@ -137,7 +162,8 @@ class Engine:
             ops.conv2d_launch(d, w, b, q, temb, addend, k, vt)
             return q, k, vt
         out = self.ws.get(name, (d.n, ho, wo, cout), act_dtype, dev)
-        ops.conv2d_launch(d, w, b, out, temb, addend)
+        stats = self._stats_for(out, d.n, cout) if ops.conv_writes_stats(d) else None
+        ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats)
         return out
 
     def gn(self, name: str, norm: nn.GroupNorm, src0: Tensor, src1: Optional[Tensor], silu: bool,
@@ -145,8 +171,10 @@ class Engine:
         n, h, w, c0 = src0.shape
         c = c0 + (src1.shape[3] if src1 is not None else 0)
         out = self.ws.get(name, (n, h, w, c), src0.dtype, src0.device)
+        st0 = self._stats.get(src0.data_ptr())
+        st1 = self._stats.get(src1.data_ptr()) if src1 is not None else None
         return ops.groupnorm(src0, src1, norm.num_groups, norm.weight.detach(), norm.bias.detach(), silu, scale, shift,
-                             mask, norm.eps, out)
+                             mask, norm.eps, out, st0, st1)
 
     # -- blocks ------------------------------------------------------------------------------
     def attention_block(self, name: str, att: nn.Module, x: Tensor) -> Tensor:
@@ -203,6 +231,7 @@ class Engine:
         if c.dim() != 1 or c.numel() not in (1, x.shape[0]):
             raise ValueError(f"timestep tensor must have shape (1,) or (N,), got {tuple(c.shape)}")
         dev = x.device
+        self._begin_stats(dev)
         cond = u.condition
         emb = ops.temb_mlp(c, cond[0].embeddings, cond[1].weight.detach(), cond[1].bias.detach(), cond[3].weight.detach(),
                            cond[3].bias.detach(), out=self.ws.get("temb.emb", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev),

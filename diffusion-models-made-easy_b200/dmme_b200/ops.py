@@ -105,6 +105,10 @@ def conv_uses_tc(desc: L.ConvDesc) -> bool:
     return bool(L.load().dmme_conv2d_uses_tc(C.byref(desc)))
 
 
+def conv_writes_stats(desc: L.ConvDesc) -> bool:
+    return bool(L.load().dmme_conv2d_writes_stats(C.byref(desc)))
+
+
 def conv_out_hw(desc: L.ConvDesc) -> Tuple[int, int]:
     h = desc.h_in * (2 if desc.upsample else 1)
     w = desc.w_in * (2 if desc.upsample else 1)
@@ -114,7 +118,7 @@ def conv_out_hw(desc: L.ConvDesc) -> Tuple[int, int]:
 
 def conv2d_launch(desc: L.ConvDesc, weight: Tensor, bias: Optional[Tensor], out: Tensor,
                   temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
-                  out2: Optional[Tensor] = None, out3: Optional[Tensor] = None) -> None:
+                  out2: Optional[Tensor] = None, out3: Optional[Tensor] = None, stats: Optional[Tensor] = None) -> None:
     """Launch one fused convolution described by ``desc`` (see include/dmme_b200.h)."""
     desc.weight, desc.bias = ptr(weight), ptr(bias)
     if temb is not None:
@@ -125,6 +129,7 @@ def conv2d_launch(desc: L.ConvDesc, weight: Tensor, bias: Optional[Tensor], out:
         desc.temb, desc.temb_rows, desc.temb_ld = None, 0, 0
     desc.addend = ptr(addend)
     desc.out, desc.out2, desc.out3 = ptr(out), ptr(out2), ptr(out3)
+    desc.stats = ptr(stats)
     L.check(L.load().dmme_conv2d_fwd(C.byref(desc), L.stream_ptr()), "conv2d_fwd")
 
 
@@ -133,8 +138,10 @@ def conv2d_launch(desc: L.ConvDesc, weight: Tensor, bias: Optional[Tensor], out:
 # ---------------------------------------------------------------------------------------------
 def groupnorm(src0: Tensor, src1: Optional[Tensor], groups: int, gamma: Tensor, beta: Tensor, silu: bool,
               scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, chan_mask: Optional[Tensor] = None,
-              eps: float = 1e-5, out: Optional[Tensor] = None) -> Tensor:
-    """GN (+ scale/shift) (+ SiLU) (+ channel mask) over the channel-concat of src0|src1 (NHWC)."""
+              eps: float = 1e-5, out: Optional[Tensor] = None, stats0: Optional[Tensor] = None,
+              stats1: Optional[Tensor] = None) -> Tensor:
+    """GN (+ scale/shift) (+ SiLU) (+ channel mask) over the channel-concat of src0|src1 (NHWC).
+    stats0/stats1: int64 micro-group sums written by the producing conv (see ``conv2d_launch(stats=)``)."""
     L.require_cuda(src0, src1, out)
     n, h, w, c0 = src0.shape
     c1 = src1.shape[3] if src1 is not None else 0
@@ -146,7 +153,7 @@ def groupnorm(src0: Tensor, src1: Optional[Tensor], groups: int, gamma: Tensor, 
         ss_rows, ss_ld = scale.shape[0], scale.stride(0)
     L.check(L.load().dmme_groupnorm_fwd(ptr(src0), ptr(src1), c0, c1, n, h * w, groups, eps, ptr(gamma), ptr(beta),
                                         ptr(scale), ptr(shift), ss_rows, ss_ld, ptr(chan_mask), int(silu), ptr(y),
-                                        L.act_code(src0.dtype), L.stream_ptr()), "groupnorm_fwd")
+                                        L.act_code(src0.dtype), ptr(stats0), ptr(stats1), L.stream_ptr()), "groupnorm_fwd")
     return y
 
 

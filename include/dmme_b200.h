@@ -26,6 +26,7 @@ extern "C" {
 #endif
 
 #define DMME_ABI_VERSION 1
+#define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
 
@@ -76,6 +77,10 @@ typedef struct dmme_conv_desc {
   int temb_rows, temb_ld;
   const void* addend;                 /* optional NHWC tensor of the output shape, act_dtype */
   void* out; void* out2; void* out3;
+  long long* stats;                   /* optional [n][cout/4][2] int64 fixed-point (2^-DMME_STATS_FRAC_BITS) sums of
+                                         the stored output and of its square per 4-channel micro-group, accumulated
+                                         with integer atomics (order-independent, hence deterministic); the caller
+                                         zeroes it.  Consumed by dmme_groupnorm_fwd.  tcgen05 path, NHWC output only. */
   int in_layout, out_layout;
   int act_dtype;
   int kernel;                         /* DMME_CONV_* */
@@ -107,6 +112,8 @@ int dmme_upsample2x_nhwc(const void* src, void* dst, int n, int h, int w, int c,
 int dmme_conv2d_fwd(const dmme_conv_desc* desc, void* stream);
 /* 1 when dmme_conv2d_fwd would take the tcgen05 path for this descriptor */
 int dmme_conv2d_uses_tc(const dmme_conv_desc* desc);
+/* 1 when the kernel dmme_conv2d_fwd would run for this descriptor fills desc->stats */
+int dmme_conv2d_writes_stats(const dmme_conv_desc* desc);
 
 /* GroupNorm (+ scale/shift) (+ SiLU) (+ channel dropout mask) -------------------------------- */
 /*
@@ -117,7 +124,10 @@ int dmme_conv2d_uses_tc(const dmme_conv_desc* desc);
 int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, int c1, int n, int hw, int groups, float eps,
                        const float* gamma, const float* beta, const float* scale, const float* shift,
                        int ss_rows, int ss_ld, const float* chan_mask, int apply_silu, void* out,
-                       int act_dtype, void* stream);
+                       int act_dtype, const long long* stats0, const long long* stats1, void* stream);
+/* stats0 / stats1: optional micro-group sums of src0 / src1 written by the producing convolution
+ * (dmme_conv_desc.stats).  When every source has them, GroupNorm is a single streaming pass
+ * (2 B read + 2 B written per element); otherwise the kernel reduces the statistics itself. */
 
 /* self-attention core ---------------------------------------------------------------------- */
 /*

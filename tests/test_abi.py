@@ -34,7 +34,7 @@ def test_argument_errors_are_reported_not_fatal():
     lib = _lib.load()
     assert lib.dmme_conv2d_fwd(None, None) == -1
     assert b"null descriptor" in lib.dmme_last_error()
-    rc = lib.dmme_groupnorm_fwd(None, None, 8, 0, 1, 4, 2, 1e-5, None, None, None, None, 0, 0, None, 1, None, 1, None)
+    rc = lib.dmme_groupnorm_fwd(None, None, 8, 0, 1, 4, 2, 1e-5, None, None, None, None, 0, 0, None, 1, None, 1, None, None, None)
     assert rc == -1 and b"groupnorm" in lib.dmme_last_error()
     d = _lib.ConvDesc()
     d.kernel = 99
@@ -53,7 +53,7 @@ def test_conv_desc_struct_matches_header_field_order():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(void|float|int)\s*\*?\s*", "", decl)
+        decl = re.sub(r"^(const\s+)?(void|float|int|long long)\s*\*?\s*", "", decl)
         names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
     assert names == [f[0] for f in _lib.ConvDesc._fields_]
 

@@ -158,6 +158,25 @@ def test_conv_in_image_to_nhwc_bf16(n, h, cout):
     assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 4e-3
 
 
+def test_conv_in_writes_groupnorm_stats():
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(33)
+    n, h, cout = 3, 32, 128
+    x = torch.randn(n, 3, h, h, generator=g)
+    w = torch.randn(cout, 3, 3, 3, generator=g) / 5
+    b = torch.randn(cout, generator=g)
+    d = ops.make_conv_desc(x.to(DEV), None, cout, 3, 1, False, None, None, True, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+    assert ops.conv_writes_stats(d) and not ops.conv_uses_tc(d)
+    out = torch.empty((n, h, h, cout), dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+    ops.conv2d_launch(d, ops.pack_conv_weight(w.to(DEV), None, False), b.to(DEV), out, stats=st)
+    torch.cuda.synchronize()
+    y = to_nchw(out.cpu()).double()
+    sums = st.cpu().view(n, cout // 4, 2).double() / 2 ** 20
+    assert torch.allclose(sums[..., 0], y.reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(sums[..., 1], (y ** 2).reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=1e-2)
+
+
 @pytest.mark.parametrize("n,h,cin,cout", [(3, 32, 128, 3), (2, 16, 128, 6), (5, 8, 64, 3), (1, 32, 256, 6)])
 def test_conv_out_nhwc_bf16_to_image(n, h, cin, cout):
     """output_conv fast path: NHWC bf16 -> eps NCHW fp32 with 3 (DDPM) or 6 (IDDPM) channels"""
@@ -304,6 +323,46 @@ def test_groupnorm(cfg):
     torch.cuda.synchronize()
     tol = 4e-3 if dtype == torch.bfloat16 else 1e-5
     assert rel_l2(to_nchw(got.cpu()), want) < tol
+
+
+@pytest.mark.parametrize("n,c0,c1,h,groups", [(3, 128, 0, 32, 32), (2, 256, 128, 16, 32), (5, 256, 256, 8, 32),
+                                                (11, 256, 0, 4, 32), (2, 64, 0, 16, 16)])
+def test_conv_stats_feed_streaming_groupnorm(n, c0, c1, h, groups):
+    """conv epilogue statistics (int64 fixed point) -> single-pass GroupNorm+SiLU == GN of the stored tensor"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(41)
+    outs, stats = [], []
+    for c in (c0, c1):
+        if c == 0:
+            outs.append(None); stats.append(None)
+            continue
+        x = bf16_round(torch.randn(n, 64, h, h, generator=g))
+        w = bf16_round(torch.randn(c, 64, 3, 3, generator=g) / 8)
+        b = torch.randn(c, generator=g) * 2
+        s0 = to_nhwc(x, torch.bfloat16).to(DEV)
+        d = ops.make_conv_desc(s0, None, c, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_TC)
+        wp = ops.pack_conv_weight(w.to(DEV), None, True)
+        out = torch.empty((n, h, h, c), dtype=torch.bfloat16, device=DEV)
+        st = torch.zeros(n * (c // 4) * 2, dtype=torch.int64, device=DEV)
+        ops.conv2d_launch(d, wp, b.to(DEV), out, stats=st)
+        outs.append(out); stats.append(st)
+    torch.cuda.synchronize()
+    y0 = to_nchw(outs[0].cpu())
+    # the statistics describe the stored (bf16) tensor
+    sums = stats[0].cpu().view(n, c0 // 4, 2).double() / 2 ** 20
+    ref1 = y0.double().reshape(n, c0 // 4, 4 * h * h).sum(-1)
+    ref2 = (y0.double() ** 2).reshape(n, c0 // 4, 4 * h * h).sum(-1)
+    assert torch.allclose(sums[..., 0], ref1, rtol=1e-5, atol=1e-2)
+    assert torch.allclose(sums[..., 1], ref2, rtol=1e-5, atol=1e-2)
+    full = y0 if c1 == 0 else torch.cat([y0, to_nchw(outs[1].cpu())], dim=1)
+    c = c0 + c1
+    gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g)
+    want = F.silu(F.group_norm(full, groups, gamma, beta, eps=1e-5))
+    got = ops.groupnorm(outs[0], outs[1], groups, gamma.to(DEV), beta.to(DEV), True, stats0=stats[0], stats1=stats[1])
+    ref_kernel = ops.groupnorm(outs[0], outs[1], groups, gamma.to(DEV), beta.to(DEV), True)
+    torch.cuda.synchronize()
+    assert rel_l2(to_nchw(got.cpu()), want) < 4e-3
+    assert rel_l2(to_nchw(got.cpu()), to_nchw(ref_kernel.cpu())) < 4e-3
 
 
 # ---------------------------------------------------------------------------------------------
