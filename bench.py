@@ -144,11 +144,11 @@ def conv_profile(model, x, t, reps=3):
     records = []
     orig = ops.conv2d_launch
 
-    def timed(desc, weight, bias, out, temb=None, addend=None, out2=None, out3=None):
+    def timed(desc, weight, bias, out, temb=None, addend=None, out2=None, out3=None, stats=None):
         tc = ops.conv_uses_tc(desc)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        orig(desc, weight, bias, out, temb, addend, out2, out3)
+        orig(desc, weight, bias, out, temb, addend, out2, out3, stats)
         e1.record()
         ho, wo = ops.conv_out_hw(desc)
         k = desc.ksize * desc.ksize * (desc.c0 + desc.c1) + desc.rc0 + desc.rc1

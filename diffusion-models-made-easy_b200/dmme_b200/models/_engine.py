@@ -114,7 +114,7 @@ class Engine:
     # -- GroupNorm statistics arena ------------------------------------------------------------
     def _begin_stats(self, device) -> None:
         if self._arena is None or self._arena.device != device or self._arena.numel() < self._arena_need:
-            self._arena = torch.zeros(max(self._arena_need, 1 << 16), dtype=torch.int64, device=device)
+            self._arena = torch.zeros(max(self._arena_need, 1 << 18), dtype=torch.int64, device=device)
         else:
             self._arena.zero_()
         self._arena_cursor = 0
@@ -125,6 +125,7 @@ class Engine:
         size = n * (cout // 4) * 2
         self._arena_need += size
         if self._arena_cursor + size > self._arena.numel():
+            self._stats.pop(out.data_ptr(), None)
             return None  # arena grows on the next forward; this tensor's consumer reduces its own statistics
         st = self._arena[self._arena_cursor:self._arena_cursor + size]
         self._arena_cursor += size
@@ -163,6 +164,8 @@ class Engine:
             return q, k, vt
         out = self.ws.get(name, (d.n, ho, wo, cout), act_dtype, dev)
         stats = self._stats_for(out, d.n, cout) if ops.conv_writes_stats(d) else None
+        if stats is None:
+            self._stats.pop(out.data_ptr(), None)  # the buffer may be a reused scratch with stale statistics
         ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats)
         return out
 
