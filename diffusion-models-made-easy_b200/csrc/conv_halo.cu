@@ -1,0 +1,375 @@
+// 3x3 stride-1 convolution on tcgen05 with the activation halo tile reused across the nine filter taps.
+//
+// conv_tc.cu fetches one [128 px][64 ch] A tile per tap: every activation byte crosses L2 -> SM nine times and
+// the kernel is bound by that feed (measured ~8.7 TB/s of operand traffic at 25% tensor-pipe utilisation).
+// Here the batch is viewed as one flat sequence of ZERO-PADDED pixels, G = n*(H+2)*(W+2) + (y+1)*(W+2) + (x+1).
+// In that space a filter tap is a constant shift d = (r-1)*(W+2) + (s-1), so for a tile of 256 consecutive
+// positions ONE halo tile [256 + 2(W+3) positions][64 ch] in shared memory serves all nine taps: the MMA's A
+// descriptor is simply advanced by d rows (128 B each; the 128-byte-swizzle phase follows the address through
+// the descriptor's base-offset field).  The halo tile is assembled by one TMA box per padded image row
+// ([W+2 px][64 ch], out-of-bounds pixels / rows / images zero-filled = the conv padding).
+// Outputs at padding positions are junk and masked in the epilogue (11% of the MMA work at 32x32, 21% at 16x16).
+//
+// Tile: 256 positions x 128 output channels per work unit (two M=128 MMAs share every weight tile), fp32
+// accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of unit i overlaps the MMAs of unit
+// i+1; persistent CTAs (one per SM), static round-robin schedule.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "tmap.cuh"
+
+namespace dmme {
+
+struct ConvHaloParams {
+  CUtensorMap a[4];  // src0, src1, res0, res1: box = one padded row [W+2 px][64 ch]
+  CUtensorMap b;     // weights [cout][K] bf16, box [128][64]
+  int chunks0, chunks1, rchunks0, rchunks1;
+  int n, h, w, wp, pimg, nr;
+  long long gtot;
+  int m_tiles, n_tiles, cout;
+  const float* bias;
+  const float* temb;
+  int temb_rows, temb_ld;
+  const __nv_bfloat16* addend;
+  __nv_bfloat16* out;
+  long long* stats;
+  int desc_mode;
+};
+
+constexpr int kHaloTM = 256;
+constexpr int kHaloBN = 128;
+constexpr int kHaloASlot = 47 * 1024;  // >= nr * (W+2) * 128 bytes
+constexpr int kHaloBSlot = kHaloBN * 128;
+constexpr int kHaloAStages = 2;
+constexpr int kHaloBStages = 4;
+constexpr int kHaloSmem = kHaloAStages * kHaloASlot + kHaloBStages * kHaloBSlot + 1024;
+constexpr int kHaloThreads = 192;
+
+__device__ __forceinline__ int floor_div(int a, int b) {
+  int q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kHaloAStages], a_empty[kHaloAStages];
+  __shared__ __align__(8) uint64_t b_full[kHaloBStages], b_empty[kHaloBStages];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* abuf = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* bbuf = abuf + kHaloAStages * kHaloASlot;
+
+  const int cchunks = p.chunks0 + p.chunks1;
+  const int nck = cchunks + p.rchunks0 + p.rchunks1;
+  const int units = p.m_tiles * p.n_tiles;
+  const int row_bytes = p.wp * 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kHaloBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a[0]);
+    if (p.chunks1) tma_prefetch_desc(&p.a[1]);
+    if (p.rchunks0) tma_prefetch_desc(&p.a[2]);
+    if (p.rchunks1) tma_prefetch_desc(&p.a[3]);
+    tma_prefetch_desc(&p.b);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int a_it = 0, b_it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int mt = u / p.n_tiles, nt = u - mt * p.n_tiles;
+        const int g0 = mt * kHaloTM, col0 = nt * kHaloBN;
+        for (int ck = 0; ck < nck; ++ck) {
+          int which, cc, halo, ntaps, kb0, kbs;
+          if (ck < cchunks) {
+            which = ck < p.chunks0 ? 0 : 1;
+            cc = (which ? ck - p.chunks0 : ck) * 64;
+            halo = p.wp + 1; ntaps = 9; kb0 = ck; kbs = cchunks;
+          } else {
+            const int rk = ck - cchunks;
+            which = rk < p.rchunks0 ? 2 : 3;
+            cc = (which == 3 ? rk - p.rchunks0 : rk) * 64;
+            halo = 0; ntaps = 1; kb0 = 9 * cchunks + rk; kbs = 0;
+          }
+          const int as = a_it % kHaloAStages;
+          mbar_wait(&a_empty[as], ((a_it / kHaloAStages) & 1) ^ 1);
+          mbar_expect_tx(&a_full[as], p.nr * row_bytes);
+          const int pr0 = floor_div(g0 - halo, p.wp);
+          uint8_t* dst = abuf + as * kHaloASlot;
+          for (int i = 0; i < p.nr; ++i) {
+            const int pr = pr0 + i;
+            const int ni = floor_div(pr, p.h + 2);         // -1 or >= n: whole row out of bounds -> zeros
+            const int yy = pr - ni * (p.h + 2) - 1;        // -1 or h: padding row -> zeros
+            tma_load_5d(dst + i * row_bytes, &p.a[which], &a_full[as], cc, -1, 0, yy, ni);
+          }
+          ++a_it;
+          for (int tap = 0; tap < ntaps; ++tap, ++b_it) {
+            const int bs = b_it % kHaloBStages;
+            mbar_wait(&b_empty[bs], ((b_it / kHaloBStages) & 1) ^ 1);
+            mbar_expect_tx(&b_full[bs], kHaloBSlot);
+            tma_load_2d(bbuf + bs * kHaloBSlot, &p.b, &b_full[bs], (kb0 + tap * kbs) * 64, col0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kHaloBN);
+      int a_it = 0, b_it = 0, u_it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
+        const int mt = u / p.n_tiles;
+        const int g0 = mt * kHaloTM;
+        const int stage = u_it & 1;
+        mbar_wait(&acc_empty[stage], ((u_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dtm = tmem_base + stage * (2 * kHaloBN);
+        for (int ck = 0; ck < nck; ++ck, ++a_it) {
+          const bool is_conv = ck < cchunks;
+          const int halo = is_conv ? p.wp + 1 : 0;
+          const int ntaps = is_conv ? 9 : 1;
+          const int as = a_it % kHaloAStages;
+          mbar_wait(&a_full[as], (a_it / kHaloAStages) & 1);
+          tc_fence_after();
+          const int pr0 = floor_div(g0 - halo, p.wp);
+          const int rowbase = g0 - pr0 * p.wp;  // row of position g0 inside the halo slot
+          const uint32_t a_addr = smem_u32(abuf + as * kHaloASlot);
+          for (int tap = 0; tap < ntaps; ++tap, ++b_it) {
+            const int bs = b_it % kHaloBStages;
+            mbar_wait(&b_full[bs], (b_it / kHaloBStages) & 1);
+            tc_fence_after();
+            const int d = is_conv ? (tap / 3 - 1) * p.wp + (tap % 3 - 1) : 0;
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(bbuf + bs * kHaloBSlot));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t addr = a_addr + static_cast<uint32_t>(rowbase + j * 128 + d) * 128u;
+              uint64_t adesc = umma_desc_sw128(addr);
+              if (p.desc_mode) adesc |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;  // swizzle phase of the start row
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(dtm + j * kHaloBN, adesc + 2 * k, bdesc + 2 * k, idesc, (ck | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&b_empty[bs]);
+          }
+          umma_commit(&a_empty[as]);
+        }
+        umma_commit(&acc_full[stage]);
+      }
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
+    int u_it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
+      const int mt = u / p.n_tiles, nt = u - mt * p.n_tiles;
+      const int g0 = mt * kHaloTM, col0 = nt * kHaloBN;
+      const int stage = u_it & 1;
+      mbar_wait(&acc_full[stage], (u_it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const long long g = static_cast<long long>(g0) + j * 128 + q * 32 + lane;
+        const int n = static_cast<int>(g / p.pimg);
+        const int rem = static_cast<int>(g - static_cast<long long>(n) * p.pimg);
+        const int yy = rem / p.wp - 1, xx = rem % p.wp - 1;
+        const bool valid = n < p.n && yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+        const long long pix = (static_cast<long long>(n) * p.h + yy) * p.w + xx;
+        const float* trow = p.temb ? p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : (n < p.n ? n : 0)) * p.temb_ld : nullptr;
+        const int n_first = __shfl_sync(0xffffffffu, n, 0);
+        const bool straddle = __any_sync(0xffffffffu, n != n_first);
+#pragma unroll 1
+        for (int c = 0; c < kHaloBN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(stage * (2 * kHaloBN) + j * kHaloBN + c), v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          const int col = col0 + c;
+          if (valid) {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
+            }
+            if (trow) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + col + i));
+                f[i] += t4.x; f[i + 1] += t4.y; f[i + 2] += t4.z; f[i + 3] += t4.w;
+              }
+            }
+            if (p.addend) {
+              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.cout + col);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 a4 = __ldg(ap + i);
+                float lo, hi;
+                unpack_bf16x2(a4.x, lo, hi); f[8 * i + 0] += lo; f[8 * i + 1] += hi;
+                unpack_bf16x2(a4.y, lo, hi); f[8 * i + 2] += lo; f[8 * i + 3] += hi;
+                unpack_bf16x2(a4.z, lo, hi); f[8 * i + 4] += lo; f[8 * i + 5] += hi;
+                unpack_bf16x2(a4.w, lo, hi); f[8 * i + 6] += lo; f[8 * i + 7] += hi;
+              }
+            }
+            uint4* dp = reinterpret_cast<uint4*>(p.out + pix * p.cout + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+              o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+              o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+              o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+              dp[i] = o;
+              unpack_bf16x2(o.x, f[8 * i + 0], f[8 * i + 1]);
+              unpack_bf16x2(o.y, f[8 * i + 2], f[8 * i + 3]);
+              unpack_bf16x2(o.z, f[8 * i + 4], f[8 * i + 5]);
+              unpack_bf16x2(o.w, f[8 * i + 6], f[8 * i + 7]);
+            }
+          }
+          if (p.stats) {
+            // GroupNorm statistics of the stored tensor; a warp's 32 positions touch at most two images
+            for (int pass = 0; pass < (straddle ? 2 : 1); ++pass) {
+              const int ntarget = n_first + pass;
+              const bool mine = valid && n == ntarget;
+              float s1[8], s2[8];
+#pragma unroll
+              for (int gi = 0; gi < 8; ++gi) {
+                const float a = f[4 * gi], b = f[4 * gi + 1], cc = f[4 * gi + 2], dd = f[4 * gi + 3];
+                s1[gi] = mine ? (a + b) + (cc + dd) : 0.f;
+                s2[gi] = mine ? (a * a + b * b) + (cc * cc + dd * dd) : 0.f;
+              }
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int gi = 0; gi < 8; ++gi) {
+                  s1[gi] += __shfl_xor_sync(0xffffffffu, s1[gi], off);
+                  s2[gi] += __shfl_xor_sync(0xffffffffu, s2[gi], off);
+                }
+              }
+              if (lane == 0 && ntarget < p.n) {
+                unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats) +
+                                         (static_cast<long long>(ntarget) * (p.cout >> 2) + (col >> 2)) * 2;
+#pragma unroll
+                for (int gi = 0; gi < 8; ++gi) {
+                  atomicAdd(st + 2 * gi, static_cast<unsigned long long>(__float2ll_rn(s1[gi] * kFix)));
+                  atomicAdd(st + 2 * gi + 1, static_cast<unsigned long long>(__float2ll_rn(s2[gi] * kFix)));
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[stage]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int halo_rows(int wp) { return (kHaloTM + 3 * wp) / wp + 1; }
+
+static int g_halo_mode = 1;     // 1: enabled with documented base-offset descriptors, 2: base offset left zero, 0: off
+static int g_sm_count = 0;
+
+bool conv_halo_supported(const dmme_conv_desc& d) {
+  if (g_halo_mode == 0) return false;
+  if (d.act_dtype != DMME_BF16 || d.in_layout != DMME_IN_NHWC || d.out_layout != DMME_OUT_NHWC) return false;
+  if (d.upsample || d.ksize != 3 || d.stride != 1) return false;
+  if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.rc0 % 64 || d.rc1 % 64 || d.cout % kHaloBN) return false;
+  if (d.h_in < 16 || d.w_in < 16) return false;  // padded-position utilisation < 75% below 16x16
+  const int wp = d.w_in + 2;
+  if (wp > 256 || halo_rows(wp) * wp * 128 > kHaloASlot) return false;
+  if (static_cast<long long>(d.n) * (d.h_in + 2) * wp > (1LL << 30)) return false;
+  return true;
+}
+
+int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
+  DMME_REQUIRE(conv_halo_supported(d), DMME_E_SHAPE, "conv_halo: unsupported shape/layout");
+  DMME_REQUIRE(d.src0 && d.weight && d.out, DMME_E_BADARG, "conv_halo: null src0/weight/out");
+  DMME_REQUIRE(d.c1 == 0 || d.src1, DMME_E_BADARG, "conv_halo: c1 > 0 but src1 is null");
+  DMME_REQUIRE(d.rc0 == 0 || d.res0, DMME_E_BADARG, "conv_halo: rc0 > 0 but res0 is null");
+  DMME_REQUIRE(d.rc1 == 0 || d.res1, DMME_E_BADARG, "conv_halo: rc1 > 0 but res1 is null");
+  DMME_REQUIRE(d.temb == nullptr || (d.temb_ld % 4 == 0), DMME_E_SHAPE, "conv_halo: temb_ld must be a multiple of 4");
+  ConvHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.chunks0 = d.c0 / 64; p.chunks1 = d.c1 / 64; p.rchunks0 = d.rc0 / 64; p.rchunks1 = d.rc1 / 64;
+  p.n = d.n; p.h = d.h_in; p.w = d.w_in; p.wp = d.w_in + 2; p.pimg = (d.h_in + 2) * p.wp;
+  p.nr = halo_rows(p.wp);
+  p.gtot = static_cast<long long>(d.n) * p.pimg;
+  p.m_tiles = static_cast<int>((p.gtot + kHaloTM - 1) / kHaloTM);
+  p.n_tiles = d.cout / kHaloBN;
+  p.cout = d.cout;
+  p.bias = d.bias; p.temb = d.temb; p.temb_rows = d.temb_rows; p.temb_ld = d.temb_ld;
+  p.addend = static_cast<const __nv_bfloat16*>(d.addend);
+  p.out = static_cast<__nv_bfloat16*>(d.out);
+  p.stats = d.stats;
+  p.desc_mode = g_halo_mode == 1 ? 1 : 0;
+
+  auto act_map = [&](CUtensorMap* m, const void* ptr, int c) -> int {
+    uint64_t dims[5] = {(uint64_t)c, (uint64_t)d.w_in, 1, (uint64_t)d.h_in, (uint64_t)d.n};
+    uint64_t strides[4] = {(uint64_t)c * 2, (uint64_t)d.w_in * c * 2, (uint64_t)d.w_in * c * 2,
+                           (uint64_t)d.h_in * d.w_in * c * 2};
+    uint32_t box[5] = {64u, (uint32_t)p.wp, 1u, 1u, 1u};
+    return encode_map(m, ptr, 5, dims, strides, box);
+  };
+  int rc;
+  if ((rc = act_map(&p.a[0], d.src0, d.c0))) return rc;
+  if (d.c1 && (rc = act_map(&p.a[1], d.src1, d.c1))) return rc;
+  if (d.rc0 && (rc = act_map(&p.a[2], d.res0, d.rc0))) return rc;
+  if (d.rc1 && (rc = act_map(&p.a[3], d.res1, d.rc1))) return rc;
+  {
+    const uint64_t ktot = 9ull * (d.c0 + d.c1) + d.rc0 + d.rc1;
+    uint64_t dims[2] = {ktot, (uint64_t)d.cout};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {64u, (uint32_t)kHaloBN};
+    if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
+  }
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    if (e != cudaSuccess) {
+      g_sm_count = 0;
+      set_error("conv_halo: cudaFuncSetAttribute(%d bytes): %s", kHaloSmem, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  const int units = p.m_tiles * p.n_tiles;
+  const int grid = units < g_sm_count ? units : g_sm_count;
+  conv_halo_kernel<<<grid, kHaloThreads, kHaloSmem, stream>>>(p);
+  return check_launch("conv_halo_kernel");
+}
+
+}  // namespace dmme
+
+// debugging / A-B measurement switch: 0 = never use the halo kernel, 1 = default, 2 = descriptors without base offset
+extern "C" void dmme_set_conv_halo_mode(int mode) { dmme::g_halo_mode = mode; }
+extern "C" int dmme_get_conv_halo_mode(void) { return dmme::g_halo_mode; }

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libdmme_b200.so")
 BF16, F32 = 0, 1
 IN_NHWC, IN_NCHW_F32 = 0, 1
 OUT_NHWC, OUT_NCHW_F32, OUT_QKV = 0, 1, 2
-CONV_AUTO, CONV_GENERIC, CONV_TC = 0, 1, 2
+CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO = 0, 1, 2, 3
 
 # every symbol include/dmme_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = (
@@ -27,7 +27,7 @@ EXPORTS = (
     "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
     "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
-    "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal",
+    "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
 )
 
 
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     lib.dmme_gather_i64.argtypes = [vp, vp, vp, vp]
     lib.dmme_add_i64.argtypes = [vp, C.c_int64, vp]
     lib.dmme_philox_normal.argtypes = [vp, ll, ull, ull, vp]
+    lib.dmme_set_conv_halo_mode.argtypes = [i]
+    lib.dmme_set_conv_halo_mode.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("dmme_abi_version",):

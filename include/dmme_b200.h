@@ -50,7 +50,9 @@ enum {
 enum {
   DMME_CONV_AUTO = 0,    /* tcgen05 when the shape allows, generic otherwise */
   DMME_CONV_GENERIC = 1, /* FFMA implicit GEMM, any shape, fp32 math */
-  DMME_CONV_TC = 2       /* tcgen05/TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate) */
+  DMME_CONV_TC = 2,      /* tcgen05/TMEM + TMA implicit GEMM, one A tile per filter tap (any supported shape) */
+  DMME_CONV_HALO = 3     /* tcgen05 3x3 stride-1 kernel that keeps the activation halo tile in shared memory for all
+                            nine taps; AUTO prefers it when the shape allows */
 };
 
 /*
@@ -92,6 +94,11 @@ const char* dmme_last_error(void);
 /* number of kernel launches issued through this library since the last reset (process-wide) */
 long long dmme_launch_count(void);
 void dmme_reset_launch_count(void);
+
+/* A/B switch for measurements: 0 = AUTO never picks the halo kernel, 1 = default, 2 = halo kernel with the
+ * shared-memory descriptor base-offset field left at zero (diagnostic) */
+void dmme_set_conv_halo_mode(int mode);
+int dmme_get_conv_halo_mode(void);
 
 /* weights ---------------------------------------------------------------------------------- */
 /*

@@ -241,6 +241,70 @@ def test_conv_tc(cfg):
     assert err < 4e-3, f"rel-L2 {err}"
 
 
+HALO_CASES = [
+    dict(n=1, cin=64, cout=128, h=16, w=16),
+    dict(n=4, cin=128, cout=128, h=32, w=32, temb="bcast"),
+    dict(n=3, cin=256, cout=256, h=16, w=16, addend=True, temb="rows"),
+    dict(n=2, cin=256, cout=128, h=32, w=32, cin1=128, res=True),
+    dict(n=37, cin=512, cout=256, h=16, w=16, cin1=256, res=True),   # > 148 work units: persistent loop, both TMEM stages
+    dict(n=150, cin=128, cout=128, h=32, w=32),                      # several units per CTA at 32x32
+]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("cfg", HALO_CASES)
+def test_conv_halo(cfg, mode):
+    """halo-reuse tcgen05 kernel (mode 1 = descriptors with base offset, the shipped default; mode 2 = diagnostic)"""
+    ops, L = _ops()
+    lib = L.load()
+    g = torch.Generator().manual_seed(23)
+    n, cin, cout, h, w = (cfg[s] for s in ("n", "cin", "cout", "h", "w"))
+    c1 = cfg.get("cin1", 0)
+    c0 = cin - c1
+    xa = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9))
+    b = torch.randn(cout, generator=g)
+    s0 = to_nhwc(xa[:, :c0], torch.bfloat16).to(DEV)
+    s1 = to_nhwc(xa[:, c0:], torch.bfloat16).to(DEV) if c1 else None
+    want = F.conv2d(xa, wt, b, padding=1)
+    wres = None
+    r0 = r1 = None
+    bias = b
+    if cfg.get("res"):
+        wres = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin))
+        bres = torch.randn(cout, generator=g)
+        want = want + F.conv2d(xa, wres, bres)
+        bias = b + bres
+        r0, r1 = s0, s1
+    temb = None
+    if cfg.get("temb"):
+        temb = torch.randn(n if cfg["temb"] == "rows" else 1, cout, generator=g)
+        want = want + (temb if temb.shape[0] == n else temb.expand(n, -1))[:, :, None, None]
+        temb = temb.to(DEV)
+    addend = None
+    if cfg.get("addend"):
+        ad = bf16_round(torch.randn(n, cout, h, w, generator=g))
+        want = want + ad
+        addend = to_nhwc(ad, torch.bfloat16).to(DEV)
+    d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_HALO)
+    assert ops.conv_uses_tc(d)
+    wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
+    out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+    lib.dmme_set_conv_halo_mode(mode)
+    try:
+        ops.conv2d_launch(d, wp, bias.to(DEV), out, temb, addend, stats=st)
+        torch.cuda.synchronize()
+    finally:
+        lib.dmme_set_conv_halo_mode(1)
+    got = to_nchw(out.cpu())
+    err = rel_l2(got, want)
+    assert err < 4e-3, f"rel-L2 {err}"
+    sums = st.cpu().view(n, cout // 4, 2).double() / 2 ** 20
+    assert torch.allclose(sums[..., 0], got.double().reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+    assert torch.allclose(sums[..., 1], (got.double() ** 2).reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+
+
 def test_conv_tc_res_two_sources():
     """fused residual conv whose operand is itself a two-source concat (the up-path ResBlocks)."""
     ops, L = _ops()
