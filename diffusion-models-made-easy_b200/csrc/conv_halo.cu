@@ -5,8 +5,8 @@
 // Here the batch is viewed as one flat sequence of ZERO-PADDED pixels, G = n*(H+2)*(W+2) + (y+1)*(W+2) + (x+1).
 // In that space a filter tap is a constant shift d = (r-1)*(W+2) + (s-1), so for a tile of 256 consecutive
 // positions ONE halo tile [256 + 2(W+3) positions][64 ch] in shared memory serves all nine taps: the MMA's A
-// descriptor is simply advanced by d rows (128 B each; the 128-byte-swizzle phase follows the address through
-// the descriptor's base-offset field).  The halo tile is assembled by one TMA box per padded image row
+// descriptor is simply advanced by d rows (128 B each; the 128-byte-swizzle phase is a function of the absolute
+// shared-memory address for both TMA writes and MMA reads, so row-granular shifts need no re-layout).  The halo tile is assembled by one TMA box per padded image row
 // ([W+2 px][64 ch], out-of-bounds pixels / rows / images zero-filled = the conv padding).
 // Outputs at padding positions are junk and masked in the epilogue (11% of the MMA work at 32x32, 21% at 16x16).
 //
@@ -35,7 +35,6 @@ struct ConvHaloParams {
   const __nv_bfloat16* addend;
   __nv_bfloat16* out;
   long long* stats;
-  int desc_mode;
 };
 
 constexpr int kHaloTM = 256;
@@ -160,8 +159,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint32_t addr = a_addr + static_cast<uint32_t>(rowbase + j * 128 + d) * 128u;
-              uint64_t adesc = umma_desc_sw128(addr);
-              if (p.desc_mode) adesc |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;  // swizzle phase of the start row
+              // the start address is 128-byte (one pixel row) aligned, not 1024: measured on B200, the MMA derives the
+              // swizzle phase from the absolute shared-memory address exactly as TMA did when writing the rows, so the
+              // descriptor's base-offset field stays 0 (setting it to (addr >> 7) & 7 produces wrong results).
+              const uint64_t adesc = umma_desc_sw128(addr);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(dtm + j * kHaloBN, adesc + 2 * k, bdesc + 2 * k, idesc, (ck | tap | k) != 0 ? 1u : 0u);
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
 static int halo_rows(int wp) { return (kHaloTM + 3 * wp) / wp + 1; }
 
-static int g_halo_mode = 1;     // 1: enabled with documented base-offset descriptors, 2: base offset left zero, 0: off
+static int g_halo_mode = 1;     // 1: AUTO prefers this kernel, 0: AUTO never picks it (A/B measurements)
 static int g_sm_count = 0;
 
 bool conv_halo_supported(const dmme_conv_desc& d) {
@@ -330,7 +331,6 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   p.addend = static_cast<const __nv_bfloat16*>(d.addend);
   p.out = static_cast<__nv_bfloat16*>(d.out);
   p.stats = d.stats;
-  p.desc_mode = g_halo_mode == 1 ? 1 : 0;
 
   auto act_map = [&](CUtensorMap* m, const void* ptr, int c) -> int {
     uint64_t dims[5] = {(uint64_t)c, (uint64_t)d.w_in, 1, (uint64_t)d.h_in, (uint64_t)d.n};
@@ -370,6 +370,6 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
 
 }  // namespace dmme
 
-// debugging / A-B measurement switch: 0 = never use the halo kernel, 1 = default, 2 = descriptors without base offset
+// A/B measurement switch: 0 = AUTO never uses the halo kernel, 1 = default
 extern "C" void dmme_set_conv_halo_mode(int mode) { dmme::g_halo_mode = mode; }
 extern "C" int dmme_get_conv_halo_mode(void) { return dmme::g_halo_mode; }

@@ -95,8 +95,7 @@ const char* dmme_last_error(void);
 long long dmme_launch_count(void);
 void dmme_reset_launch_count(void);
 
-/* A/B switch for measurements: 0 = AUTO never picks the halo kernel, 1 = default, 2 = halo kernel with the
- * shared-memory descriptor base-offset field left at zero (diagnostic) */
+/* A/B switch for measurements: 0 = AUTO never picks the halo kernel, 1 = default */
 void dmme_set_conv_halo_mode(int mode);
 int dmme_get_conv_halo_mode(void);
 
