@@ -10,13 +10,21 @@
 // ([W+2 px][64 ch], out-of-bounds pixels / rows / images zero-filled = the conv padding).
 // Outputs at padding positions are junk and masked in the epilogue (11% of the MMA work at 32x32, 21% at 16x16).
 //
-// Tile: 256 positions x 128 output channels per work unit (two M=128 MMAs share every weight tile), fp32
-// accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of unit i overlaps the MMAs of unit
-// i+1; persistent CTAs (one per SM), static round-robin schedule.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue.
+// Work unit: 128 output channels x 256 positions, computed TRANSPOSED: the weight tile [128 cout][64] is the
+// MMA's M-side operand and the pixel rows are its N-side operand (D^T = W X^T, one M=128, N=256 instruction per
+// 16 channels).  A 128x128 tile would make every MMA read 8 KB of shared memory per 64 cycles = the whole
+// 128 B/cycle shared-memory bandwidth (measured: 35% tensor utilisation); 128x256 needs 96 B/cycle.  The
+// accumulator therefore has TMEM lane = output channel and column = position; two accumulators (2 x 256
+// columns) are double-buffered so the epilogue of unit i overlaps the MMAs of unit i+1.  Persistent CTAs (one
+// per SM), static round-robin schedule.
+// Warp roles: 0..7 = epilogue (two warps per TMEM lane quarter), 8 = halo-tile TMA producer, 9 = weight-tile
+// TMA producer, 10 = MMA issuer / TMEM owner.  The single-thread issue loops sit in the HIGHEST warp ids because
+// the SM's warp arbiter favours high ids: with the issuer in warp 1 the eight busy epilogue warps starved it
+// (measured: 1186 cycles per tap iteration for 512 cycles of MMA work).
 #include <cuda.h>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptx_sm100.cuh"
 #include "tmap.cuh"
 
@@ -41,10 +49,12 @@ constexpr int kHaloTM = 256;
 constexpr int kHaloBN = 128;
 constexpr int kHaloASlot = 47 * 1024;  // >= nr * (W+2) * 128 bytes
 constexpr int kHaloBSlot = kHaloBN * 128;
-constexpr int kHaloAStages = 2;
+constexpr int kHaloAStages = 3;
 constexpr int kHaloBStages = 4;
 constexpr int kHaloSmem = kHaloAStages * kHaloASlot + kHaloBStages * kHaloBSlot + 1024;
-constexpr int kHaloThreads = 192;
+constexpr int kHaloEpiWarps = 8;                       // two warps per TMEM lane quarter, alternating column chunks
+constexpr int kHaloThreads = (kHaloEpiWarps + 3) * 32;
+constexpr int kWarpProdA = kHaloEpiWarps, kWarpProdB = kHaloEpiWarps + 1, kWarpMma = kHaloEpiWarps + 2;
 
 __device__ __forceinline__ int floor_div(int a, int b) {
   int q = a / b;
@@ -71,41 +81,41 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kHaloBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kHaloEpiWarps * 32); }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpProdA && lane == 0) {
     tma_prefetch_desc(&p.a[0]);
     if (p.chunks1) tma_prefetch_desc(&p.a[1]);
     if (p.rchunks0) tma_prefetch_desc(&p.a[2]);
     if (p.rchunks1) tma_prefetch_desc(&p.a[3]);
     tma_prefetch_desc(&p.b);
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (warp == kWarpMma) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
+  if (warp == kWarpProdA) {
+    // =========================== halo-tile producer ===========================
     if (lane == 0) {
-      int a_it = 0, b_it = 0;
+      int a_it = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int mt = u / p.n_tiles, nt = u - mt * p.n_tiles;
-        const int g0 = mt * kHaloTM, col0 = nt * kHaloBN;
-        for (int ck = 0; ck < nck; ++ck) {
-          int which, cc, halo, ntaps, kb0, kbs;
+        const int mt = u / p.n_tiles;
+        const int g0 = mt * kHaloTM;
+        for (int ck = 0; ck < nck; ++ck, ++a_it) {
+          int which, cc, halo;
           if (ck < cchunks) {
             which = ck < p.chunks0 ? 0 : 1;
             cc = (which ? ck - p.chunks0 : ck) * 64;
-            halo = p.wp + 1; ntaps = 9; kb0 = ck; kbs = cchunks;
+            halo = p.wp + 1;
           } else {
             const int rk = ck - cchunks;
             which = rk < p.rchunks0 ? 2 : 3;
             cc = (which == 3 ? rk - p.rchunks0 : rk) * 64;
-            halo = 0; ntaps = 1; kb0 = 9 * cchunks + rk; kbs = 0;
+            halo = 0;
           }
           const int as = a_it % kHaloAStages;
           mbar_wait(&a_empty[as], ((a_it / kHaloAStages) & 1) ^ 1);
@@ -118,7 +128,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const int yy = pr - ni * (p.h + 2) - 1;        // -1 or h: padding row -> zeros
             tma_load_5d(dst + i * row_bytes, &p.a[which], &a_full[as], cc, -1, 0, yy, ni);
           }
-          ++a_it;
+        }
+      }
+    }
+  } else if (warp == kWarpProdB) {
+    // =========================== weight-tile producer ===========================
+    if (lane == 0) {
+      int b_it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int nt = u % p.n_tiles;
+        const int col0 = nt * kHaloBN;
+        for (int ck = 0; ck < nck; ++ck) {
+          const bool is_conv = ck < cchunks;
+          const int ntaps = is_conv ? 9 : 1;
+          const int kb0 = is_conv ? ck : 9 * cchunks + (ck - cchunks);
+          const int kbs = is_conv ? cchunks : 0;
           for (int tap = 0; tap < ntaps; ++tap, ++b_it) {
             const int bs = b_it % kHaloBStages;
             mbar_wait(&b_empty[bs], ((b_it / kHaloBStages) & 1) ^ 1);
@@ -128,10 +152,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, kHaloBN);
+    // the whole warp walks the loop (converged waits); one elected lane issues the MMAs and their commits
+    {
+      constexpr uint32_t idesc = umma_idesc_bf16(kHaloBN, kHaloTM);  // M = 128 output channels, N = 256 positions
       int a_it = 0, b_it = 0, u_it = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
         const int mt = u / p.n_tiles;
@@ -139,7 +164,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int stage = u_it & 1;
         mbar_wait(&acc_empty[stage], ((u_it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t dtm = tmem_base + stage * (2 * kHaloBN);
+        const uint32_t dtm = tmem_base + stage * kHaloTM;
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           const bool is_conv = ck < cchunks;
           const int halo = is_conv ? p.wp + 1 : 0;
@@ -155,140 +180,126 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             mbar_wait(&b_full[bs], (b_it / kHaloBStages) & 1);
             tc_fence_after();
             const int d = is_conv ? (tap / 3 - 1) * p.wp + (tap % 3 - 1) : 0;
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(bbuf + bs * kHaloBSlot));
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t addr = a_addr + static_cast<uint32_t>(rowbase + j * 128 + d) * 128u;
-              // the start address is 128-byte (one pixel row) aligned, not 1024: measured on B200, the MMA derives the
-              // swizzle phase from the absolute shared-memory address exactly as TMA did when writing the rows, so the
-              // descriptor's base-offset field stays 0 (setting it to (addr >> 7) & 7 produces wrong results).
-              const uint64_t adesc = umma_desc_sw128(addr);
+            const uint64_t wdesc = umma_desc_sw128(smem_u32(bbuf + bs * kHaloBSlot));  // [128 cout][64]: M side
+            // pixel rows [256][64] shifted by the tap: N side.  The start address is 128-byte (one pixel row)
+            // aligned, not 1024: measured on B200, the MMA derives the swizzle phase from the absolute shared-memory
+            // address exactly as TMA did when writing the rows, so the descriptor's base-offset field stays 0
+            // (setting it to (addr >> 7) & 7 produces wrong results).
+            const uint64_t xdesc = umma_desc_sw128(a_addr + static_cast<uint32_t>(rowbase + d) * 128u);
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(dtm + j * kHaloBN, adesc + 2 * k, bdesc + 2 * k, idesc, (ck | tap | k) != 0 ? 1u : 0u);
+                umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (ck | tap | k) != 0 ? 1u : 0u);
+              umma_commit(&b_empty[bs]);
+              if (tap == ntaps - 1) {
+                umma_commit(&a_empty[as]);
+                if (ck == nck - 1) umma_commit(&acc_full[stage]);
+              }
             }
-            umma_commit(&b_empty[bs]);
+            __syncwarp();
           }
-          umma_commit(&a_empty[as]);
         }
-        umma_commit(&acc_full[stage]);
       }
     }
   } else {
     // =========================== epilogue ===========================
+    // thread = one output channel (TMEM lane), columns = positions; warp (q, half) drains channels
+    // [32q, 32q+32) x positions [128 half, 128 half + 128) of every unit.  Valid positions in increasing order map
+    // to consecutive pixels, so per 32-position chunk one ballot gives the validity mask and the stores just walk
+    // a pointer: ~10 instructions per position (the first version spent 66 on index arithmetic and was the
+    // kernel's bottleneck).
     const int q = warp & 3;
+    const int half = warp >> 2;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
+    const bool temb_per_image = p.temb && p.temb_rows != 1;
     int u_it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
       const int mt = u / p.n_tiles, nt = u - mt * p.n_tiles;
-      const int g0 = mt * kHaloTM, col0 = nt * kHaloBN;
+      const int ch = nt * kHaloBN + q * 32 + lane;
+      const float bias_c = p.bias ? __ldg(p.bias + ch) : 0.f;
+      const long long gs = static_cast<long long>(mt) * kHaloTM + half * 128;
+      const int n_a = static_cast<int>(gs / p.pimg);                       // image of the first position
+      const int boundary = static_cast<int>(static_cast<long long>(n_a + 1) * p.pimg - gs);  // first position of image n_a+1
+      float bt = bias_c;
+      if (p.temb && n_a < p.n) bt += __ldg(p.temb + static_cast<long long>(temb_per_image ? n_a : 0) * p.temb_ld + ch);
+      float s1 = 0.f, s2 = 0.f, s1a = 0.f, s2a = 0.f;
       const int stage = u_it & 1;
       mbar_wait(&acc_full[stage], (u_it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const long long g = static_cast<long long>(g0) + j * 128 + q * 32 + lane;
+      for (int c = 0; c < 128; c += 32) {
+        // lane l classifies position c + l; the ballot is the chunk's validity mask
+        const long long g = gs + c + lane;
         const int n = static_cast<int>(g / p.pimg);
         const int rem = static_cast<int>(g - static_cast<long long>(n) * p.pimg);
-        const int yy = rem / p.wp - 1, xx = rem % p.wp - 1;
-        const bool valid = n < p.n && yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
-        const long long pix = (static_cast<long long>(n) * p.h + yy) * p.w + xx;
-        const float* trow = p.temb ? p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : (n < p.n ? n : 0)) * p.temb_ld : nullptr;
-        const int n_first = __shfl_sync(0xffffffffu, n, 0);
-        const bool straddle = __any_sync(0xffffffffu, n != n_first);
-#pragma unroll 1
-        for (int c = 0; c < kHaloBN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(stage * (2 * kHaloBN) + j * kHaloBN + c), v);
-          tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          const int col = col0 + c;
-          if (valid) {
-            if (p.bias) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
-                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-              }
-            }
-            if (trow) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + col + i));
-                f[i] += t4.x; f[i + 1] += t4.y; f[i + 2] += t4.z; f[i + 3] += t4.w;
-              }
-            }
-            if (p.addend) {
-              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.cout + col);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 a4 = __ldg(ap + i);
-                float lo, hi;
-                unpack_bf16x2(a4.x, lo, hi); f[8 * i + 0] += lo; f[8 * i + 1] += hi;
-                unpack_bf16x2(a4.y, lo, hi); f[8 * i + 2] += lo; f[8 * i + 3] += hi;
-                unpack_bf16x2(a4.z, lo, hi); f[8 * i + 4] += lo; f[8 * i + 5] += hi;
-                unpack_bf16x2(a4.w, lo, hi); f[8 * i + 6] += lo; f[8 * i + 7] += hi;
-              }
-            }
-            uint4* dp = reinterpret_cast<uint4*>(p.out + pix * p.cout + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o;
-              o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
-              o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
-              o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
-              o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
-              dp[i] = o;
-              unpack_bf16x2(o.x, f[8 * i + 0], f[8 * i + 1]);
-              unpack_bf16x2(o.y, f[8 * i + 2], f[8 * i + 3]);
-              unpack_bf16x2(o.z, f[8 * i + 4], f[8 * i + 5]);
-              unpack_bf16x2(o.w, f[8 * i + 6], f[8 * i + 7]);
-            }
+        const int yy = rem / p.wp - 1, xx = rem - (yy + 1) * p.wp - 1;
+        const bool ok = n < p.n && yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(stage * kHaloTM + half * 128 + c), v);
+        tmem_ld_wait();
+        const int brel = boundary - c;  // chunk-relative index at which the next image starts (may be out of range)
+        if (mask == 0u) {  // warp-uniform: a chunk of pure padding; it may still contain the image boundary
+          if (brel >= 0 && brel < 32) {
+            s1a = s1; s2a = s2; s1 = 0.f; s2 = 0.f;
+            if (temb_per_image && n_a + 1 < p.n) bt = bias_c + __ldg(p.temb + static_cast<long long>(n_a + 1) * p.temb_ld + ch);
           }
-          if (p.stats) {
-            // GroupNorm statistics of the stored tensor; a warp's 32 positions touch at most two images
-            for (int pass = 0; pass < (straddle ? 2 : 1); ++pass) {
-              const int ntarget = n_first + pass;
-              const bool mine = valid && n == ntarget;
-              float s1[8], s2[8];
+          continue;
+        }
+        const long long mypix = (static_cast<long long>(n) * p.h + yy) * p.w + xx;
+        const long long pix0 = __shfl_sync(0xffffffffu, mypix, __ffs(mask) - 1);
+        __nv_bfloat16* op = p.out + pix0 * p.cout + ch;
+        const __nv_bfloat16* ap = p.addend ? p.addend + pix0 * p.cout + ch : nullptr;
 #pragma unroll
-              for (int gi = 0; gi < 8; ++gi) {
-                const float a = f[4 * gi], b = f[4 * gi + 1], cc = f[4 * gi + 2], dd = f[4 * gi + 3];
-                s1[gi] = mine ? (a + b) + (cc + dd) : 0.f;
-                s2[gi] = mine ? (a * a + b * b) + (cc * cc + dd * dd) : 0.f;
-              }
-#pragma unroll
-              for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                for (int gi = 0; gi < 8; ++gi) {
-                  s1[gi] += __shfl_xor_sync(0xffffffffu, s1[gi], off);
-                  s2[gi] += __shfl_xor_sync(0xffffffffu, s2[gi], off);
-                }
-              }
-              if (lane == 0 && ntarget < p.n) {
-                unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats) +
-                                         (static_cast<long long>(ntarget) * (p.cout >> 2) + (col >> 2)) * 2;
-#pragma unroll
-                for (int gi = 0; gi < 8; ++gi) {
-                  atomicAdd(st + 2 * gi, static_cast<unsigned long long>(__float2ll_rn(s1[gi] * kFix)));
-                  atomicAdd(st + 2 * gi + 1, static_cast<unsigned long long>(__float2ll_rn(s2[gi] * kFix)));
-                }
-              }
-            }
+        for (int i = 0; i < 32; ++i) {
+          if (i == brel) {  // crossed into image n_a + 1: park the first image's sums, switch the per-image temb
+            s1a = s1; s2a = s2; s1 = 0.f; s2 = 0.f;
+            if (temb_per_image && n_a + 1 < p.n) bt = bias_c + __ldg(p.temb + static_cast<long long>(n_a + 1) * p.temb_ld + ch);
+          }
+          if (mask & (1u << i)) {
+            float val = __uint_as_float(v[i]) + bt;
+            if (ap) { val += __bfloat162float(*ap); ap += p.cout; }
+            const __nv_bfloat16 r = __float2bfloat16_rn(val);
+            *op = r;
+            op += p.cout;
+            const float rf = __bfloat162float(r);
+            s1 += rf;
+            s2 = fmaf(rf, rf, s2);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[stage]);
+      if (p.stats) {
+        const bool crossed = boundary < 128;    // sums of image n_a are parked in (s1a, s2a), (s1, s2) belong to n_a + 1
+        float fa1 = crossed ? s1a : s1, fa2 = crossed ? s2a : s2;
+        float fb1 = crossed ? s1 : 0.f, fb2 = crossed ? s2 : 0.f;
+        // micro-group = 4 adjacent channels = 4 adjacent lanes
+        fa1 += __shfl_xor_sync(0xffffffffu, fa1, 1); fa2 += __shfl_xor_sync(0xffffffffu, fa2, 1);
+        fb1 += __shfl_xor_sync(0xffffffffu, fb1, 1); fb2 += __shfl_xor_sync(0xffffffffu, fb2, 1);
+        fa1 += __shfl_xor_sync(0xffffffffu, fa1, 2); fa2 += __shfl_xor_sync(0xffffffffu, fa2, 2);
+        fb1 += __shfl_xor_sync(0xffffffffu, fb1, 2); fb2 += __shfl_xor_sync(0xffffffffu, fb2, 2);
+        if ((lane & 3) == 0) {
+          unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats);
+          if (n_a < p.n) {
+            unsigned long long* sa = st + (static_cast<long long>(n_a) * (p.cout >> 2) + (ch >> 2)) * 2;
+            atomicAdd(sa, static_cast<unsigned long long>(__float2ll_rn(fa1 * kFix)));
+            atomicAdd(sa + 1, static_cast<unsigned long long>(__float2ll_rn(fa2 * kFix)));
+          }
+          if (crossed && n_a + 1 < p.n) {
+            unsigned long long* sb = st + (static_cast<long long>(n_a + 1) * (p.cout >> 2) + (ch >> 2)) * 2;
+            atomicAdd(sb, static_cast<unsigned long long>(__float2ll_rn(fb1 * kFix)));
+            atomicAdd(sb + 1, static_cast<unsigned long long>(__float2ll_rn(fb2 * kFix)));
+          }
+        }
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
