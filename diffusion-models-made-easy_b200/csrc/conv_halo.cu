@@ -237,31 +237,30 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const long long o = (static_cast<long long>(n) * p.h + yy) * W * COUT + ch;
         __nv_bfloat16* op = p.out + o;
         const uint32_t taddr = tmem_base + lane_off + static_cast<uint32_t>(stage * kHaloCols + rr * WP + 1);
+        // the addend row is fetched before the accumulator row is awaited, and every load is issued before the first
+        // store: out and addend may alias as far as the compiler knows, and a load placed after a store waits for it
+        // (measured: 550 us instead of 71 us per launch)
+        float av[W];
+        if (p.addend) {
+          const __nv_bfloat16* __restrict__ ap = p.addend + o;
+#pragma unroll
+          for (int i = 0; i < W; ++i) av[i] = __bfloat162float(__ldg(ap + i * COUT));
+        } else {
+#pragma unroll
+          for (int i = 0; i < W; ++i) av[i] = 0.f;
+        }
         uint32_t v[W];
         if constexpr (W == 32) tmem_ld32(taddr, v);
         else tmem_ld16(taddr, v);
         tmem_ld_wait();
-        if (p.addend) {
-          const __nv_bfloat16* ap = p.addend + o;
 #pragma unroll
-          for (int i = 0; i < W; ++i) {
-            const float val = __uint_as_float(v[i]) + bt + __bfloat162float(ap[i * COUT]);
-            const __nv_bfloat16 r = __float2bfloat16_rn(val);
-            op[i * COUT] = r;
-            const float rf = __bfloat162float(r);
-            s1 += rf;
-            s2 = fmaf(rf, rf, s2);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < W; ++i) {
-            const float val = __uint_as_float(v[i]) + bt;
-            const __nv_bfloat16 r = __float2bfloat16_rn(val);
-            op[i * COUT] = r;
-            const float rf = __bfloat162float(r);
-            s1 += rf;
-            s2 = fmaf(rf, rf, s2);
-          }
+        for (int i = 0; i < W; ++i) {
+          const float val = __uint_as_float(v[i]) + bt + av[i];
+          const __nv_bfloat16 r = __float2bfloat16_rn(val);
+          op[i * COUT] = r;
+          const float rf = __bfloat162float(r);
+          s1 += rf;
+          s2 = fmaf(rf, rf, s2);
         }
       }
       tc_fence_before();
