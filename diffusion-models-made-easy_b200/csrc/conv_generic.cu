@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(const ConvGenParams p
           if (!is_res) {
             const int iy = a_y[j] * p.stride + r - pad;
             const int ix = a_x[j] * p.stride + s - pad;
-            if (iy >= 0 && iy < hin_eff && ix >= 0 && ix < win_eff) {
+            // upsample == 2: zero-dilated source (values at even coordinates only) = the data gradient of a stride-2 conv
+            if (iy >= 0 && iy < hin_eff && ix >= 0 && ix < win_eff && (p.upsample != 2 || ((iy | ix) & 1) == 0)) {
               const int sy = p.upsample ? (iy >> 1) : iy;
               const int sx = p.upsample ? (ix >> 1) : ix;
               if (p.in_layout == DMME_IN_NCHW_F32) {
@@ -167,6 +168,7 @@ int conv_generic_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   DMME_REQUIRE(d.ksize == 1 || d.ksize == 3, DMME_E_SHAPE, "conv_generic: ksize must be 1 or 3 (got %d)", d.ksize);
   DMME_REQUIRE(d.stride == 1 || d.stride == 2, DMME_E_SHAPE, "conv_generic: stride must be 1 or 2");
   DMME_REQUIRE(!(d.upsample && d.stride != 1), DMME_E_SHAPE, "conv_generic: upsample needs stride 1");
+  DMME_REQUIRE(d.upsample >= 0 && d.upsample <= 2, DMME_E_BADARG, "conv_generic: upsample must be 0, 1 (nearest) or 2 (zero-dilated)");
   DMME_REQUIRE(d.n > 0 && d.h_in > 0 && d.w_in > 0 && d.c0 > 0 && d.cout > 0, DMME_E_BADARG, "conv_generic: bad sizes");
   DMME_REQUIRE(d.c1 == 0 || d.src1, DMME_E_BADARG, "conv_generic: c1 > 0 but src1 is null");
   DMME_REQUIRE(d.rc0 == 0 || d.res0, DMME_E_BADARG, "conv_generic: rc0 > 0 but res0 is null");
@@ -218,6 +220,26 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     } else {
       v = wres[static_cast<long long>(co) * rc + (k - static_cast<long long>(taps) * cin)];
     }
+    if (tc) static_cast<__nv_bfloat16*>(packed)[i] = __float2bfloat16_rn(v);
+    else static_cast<float*>(packed)[i] = v;
+  }
+}
+
+// Data-gradient weights: the dgrad of conv(w) w.r.t. input channels [ci_off, ci_off + ci_cnt) is itself a convolution of
+// grad_out with  w'[co' = ci - ci_off][k' = tap' * cout + co] = w[co][ci][taps - 1 - tap']  (spatial flip, in/out swapped).
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int ksize, int ci_off, int ci_cnt,
+                                         void* __restrict__ packed, int tc) {
+  const int taps = ksize * ksize;
+  const long long ktot = static_cast<long long>(taps) * cout;
+  const long long total = ktot * ci_cnt;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long k;
+    int cn;
+    if (tc) { cn = static_cast<int>(i / ktot); k = i - cn * ktot; }     // [ci_cnt][K']
+    else { k = i / ci_cnt; cn = static_cast<int>(i - k * ci_cnt); }     // [K'][ci_cnt]
+    const int tap = static_cast<int>(k / cout), co = static_cast<int>(k - static_cast<long long>(tap) * cout);
+    const float v = w[(static_cast<long long>(co) * cin + (ci_off + cn)) * taps + (taps - 1 - tap)];
     if (tc) static_cast<__nv_bfloat16*>(packed)[i] = __float2bfloat16_rn(v);
     else static_cast<float*>(packed)[i] = v;
   }
@@ -287,6 +309,18 @@ extern "C" int dmme_pack_conv_weight(const float* w_oihw, int cout, int cin, int
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w_oihw, cout, cin, ksize, w_res, rc, packed, kernel == DMME_CONV_TC ? 1 : 0);
   return check_launch("pack_weight_kernel");
+}
+
+extern "C" int dmme_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, int ci_off, int ci_cnt,
+                                           void* packed, int kernel, void* stream) {
+  DMME_REQUIRE(w_oihw && packed, DMME_E_BADARG, "pack_conv_weight_dgrad: null pointer");
+  DMME_REQUIRE(cout > 0 && cin > 0 && (ksize == 1 || ksize == 3) && ci_off >= 0 && ci_cnt > 0 && ci_off + ci_cnt <= cin,
+               DMME_E_BADARG, "pack_conv_weight_dgrad: bad sizes");
+  DMME_REQUIRE(kernel == DMME_CONV_TC || kernel == DMME_CONV_GENERIC, DMME_E_BADARG, "pack_conv_weight_dgrad: kernel must be TC or GENERIC");
+  const long long total = static_cast<long long>(ksize) * ksize * cout * ci_cnt;
+  pack_weight_dgrad_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, cout, cin, ksize, ci_off, ci_cnt, packed, kernel == DMME_CONV_TC ? 1 : 0);
+  return check_launch("pack_weight_dgrad_kernel");
 }
 
 extern "C" int dmme_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int act_dtype, void* stream) {

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) temb_linear_kernel(const float* __restric
   }
 }
 
-static int launch_linear(const float* in, const int64_t* t, const float* freq, int rows, int in_dim, const float* w,
+int launch_linear(const float* in, const int64_t* t, const float* freq, int rows, int in_dim, const float* w,
                          const float* b, int out_dim, int act, float* out, cudaStream_t st, const char* what) {
   const size_t smem = sizeof(float) * kProjRows * static_cast<size_t>(in_dim);
   DMME_REQUIRE(smem <= 48 * 1024, DMME_E_SHAPE, "%s: input width %d too large", what, in_dim);

@@ -28,6 +28,9 @@ EXPORTS = (
     "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
+    "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_groupnorm_bwd",
+    "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
+    "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
 
 
@@ -84,6 +87,26 @@ def load() -> C.CDLL:
     lib.dmme_add_i64.argtypes = [vp, C.c_int64, vp]
     lib.dmme_philox_normal.argtypes = [vp, ll, ull, ull, vp]
     lib.dmme_set_conv_halo_mode.argtypes = [i]
+    lib.dmme_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, i, vp, i, vp]
+    lib.dmme_conv2d_wgrad_workspace.argtypes = [C.POINTER(ConvDesc)]
+    lib.dmme_conv2d_wgrad_workspace.restype = ll
+    lib.dmme_conv2d_wgrad.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, ll, vp]
+    lib.dmme_groupnorm_bwd.argtypes = [vp, vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, i,
+                                       vp, vp, vp, vp, vp, vp, vp, vp, i, vp, i, vp]
+    lib.dmme_attention_bwd_workspace.argtypes = [i, i, i, i]
+    lib.dmme_attention_bwd_workspace.restype = ll
+    lib.dmme_attention_bwd.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, f, i, vp, vp, vp, vp, i, vp, ll, vp]
+    lib.dmme_temb_bwd_workspace.argtypes = [i, i, i]
+    lib.dmme_temb_bwd_workspace.restype = ll
+    lib.dmme_temb_bwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, ll, vp]
+    lib.dmme_gemm_strided.argtypes = [vp, i, ll, ll, ll, ll, vp, i, ll, ll, ll, ll, vp, i, ll, ll, ll, ll,
+                                      i, i, i, i, i, f, i, vp]
+    lib.dmme_add.argtypes = [vp, vp, vp, ll, i, vp]
+    lib.dmme_pixel_sum.argtypes = [vp, i, i, i, vp, ll, i, vp]
+    lib.dmme_pool2x_sum_nhwc.argtypes = [vp, vp, i, i, i, i, i, vp]
+    lib.dmme_colsum_f32.argtypes = [vp, i, i, ll, vp, i, vp]
+    lib.dmme_mse_loss.argtypes = [vp, vp, ll, f, vp, vp, vp, vp]
+    lib.dmme_iddpm_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, f, f, f, vp, vp, vp, vp]
     lib.dmme_set_conv_halo_mode.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -15,7 +15,7 @@ import torch
 from torch import nn, Tensor
 
 from .. import ops
-from ..common.noise import gaussian
+from ..common.noise import gaussian, uniform_int
 from ..equations import ddpm as eq_ddpm
 
 
@@ -136,7 +136,51 @@ class DDPM(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         return self._run_steps(x, self._num_steps(), seed, graph, on_step)
 
-    def training_step(self, x_0: Tensor) -> Tensor:
-        raise NotImplementedError(
-            "dmme_b200: the backward kernels (conv dgrad/wgrad, GroupNorm/attention backward) are not built yet; "
-            "training_step is the next row of the scope table (DESIGN.md)")
+    def _noised(self, x_0: Tensor, t: Optional[Tensor] = None, noise: Optional[Tensor] = None):
+        """t ~ U{1..T-1} (randint excludes T), x_t ~ q(x_t | x_0); RNG order as the reference:
+        randint, then one normal draw (diffusion_models/ddpm.py:65-75).  ``t`` / ``noise`` inject fixed draws
+        (Normal.sample() == noise * std + mean)."""
+        if not x_0.is_cuda:
+            raise RuntimeError("dmme_b200 training runs on CUDA only; there is no CPU path")
+        x_0 = x_0.detach().float().contiguous()
+        if t is None:
+            t = uniform_int(1, self.timesteps, x_0.size(0), device=x_0.device)
+        t = t.to(device=x_0.device, dtype=torch.int64).contiguous()
+        alpha_bar_t = self.alpha_bar[t]
+        mean, std = torch.sqrt(alpha_bar_t) * x_0, torch.sqrt(1 - alpha_bar_t)
+        if noise is None:
+            x_t = torch.normal(mean, std.expand_as(mean))
+        else:
+            x_t = noise.to(x_0.device) * std + mean
+        return x_0, t, x_t.contiguous(), mean, std
+
+    def training_step(self, x_0: Tensor, *, t: Optional[Tensor] = None, noise: Optional[Tensor] = None) -> Tensor:
+        r"""Training step except for optimization
+
+        Args:
+            x_0: image from dataset
+
+        Returns:
+            loss, :math:`L_\text{simple}` (0-dim tensor; ``loss.backward()`` runs the explicit backward kernels)
+        """
+        x_0, t, x_t, mean, std = self._noised(x_0, t, noise)
+        noise_in_x_t = self.model(x_t, t)
+        noise = ((x_t - mean) / std).contiguous()
+        return _SimpleLoss.apply(noise_in_x_t, noise)
+
+
+class _SimpleLoss(torch.autograd.Function):
+    """L_simple = mse_loss(noise, eps) (equations/ddpm/losses.py:5-13): value and gradient from one fused kernel."""
+
+    @staticmethod
+    def forward(ctx, eps: Tensor, noise: Tensor) -> Tensor:
+        eps = eps.contiguous()
+        d_eps = torch.empty_like(eps)
+        loss = ops.mse_loss(eps, noise, d_eps)
+        ctx.save_for_backward(d_eps)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_eps,) = ctx.saved_tensors
+        return d_eps * g, None

@@ -42,3 +42,40 @@ class IDDPM(DDPM):
 
     def _update_(self, x: Tensor, model_out: Tensor, noise: Optional[Tensor], t: Tensor, seed: int) -> Tensor:
         return ops.iddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed)
+
+    def forward_model(self, x_t: Tensor, t: Tensor, beta_t: Tensor, alpha_bar_t: Tensor,
+                      alpha_bar_t_minus_one: Tensor) -> NoiseVariance:
+        """(noise, variance) with the interpolated learned variance (diffusion_models/iddpm.py:150-164)."""
+        noise, v = self.model(x_t, t).chunk(2, dim=1)
+        beta_tilde_t = (1 - alpha_bar_t_minus_one) / (1 - alpha_bar_t) * beta_t
+        variance = torch.exp(v * torch.log(beta_t) + (1 - v) * torch.log(beta_tilde_t.clamp(1e-12)))
+        return NoiseVariance(noise, variance)
+
+    def training_step(self, x_0: Tensor, *, t: Optional[Tensor] = None, noise: Optional[Tensor] = None) -> Optional[Tensor]:
+        r"""Hybrid loss :math:`L_\text{simple} + \gamma L_\text{vlb}` (or :math:`L_\text{vlb}` alone for
+        ``loss_type="vlb"``), diffusion_models/iddpm.py:62-116.  The whole loss tail (learned-variance
+        interpolation, discrete NLL at t = 1, KL elsewhere, MSE) and its gradient run as one fused kernel."""
+        x_0, t, x_t, _, _ = self._noised(x_0, t, noise)
+        model_out = self.model(x_t, t)
+        if self.loss_type == "hybrid":
+            w_simple, w_vlb = 1.0, float(self.gamma)
+        elif self.loss_type == "vlb":
+            w_simple, w_vlb = 0.0, 1.0
+        else:
+            return None  # the reference falls off the end of training_step for any other loss_type
+        return _HybridLoss.apply(model_out, x_t, x_0, t, self.beta, self.alpha, self.alpha_bar, w_simple, w_vlb)
+
+
+class _HybridLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model_out, x_t, x_0, t, beta, alpha, alpha_bar, w_simple, w_vlb):
+        model_out = model_out.contiguous()
+        d_out = torch.empty_like(model_out)
+        loss = ops.iddpm_loss(model_out, x_t.contiguous(), x_0, t, beta, alpha, alpha_bar, w_simple, w_vlb, d_out)
+        ctx.save_for_backward(d_out)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_out,) = ctx.saved_tensors
+        return (d_out * g,) + (None,) * 8

@@ -16,6 +16,7 @@ import torch
 from torch import nn, Tensor
 
 from ._engine import Engine
+from ._train import TrainEngine
 
 _PRECISIONS = {"bf16": torch.bfloat16, "fp32": torch.float32}
 
@@ -155,13 +156,19 @@ class _UNetBase(nn.Module):
                 masks[name] = keep.float() / (1.0 - blk.p)
         return masks or None
 
+    @property
+    def train_engine(self) -> TrainEngine:
+        eng = self.__dict__.get("_train_engine_obj")
+        if eng is None:
+            eng = TrainEngine(self, self.flavour)
+            object.__setattr__(self, "_train_engine_obj", eng)
+        return eng
+
     def forward_raw(self, x: Tensor, c: Tensor, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
-        """Like ``forward`` but returns the executor's own output buffer (overwritten by the next call)."""
+        """Inference forward: returns the executor's own output buffer (overwritten by the next call).  No
+        autograd graph is recorded; use ``forward`` (with gradients enabled) for training."""
         if not x.is_cuda:
             raise RuntimeError("dmme_b200.UNet runs on CUDA (sm_100a) only; there is no CPU path")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "dmme_b200: backward kernels are not built yet; run training-mode forwards under torch.no_grad()")
         with torch.no_grad():
             if masks is None:
                 masks = self._dropout_masks(x.shape[0], x.device)
@@ -177,9 +184,42 @@ class _UNetBase(nn.Module):
             c: timestep of shape (N,) or (1,), integer
 
         Returns:
-            estimated noise (N, C, H, W) (IDDPM flavour: (N, 2C, H, W)), float32
+            estimated noise (N, C, H, W) (IDDPM flavour: (N, 2C, H, W)), float32.  With gradients enabled the
+            result carries an autograd node whose backward runs the explicit backward kernels (``_train.py``).
         """
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if not x.is_cuda:
+                raise RuntimeError("dmme_b200.UNet runs on CUDA (sm_100a) only; there is no CPU path")
+            return _UNetFunction.apply(self, x, c, *self.parameters())
         return self.forward_raw(x, c).clone()
+
+
+class _UNetFunction(torch.autograd.Function):
+    """Autograd node of one UNet call: forward = TrainEngine.forward, backward = TrainEngine.backward."""
+
+    @staticmethod
+    def forward(ctx, unet, x, c, *params):
+        eng = unet.train_engine
+        eng.force_generic = unet.precision == "fp32"
+        masks = getattr(unet, "_injected_masks", None) or unet._dropout_masks(x.shape[0], x.device)
+        out = eng.forward(x.detach(), c, _PRECISIONS[unet.precision], masks)
+        eng.generation = getattr(eng, "generation", 0) + 1
+        ctx.unet, ctx.generation = unet, eng.generation
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        unet = ctx.unet
+        eng = unet.train_engine
+        if eng.generation != ctx.generation:
+            raise RuntimeError("dmme_b200: backward() of a UNet call whose saved activations were overwritten by a later "
+                               "forward; run backward before the next training forward of the same module")
+        grads = eng.backward(d_out.contiguous())
+        out = []
+        for p in unet.parameters():
+            g = grads.get(id(p)) if p.requires_grad else None
+            out.append(g.clone() if g is not None else None)
+        return (None, None, None) + tuple(out)
 
 
 class UNet(_UNetBase):

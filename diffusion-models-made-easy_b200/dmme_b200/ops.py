@@ -238,3 +238,144 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     L.load().dmme_reset_launch_count()
+
+
+# ---------------------------------------------------------------------------------------------
+# backward pass
+# ---------------------------------------------------------------------------------------------
+def pack_conv_weight_dgrad(w: Tensor, ci_off: int, ci_cnt: int, tc: bool) -> Tensor:
+    """Weights of the convolution that maps grad_out to the gradient of input channels [ci_off, ci_off+ci_cnt)."""
+    L.require_cuda(w)
+    w = w.detach().float().contiguous()
+    cout, cin, kh, _ = w.shape
+    k = kh * kh * cout
+    packed = torch.empty((ci_cnt, k) if tc else (k, ci_cnt), dtype=torch.bfloat16 if tc else torch.float32, device=w.device)
+    L.check(L.load().dmme_pack_conv_weight_dgrad(ptr(w), cout, cin, kh, ci_off, ci_cnt, ptr(packed),
+                                                 L.CONV_TC if tc else L.CONV_GENERIC, L.stream_ptr()), "pack_conv_weight_dgrad")
+    return packed
+
+
+def conv_wgrad_workspace(desc: L.ConvDesc) -> int:
+    return int(L.load().dmme_conv2d_wgrad_workspace(C.byref(desc)))
+
+
+def conv2d_wgrad(desc: L.ConvDesc, grad_out: Tensor, dweight: Tensor, dweight_res: Optional[Tensor],
+                 dbias: Optional[Tensor], workspace: Tensor) -> None:
+    """Weight / fused-residual-weight / bias gradients of the forward call described by ``desc``."""
+    L.require_cuda(grad_out, dweight, dweight_res, dbias, workspace)
+    L.check(L.load().dmme_conv2d_wgrad(C.byref(desc), ptr(grad_out), ptr(dweight), ptr(dweight_res), ptr(dbias),
+                                       ptr(workspace), workspace.numel() * workspace.element_size(), L.stream_ptr()),
+            "conv2d_wgrad")
+
+
+def groupnorm_bwd(grad_out: Tensor, src0: Tensor, src1: Optional[Tensor], groups: int, gamma: Tensor, beta: Tensor,
+                  silu: bool, scale: Optional[Tensor], shift: Optional[Tensor], chan_mask: Optional[Tensor], eps: float,
+                  gin0: Optional[Tensor], gin1: Optional[Tensor], add0: Optional[Tensor], add1: Optional[Tensor],
+                  dgamma: Tensor, dbeta: Tensor, dscale: Optional[Tensor], dshift: Optional[Tensor], sums: Tensor) -> None:
+    L.require_cuda(grad_out, src0, src1, gin0, gin1, add0, add1)
+    n, h, w, c0 = src0.shape
+    c1 = src1.shape[3] if src1 is not None else 0
+    ss_rows = ss_ld = dss_ld = 0
+    if scale is not None:
+        ss_rows, ss_ld = scale.shape[0], scale.stride(0)
+    if dscale is not None:
+        dss_ld = dscale.stride(0)
+        if dshift is None or dshift.stride(0) != dss_ld:
+            raise ValueError("dscale/dshift must be 2-D fp32 views with equal row stride")
+    L.check(L.load().dmme_groupnorm_bwd(ptr(grad_out), ptr(src0), ptr(src1), c0, c1, n, h * w, groups, eps, ptr(gamma),
+                                        ptr(beta), ptr(scale), ptr(shift), ss_rows, ss_ld, ptr(chan_mask), int(silu),
+                                        ptr(gin0), ptr(gin1), ptr(add0), ptr(add1), ptr(dgamma), ptr(dbeta), ptr(dscale),
+                                        ptr(dshift), dss_ld, ptr(sums), L.act_code(src0.dtype), L.stream_ptr()),
+            "groupnorm_bwd")
+
+
+def attention_bwd_workspace(n: int, heads: int, seq: int, dh: int) -> int:
+    return int(L.load().dmme_attention_bwd_workspace(n, heads, seq, dh))
+
+
+def attention_bwd(q: Tensor, k: Tensor, v: Tensor, n: int, heads: int, seq: int, dh: int, scale: float, batch_stride: int,
+                  row_stride: int, head_stride: int, head_batch_swap: bool, dout: Tensor, dq: Tensor, dk: Tensor,
+                  dv: Tensor, workspace: Tensor) -> None:
+    L.check(L.load().dmme_attention_bwd(ptr(q), ptr(k), ptr(v), batch_stride, row_stride, head_stride, n, heads, seq, dh,
+                                        scale, int(head_batch_swap), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
+                                        L.act_code(dout.dtype), ptr(workspace),
+                                        workspace.numel() * workspace.element_size(), L.stream_ptr()), "attention_bwd")
+
+
+def temb_bwd_workspace(rows: int, half: int, emb_dim: int) -> int:
+    return int(L.load().dmme_temb_bwd_workspace(rows, half, emb_dim))
+
+
+def temb_bwd(t: Tensor, freq: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, hidden: Tensor, emb: Tensor,
+             wcat: Tensor, d_all: Tensor, dw1: Tensor, db1: Tensor, dw2: Tensor, db2: Tensor, dwcat: Tensor, dbcat: Tensor,
+             workspace: Tensor) -> None:
+    L.require_cuda(t, freq, w1, b1, w2, b2, hidden, emb, wcat, d_all, dw1, db1, dw2, db2, dwcat, dbcat, workspace)
+    rows, emb_dim = emb.shape
+    L.check(L.load().dmme_temb_bwd(ptr(t), rows, ptr(freq), freq.numel(), ptr(w1), ptr(b1), ptr(w2), ptr(b2), emb_dim,
+                                   ptr(hidden), ptr(emb), ptr(wcat), wcat.shape[0], ptr(d_all), ptr(dw1), ptr(db1), ptr(dw2),
+                                   ptr(db2), ptr(dwcat), ptr(dbcat), ptr(workspace),
+                                   workspace.numel() * workspace.element_size(), L.stream_ptr()), "temb_bwd")
+
+
+def gemm_strided(a: Tensor, a_str, b: Tensor, b_str, c: Tensor, c_str, m: int, n: int, k: int, outer: int = 1,
+                 heads: int = 1, alpha: float = 1.0, accumulate: bool = False) -> Tensor:
+    """c[b](i,j) = alpha * sum_k a[b](i,k) b[b](k,j); *_str = (outer-batch, head, row, column) element strides."""
+    L.check(L.load().dmme_gemm_strided(ptr(a), L.act_code(a.dtype), *a_str, ptr(b), L.act_code(b.dtype), *b_str, ptr(c),
+                                       L.act_code(c.dtype), *c_str, m, n, k, outer, heads, alpha, int(accumulate),
+                                       L.stream_ptr()), "gemm_strided")
+    return c
+
+
+def add(a: Tensor, b: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    L.require_cuda(a, b, out)
+    y = _empty(tuple(a.shape), a.dtype, a.device, out)
+    L.check(L.load().dmme_add(ptr(y), ptr(a), ptr(b), a.numel(), L.act_code(a.dtype), L.stream_ptr()), "add")
+    return y
+
+
+def pixel_sum(g: Tensor, out: Tensor) -> Tensor:
+    """out[n][c] = sum over pixels of g[n][y][x][c]; ``out`` is a 2-D fp32 view (row stride honoured)."""
+    n, h, w, c = g.shape
+    L.check(L.load().dmme_pixel_sum(ptr(g), n, h * w, c, ptr(out), out.stride(0), L.act_code(g.dtype), L.stream_ptr()),
+            "pixel_sum")
+    return out
+
+
+def pool2x_sum(g: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    L.require_cuda(g, out)
+    n, h2, w2, c = g.shape
+    y = _empty((n, h2 // 2, w2 // 2, c), g.dtype, g.device, out)
+    L.check(L.load().dmme_pool2x_sum_nhwc(ptr(g), ptr(y), n, h2 // 2, w2 // 2, c, L.act_code(g.dtype), L.stream_ptr()),
+            "pool2x_sum")
+    return y
+
+
+def colsum(x: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
+    """out[c] (+)= sum_r x[r][c] for a 2-D fp32 view."""
+    L.check(L.load().dmme_colsum_f32(ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(out), int(accumulate),
+                                     L.stream_ptr()), "colsum")
+    return out
+
+
+def mse_loss(eps: Tensor, noise: Tensor, d_eps: Optional[Tensor], grad_scale: float = 1.0) -> Tensor:
+    """L_simple = mean((eps - noise)^2) as a 1-element fp32 tensor; fills ``d_eps`` with its gradient w.r.t. eps."""
+    L.require_cuda(eps, noise, d_eps)
+    loss = torch.empty(1, dtype=torch.float32, device=eps.device)
+    partial = torch.empty(1024, dtype=torch.float32, device=eps.device)
+    L.check(L.load().dmme_mse_loss(ptr(eps), ptr(noise), eps.numel(), grad_scale, ptr(d_eps), ptr(loss), ptr(partial),
+                                   L.stream_ptr()), "mse_loss")
+    return loss
+
+
+def iddpm_loss(model_out: Tensor, x_t: Tensor, x_0: Tensor, t: Tensor, beta: Tensor, alpha: Tensor, alpha_bar: Tensor,
+               w_simple: float, w_vlb: float, d_out: Optional[Tensor], grad_scale: float = 1.0) -> Tensor:
+    """[w_simple L_simple + w_vlb L_vlb, L_simple, L_vlb] as a 3-element fp32 tensor; fills ``d_out`` with the
+    gradient of the first entry w.r.t. ``model_out``."""
+    L.require_cuda(model_out, x_t, x_0, t, beta, alpha, alpha_bar, d_out)
+    n, c, h, w = x_t.shape
+    loss = torch.empty(3, dtype=torch.float32, device=x_t.device)
+    partial = torch.empty(2048, dtype=torch.float32, device=x_t.device)
+    L.check(L.load().dmme_iddpm_loss(ptr(model_out), ptr(x_t), ptr(x_0), ptr(t), ptr(beta), ptr(alpha), ptr(alpha_bar), n, c,
+                                     h * w, w_simple, w_vlb, grad_scale, ptr(d_out), ptr(loss), ptr(partial),
+                                     L.stream_ptr()), "iddpm_loss")
+    return loss

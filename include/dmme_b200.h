@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMME_ABI_VERSION 1
+#define DMME_ABI_VERSION 2
 #define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
@@ -71,7 +71,8 @@ typedef struct dmme_conv_desc {
   int n, h_in, w_in;                  /* batch and spatial size of src0/src1 */
   int ksize;                          /* 1 or 3 */
   int stride;                         /* 1 or 2 */
-  int upsample;                       /* 1: nearest-neighbour x2 of the source before the conv */
+  int upsample;                       /* 1: nearest-neighbour x2 of the source before the conv;
+                                         2: zero-dilated x2 source (data gradient of a stride-2 conv; generic kernel) */
   int cout;
   const void* weight;                 /* packed by dmme_pack_conv_weight for the chosen kernel */
   const float* bias;                  /* [cout] fp32, may be NULL */
@@ -194,6 +195,83 @@ int dmme_add_i64(int64_t* value, int64_t delta, void* stream);
 /* standard normals from Philox4x32-10 keyed by (seed, stream_id): used for x_T and per-step z */
 int dmme_philox_normal(float* out, long long numel, unsigned long long seed, unsigned long long stream_id,
                        void* stream);
+
+/* ============================================================================================
+ * Backward pass.  The reference obtains it from autograd through ATen after
+ * DDPM.training_step (diffusion_models/ddpm.py:53-81) / IDDPM.training_step
+ * (diffusion_models/iddpm.py:62-116); here each backward op is an explicit kernel.
+ * ============================================================================================ */
+
+/* Data-gradient weights of a convolution: the gradient w.r.t. input channels [ci_off, ci_off + ci_cnt) of
+ * conv(w_oihw) is dmme_conv2d_fwd(grad_out) with these weights (cout' = ci_cnt, cin' = cout; spatially flipped).
+ * Stride-2 convs (models/ddpm.py:147) additionally set desc.upsample = 2 on the grad_out source. */
+int dmme_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, int ci_off, int ci_cnt,
+                                void* packed, int kernel, void* stream);
+
+/* Weight, fused-residual-weight and bias gradients of the forward call described by `fwd` (sources and geometry;
+ * its weight/out fields are ignored).  grad_out: NHWC act dtype [n][ho][wo][cout] (NCHW fp32 when fwd->out_layout
+ * is DMME_OUT_NCHW_F32).  dweight: OIHW fp32 [cout][c0+c1][k][k]; dweight_res: [cout][rc0+rc1] or NULL; dbias:
+ * [cout] or NULL.  Results are written (not accumulated).  Deterministic two-stage reduction through `workspace`
+ * (dmme_conv2d_wgrad_workspace bytes). */
+long long dmme_conv2d_wgrad_workspace(const dmme_conv_desc* fwd);
+int dmme_conv2d_wgrad(const dmme_conv_desc* fwd, const void* grad_out, float* dweight, float* dweight_res,
+                      float* dbias, void* workspace, long long workspace_bytes, void* stream);
+
+/* Backward of dmme_groupnorm_fwd.  gin0/gin1: gradients w.r.t. src0/src1 (act dtype; NULL: not needed);
+ * add0/add1: optional tensors added into gin0/gin1 (gradient accumulation of skip / residual branches);
+ * dgamma/dbeta [C] written; dscale/dshift [n][dss_ld] written when given (IDDPM scale-shift, per-image rows);
+ * sums: fp32 workspace [n][C][2]. */
+int dmme_groupnorm_bwd(const void* grad_out, const void* src0, const void* src1, int c0, int c1, int n, int hw,
+                       int groups, float eps, const float* gamma, const float* beta, const float* scale,
+                       const float* shift, int ss_rows, int ss_ld, const float* chan_mask, int apply_silu,
+                       void* gin0, void* gin1, const void* add0, const void* add1, float* dgamma, float* dbeta,
+                       float* dscale, float* dshift, int dss_ld, float* sums, int act_dtype, void* stream);
+
+/* Backward of dmme_attention_fwd for q/k/v stored as strided views of one tensor (v not transposed):
+ * dq/dk/dv use the same strides as q/k/v.  dout has the layout of the forward output [n][L][heads*dh]. */
+long long dmme_attention_bwd_workspace(int n, int heads, int L, int dh);
+int dmme_attention_bwd(const void* q, const void* k, const void* v, long long batch_stride, int row_stride,
+                       int head_stride, int n, int heads, int L, int dh, float scale, int head_batch_swap,
+                       const void* dout, void* dq, void* dk, void* dv, int act_dtype, void* workspace,
+                       long long workspace_bytes, void* stream);
+
+/* Backward of dmme_temb_mlp_fwd + dmme_temb_proj_fwd.  hidden/emb: the forward's scratch / emb_out;
+ * d_all [rows][total]: gradient of the batched projection output.  All parameter gradients are written. */
+long long dmme_temb_bwd_workspace(int rows, int half, int emb_dim);
+int dmme_temb_bwd(const int64_t* t, int rows, const float* freq, int half, const float* w1, const float* b1,
+                  const float* w2, const float* b2, int emb_dim, const float* hidden, const float* emb,
+                  const float* wcat, int total, const float* d_all, float* dw1, float* db1, float* dw2, float* db2,
+                  float* dwcat, float* dbcat, void* workspace, long long workspace_bytes, void* stream);
+
+/* C[b](i,j) = alpha * sum_k A[b](i,k) B[b](k,j) (+ C when accumulate); b = bo*heads + h; element strides per operand
+ * (outer batch, head, row, column); dtypes DMME_BF16 / DMME_F32.  CUDA-core product used by the attention and
+ * timestep-MLP backward passes. */
+int dmme_gemm_strided(const void* a, int a_dtype, long long a_bo, long long a_h, long long a_r, long long a_c,
+                      const void* b, int b_dtype, long long b_bo, long long b_h, long long b_r, long long b_c,
+                      void* c, int c_dtype, long long c_bo, long long c_h, long long c_r, long long c_c, int M,
+                      int N, int K, int outer, int heads, float alpha, int accumulate, void* stream);
+
+/* glue */
+/* dst = a + b (act dtype; dst may alias a or b): gradient accumulation where no kernel can fuse it */
+int dmme_add(void* dst, const void* a, const void* b, long long numel, int act_dtype, void* stream);
+/* out[n][c] = sum over pixels of g[n][px][c]: gradient of the broadcast timestep-embedding add (models/ddpm.py:129) */
+int dmme_pixel_sum(const void* g, int n, int hw, int c, float* out, long long out_ld, int act_dtype, void* stream);
+/* backward of nearest x2 upsampling (models/ddpm.py:161): out[n][y][x][c] = sum of the 2x2 block of g [n][2h][2w][c] */
+int dmme_pool2x_sum_nhwc(const void* g, void* out, int n, int h, int w, int c, int act_dtype, void* stream);
+int dmme_colsum_f32(const float* in, int rows, int cols, long long ld, float* out, int accumulate, void* stream);
+
+/* L_simple (equations/ddpm/losses.py:5-13): loss_out[0] = mean((eps - noise)^2);
+ * d_eps (optional) = grad_scale * 2 (eps - noise) / numel.  partial: fp32 workspace of >= 1024 floats. */
+int dmme_mse_loss(const float* eps, const float* noise, long long numel, float grad_scale, float* d_eps,
+                  float* loss_out, float* partial, void* stream);
+/* IDDPM hybrid / VLB loss and its gradient w.r.t. the network output in one pass (IDDPM.training_step
+ * diffusion_models/iddpm.py:62-116, forward_model :150-164, equations/iddpm/losses.py:8-90).
+ * model_out NCHW fp32 [n][2c][hw]; x_t, x_0 [n][c][hw]; t int64 [n]; tables of length T+1.
+ * loss_out[0] = w_simple L_simple + w_vlb L_vlb, [1] = L_simple, [2] = L_vlb; d_out optional [n][2c][hw];
+ * partial: fp32 workspace of >= 2048 floats. */
+int dmme_iddpm_loss(const float* model_out, const float* x_t, const float* x_0, const int64_t* t, const float* beta,
+                    const float* alpha, const float* alpha_bar, int n, int c, int hw, float w_simple, float w_vlb,
+                    float grad_scale, float* d_out, float* loss_out, float* partial, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,14 @@ BF16_TOL = 1e-2
 FP32_TOL = 1e-4
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """these tests cover the inference executor; with gradients enabled UNet.forward records the training tape
+    (covered by tests/test_backward_gpu.py)."""
+    with torch.no_grad():
+        yield
+
+
 def _unet(flavour, seed=0, **kw):
     from dmme_b200.models import ddpm, iddpm
     torch.manual_seed(seed)
