@@ -38,11 +38,11 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsign
 }
 
 __global__ void philox_normal_kernel(float* __restrict__ out, long long numel, unsigned long long seed,
-                                     unsigned long long sid) {
+                                     unsigned long long sid, unsigned long long goff) {
   const long long groups = (numel + 3) / 4;
   for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups;
        g += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 z = philox_normal4(seed, sid, g);
+    const float4 z = philox_normal4(seed, sid, goff + g);
     const float zz[4] = {z.x, z.y, z.z, z.w};
     for (int j = 0; j < 4; ++j)
       if (g * 4 + j < numel) out[g * 4 + j] = zz[j];
@@ -53,7 +53,7 @@ __global__ void philox_normal_kernel(float* __restrict__ out, long long numel, u
 __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
                                  const float* __restrict__ beta, const float* __restrict__ alpha,
                                  const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr,
-                                 long long numel, unsigned long long seed) {
+                                 long long numel, unsigned long long seed, unsigned long long goff) {
   const long long t = *t_ptr;
   const float b = beta[t], a = alpha[t], ab = alpha_bar[t];
   const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
@@ -65,7 +65,7 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
        g += static_cast<long long>(gridDim.x) * blockDim.x) {
     float zz[4] = {0.f, 0.f, 0.f, 0.f};
     if (!noise && !last) {
-      const float4 z = philox_normal4(seed, static_cast<unsigned long long>(t), g);
+      const float4 z = philox_normal4(seed, static_cast<unsigned long long>(t), goff + g);
       zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
     }
 #pragma unroll
@@ -100,7 +100,7 @@ __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict_
 __global__ void iddpm_step_kernel(float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ noise,
                                   const float* __restrict__ beta, const float* __restrict__ alpha,
                                   const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr, int n, int c,
-                                  int hw, unsigned long long seed) {
+                                  int hw, unsigned long long seed, unsigned long long goff) {
   const long long t = *t_ptr;
   const float b = beta[t], a = alpha[t], ab = alpha_bar[t], abp = alpha_bar[t - 1];
   const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
@@ -114,7 +114,7 @@ __global__ void iddpm_step_kernel(float* __restrict__ x, const float* __restrict
        g += static_cast<long long>(gridDim.x) * blockDim.x) {
     float zz[4] = {0.f, 0.f, 0.f, 0.f};
     if (!noise && !last) {
-      const float4 z = philox_normal4(seed, static_cast<unsigned long long>(t), g);
+      const float4 z = philox_normal4(seed, static_cast<unsigned long long>(t), goff + g);
       zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
     }
 #pragma unroll
@@ -149,10 +149,11 @@ using namespace dmme;
 
 extern "C" int dmme_ddpm_step(float* x, const float* eps, const float* noise, const float* beta, const float* alpha,
                               const float* alpha_bar, const int64_t* t_ptr, long long numel, unsigned long long seed,
-                              void* stream) {
+                              unsigned long long noise_offset, void* stream) {
   DMME_REQUIRE(x && eps && beta && alpha && alpha_bar && t_ptr && numel > 0, DMME_E_BADARG, "ddpm_step: bad arguments");
+  DMME_REQUIRE(noise_offset % 4 == 0, DMME_E_BADARG, "ddpm_step: noise_offset must be a multiple of 4");
   ddpm_step_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, eps, noise, beta, alpha, alpha_bar, t_ptr, numel, seed);
+      x, eps, noise, beta, alpha, alpha_bar, t_ptr, numel, seed, noise_offset / 4);
   return check_launch("ddpm_step_kernel");
 }
 
@@ -165,12 +166,13 @@ extern "C" int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar
 
 extern "C" int dmme_iddpm_step(float* x, const float* model_out, const float* noise, const float* beta,
                                const float* alpha, const float* alpha_bar, const int64_t* t_ptr, int n, int c, int hw,
-                               unsigned long long seed, void* stream) {
+                               unsigned long long seed, unsigned long long noise_offset, void* stream) {
   DMME_REQUIRE(x && model_out && beta && alpha && alpha_bar && t_ptr && n > 0 && c > 0 && hw > 0, DMME_E_BADARG,
                "iddpm_step: bad arguments");
+  DMME_REQUIRE(noise_offset % 4 == 0, DMME_E_BADARG, "iddpm_step: noise_offset must be a multiple of 4");
   const long long numel = static_cast<long long>(n) * c * hw;
   iddpm_step_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, model_out, noise, beta, alpha, alpha_bar, t_ptr, n, c, hw, seed);
+      x, model_out, noise, beta, alpha, alpha_bar, t_ptr, n, c, hw, seed, noise_offset / 4);
   return check_launch("iddpm_step_kernel");
 }
 
@@ -187,8 +189,8 @@ extern "C" int dmme_add_i64(int64_t* value, int64_t delta, void* stream) {
 }
 
 extern "C" int dmme_philox_normal(float* out, long long numel, unsigned long long seed, unsigned long long stream_id,
-                                  void* stream) {
-  DMME_REQUIRE(out && numel > 0, DMME_E_BADARG, "philox_normal: bad arguments");
-  philox_normal_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, numel, seed, stream_id);
+                                  unsigned long long noise_offset, void* stream) {
+  DMME_REQUIRE(out && numel > 0 && noise_offset % 4 == 0, DMME_E_BADARG, "philox_normal: bad arguments");
+  philox_normal_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, numel, seed, stream_id, noise_offset / 4);
   return check_launch("philox_normal_kernel");
 }

@@ -80,12 +80,12 @@ def load() -> C.CDLL:
     lib.dmme_attention_uses_tc.argtypes = [ll, i, i, ll, i, i, i, i, i]
     lib.dmme_temb_mlp_fwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp]
     lib.dmme_temb_proj_fwd.argtypes = [vp, i, i, vp, vp, i, vp, vp]
-    lib.dmme_ddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, ull, vp]
+    lib.dmme_ddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, ull, ull, vp]
     lib.dmme_ddim_step.argtypes = [vp, vp, vp, vp, vp, ll, vp]
-    lib.dmme_iddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, ull, vp]
+    lib.dmme_iddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, ull, ull, vp]
     lib.dmme_gather_i64.argtypes = [vp, vp, vp, vp]
     lib.dmme_add_i64.argtypes = [vp, C.c_int64, vp]
-    lib.dmme_philox_normal.argtypes = [vp, ll, ull, ull, vp]
+    lib.dmme_philox_normal.argtypes = [vp, ll, ull, ull, ull, vp]
     lib.dmme_set_conv_halo_mode.argtypes = [i]
     lib.dmme_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, i, vp, i, vp]
     lib.dmme_conv2d_wgrad_workspace.argtypes = [C.POINTER(ConvDesc)]

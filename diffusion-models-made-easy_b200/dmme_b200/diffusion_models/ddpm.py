@@ -56,7 +56,8 @@ class DDPM(nn.Module):
         return t.reshape(1).to(device=self.beta.device, dtype=torch.int64).contiguous()
 
     def _update_(self, x: Tensor, model_out: Tensor, noise: Optional[Tensor], t: Tensor, seed: int) -> Tensor:
-        return ops.ddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed)
+        return ops.ddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed,
+                              getattr(self, "_noise_offset", 0))
 
     def sampling_step(self, x_t: Tensor, t: Tensor, noise: Optional[Tensor] = None) -> Tensor:
         r"""Denoise by sampling from :math:`p_\theta(x_{t-1}|x_t)`.
@@ -117,7 +118,8 @@ class DDPM(nn.Module):
 
     @torch.no_grad()
     def generate(self, img_size: Tuple[int, int, int, int], *, x_T: Optional[Tensor] = None, seed: Optional[int] = None,
-                 graph: bool = True, on_step: Optional[Callable[[int, Tensor], None]] = None) -> Tensor:
+                 graph: bool = True, on_step: Optional[Callable[[int, Tensor], None]] = None,
+                 noise_offset: int = 0) -> Tensor:
         """Generate images of shape (N, C, H, W) by running the full denoising chain.
 
         Args:
@@ -126,6 +128,7 @@ class DDPM(nn.Module):
             seed: Philox seed of the per-step noise (default: drawn from torch's CPU generator)
             graph: replay one captured CUDA graph per step (default) or launch eagerly
             on_step: optional callback ``(k, x)`` after each step (k = 0 is t = T)
+            noise_offset: element index of this batch inside a larger sharded batch (``parallel.generate_sharded``)
         """
         dev = self.beta.device
         if dev.type != "cuda":
@@ -134,7 +137,11 @@ class DDPM(nn.Module):
         x = x.contiguous()
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        return self._run_steps(x, self._num_steps(), seed, graph, on_step)
+        self._noise_offset = int(noise_offset)
+        try:
+            return self._run_steps(x, self._num_steps(), seed, graph, on_step)
+        finally:
+            self._noise_offset = 0
 
     def _noised(self, x_0: Tensor, t: Optional[Tensor] = None, noise: Optional[Tensor] = None):
         """t ~ U{1..T-1} (randint excludes T), x_t ~ q(x_t | x_0); RNG order as the reference:

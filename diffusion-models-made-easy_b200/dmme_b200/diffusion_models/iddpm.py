@@ -41,7 +41,8 @@ class IDDPM(DDPM):
             raise NotImplementedError
 
     def _update_(self, x: Tensor, model_out: Tensor, noise: Optional[Tensor], t: Tensor, seed: int) -> Tensor:
-        return ops.iddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed)
+        return ops.iddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed,
+                               getattr(self, "_noise_offset", 0))
 
     def forward_model(self, x_t: Tensor, t: Tensor, beta_t: Tensor, alpha_bar_t: Tensor,
                       alpha_bar_t_minus_one: Tensor) -> NoiseVariance:

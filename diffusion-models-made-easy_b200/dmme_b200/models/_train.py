@@ -39,6 +39,12 @@ class TrainEngine(Engine):
         self._k = 0
         self._d_all: Optional[Tensor] = None
         self._temb_ctx = None
+        # parameter gradients live in one flat fp32 arena, handed out in backward order: a finished prefix of the
+        # arena is a contiguous bucket that parallel.GradBucketer all-reduces in place while backward continues
+        self._garena: Optional[Tensor] = None
+        self._gcur = 0
+        self.grad_sync = None          # None: single process; else dict(group=..., bucket_bytes=...)
+        self.last_buckets = []
 
     # -- buffers -------------------------------------------------------------------------------
     def _buf(self, tag: str, shape, dtype, dev) -> Tensor:
@@ -48,10 +54,23 @@ class TrainEngine(Engine):
     def _like(self, tag: str, t: Tensor) -> Tensor:
         return self._buf(tag, tuple(t.shape), t.dtype, t.device)
 
+    def _arena_take(self, shape, dev) -> Tensor:
+        numel = 1
+        for v in shape:
+            numel *= int(v)
+        if self._garena is None or self._garena.device != dev:
+            need = sum(p.numel() + 4 for p in self.unet.parameters()) + 64
+            self._garena = torch.zeros(need, dtype=torch.float32, device=dev)
+        if self._gcur + numel > self._garena.numel():
+            raise RuntimeError("dmme_b200: gradient arena overflow (parameters were added after the first backward?)")
+        g = self._garena[self._gcur:self._gcur + numel].view(tuple(shape))
+        self._gcur += (numel + 3) // 4 * 4
+        return g
+
     def _pgrad(self, p: Optional[Tensor]) -> Optional[Tensor]:
         if p is None:
             return None
-        g = self._buf("pgrad", tuple(p.shape), torch.float32, p.device)
+        g = self._arena_take(tuple(p.shape), p.device)
         self.param_grads[id(p)] = g
         return g
 
@@ -116,9 +135,7 @@ class TrainEngine(Engine):
             if res is not None and res.bias is not None:
                 self.param_grads[id(res.bias)] = db  # out = conv + res: both biases see the same gradient
             wsz = ops.conv_wgrad_workspace(d)
-            wsb = self.ws.get("train.wgrad_ws", (max(wsz, 4) // 4,), torch.float32, dev) if wsz <= self._wgrad_ws_cap() else None
-            if wsb is None:
-                wsb = torch.empty(wsz // 4, dtype=torch.float32, device=dev)
+            wsb = self.ws.get("train.wgrad_ws", (max(wsz, 4) // 4,), torch.float32, dev)
             ops.conv2d_wgrad(d, g, dw, dwr, db, wsb)
             # timestep-embedding gradient: column block of d_all
             if temb is not None and temb_cols is not None:
@@ -164,10 +181,6 @@ class TrainEngine(Engine):
 
         self.tape.append(backward)
         return out
-
-    @staticmethod
-    def _wgrad_ws_cap() -> int:
-        return 1 << 62
 
     # -- GroupNorm -----------------------------------------------------------------------------
     def gn(self, name: str, norm: nn.GroupNorm, src0: Tensor, src1: Optional[Tensor], silu: bool,
@@ -321,15 +334,23 @@ class TrainEngine(Engine):
         u = self.unet
         dev = d_out.device
         self._contribute(self._out, d_out.float().contiguous())
+        self._gcur = 0
+        bucketer = None
+        if self.grad_sync is not None:
+            from ..parallel import GradBucketer
+            self._arena_take((0,), dev)  # make sure the arena exists
+            bucketer = GradBucketer(self._garena, self.grad_sync.get("group"), self.grad_sync.get("bucket_bytes", 32 << 20))
         for fn in reversed(self.tape):
             fn()
+            if bucketer is not None:
+                bucketer.mark(self._gcur)
         # conditioning: batched ResBlock projections, then the two-layer MLP
         c, hidden, emb, wcat = self._temb_ctx
         cond = u.condition
         dw1, db1 = self._pgrad(cond[1].weight), self._pgrad(cond[1].bias)
         dw2, db2 = self._pgrad(cond[3].weight), self._pgrad(cond[3].bias)
-        dwcat = self._buf("temb.dwcat", tuple(wcat.shape), torch.float32, dev)
-        dbcat = self._buf("temb.dbcat", (wcat.shape[0],), torch.float32, dev)
+        dwcat = self._arena_take(tuple(wcat.shape), dev)
+        dbcat = self._arena_take((wcat.shape[0],), dev)
         half = cond[0].embeddings.numel()
         wsz = ops.temb_bwd_workspace(c.numel(), half, emb.shape[1])
         wsb = self._buf("temb.bwd_ws", (wsz // 4,), torch.float32, dev)
@@ -341,6 +362,9 @@ class TrainEngine(Engine):
             lin = blk.condition[0]
             self.param_grads[id(lin.weight)] = dwcat[o:o + width]
             self.param_grads[id(lin.bias)] = dbcat[o:o + width]
+        if bucketer is not None:
+            bucketer.finish(self._gcur)
+            self.last_buckets = bucketer.buckets
         self.tape.clear()
         self.pending.clear()
         return self.param_grads

@@ -193,10 +193,10 @@ def temb_proj(emb: Tensor, wcat: Tensor, bcat: Tensor, out: Optional[Tensor] = N
 # sampler updates (in place on x)
 # ---------------------------------------------------------------------------------------------
 def ddpm_step_(x: Tensor, eps: Tensor, noise: Optional[Tensor], beta: Tensor, alpha: Tensor, alpha_bar: Tensor,
-               t: Tensor, seed: int = 0) -> Tensor:
+               t: Tensor, seed: int = 0, noise_offset: int = 0) -> Tensor:
     L.require_cuda(x, eps, noise, beta, alpha, alpha_bar, t)
     L.check(L.load().dmme_ddpm_step(ptr(x), ptr(eps), ptr(noise), ptr(beta), ptr(alpha), ptr(alpha_bar), ptr(t),
-                                    x.numel(), seed, L.stream_ptr()), "ddpm_step")
+                                    x.numel(), seed, noise_offset, L.stream_ptr()), "ddpm_step")
     return x
 
 
@@ -208,11 +208,11 @@ def ddim_step_(x: Tensor, eps: Tensor, alpha_bar: Tensor, tau: Tensor, i: Tensor
 
 
 def iddpm_step_(x: Tensor, model_out: Tensor, noise: Optional[Tensor], beta: Tensor, alpha: Tensor,
-                alpha_bar: Tensor, t: Tensor, seed: int = 0) -> Tensor:
+                alpha_bar: Tensor, t: Tensor, seed: int = 0, noise_offset: int = 0) -> Tensor:
     L.require_cuda(x, model_out, noise, beta, alpha, alpha_bar, t)
     n, c, h, w = x.shape
     L.check(L.load().dmme_iddpm_step(ptr(x), ptr(model_out), ptr(noise), ptr(beta), ptr(alpha), ptr(alpha_bar), ptr(t),
-                                     n, c, h * w, seed, L.stream_ptr()), "iddpm_step")
+                                     n, c, h * w, seed, noise_offset, L.stream_ptr()), "iddpm_step")
     return x
 
 
@@ -226,9 +226,9 @@ def add_i64_(value: Tensor, delta: int) -> Tensor:
     return value
 
 
-def philox_normal(shape, seed: int, stream_id: int, device, out: Optional[Tensor] = None) -> Tensor:
+def philox_normal(shape, seed: int, stream_id: int, device, out: Optional[Tensor] = None, noise_offset: int = 0) -> Tensor:
     y = _empty(tuple(shape), torch.float32, device, out)
-    L.check(L.load().dmme_philox_normal(ptr(y), y.numel(), seed, stream_id, L.stream_ptr()), "philox_normal")
+    L.check(L.load().dmme_philox_normal(ptr(y), y.numel(), seed, stream_id, noise_offset, L.stream_ptr()), "philox_normal")
     return y
 
 

@@ -171,13 +171,15 @@ int dmme_temb_proj_fwd(const float* emb, int rows, int emb_dim, const float* wca
 /*
  * tables: fp32 device arrays of length T+1 (beta, alpha, alpha_bar as registered by
  * DDPM.__init__ diffusion_models/ddpm.py:41-51); t_ptr: int64 device scalar holding the current t.
- * noise: fp32 tensor of standard normals (NULL: draw Philox4x32-10 normals from (seed, *t_ptr)).
+ * noise: fp32 tensor of standard normals (NULL: draw Philox4x32-10 normals from (seed, *t_ptr, element index)).
+ * noise_offset: index of x[0] inside the whole (unsharded) sample batch, a multiple of 4 -- a rank that owns images
+ * [i0, i1) passes i0 * C*H*W and draws exactly the noise the single-GPU run draws for those images.
  * ddpm:  x <- where(t==1, mean, mean + sqrt(beta_t) z), mean = 1/sqrt(alpha_t) (x - beta_t/sqrt(1-abar_t) eps)
  *        (diffusion_models/ddpm.py:83-111, equations/ddpm/ddpm.py:44-72)
  */
 int dmme_ddpm_step(float* x, const float* eps, const float* noise, const float* beta, const float* alpha,
                    const float* alpha_bar, const int64_t* t_ptr, long long numel, unsigned long long seed,
-                   void* stream);
+                   unsigned long long noise_offset, void* stream);
 /* ddim (as written in equations/ddim/ddim.py:52-57): x0 = (x - sqrt(1-abar_i) eps)/sqrt(abar_prev); x <- sqrt(abar_prev) x0
  * i_ptr: int64 device scalar with the sub-sequence index i; tau: int64 [S+1]. */
 int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar, const int64_t* tau, const int64_t* i_ptr,
@@ -186,7 +188,7 @@ int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar, const int
  * model_out NCHW fp32 [n][2*c][hw]: first c channels eps, last c channels v. */
 int dmme_iddpm_step(float* x, const float* model_out, const float* noise, const float* beta, const float* alpha,
                     const float* alpha_bar, const int64_t* t_ptr, int n, int c, int hw, unsigned long long seed,
-                    void* stream);
+                    unsigned long long noise_offset, void* stream);
 /* writes tau[*i_ptr] into *t_out (DDIM: the model is evaluated at tau_i) */
 int dmme_gather_i64(const int64_t* table, const int64_t* idx_ptr, int64_t* out, void* stream);
 /* *value += delta: advances the device-resident step counter between graph replays
@@ -194,7 +196,7 @@ int dmme_gather_i64(const int64_t* table, const int64_t* idx_ptr, int64_t* out, 
 int dmme_add_i64(int64_t* value, int64_t delta, void* stream);
 /* standard normals from Philox4x32-10 keyed by (seed, stream_id): used for x_T and per-step z */
 int dmme_philox_normal(float* out, long long numel, unsigned long long seed, unsigned long long stream_id,
-                       void* stream);
+                       unsigned long long noise_offset, void* stream);
 
 /* ============================================================================================
  * Backward pass.  The reference obtains it from autograd through ATen after

@@ -308,9 +308,26 @@ def test_mse_loss_value_and_gradient():
     assert rel_l2(d.cpu(), eps.grad) < 1e-6
 
 
+def _oracle_iddpm_loss(dtype, tabs, t, x0, z, out_init, loss_type):
+    tb = [x.to(dtype) for x in tabs]
+    out = out_init.to(dtype).requires_grad_()
+    x_t, qm, qs = O.forward_noising(x0.to(dtype), t, z.to(dtype), tb[2])
+    eps, var = O.iddpm_split(out, t, tb)
+    vlb = O.vlb_loss(eps, var, x_t, t, x0.to(dtype), tb)
+    simple = O.ddpm_loss(x_t, qm, qs, eps)
+    total = simple + 0.001 * vlb if loss_type == "hybrid" else vlb
+    total.backward()
+    return float(total.detach()), float(simple.detach()), float(vlb.detach()), out.grad.double(), x_t
+
+
 @pytest.mark.parametrize("schedule", ["cosine", "linear"])
 @pytest.mark.parametrize("loss_type", ["hybrid", "vlb"])
 def test_iddpm_loss_value_and_gradient(schedule, loss_type):
+    """The t = 1 discrete-NLL term is a difference of two normal CDFs at a standard deviation down to 1e-6: in fp32 it
+    cancels catastrophically, so the reference's own fp32 arithmetic (the oracle) is far from its fp64 evaluation on
+    part of the elements (measured here: 1e-3 on the loss, 0.7-0.9 rel-L2 on the gradient).  Parity is therefore
+    asserted (a) on the loss within 3x the fp32 oracle's own distance from fp64 and (b) on the gradient over the
+    elements where fp32 and fp64 oracle agree to 1e-3 (the well-conditioned ones, required to be > 90% of all)."""
     ops, L = _ops()
     T = 100
     tabs = O.cosine_tables(T) if schedule == "cosine" else O.linear_tables(T)
@@ -319,24 +336,19 @@ def test_iddpm_loss_value_and_gradient(schedule, loss_type):
     x0 = _rand(n, 3, 16, 16, seed=1).clamp(-1, 1)
     x0[0, 0, 0, :4] = torch.tensor([1.0, -1.0, 0.999, -0.999])  # the edge bins of the discrete NLL
     z = _rand(n, 3, 16, 16, seed=2)
-    out = (0.5 * _rand(n, 6, 16, 16, seed=3)).requires_grad_()
-    x_t, qm, qs = O.forward_noising(x0, t, z, tabs[2])
-    eps, var = O.iddpm_split(out, t, tabs)
-    vlb = O.vlb_loss(eps, var, x_t, t, x0, tabs)
-    simple = O.ddpm_loss(x_t, qm, qs, eps)
-    want = simple + 0.001 * vlb if loss_type == "hybrid" else vlb
-    want.backward()
+    out0 = 0.5 * _rand(n, 6, 16, 16, seed=3)
+    w32, s32, v32, g32, x_t = _oracle_iddpm_loss(torch.float32, tabs, t, x0, z, out0, loss_type)
+    w64, s64, v64, g64, _ = _oracle_iddpm_loss(torch.float64, tabs, t, x0, z, out0, loss_type)
     ws, wv = (1.0, 0.001) if loss_type == "hybrid" else (0.0, 1.0)
     d = torch.empty(n, 6, 16, 16, device=DEV)
-    got = ops.iddpm_loss(out.detach().to(DEV), x_t.to(DEV), x0.to(DEV), t.to(DEV), *[tb.to(DEV) for tb in tabs], ws, wv, d)
-    # The t = 1 discrete-NLL term is a difference of two normal CDFs: in fp32 it cancels catastrophically (the fp32
-    # oracle itself is 1.0e-3 .. 1.3e-3 away from its own fp64 evaluation on these inputs, and 0.7 .. 0.9 rel-L2 on the
-    # gradient, because bins whose probability underflows are clamped).  The bar is therefore agreement with the
-    # reference's fp32 arithmetic up to libm differences (erff / expf / logf on the device vs the host).
-    assert abs(float(got[1]) - float(simple)) < 2e-5 * abs(float(simple))
-    assert abs(float(got[2]) - float(vlb)) < 1e-3 * abs(float(vlb)), (float(got[2]), float(vlb))
-    assert abs(float(got[0]) - float(want)) < 1e-3 * abs(float(want)), (float(got[0]), float(want))
-    assert rel_l2(d.cpu(), out.grad) < 2e-3
+    got = ops.iddpm_loss(out0.to(DEV), x_t.to(DEV), x0.to(DEV), t.to(DEV), *[tb.to(DEV) for tb in tabs], ws, wv, d)
+    assert abs(float(got[1]) - s64) < 2e-5 * abs(s64)
+    assert abs(float(got[2]) - v64) < 3 * abs(v32 - v64) + 1e-5 * abs(v64), (float(got[2]), v32, v64)
+    assert abs(float(got[0]) - w64) < 3 * abs(w32 - w64) + 1e-5 * abs(w64), (float(got[0]), w32, w64)
+    good = (g32 - g64).abs() <= 1e-3 * g64.abs() + 1e-12
+    assert float(good.float().mean()) > 0.9
+    dd = d.cpu().double()
+    assert float(((dd - g64) * good).norm() / (g64 * good).norm()) < 2e-3
 
 
 # ---------------------------------------------------------------------------------------------
