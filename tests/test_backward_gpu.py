@@ -310,7 +310,7 @@ def test_mse_loss_value_and_gradient():
 
 def _oracle_iddpm_loss(dtype, tabs, t, x0, z, out_init, loss_type):
     tb = [x.to(dtype) for x in tabs]
-    out = out_init.to(dtype).requires_grad_()
+    out = out_init.detach().to(dtype).clone().requires_grad_()
     x_t, qm, qs = O.forward_noising(x0.to(dtype), t, z.to(dtype), tb[2])
     eps, var = O.iddpm_split(out, t, tb)
     vlb = O.vlb_loss(eps, var, x_t, t, x0.to(dtype), tb)
