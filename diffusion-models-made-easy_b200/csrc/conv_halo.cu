@@ -36,6 +36,7 @@ struct ConvHaloParams {
   int rt;            // padded rows per tile
   int n_mma;         // MMA N: rt * wp rounded up to a multiple of 16
   int total_rows;    // n * (h + 2)
+  int imgs_per_tile; // > 0: tiles hold whole padded images (small resolutions), one TMA box per image
   int m_tiles, n_tiles;
   const float* bias;
   const float* temb;
@@ -115,6 +116,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           const int as = a_it % kHaloAStages;
           mbar_wait(&a_empty[as], ((a_it / kHaloAStages) & 1) ^ 1);
+          if (p.imgs_per_tile > 0) {
+            // whole padded images: box = [64 ch][W+2 px][h+2 rows] from (x, y) = (-1, -1); rows outside the tile are only
+            // ever read for padding-position outputs, so the two halo rows are not loaded at all
+            mbar_expect_tx(&a_full[as], p.rt * kRowBytes);
+            uint8_t* dst = abuf + as * kHaloASlot + 128 + kRowBytes;
+            for (int i = 0; i < p.imgs_per_tile; ++i)
+              tma_load_5d(dst + i * (p.h + 2) * kRowBytes, &p.a[which], &a_full[as], cc, -1, 0, -1, mt * p.imgs_per_tile + i);
+            continue;
+          }
           mbar_expect_tx(&a_full[as], nr * kRowBytes);
           // slot layout: 128 bytes of slack (tap (-1,-1) of position 0 reaches one row back), then the halo rows
           uint8_t* dst = abuf + as * kHaloASlot + 128;
@@ -251,7 +261,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
         uint32_t v[W];
         if constexpr (W == 32) tmem_ld32(taddr, v);
-        else tmem_ld16(taddr, v);
+        else if constexpr (W == 16) tmem_ld16(taddr, v);
+        else if constexpr (W == 8) tmem_ld8(taddr, v);
+        else tmem_ld4(taddr, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < W; ++i) {
@@ -286,16 +298,21 @@ bool conv_halo_supported(const dmme_conv_desc& d) {
   if (d.upsample || d.ksize != 3 || d.stride != 1) return false;
   if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.rc0 % 64 || d.rc1 % 64) return false;
   if (d.cout != 128 && d.cout != 256) return false;
-  if (d.w_in != 16 && d.w_in != 32) return false;  // padded-position utilisation < 75% below 16x16
+  if (d.w_in != 4 && d.w_in != 8 && d.w_in != 16 && d.w_in != 32) return false;
+  if (d.h_in != d.w_in) return false;
   if (d.h_in < 4 || static_cast<long long>(d.n) * (d.h_in + 2) > (1 << 24)) return false;
   return true;
 }
 
-// AUTO's choice between the two tcgen05 kernels (both are correct wherever both are supported).  Measured at batch
-// 256 (tools/prof_conv.py): the halo kernel wins everywhere except 16x16 convs with a fused 1x1 residual, where each
-// residual chunk reloads a whole halo tile for a single tap (216 us vs 170 us on 512->256).
+
+// AUTO's choice between the two tcgen05 kernels (both are correct wherever both are supported).  Measured at batch 256
+// (tools/prof_conv.py, profiles/): both kernels are bound by the L2 -> SM operand feed (~43 B/clk/SM of the ~6300 B/clk
+// chip-wide cap); the halo kernel's 9-tap reuse of the activation tile wins at 32x32 and 16x16 (75 vs 142 us, 76 vs
+// 102 us) except when a fused 1x1 residual adds single-tap chunks (16x16: 217 vs 171 us), and the padded-position
+// overhead (36% at 8x8, 56% at 4x4) cancels the gain below 16x16 (36.8 vs 35.6 us, 26.7 vs 25.5 us).
 bool conv_halo_preferred(const dmme_conv_desc& d) {
   if (!conv_halo_supported(d)) return false;
+  if (d.w_in < 16) return false;
   if (d.w_in == 16 && (d.rc0 + d.rc1) > 0) return false;
   return true;
 }
@@ -330,11 +347,41 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.chunks0 = d.c0 / 64; p.chunks1 = d.c1 / 64; p.rchunks0 = d.rc0 / 64; p.rchunks1 = d.rc1 / 64;
   p.n = d.n; p.h = d.h_in; p.wp = d.w_in + 2;
-  p.rt = kHaloCols / p.wp;                        // 7 rows of 34, 14 rows of 18
-  p.n_mma = ((p.rt * p.wp + 15) / 16) * 16;       // 240, 256
   p.total_rows = d.n * (d.h_in + 2);
-  p.m_tiles = (p.total_rows + p.rt - 1) / p.rt;
   p.n_tiles = d.cout / kHaloBN;
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  const int img_pos = (d.h_in + 2) * p.wp;
+  p.imgs_per_tile = 0;
+  if (img_pos <= kHaloCols) {
+    // small resolutions: a tile is k whole padded images (2 at 8x8, 7 at 4x4), or fewer when that fills more SMs
+    long long best_cost = -1;
+    for (int k = kHaloCols / img_pos; k >= 1; k = k / 2) {
+      const int n_mma = ((k * img_pos + 15) / 16) * 16;
+      const long long units = static_cast<long long>((d.n + k - 1) / k) * p.n_tiles;
+      const long long cost = ((units + g_sm_count - 1) / g_sm_count) * (n_mma + 48);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.imgs_per_tile = k; p.n_mma = n_mma; }
+      if (k == 1) break;
+    }
+    p.rt = p.imgs_per_tile * (d.h_in + 2);
+  } else {
+    // rows per tile: as many as fit 256 accumulator columns (7 rows of 34, 14 of 18), or half of that when the launch
+    // would otherwise leave SMs idle / quantise badly (cost ~ waves x (MMA width + fixed overhead))
+    long long best_cost = -1;
+    for (int cols = kHaloCols; cols >= kHaloCols / 2; cols /= 2) {
+      const int rt = cols / p.wp;
+      if (rt < 1) continue;
+      const int n_mma = ((rt * p.wp + 15) / 16) * 16;
+      const long long units = static_cast<long long>((p.total_rows + rt - 1) / rt) * p.n_tiles;
+      const long long cost = ((units + g_sm_count - 1) / g_sm_count) * (n_mma + 48);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.rt = rt; p.n_mma = n_mma; }
+    }
+  }
+  p.m_tiles = (p.total_rows + p.rt - 1) / p.rt;
   p.bias = d.bias; p.temb = d.temb; p.temb_rows = d.temb_rows; p.temb_ld = d.temb_ld;
   p.addend = static_cast<const __nv_bfloat16*>(d.addend);
   p.out = static_cast<__nv_bfloat16*>(d.out);
@@ -347,7 +394,7 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     uint64_t dims[5] = {(uint64_t)c, (uint64_t)d.w_in, 1, (uint64_t)d.h_in, (uint64_t)d.n};
     uint64_t strides[4] = {(uint64_t)c * 2, (uint64_t)d.w_in * c * 2, (uint64_t)d.w_in * c * 2,
                            (uint64_t)d.h_in * d.w_in * c * 2};
-    uint32_t box[5] = {64u, (uint32_t)p.wp, 1u, 1u, 1u};
+    uint32_t box[5] = {64u, (uint32_t)p.wp, 1u, p.imgs_per_tile > 0 ? (uint32_t)(d.h_in + 2) : 1u, 1u};
     return encode_map(m, ptr, 5, dims, strides, box);
   };
   int rc;
@@ -363,7 +410,9 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
   }
   if (d.w_in == 32) return d.cout == 128 ? launch_halo<32, 128>(p, stream) : launch_halo<32, 256>(p, stream);
-  return d.cout == 128 ? launch_halo<16, 128>(p, stream) : launch_halo<16, 256>(p, stream);
+  if (d.w_in == 16) return d.cout == 128 ? launch_halo<16, 128>(p, stream) : launch_halo<16, 256>(p, stream);
+  if (d.w_in == 8) return d.cout == 128 ? launch_halo<8, 128>(p, stream) : launch_halo<8, 256>(p, stream);
+  return d.cout == 128 ? launch_halo<4, 128>(p, stream) : launch_halo<4, 256>(p, stream);
 }
 
 }  // namespace dmme

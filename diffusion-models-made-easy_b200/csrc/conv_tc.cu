@@ -397,6 +397,8 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   if (unit % 128 == 0) bn = 128;
   if (unit % 256 == 0 && (long long)m_tiles * (d.cout / 256) >= 296) bn = 256;
   if (bn == 128 && (long long)m_tiles * (d.cout / 128) < 148) bn = 64;
+  // (measured: deeper TMA rings / wider N tiles for the one-wave 8x8 and 4x4 launches do not help -- 38.9 vs 35.6 us --
+  //  these launches are bound by the L2 -> SM operand feed, not by load latency)
   {
     uint64_t dims[2] = {ktot, (uint64_t)d.cout};
     uint64_t strides[1] = {ktot * 2};

@@ -241,76 +241,108 @@ struct GnApplyParams {
   int chunks;  // CTAs per image
 };
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams q) {
+// Persistent layout: the whole tensor is one range of 16-byte vectors split evenly over the grid (one wave of CTAs, four
+// per SM); a CTA walks its range image by image and rebuilds the per-channel coefficients only when the image changes.
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams q) {
   extern __shared__ float ab[];  // a[C], b[C], m[C]
   const GnParams& p = q.g;
   const int C = p.c0 + p.c1;
   const int cpg = C / p.groups;
-  const int n = blockIdx.y;
   float* sa = ab;
   float* sb = ab + C;
   float* sm = ab + 2 * C;
   const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * cpg);
   const double unfix = 1.0 / static_cast<double>(1 << DMME_STATS_FRAC_BITS);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g0 = (c / cpg) * cpg;  // first channel of this channel's group
-    long long s1 = 0, s2 = 0;
-    for (int cc = g0; cc < g0 + cpg; cc += 4) {
-      const long long* st = cc < p.c0 ? q.stats0 + (static_cast<long long>(n) * (p.c0 >> 2) + (cc >> 2)) * 2
-                                      : q.stats1 + (static_cast<long long>(n) * (p.c1 >> 2) + ((cc - p.c0) >> 2)) * 2;
-      s1 += st[0];
-      s2 += st[1];
-    }
-    const float mean = static_cast<float>(static_cast<double>(s1) * unfix) * inv_cnt;
-    const float ex2 = static_cast<float>(static_cast<double>(s2) * unfix) * inv_cnt;
-    const float var = fmaxf(ex2 - mean * mean, 0.f);
-    const float rs = rsqrtf(var + p.eps);
-    const float ga = p.gamma ? p.gamma[c] : 1.f, be = p.beta ? p.beta[c] : 0.f;
-    float aa = rs * ga, bb = be - mean * rs * ga;
-    if (p.scale) {
-      const long long r = static_cast<long long>(p.ss_rows == 1 ? 0 : n) * p.ss_ld;
-      const float sc = 1.f + p.scale[r + c], sh = p.shift[r + c];
-      aa *= sc;
-      bb = bb * sc + sh;
-    }
-    sa[c] = aa;
-    sb[c] = bb;
-    sm[c] = p.mask ? p.mask[static_cast<long long>(n) * C + c] : 1.f;
-  }
-  __syncthreads();
-
   const int cv = C >> 3;  // 16-byte vectors per pixel
-  const long long nvec = static_cast<long long>(p.hw) * cv;
-  const long long per = (nvec + q.chunks - 1) / q.chunks;
-  const long long v0 = blockIdx.x * per;
-  const long long v1 = v0 + per < nvec ? v0 + per : nvec;
-  const __nv_bfloat16* s0 = static_cast<const __nv_bfloat16*>(p.src0) + static_cast<long long>(n) * p.hw * p.c0;
-  const __nv_bfloat16* s1p = p.c1 ? static_cast<const __nv_bfloat16*>(p.src1) + static_cast<long long>(n) * p.hw * p.c1 : nullptr;
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(n) * p.hw * C;
-  for (long long vi = v0 + threadIdx.x; vi < v1; vi += blockDim.x) {
-    const int pixel = static_cast<int>(vi / cv);
-    const int c = static_cast<int>(vi - static_cast<long long>(pixel) * cv) << 3;
-    const uint4 v = c < p.c0 ? __ldg(reinterpret_cast<const uint4*>(s0 + static_cast<long long>(pixel) * p.c0 + c))
-                             : __ldg(reinterpret_cast<const uint4*>(s1p + static_cast<long long>(pixel) * p.c1 + (c - p.c0)));
-    float f[8];
-    unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
-    unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
-    const float4 a0 = *reinterpret_cast<const float4*>(sa + c), a1 = *reinterpret_cast<const float4*>(sa + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
-    f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
-    f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
-    if (p.silu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+  const long long nvec = static_cast<long long>(p.hw) * cv;      // per image
+  const long long total = nvec * p.n;
+  long long per = (total + gridDim.x - 1) / gridDim.x;
+  per = (per + 255) / 256 * 256;
+  const long long r0 = blockIdx.x * per;
+  const long long r1 = r0 + per < total ? r0 + per : total;
+
+  for (long long seg = r0; seg < r1;) {
+    const int n = static_cast<int>(seg / nvec);
+    const long long v0 = seg - static_cast<long long>(n) * nvec;
+    const long long v1 = (r1 - static_cast<long long>(n) * nvec) < nvec ? (r1 - static_cast<long long>(n) * nvec) : nvec;
+    __syncthreads();  // the previous image's coefficients are no longer read
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g0 = (c / cpg) * cpg;  // first channel of this channel's group
+      long long s1 = 0, s2 = 0;
+      for (int cc = g0; cc < g0 + cpg; cc += 4) {
+        const long long* st = cc < p.c0 ? q.stats0 + (static_cast<long long>(n) * (p.c0 >> 2) + (cc >> 2)) * 2
+                                        : q.stats1 + (static_cast<long long>(n) * (p.c1 >> 2) + ((cc - p.c0) >> 2)) * 2;
+        s1 += st[0];
+        s2 += st[1];
+      }
+      const float mean = static_cast<float>(static_cast<double>(s1) * unfix) * inv_cnt;
+      const float ex2 = static_cast<float>(static_cast<double>(s2) * unfix) * inv_cnt;
+      const float var = fmaxf(ex2 - mean * mean, 0.f);
+      const float rs = rsqrtf(var + p.eps);
+      const float ga = p.gamma ? p.gamma[c] : 1.f, be = p.beta ? p.beta[c] : 0.f;
+      float aa = rs * ga, bb = be - mean * rs * ga;
+      if (p.scale) {
+        const long long r = static_cast<long long>(p.ss_rows == 1 ? 0 : n) * p.ss_ld;
+        const float sc = 1.f + p.scale[r + c], sh = p.shift[r + c];
+        aa *= sc;
+        bb = bb * sc + sh;
+      }
+      sa[c] = aa;
+      sb[c] = bb;
+      sm[c] = p.mask ? p.mask[static_cast<long long>(n) * C + c] : 1.f;
     }
-    if (p.mask) {
+    __syncthreads();
+
+    const __nv_bfloat16* s0 = static_cast<const __nv_bfloat16*>(p.src0) + static_cast<long long>(n) * p.hw * p.c0;
+    const __nv_bfloat16* s1p = p.c1 ? static_cast<const __nv_bfloat16*>(p.src1) + static_cast<long long>(n) * p.hw * p.c1 : nullptr;
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(n) * p.hw * C;
+    // four independent 16-byte loads in flight per thread, then the arithmetic, then four stores
+    auto apply = [&](const uint4& v, int c, long long o) {
+      float f[8];
+      unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+      unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+      const float4 a0 = *reinterpret_cast<const float4*>(sa + c), a1 = *reinterpret_cast<const float4*>(sa + c + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
+      f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+      f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+      if (p.silu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] *= sm[c + j];
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+      }
+      if (p.mask) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= sm[c + j];
+      }
+      uint4 o4;
+      o4.x = pack_bf16x2(f[0], f[1]); o4.y = pack_bf16x2(f[2], f[3]);
+      o4.z = pack_bf16x2(f[4], f[5]); o4.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(out + o) = o4;
+    };
+    auto src_of = [&](long long vi, int& c, long long& o) -> const uint4* {
+      const int pixel = static_cast<int>(vi / cv);
+      c = static_cast<int>(vi - static_cast<long long>(pixel) * cv) << 3;
+      o = static_cast<long long>(pixel) * C + c;
+      return c < p.c0 ? reinterpret_cast<const uint4*>(s0 + static_cast<long long>(pixel) * p.c0 + c)
+                      : reinterpret_cast<const uint4*>(s1p + static_cast<long long>(pixel) * p.c1 + (c - p.c0));
+    };
+    constexpr int U = 4;
+    long long vi = v0 + threadIdx.x;
+    for (; vi + (U - 1) * 256 < v1; vi += U * 256) {
+      uint4 v[U];
+      int c[U];
+      long long o[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = __ldg(src_of(vi + u * 256, c[u], o[u]));
+#pragma unroll
+      for (int u = 0; u < U; ++u) apply(v[u], c[u], o[u]);
     }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out + static_cast<long long>(pixel) * C + c) = o;
+    for (; vi < v1; vi += 256) {
+      int c;
+      long long o;
+      const uint4 v = __ldg(src_of(vi, c, o));
+      apply(v, c, o);
+    }
+    seg = static_cast<long long>(n) * nvec + v1;
   }
 }
 
@@ -339,12 +371,11 @@ extern "C" int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, in
   if (have_stats && act_dtype == DMME_BF16 && c0 % 8 == 0 && c1 % 8 == 0 && cpg % 4 == 0 && c0 % cpg == 0 && C <= 4096) {
     GnApplyParams q;
     q.g = p; q.stats0 = stats0; q.stats1 = stats1;
-    const long long elems = static_cast<long long>(hw) * C;
-    int chunks = static_cast<int>(elems / 16384);
-    if (chunks < 1) chunks = 1;
-    q.chunks = chunks;
-    dim3 grid(chunks, n);
-    gn_apply_kernel<<<grid, 256, sizeof(float) * 3 * C, st>>>(q);
+    const long long total_vec = static_cast<long long>(n) * hw * (C >> 3);
+    long long grid = ceil_div_ll(total_vec, 256);  // at least one vector per thread
+    if (grid > 148 * 4) grid = 148 * 4;            // one wave, four CTAs per SM
+    q.chunks = 0;
+    gn_apply_kernel<<<static_cast<int>(grid), 256, sizeof(float) * 3 * C, st>>>(q);
     return check_launch("gn_apply_kernel");
   }
   const bool fast = act_dtype == DMME_BF16 && C % 32 == 0 && c0 % 32 == 0 && (32 % cpg == 0) && hw <= 1024 &&

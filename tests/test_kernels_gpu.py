@@ -248,6 +248,11 @@ HALO_CASES = [
     dict(n=2, cin=256, cout=128, h=32, w=32, cin1=128, res=True),
     dict(n=37, cin=512, cout=256, h=16, w=16, cin1=256, res=True),   # > 148 work units: persistent loop, both TMEM stages
     dict(n=150, cin=128, cout=128, h=32, w=32),                      # several units per CTA at 32x32
+    dict(n=5, cin=256, cout=256, h=8, w=8, temb="rows"),             # 8x8: tiles span several images
+    dict(n=70, cin=256, cout=256, h=8, w=8, addend=True),
+    dict(n=3, cin=256, cout=256, h=4, w=4, temb="bcast"),            # 4x4: 42 padded rows = 7 images per tile
+    dict(n=256, cin=512, cout=256, h=4, w=4, cin1=256, res=True),
+    dict(n=64, cin=128, cout=128, h=8, w=8),
 ]
 
 

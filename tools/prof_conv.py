@@ -20,6 +20,8 @@ SHAPES = [  # (name, n, h, c0, c1, cout, res)
     ("512->256 @16 +res", 256, 16, 256, 256, 256, True),
     ("256->256 @8", 256, 8, 256, 0, 256, False),
     ("256->256 @4", 256, 4, 256, 0, 256, False),
+    ("512->256 @8 +res", 256, 8, 256, 256, 256, True),
+    ("512->256 @4 +res", 256, 4, 256, 256, 256, True),
 ]
 
 
