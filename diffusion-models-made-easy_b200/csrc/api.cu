@@ -27,6 +27,8 @@ int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_halo_supported(const dmme_conv_desc& d);
 bool conv_halo_preferred(const dmme_conv_desc& d);
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream);
+bool conv_halo2_supported(const dmme_conv_desc& d);
+int conv_halo2_forward(const dmme_conv_desc& d, cudaStream_t stream);
 
 }  // namespace dmme
 
@@ -41,12 +43,14 @@ extern "C" int dmme_conv2d_uses_tc(const dmme_conv_desc* d) {
   if (!d) return 0;
   if (d->kernel == DMME_CONV_GENERIC) return 0;
   if (d->kernel == DMME_CONV_HALO) return conv_halo_supported(*d) ? 1 : 0;
+  if (d->kernel == DMME_CONV_HALO2) return conv_halo2_supported(*d) ? 1 : 0;
   return conv_tc_supported(*d) ? 1 : 0;
 }
 
 extern "C" int dmme_conv2d_writes_stats(const dmme_conv_desc* d) {
   if (!d || d->kernel == DMME_CONV_GENERIC || d->out_layout != DMME_OUT_NHWC || d->cout % 4) return 0;
   if (d->kernel == DMME_CONV_HALO) return conv_halo_supported(*d) ? 1 : 0;
+  if (d->kernel == DMME_CONV_HALO2) return conv_halo2_supported(*d) ? 1 : 0;
   if (conv_tc_supported(*d)) return 1;
   if (d->kernel == DMME_CONV_AUTO && conv_in_supported(*d) && (static_cast<long long>(d->h_in) * d->w_in) % 64 == 0) return 1;
   return 0;
@@ -62,6 +66,8 @@ extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
       return conv_generic_forward(*d, st);
     case DMME_CONV_HALO:
       return conv_halo_forward(*d, st);
+    case DMME_CONV_HALO2:
+      return conv_halo2_forward(*d, st);
     case DMME_CONV_AUTO:
       if (conv_tc_supported(*d)) return conv_halo_preferred(*d) ? conv_halo_forward(*d, st) : conv_tc_forward(*d, st);
       if (conv_in_supported(*d) || conv_out_supported(*d)) return conv_small_forward(*d, st);

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libdmme_b200.so")
 BF16, F32 = 0, 1
 IN_NHWC, IN_NCHW_F32 = 0, 1
 OUT_NHWC, OUT_NCHW_F32, OUT_QKV = 0, 1, 2
-CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO = 0, 1, 2, 3
+CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO, CONV_HALO2 = 0, 1, 2, 3, 4
 
 # every symbol include/dmme_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = (

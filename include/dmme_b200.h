@@ -51,8 +51,10 @@ enum {
   DMME_CONV_AUTO = 0,    /* tcgen05 when the shape allows, generic otherwise */
   DMME_CONV_GENERIC = 1, /* FFMA implicit GEMM, any shape, fp32 math */
   DMME_CONV_TC = 2,      /* tcgen05/TMEM + TMA implicit GEMM, one A tile per filter tap (any supported shape) */
-  DMME_CONV_HALO = 3     /* tcgen05 3x3 stride-1 kernel that keeps the activation halo tile in shared memory for all
-                            nine taps; AUTO prefers it when the shape allows */
+  DMME_CONV_HALO = 3,    /* tcgen05 3x3 stride-1 kernel that keeps the activation halo tile in shared memory for all
+                            nine taps */
+  DMME_CONV_HALO2 = 4    /* the same with one weight tile feeding two position tiles (all 512 TMEM columns): the 32x32
+                            and 16x16 levels; AUTO prefers it where it measured fastest */
 };
 
 /*

@@ -256,9 +256,18 @@ HALO_CASES = [
 ]
 
 
-@pytest.mark.parametrize("cfg", HALO_CASES)
-def test_conv_halo(cfg):
-    """halo-reuse persistent tcgen05 kernel against fp32 conv on the same bf16 operands, plus its GroupNorm stats"""
+def _halo_params():
+    out = [pytest.param(c, "halo", id=f"halo-{i}") for i, c in enumerate(HALO_CASES)]
+    out += [pytest.param(c, "halo2", id=f"halo2-{i}") for i, c in enumerate(HALO_CASES) if c["w"] >= 16]
+    out.append(pytest.param(dict(n=256, cin=128, cout=128, h=32, w=32, temb="bcast", addend=True), "halo2", id="halo2-batch256"))
+    out.append(pytest.param(dict(n=97, cin=256, cout=256, h=16, w=16, temb="rows"), "halo2", id="halo2-odd-batch"))
+    return out
+
+
+@pytest.mark.parametrize("cfg,which", _halo_params())
+def test_conv_halo(cfg, which):
+    """halo-reuse persistent tcgen05 kernels (one / two position tiles per weight tile) against fp32 conv on the same
+    bf16 operands, plus their GroupNorm stats"""
     ops, L = _ops()
     g = torch.Generator().manual_seed(23)
     n, cin, cout, h, w = (cfg[s] for s in ("n", "cin", "cout", "h", "w"))
@@ -289,7 +298,8 @@ def test_conv_halo(cfg):
         ad = bf16_round(torch.randn(n, cout, h, w, generator=g))
         want = want + ad
         addend = to_nhwc(ad, torch.bfloat16).to(DEV)
-    d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_HALO)
+    d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16,
+                           L.CONV_HALO if which == "halo" else L.CONV_HALO2)
     assert ops.conv_uses_tc(d)
     wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
     out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV)
