@@ -58,7 +58,15 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) 
   hi = __uint_as_float(u & 0xffff0000u);
 }
 
-__device__ __forceinline__ float silu_f(float y) { return y / (1.0f + __expf(-y)); }
+// bf16 paths: silu(y) = y * sigmoid(y) = h + h * tanh(h), h = y/2 -- one MUFU (tanh.approx, rel. error 2^-11, far below the
+// 2^-9 rounding of the bf16 result) and two FMA-pipe instructions; exp + full-precision division cost ~14 and made the
+// streaming GroupNorm pass instruction-bound instead of HBM-bound
+__device__ __forceinline__ float silu_f(float y) {
+  const float h = 0.5f * y;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float silu_precise(float y) { return y / (1.0f + expf(-y)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -29,6 +29,7 @@ struct ConvTcParams {
   int n, ho, wo;
   int bw, bh, bni;
   int tiles_x, tiles_y;
+  int m_tiles, n_tiles;  // work units = m_tiles x n_tiles, walked by a persistent grid (n fastest: neighbours share A)
   int cout;
   const float* bias;
   const float* temb;
@@ -44,7 +45,8 @@ struct ConvTcParams {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KB
-constexpr int kConvThreads = 192;
+constexpr int kConvEpiWarps = 8;                       // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int kConvThreads = (2 + kConvEpiWarps) * 32;
 
 template <int BN>
 __host__ __device__ constexpr int stage_bytes() { return kABytes + BN * kBlockK * 2; }
@@ -54,25 +56,28 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;      // one accumulator stage
+  constexpr uint32_t kTmemCols = 2 * kAccCols;           // double-buffered: epilogue of tile i overlaps the MMAs of tile i+1
   constexpr int kStage = stage_bytes<BN>();
 
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 1024 B)
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* ring = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  // ---- tile coordinates ----
-  const int mt = blockIdx.x;
-  const int tx = mt % p.tiles_x;
-  const int ty = (mt / p.tiles_x) % p.tiles_y;
-  const int ng = mt / (p.tiles_x * p.tiles_y);
+  // ---- persistent schedule: tile t -> (m tile, n tile) ----
+  const int total_tiles = p.m_tiles * p.n_tiles;
+#define DMME_TILE_COORDS(t)                                   \
+  const int mt = (t) / p.n_tiles;                             \
+  const int col0 = ((t) - mt * p.n_tiles) * BN;               \
+  const int tx = mt % p.tiles_x;                              \
+  const int ty = (mt / p.tiles_x) % p.tiles_y;                \
+  const int ng = mt / (p.tiles_x * p.tiles_y);                \
   const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = ng * p.bni;
-  const int col0 = blockIdx.y * BN;
 
   const int cchunks = p.chunks0 + p.chunks1;
   const int conv_kb = p.taps * cchunks;
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(&acc_full[st], 1); mbar_init(&acc_empty[st], kConvEpiWarps * 32); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -104,9 +109,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      DMME_TILE_COORDS(t)
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], kStage);
         uint8_t* sa = ring + s * kStage;
@@ -141,14 +149,21 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         tma_load_5d(sa, &p.a[which], &full_bar[s], cc, cx, cp, cy, n0);
         tma_load_2d(sb, &p.b, &full_bar[s], kb * kBlockK, col0);
       }
+      }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      int it = 0, t_it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
+      const int stage = t_it & 1;
+      mbar_wait(&acc_empty[stage], ((t_it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t dtm = tmem_base + stage * kAccCols;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + s * kStage);
@@ -157,15 +172,21 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: start-address field += 2
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_bf16(dtm, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
       }
-      umma_commit(&accum_bar);  // accumulator complete
+      umma_commit(&acc_full[stage]);  // accumulator complete
+      }
     }
   } else {
     // =========================== epilogue ===========================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the quarter's two warps: even / odd 32-column chunks
+    int t_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
+    DMME_TILE_COORDS(t)
+    const int stage = t_it & 1;
     const int row = q * 32 + lane;
     const int wx = row % p.bw;
     const int hy = (row / p.bw) % p.bh;
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const long long pix = (static_cast<long long>(n) * p.ho + y) * p.wo + x;
     const float* trow = p.temb ? p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : n) * p.temb_ld : nullptr;
 
-    mbar_wait(&accum_bar, 0);
+    mbar_wait(&acc_full[stage], (t_it >> 1) & 1);
     tc_fence_after();
 
     int which = 0, ccol0 = col0, cmod = p.cout;
@@ -191,9 +212,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
 
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = half * 32; c < BN; c += 64) {
       uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(stage * kAccCols + c), v);
       tmem_ld_wait();
       float f[32];
 #pragma unroll
@@ -281,7 +302,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
       }
     }
+    tc_fence_before();
+    mbar_arrive(&acc_empty[stage]);
+    }
   }
+#undef DMME_TILE_COORDS
 
   tc_fence_before();
   __syncthreads();
@@ -347,8 +372,20 @@ static int launch_conv_tc(const ConvTcParams& p, int m_tiles, cudaStream_t strea
     }
     configured = true;
   }
-  dim3 grid(m_tiles, p.cout / BN);
-  conv_tc_kernel<BN, STAGES><<<grid, kConvThreads, smem, stream>>>(p);
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  ConvTcParams q = p;
+  q.m_tiles = m_tiles;
+  q.n_tiles = p.cout / BN;
+  const int total = q.m_tiles * q.n_tiles;
+  // persistent: one CTA per SM (it owns the whole TMEM: two accumulator stages), tiles dealt round-robin
+  const int grid = total < sm_count ? total : sm_count;
+  conv_tc_kernel<BN, STAGES><<<grid, kConvThreads, smem, stream>>>(q);
   return check_launch("conv_tc_kernel");
 }
 
@@ -390,25 +427,23 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   if (d.rc1 && (rc = make_act_map(&p.a[3], d.res1, d.n, ho, wo, d.rc1, 1, p.bw, p.bh, p.bni))) return rc;
 
   const uint64_t ktot = (uint64_t)p.taps * (d.c0 + d.c1) + d.rc0 + d.rc1;
-  // widest N tile that divides cout (and, for q/k/v splitting, the per-tensor width), but keep
-  // enough CTAs in flight: prefer >= 2 waves of 148 SMs x 2 resident CTAs.
+  // widest N tile that divides cout (and, for q/k/v splitting, the per-tensor width) while the persistent grid still
+  // has a tile for every SM: wider tiles re-read the activation tile less often
   int unit = d.out_layout == DMME_OUT_QKV ? d.cout / 3 : d.cout;
   int bn = 64;
-  if (unit % 128 == 0) bn = 128;
-  if (unit % 256 == 0 && (long long)m_tiles * (d.cout / 256) >= 296) bn = 256;
-  if (bn == 128 && (long long)m_tiles * (d.cout / 128) < 148) bn = 64;
-  // (measured: deeper TMA rings / wider N tiles for the one-wave 8x8 and 4x4 launches do not help -- 38.9 vs 35.6 us --
-  //  these launches are bound by the L2 -> SM operand feed, not by load latency)
+  if (unit % 128 == 0 && (long long)m_tiles * (d.cout / 128) >= 120) bn = 128;
+  if (unit % 256 == 0 && (long long)m_tiles * (d.cout / 256) >= 120) bn = 256;
   {
     uint64_t dims[2] = {ktot, (uint64_t)d.cout};
     uint64_t strides[1] = {ktot * 2};
     uint32_t box[2] = {64u, (uint32_t)bn};
     if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
   }
+  // one CTA per SM: the TMA ring takes the whole shared memory (192 KB each)
   switch (bn) {
-    case 256: return launch_conv_tc<256, 2>(p, m_tiles, stream);
-    case 128: return launch_conv_tc<128, 3>(p, m_tiles, stream);
-    default: return launch_conv_tc<64, 4>(p, m_tiles, stream);
+    case 256: return launch_conv_tc<256, 4>(p, m_tiles, stream);
+    case 128: return launch_conv_tc<128, 6>(p, m_tiles, stream);
+    default: return launch_conv_tc<64, 8>(p, m_tiles, stream);
   }
 }
 

@@ -318,12 +318,20 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams q)
       o4.z = pack_bf16x2(f[4], f[5]); o4.w = pack_bf16x2(f[6], f[7]);
       *reinterpret_cast<uint4*>(out + o) = o4;
     };
-    auto src_of = [&](long long vi, int& c, long long& o) -> const uint4* {
-      const int pixel = static_cast<int>(vi / cv);
-      c = static_cast<int>(vi - static_cast<long long>(pixel) * cv) << 3;
+    // (pixel, vector-in-pixel) of this thread's current vector; successive vectors are 256 apart, so the pair advances
+    // by a constant step with one conditional carry -- no division in the streaming loop
+    const int step_p = 256 / cv, step_c = 256 - step_p * cv;
+    int pixel = static_cast<int>((v0 + threadIdx.x) / cv);
+    int cidx = static_cast<int>((v0 + threadIdx.x) - static_cast<long long>(pixel) * cv);
+    auto src_of = [&](int& c, long long& o) -> const uint4* {
+      c = cidx << 3;
       o = static_cast<long long>(pixel) * C + c;
-      return c < p.c0 ? reinterpret_cast<const uint4*>(s0 + static_cast<long long>(pixel) * p.c0 + c)
-                      : reinterpret_cast<const uint4*>(s1p + static_cast<long long>(pixel) * p.c1 + (c - p.c0));
+      const uint4* ptr = c < p.c0 ? reinterpret_cast<const uint4*>(s0 + static_cast<long long>(pixel) * p.c0 + c)
+                                  : reinterpret_cast<const uint4*>(s1p + static_cast<long long>(pixel) * p.c1 + (c - p.c0));
+      pixel += step_p;
+      cidx += step_c;
+      if (cidx >= cv) { cidx -= cv; ++pixel; }
+      return ptr;
     };
     constexpr int U = 4;
     long long vi = v0 + threadIdx.x;
@@ -332,14 +340,14 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams q)
       int c[U];
       long long o[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = __ldg(src_of(vi + u * 256, c[u], o[u]));
+      for (int u = 0; u < U; ++u) v[u] = __ldg(src_of(c[u], o[u]));
 #pragma unroll
       for (int u = 0; u < U; ++u) apply(v[u], c[u], o[u]);
     }
     for (; vi < v1; vi += 256) {
       int c;
       long long o;
-      const uint4 v = __ldg(src_of(vi, c, o));
+      const uint4 v = __ldg(src_of(c, o));
       apply(v, c, o);
     }
     seg = static_cast<long long>(n) * nvec + v1;
