@@ -649,6 +649,10 @@ __global__ void iddpm_loss_finish_kernel(const float* __restrict__ partial, int 
   }
 }
 
+bool conv_wgrad_tc_supported(const dmme_conv_desc& d);
+void conv_wgrad_tc_geometry(const dmme_conv_desc& d, int& items, int& chunks_total, int& chunks_per_slice, int& slices);
+int conv_wgrad_tc_partials(const dmme_conv_desc& d, const void* grad_out, float* partial, int& slices, cudaStream_t stream);
+
 int launch_linear(const float* in, const int64_t* t, const float* freq, int rows, int in_dim, const float* w,
                   const float* b, int out_dim, int act, float* out, cudaStream_t st, const char* what);
 
@@ -722,10 +726,20 @@ static void wgrad_geometry(const dmme_conv_desc& d, int& ho, int& wo, int& kp, i
   slices = static_cast<int>(ceil_div_ll(mtot, pps));
 }
 
+static bool wgrad_use_tc(const dmme_conv_desc& d) { return d.kernel != DMME_CONV_GENERIC && conv_wgrad_tc_supported(d); }
+
+extern "C" int dmme_conv2d_wgrad_uses_tc(const dmme_conv_desc* d) { return d && wgrad_use_tc(*d) ? 1 : 0; }
+
 extern "C" long long dmme_conv2d_wgrad_workspace(const dmme_conv_desc* d) {
   if (!d || d->n <= 0 || d->cout <= 0) return 0;
   int ho, wo, kp, slices; long long pps;
   wgrad_geometry(*d, ho, wo, kp, slices, pps);
+  if (wgrad_use_tc(*d)) {
+    int items, chunks_total, cps, tslices;
+    conv_wgrad_tc_geometry(*d, items, chunks_total, cps, tslices);
+    // partials + the per-image pixel sums of grad_out for the bias gradient
+    return (static_cast<long long>(tslices) * d->cout * kp + static_cast<long long>(d->n) * d->cout) * sizeof(float);
+  }
   return static_cast<long long>(slices) * d->cout * kp * sizeof(float);
 }
 
@@ -738,8 +752,30 @@ extern "C" int dmme_conv2d_wgrad(const dmme_conv_desc* d, const void* grad_out, 
   DMME_REQUIRE((d->rc0 + d->rc1 == 0) || dweight_res, DMME_E_BADARG, "conv2d_wgrad: fused residual needs dweight_res");
   int ho, wo, kp, slices; long long pps;
   wgrad_geometry(*d, ho, wo, kp, slices, pps);
-  DMME_REQUIRE(workspace_bytes >= static_cast<long long>(slices) * d->cout * kp * (long long)sizeof(float), DMME_E_BADARG,
+  DMME_REQUIRE(workspace_bytes >= dmme_conv2d_wgrad_workspace(d), DMME_E_BADARG,
                "conv2d_wgrad: workspace too small (%lld bytes)", workspace_bytes);
+  if (wgrad_use_tc(*d)) {
+    // tensor-core path: MN-major tcgen05 products into per-slice partials, the same deterministic reduction, and the
+    // bias gradient as pixel sums per image followed by a column sum over the images
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* partial = static_cast<float*>(workspace);
+    int tslices = 0;
+    int rc = conv_wgrad_tc_partials(*d, grad_out, partial, tslices, st);
+    if (rc) return rc;
+    const long long total = static_cast<long long>(d->cout) * kp;
+    wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(partial, tslices, d->cout, kp, d->c0 + d->c1, d->ksize * d->ksize,
+                                                            d->rc0 + d->rc1, dweight, dweight_res, nullptr);
+    if ((rc = check_launch("wgrad_reduce_kernel"))) return rc;
+    if (dbias) {
+      float* img_sums = partial + static_cast<long long>(tslices) * d->cout * kp;
+      dim3 grid(ceil_div(d->cout, 32), d->n), block(32, 8);
+      pixel_sum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(grad_out), ho * wo, d->cout, img_sums, d->cout);
+      if ((rc = check_launch("pixel_sum_kernel"))) return rc;
+      colsum_kernel<<<ceil_div(d->cout, 128), 128, 0, st>>>(img_sums, d->n, d->cout, d->cout, dbias, 0);
+      if ((rc = check_launch("colsum_kernel"))) return rc;
+    }
+    return 0;
+  }
   WgradParams p;
   p.g = grad_out; p.g_nchw = d->out_layout == DMME_OUT_NCHW_F32;
   p.src0 = d->src0; p.src1 = d->src1; p.c0 = d->c0; p.c1 = d->c1;

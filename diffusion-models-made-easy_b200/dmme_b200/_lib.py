@@ -28,7 +28,7 @@ EXPORTS = (
     "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
-    "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_groupnorm_bwd",
+    "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
     "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
     "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
@@ -90,6 +90,7 @@ def load() -> C.CDLL:
     lib.dmme_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, i, vp, i, vp]
     lib.dmme_conv2d_wgrad_workspace.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_conv2d_wgrad_workspace.restype = ll
+    lib.dmme_conv2d_wgrad_uses_tc.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_conv2d_wgrad.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, ll, vp]
     lib.dmme_groupnorm_bwd.argtypes = [vp, vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, i,
                                        vp, vp, vp, vp, vp, vp, vp, vp, i, vp, i, vp]

@@ -259,6 +259,10 @@ def conv_wgrad_workspace(desc: L.ConvDesc) -> int:
     return int(L.load().dmme_conv2d_wgrad_workspace(C.byref(desc)))
 
 
+def conv_wgrad_uses_tc(desc: L.ConvDesc) -> bool:
+    return bool(L.load().dmme_conv2d_wgrad_uses_tc(C.byref(desc)))
+
+
 def conv2d_wgrad(desc: L.ConvDesc, grad_out: Tensor, dweight: Tensor, dweight_res: Optional[Tensor],
                  dbias: Optional[Tensor], workspace: Tensor) -> None:
     """Weight / fused-residual-weight / bias gradients of the forward call described by ``desc``."""

@@ -218,6 +218,9 @@ int dmme_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksiz
  * [cout] or NULL.  Results are written (not accumulated).  Deterministic two-stage reduction through `workspace`
  * (dmme_conv2d_wgrad_workspace bytes). */
 long long dmme_conv2d_wgrad_workspace(const dmme_conv_desc* fwd);
+/* 1 when dmme_conv2d_wgrad takes the tcgen05 path (bf16 NHWC, stride 1, cout % 128 == 0, channels % 64 == 0, fwd->kernel
+ * != DMME_CONV_GENERIC); the CUDA-core kernel handles everything else */
+int dmme_conv2d_wgrad_uses_tc(const dmme_conv_desc* fwd);
 int dmme_conv2d_wgrad(const dmme_conv_desc* fwd, const void* grad_out, float* dweight, float* dweight_res,
                       float* dbias, void* workspace, long long workspace_bytes, void* stream);
 

@@ -106,6 +106,62 @@ def test_conv_wgrad_generic_fp32(cfg):
         assert rel_l2(dwr.cpu(), wres.grad.flatten(1)) < 1e-4
 
 
+WGRAD_TC = [
+    dict(n=4, h=32, cin=128, cout=128, ks=3),
+    dict(n=8, h=16, cin=256, cin1=128, cout=256, ks=3, res=True),
+    dict(n=16, h=8, cin=64, cout=128, ks=3),                  # 64-channel blocks
+    dict(n=6, h=16, cin=256, cout=384, ks=1),                 # 1x1 (qkv projection)
+    dict(n=33, h=4, cin=256, cout=256, ks=3),                 # ragged last chunk: out-of-range images are zero-filled
+    dict(n=64, h=32, cin=128, cout=128, ks=3),                # many pixel slices
+]
+
+
+@pytest.mark.parametrize("cfg", WGRAD_TC)
+def test_conv_wgrad_tc(cfg):
+    """tcgen05 weight gradient (MN-major operands straight from the NHWC tensors) against fp32 autograd on the same
+    bf16-rounded operands: only the fp32 accumulation order differs."""
+    ops, L = _ops()
+    n, h, cout, ks = cfg["n"], cfg["h"], cfg["cout"], cfg["ks"]
+    cin, cin1 = cfg["cin"], cfg.get("cin1", 0)
+    c0 = cin - cin1
+    bf = lambda t: t.to(torch.bfloat16).float()
+    a = bf(_rand(n, cin, h, h, seed=1))
+    w = (_rand(cout, cin, ks, ks, seed=3) / math.sqrt(ks * ks * cin)).requires_grad_()
+    b = _rand(cout, seed=4).requires_grad_()
+    y = F.conv2d(a, w, b, padding=ks // 2)
+    wres = xr = None
+    if cfg.get("res"):
+        xr = bf(_rand(n, cin, h, h, seed=5))
+        wres = (_rand(cout, cin, 1, 1, seed=6) / math.sqrt(cin)).requires_grad_()
+        y = y + F.conv2d(xr, wres)
+    g = bf(_rand(*y.shape, seed=7))
+    y.backward(g)
+    dt = torch.bfloat16
+    s0 = to_nhwc(a[:, :c0], dt).to(DEV)
+    s1 = to_nhwc(a[:, c0:], dt).to(DEV) if cin1 else None
+    r0 = to_nhwc(xr[:, :c0], dt).to(DEV) if xr is not None else None
+    r1 = to_nhwc(xr[:, c0:], dt).to(DEV) if xr is not None and cin1 else None
+    d = ops.make_conv_desc(s0, s1, cout, ks, 1, False, r0, r1, False, L.OUT_NHWC, dt, L.CONV_AUTO)
+    assert ops.conv_wgrad_uses_tc(d)
+    dw = torch.empty_like(w, device=DEV)
+    db = torch.empty(cout, device=DEV)
+    dwr = torch.empty(cout, cin, device=DEV) if wres is not None else None
+    ws = torch.empty(ops.conv_wgrad_workspace(d) // 4, device=DEV)
+    gd = to_nhwc(g, dt).to(DEV)
+    ops.conv2d_wgrad(d, gd, dw, dwr, db, ws)
+    assert rel_l2(dw.cpu(), w.grad) < 1e-4, rel_l2(dw.cpu(), w.grad)
+    assert rel_l2(db.cpu(), b.grad) < 1e-4
+    if wres is not None:
+        assert rel_l2(dwr.cpu(), wres.grad.flatten(1)) < 1e-4
+    # and the CUDA-core kernel agrees on the same inputs
+    d.kernel = L.CONV_GENERIC
+    assert not ops.conv_wgrad_uses_tc(d)
+    dw2 = torch.empty_like(dw)
+    ws2 = torch.empty(ops.conv_wgrad_workspace(d) // 4, device=DEV)
+    ops.conv2d_wgrad(d, gd, dw2, torch.empty_like(dwr) if dwr is not None else None, torch.empty_like(db), ws2)
+    assert rel_l2(dw2.cpu(), dw.cpu()) < 1e-4
+
+
 def test_conv_wgrad_nchw_image_ends():
     """input conv reads the NCHW fp32 image; output conv's grad_out is the NCHW fp32 image gradient."""
     ops, L = _ops()
