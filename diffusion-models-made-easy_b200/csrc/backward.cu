@@ -207,6 +207,33 @@ __global__ void pool2x_sum_kernel(const T* __restrict__ g, T* __restrict__ out, 
   }
 }
 
+// zero-dilation x2 (NHWC): dst[n][2y][2x] = src[n][y][x], all other pixels 0.  The gradient of a stride-2 conv
+// (models/ddpm.py:147) w.r.t. its input / weights is the stride-1 data / weight gradient of this dilated grad_out, so
+// both run on the stride-1 tensor-core kernels.
+template <typename T, int VEC>
+__global__ void dilate2x_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int h, int w, int c) {
+  const int cv = c / VEC;
+  const long long total = static_cast<long long>(n) * (2 * h) * (2 * w) * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    long long pix = i / cv;
+    const int x = static_cast<int>(pix % (2 * w));
+    pix /= (2 * w);
+    const int y = static_cast<int>(pix % (2 * h));
+    const long long ni = pix / (2 * h);
+    T* d = dst + i * VEC;
+    if (((x | y) & 1) == 0) {
+      const T* sp = src + ((ni * h + (y >> 1)) * w + (x >> 1)) * c + v * VEC;
+      if (VEC * sizeof(T) == 16) *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(sp));
+      else *d = *sp;
+    } else {
+      if (VEC * sizeof(T) == 16) *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+      else st_act<T>(d, 0.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // convolution weight gradient
 //   dW[co][k] = sum over output pixels of g[pix][co] * in[pix, k],  k = tap * (c0 + c1) + ci | residual channel | 1 (bias)
@@ -451,6 +478,211 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p) {
       const long long o = pix * p.c1 + (c - p.c0);
       if (p.add1) gx += ld_act<T>(static_cast<const T*>(p.add1) + o);
       if (p.gin1) st_act<T>(static_cast<T*>(p.gin1) + o, gx);
+    }
+  }
+}
+
+// Fast path of the same backward (bf16, C % 32 == 0, channels-per-group in {1..32} dividing 32, HW <= 1024): one CTA owns
+// one (image, 32-channel slab).  x and grad_out of the slab are read ONCE into registers (16-byte vectors, 64 contiguous
+// bytes per pixel), the statistics are recomputed from the registers exactly like the forward slab kernel, the
+// per-channel sums A, B and the group means m1, m2 are reduced with shuffles + shared memory (no atomics), and the input
+// gradient is written once: 2 + 2 bytes read, 2 bytes written per element.
+template <int MAXV>
+__global__ void __launch_bounds__(256, MAXV > 4 ? 1 : 2) gn_bwd_slab_kernel(const GnBwdParams p) {
+  __shared__ float red[8][64];
+  __shared__ float chan[64];      // per-channel scratch: [0,32) and [32,64)
+  __shared__ float grp[64];       // per-channel broadcast of group quantities
+  const int C = p.c0 + p.c1;
+  const int slabs = C / 32;
+  const int n = blockIdx.x / slabs;
+  const int slab = blockIdx.x - n * slabs;
+  const int cbase = slab * 32;
+  const int cpg = C / p.groups;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int chunk = tid & 3;
+  const int nvec = p.hw * 4;
+  const bool first = cbase < p.c0;
+  const int csrc = first ? p.c0 : p.c1, coff = first ? cbase : cbase - p.c0;
+  const __nv_bfloat16* xsrc = static_cast<const __nv_bfloat16*>(first ? p.src0 : p.src1) +
+                              static_cast<long long>(n) * p.hw * csrc + coff + chunk * 8;
+  const __nv_bfloat16* gsrc = static_cast<const __nv_bfloat16*>(p.gout) + static_cast<long long>(n) * p.hw * C + cbase + chunk * 8;
+
+  uint4 xv[MAXV], gv[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * blockDim.x;
+    if (vi < nvec) {
+      xv[i] = __ldg(reinterpret_cast<const uint4*>(xsrc + static_cast<long long>(vi >> 2) * csrc));
+      gv[i] = __ldg(reinterpret_cast<const uint4*>(gsrc + static_cast<long long>(vi >> 2) * C));
+    } else {
+      xv[i] = make_uint4(0, 0, 0, 0);
+      gv[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  auto unpack8 = [](const uint4& v, float (&f)[8]) {
+    unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+    unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+  };
+  // block reduction of 8 per-thread values per chunk -> chan[off + chunk*8 + j] (sum over all pixels)
+  auto reduce8 = [&](float (&s)[8], int off) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 4);
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+    }
+    __syncthreads();
+    if (lane < 4) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][off + lane * 8 + j] = s[j];
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[w][off + tid];
+      chan[off + tid] = t;
+    }
+    __syncthreads();
+  };
+  const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * cpg);
+
+  // ---- statistics (two register passes, biased variance) ----
+  float s[8], f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    unpack8(xv[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+  }
+  reduce8(s, 0);
+  if (tid < 32) {
+    const int g0 = (tid / cpg) * cpg;
+    float t = 0.f;
+    for (int j = 0; j < cpg; ++j) t += chan[g0 + j];
+    grp[tid] = t * inv_cnt;
+  }
+  __syncthreads();
+  float mean[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mean[j] = grp[chunk * 8 + j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * blockDim.x;
+    if (vi < nvec) {
+      unpack8(xv[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[j] - mean[j]; s[j] = fmaf(d, d, s[j]); }
+    }
+  }
+  reduce8(s, 0);
+  if (tid < 32) {
+    const int g0 = (tid / cpg) * cpg;
+    float t = 0.f;
+    for (int j = 0; j < cpg; ++j) t += chan[g0 + j];
+    grp[32 + tid] = rsqrtf(t * inv_cnt + p.eps);
+  }
+  __syncthreads();
+
+  // ---- per-channel coefficients: xhat = x ha + hb, z = x za + zb, ge = (1 + scale) gamma ----
+  float ha[8], hb[8], za[8], zb[8], ge[8], mk[8];
+  const int ssr = p.scale ? (p.ss_rows == 1 ? 0 : n) : 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cbase + chunk * 8 + j;
+    const float rs = grp[32 + chunk * 8 + j];
+    float gam = p.gamma[c], bet = p.beta[c];
+    if (p.scale) {
+      const float sc = 1.0f + p.scale[static_cast<long long>(ssr) * p.ss_ld + c];
+      gam *= sc;
+      bet = bet * sc + p.shift[static_cast<long long>(ssr) * p.ss_ld + c];
+    }
+    ha[j] = rs; hb[j] = -mean[j] * rs;
+    za[j] = rs * gam; zb[j] = bet - mean[j] * rs * gam;
+    ge[j] = gam;
+    mk[j] = p.mask ? p.mask[static_cast<long long>(n) * C + c] : 1.f;
+  }
+  auto gz8 = [&](const uint4& xq, const uint4& gq, float (&xh)[8], float (&gz)[8]) {
+    float xf[8], gf[8];
+    unpack8(xq, xf);
+    unpack8(gq, gf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh[j] = fmaf(xf[j], ha[j], hb[j]);
+      float gval = gf[j] * mk[j];
+      if (p.silu) gval *= dsilu_f(fmaf(xf[j], za[j], zb[j]));
+      gz[j] = gval;
+    }
+  };
+
+  // ---- A_c = sum gz, B_c = sum gz xhat ----
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sa[j] = 0.f; sb[j] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * blockDim.x;
+    if (vi < nvec) {
+      float xh[8], gz[8];
+      gz8(xv[i], gv[i], xh, gz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sa[j] += gz[j]; sb[j] = fmaf(gz[j], xh[j], sb[j]); }
+    }
+  }
+  reduce8(sa, 0);
+  reduce8(sb, 32);
+  if (tid < 32) {
+    const int c = cbase + tid;
+    p.sums[(static_cast<long long>(n) * C + c) * 2 + 0] = chan[tid];
+    p.sums[(static_cast<long long>(n) * C + c) * 2 + 1] = chan[32 + tid];
+  }
+  // group means of ge gz and ge gz xhat
+  if (tid < 32) {
+    const int g0 = (tid / cpg) * cpg;
+    float t1 = 0.f, t2 = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const int c = cbase + g0 + j;
+      float gam = p.gamma[c];
+      if (p.scale) gam *= 1.0f + p.scale[static_cast<long long>(ssr) * p.ss_ld + c];
+      t1 += gam * chan[g0 + j];
+      t2 += gam * chan[32 + g0 + j];
+    }
+    grp[tid] = t1 * inv_cnt;
+    red[0][tid] = t2 * inv_cnt;
+  }
+  __syncthreads();
+  float m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { m1[j] = grp[chunk * 8 + j]; m2[j] = red[0][chunk * 8 + j]; }
+
+  // ---- gx = rstd (ge gz - m1 - xhat m2) (+ addend) ----
+  __nv_bfloat16* gin = static_cast<__nv_bfloat16*>(first ? p.gin0 : p.gin1);
+  const __nv_bfloat16* add = static_cast<const __nv_bfloat16*>(first ? p.add0 : p.add1);
+  if (gin == nullptr) return;
+  const long long obase = static_cast<long long>(n) * p.hw * csrc + coff + chunk * 8;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * blockDim.x;
+    if (vi < nvec) {
+      float xh[8], gz[8], o[8];
+      gz8(xv[i], gv[i], xh, gz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = ha[j] * (ge[j] * gz[j] - m1[j] - xh[j] * m2[j]);
+      const long long off = obase + static_cast<long long>(vi >> 2) * csrc;
+      if (add) {
+        float af[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(add + off)), af);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += af[j];
+      }
+      uint4 ov;
+      ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+      ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(gin + off) = ov;
     }
   }
 }
@@ -708,6 +940,22 @@ extern "C" int dmme_pool2x_sum_nhwc(const void* g, void* out, int n, int h, int 
   return check_launch("pool2x_sum_kernel");
 }
 
+extern "C" int dmme_dilate2x_nhwc(const void* src, void* dst, int n, int h, int w, int c, int act_dtype, void* stream) {
+  DMME_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0, DMME_E_BADARG, "dilate2x: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (act_dtype == DMME_BF16 && c % 8 == 0) {
+    const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+    dilate2x_kernel<__nv_bfloat16, 8><<<grid_1d(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n, h, w, c);
+  } else if (act_dtype == DMME_BF16) {
+    const long long total = static_cast<long long>(n) * 4 * h * w * c;
+    dilate2x_kernel<__nv_bfloat16, 1><<<grid_1d(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n, h, w, c);
+  } else {
+    const long long total = static_cast<long long>(n) * 4 * h * w * c;
+    dilate2x_kernel<float, 1><<<grid_1d(total, 256), 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), n, h, w, c);
+  }
+  return check_launch("dilate2x_kernel");
+}
+
 // ---- conv wgrad ----------------------------------------------------------------------------------
 static void wgrad_geometry(const dmme_conv_desc& d, int& ho, int& wo, int& kp, int& slices, long long& pps) {
   const int hin_eff = d.upsample ? 2 * d.h_in : d.h_in, win_eff = d.upsample ? 2 * d.w_in : d.w_in;
@@ -817,9 +1065,22 @@ extern "C" int dmme_groupnorm_bwd(const void* grad_out, const void* src0, const 
   const size_t smem = sizeof(float) * (2 * cpg + 32);
   DMME_REQUIRE(smem <= 48 * 1024, DMME_E_SHAPE, "groupnorm_bwd: %d channels per group is too many", cpg);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (act_dtype == DMME_BF16) gn_bwd_kernel<__nv_bfloat16><<<n * groups, 256, smem, st>>>(p);
-  else gn_bwd_kernel<float><<<n * groups, 256, smem, st>>>(p);
-  int rc = check_launch("gn_bwd_kernel");
+  int rc;
+  const bool fast = act_dtype == DMME_BF16 && C % 32 == 0 && c0 % 32 == 0 && (32 % cpg == 0) && hw <= 1024 && (hw * 4) % 32 == 0;
+  if (fast) {
+    const int nvec = hw * 4;
+    const int threads = nvec < 256 ? nvec : 256;
+    const int maxv = ceil_div(nvec, threads);
+    const int blocks = n * (C / 32);
+    if (maxv <= 1) gn_bwd_slab_kernel<1><<<blocks, threads, 0, st>>>(p);
+    else if (maxv <= 4) gn_bwd_slab_kernel<4><<<blocks, threads, 0, st>>>(p);
+    else gn_bwd_slab_kernel<16><<<blocks, threads, 0, st>>>(p);
+    rc = check_launch("gn_bwd_slab_kernel");
+  } else {
+    if (act_dtype == DMME_BF16) gn_bwd_kernel<__nv_bfloat16><<<n * groups, 256, smem, st>>>(p);
+    else gn_bwd_kernel<float><<<n * groups, 256, smem, st>>>(p);
+    rc = check_launch("gn_bwd_kernel");
+  }
   if (rc) return rc;
   gn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, n, C, gamma, beta, scale, ss_rows, ss_ld, dgamma, dbeta,
                                                          dscale, dshift, dss_ld);

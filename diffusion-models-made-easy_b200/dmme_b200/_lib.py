@@ -30,7 +30,7 @@ EXPORTS = (
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
     "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
     "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
-    "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
+    "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_dilate2x_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
 
 
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
     lib.dmme_add.argtypes = [vp, vp, vp, ll, i, vp]
     lib.dmme_pixel_sum.argtypes = [vp, i, i, i, vp, ll, i, vp]
     lib.dmme_pool2x_sum_nhwc.argtypes = [vp, vp, i, i, i, i, i, vp]
+    lib.dmme_dilate2x_nhwc.argtypes = [vp, vp, i, i, i, i, i, vp]
     lib.dmme_colsum_f32.argtypes = [vp, i, i, ll, vp, i, vp]
     lib.dmme_mse_loss.argtypes = [vp, vp, ll, f, vp, vp, vp, vp]
     lib.dmme_iddpm_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, f, f, f, vp, vp, vp, vp]

@@ -129,14 +129,20 @@ class TrainEngine(Engine):
             g = self._grad_of(out)
             if g is None:
                 return
+            # stride-2 conv on the tensor-core path: dilate grad_out once, then both gradients are stride-1 problems
+            g_w, d_w, g_dil = g, d, None
+            if stride == 2 and tc and out_layout == L.OUT_NHWC and not in_nchw:
+                g_dil = ops.dilate2x(g, out=self._buf(name + ".gdil", (d.n, 2 * ho, 2 * wo, cout), g.dtype, dev))
+                d_w = ops.make_conv_desc(src0, None, cout, ks, 1, False, None, None, False, L.OUT_NHWC, act_dtype, kernel)
+                g_w = g_dil
             # weight / bias gradients (the forward descriptor still holds the source pointers and geometry)
             dw, db = self._pgrad(conv.weight), self._pgrad(conv.bias)
             dwr = self._pgrad(res.weight) if res is not None else None
             if res is not None and res.bias is not None:
                 self.param_grads[id(res.bias)] = db  # out = conv + res: both biases see the same gradient
-            wsz = ops.conv_wgrad_workspace(d)
+            wsz = ops.conv_wgrad_workspace(d_w)
             wsb = self.ws.get("train.wgrad_ws", (max(wsz, 4) // 4,), torch.float32, dev)
-            ops.conv2d_wgrad(d, g, dw, dwr, db, wsb)
+            ops.conv2d_wgrad(d_w, g_w, dw, dwr, db, wsb)
             # timestep-embedding gradient: column block of d_all
             if temb is not None and temb_cols is not None:
                 o, width = temb_cols
@@ -152,8 +158,11 @@ class TrainEngine(Engine):
             g_nchw = out_layout == L.OUT_NCHW_F32
             # data gradient of the main source
             cin = conv.weight.shape[1]
-            dd = ops.make_conv_desc(g, None, cin, ks, 1, 2 if stride == 2 else False, None, None, g_nchw, L.OUT_NHWC,
-                                    act_dtype, kernel)
+            if g_dil is not None:
+                dd = ops.make_conv_desc(g_dil, None, cin, ks, 1, False, None, None, False, L.OUT_NHWC, act_dtype, kernel)
+            else:
+                dd = ops.make_conv_desc(g, None, cin, ks, 1, 2 if stride == 2 else False, None, None, g_nchw, L.OUT_NHWC,
+                                        act_dtype, kernel)
             dtc = ops.conv_uses_tc(dd)
             hi, wi = ops.conv_out_hw(dd)
             target = src0 if src_lo is None and not upsample else None

@@ -354,6 +354,15 @@ def pool2x_sum(g: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return y
 
 
+def dilate2x(g: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """Zero-dilation x2 of an NHWC tensor (values at even coordinates)."""
+    L.require_cuda(g, out)
+    n, h, w, c = g.shape
+    y = _empty((n, 2 * h, 2 * w, c), g.dtype, g.device, out)
+    L.check(L.load().dmme_dilate2x_nhwc(ptr(g), ptr(y), n, h, w, c, L.act_code(g.dtype), L.stream_ptr()), "dilate2x")
+    return y
+
+
 def colsum(x: Tensor, out: Tensor, accumulate: bool = False) -> Tensor:
     """out[c] (+)= sum_r x[r][c] for a 2-D fp32 view."""
     L.check(L.load().dmme_colsum_f32(ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(out), int(accumulate),

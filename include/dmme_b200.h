@@ -265,6 +265,9 @@ int dmme_add(void* dst, const void* a, const void* b, long long numel, int act_d
 int dmme_pixel_sum(const void* g, int n, int hw, int c, float* out, long long out_ld, int act_dtype, void* stream);
 /* backward of nearest x2 upsampling (models/ddpm.py:161): out[n][y][x][c] = sum of the 2x2 block of g [n][2h][2w][c] */
 int dmme_pool2x_sum_nhwc(const void* g, void* out, int n, int h, int w, int c, int act_dtype, void* stream);
+/* dst[n][2y][2x] = src[n][y][x], zeros elsewhere: turns the gradients of a stride-2 conv (models/ddpm.py:147) into the
+ * stride-1 data / weight gradients of the dilated grad_out (tensor-core kernels) */
+int dmme_dilate2x_nhwc(const void* src, void* dst, int n, int h, int w, int c, int act_dtype, void* stream);
 int dmme_colsum_f32(const float* in, int rows, int cols, long long ld, float* out, int accumulate, void* stream);
 
 /* L_simple (equations/ddpm/losses.py:5-13): loss_out[0] = mean((eps - noise)^2);

@@ -289,6 +289,62 @@ def test_groupnorm_bwd(cfg):
         assert rel_l2(dss[:, C + 3:].cpu(), scale.grad) < 1e-4 and rel_l2(dss[:, :C].cpu(), shift.grad) < 1e-4
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(n=3, c0=128, c1=0, h=16, groups=32, silu=True, mask=True),
+    dict(n=2, c0=128, c1=128, h=32, groups=32, silu=True, adds=True),
+    dict(n=2, c0=256, c1=0, h=8, groups=32, silu=True, ss=True),
+    dict(n=5, c0=64, c1=0, h=4, groups=32, silu=False),
+])
+def test_groupnorm_bwd_bf16_slab(cfg):
+    """register-resident slab kernel (bf16 storage) against fp32 autograd on the same bf16-rounded tensors; the only
+    differences are fp32 summation order and the bf16 rounding of the stored gradient (2^-9 relative)."""
+    ops, L = _ops()
+    n, c0, c1, h, groups = (cfg[k] for k in ("n", "c0", "c1", "h", "groups"))
+    C = c0 + c1
+    bf = lambda t: t.to(torch.bfloat16).float()
+    x0 = bf(_rand(n, c0, h, h, seed=1)).requires_grad_()
+    x1 = bf(_rand(n, c1, h, h, seed=2)).requires_grad_() if c1 else None
+    gamma = (1 + 0.3 * _rand(C, seed=3)).requires_grad_()
+    beta = (0.2 * _rand(C, seed=4)).requires_grad_()
+    scale = (0.5 * _rand(n, C, seed=5)).requires_grad_() if cfg.get("ss") else None
+    shift = (0.5 * _rand(n, C, seed=6)).requires_grad_() if cfg.get("ss") else None
+    mask = ((torch.rand(n, C, generator=torch.Generator().manual_seed(7)) > 0.3).float() / 0.7) if cfg.get("mask") else None
+    xin = x0 if x1 is None else torch.cat([x0, x1], 1)
+    y = F.group_norm(xin, groups, gamma, beta, 1e-5)
+    if scale is not None:
+        y = y * (1 + scale[:, :, None, None]) + shift[:, :, None, None]
+    if cfg["silu"]:
+        y = F.silu(y)
+    if mask is not None:
+        y = y * mask[:, :, None, None]
+    g = bf(_rand(*y.shape, seed=8))
+    y.backward(g)
+    dt = torch.bfloat16
+    add0 = bf(_rand(n, h, h, c0, seed=9)) if cfg.get("adds") else None
+    add1 = bf(_rand(n, h, h, c1, seed=10)) if cfg.get("adds") and c1 else None
+    s0 = to_nhwc(x0.detach(), dt).to(DEV)
+    s1 = to_nhwc(x1.detach(), dt).to(DEV) if c1 else None
+    gin0 = torch.empty_like(s0)
+    gin1 = torch.empty_like(s1) if c1 else None
+    dgamma, dbeta = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    dss = torch.zeros(n, 2 * C, device=DEV) if scale is not None else None
+    sums = torch.empty(n, C, 2, device=DEV)
+    ops.groupnorm_bwd(to_nhwc(g, dt).to(DEV), s0, s1, groups, gamma.detach().to(DEV), beta.detach().to(DEV), cfg["silu"],
+                      scale.detach().to(DEV) if scale is not None else None,
+                      shift.detach().to(DEV) if shift is not None else None,
+                      mask.to(DEV) if mask is not None else None, 1e-5, gin0, gin1,
+                      add0.to(dt).to(DEV) if add0 is not None else None, add1.to(dt).to(DEV) if add1 is not None else None,
+                      dgamma, dbeta, dss[:, C:] if dss is not None else None, dss[:, :C] if dss is not None else None, sums)
+    want0 = x0.grad + (to_nchw(add0) if add0 is not None else 0)
+    assert rel_l2(to_nchw(gin0.cpu()), want0) < 4e-3
+    if c1:
+        want1 = x1.grad + (to_nchw(add1) if add1 is not None else 0)
+        assert rel_l2(to_nchw(gin1.cpu()), want1) < 4e-3
+    assert rel_l2(dgamma.cpu(), gamma.grad) < 1e-4 and rel_l2(dbeta.cpu(), beta.grad) < 1e-4
+    if scale is not None:
+        assert rel_l2(dss[:, C:].cpu(), scale.grad) < 1e-4 and rel_l2(dss[:, :C].cpu(), shift.grad) < 1e-4
+
+
 # ---------------------------------------------------------------------------------------------
 # attention backward
 # ---------------------------------------------------------------------------------------------
