@@ -179,6 +179,38 @@ def conv_profile(model, x, t, reps=3):
     return best
 
 
+def gn_profile(model, x, t, reps=3):
+    """Per-launch CUDA-event timing of every GroupNorm(+SiLU) launch of one UNet forward; algorithmic bytes = 2 B read +
+    2 B written per element (SURVEY par. 8d).  Returns (launches, bytes, ms) of the best repetition."""
+    from dmme_b200 import ops
+    from dmme_b200.models import _engine
+    records = []
+    orig = ops.groupnorm
+
+    def timed(src0, src1, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(src0, src1, *a, **k)
+        e1.record()
+        elems = src0.numel() + (src1.numel() if src1 is not None else 0)
+        records.append((4.0 * elems, e0, e1))
+        return out
+
+    _engine.ops.groupnorm = timed
+    try:
+        best = None
+        for _ in range(reps):
+            records.clear()
+            model.forward_raw(x, t)
+            torch.cuda.synchronize()
+            tot = (len(records), sum(b for b, _, _ in records), sum(a.elapsed_time(b) for _, a, b in records))
+            if best is None or tot[2] < best[2]:
+                best = tot
+    finally:
+        _engine.ops.groupnorm = orig
+    return best
+
+
 def traffic_for(sig):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json,
     written from profiles/*_ncu_full.txt); None when that launch signature was not captured."""
@@ -298,6 +330,8 @@ def run_gpu(args):
         achieved = dom_flop / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         all_tc = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
+        gn_n, gn_bytes, gn_ms = gn_profile(model, x, counter)
+        gn_gbs = gn_bytes / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0
         step_flop = FLOP_PER_IMAGE * B
         cpu = None
         if not args.no_cpu:
@@ -329,6 +363,11 @@ def run_gpu(args):
                          "all_tensor_core_convs": {"launches_per_step": n_tc, "flop_per_step": tc_flop, "ms_per_step": tc_ms,
                                                    "achieved": all_tc, "frac": all_tc / peak},
                          "step_tensor_frac": step_flop / (ms_dev * 1e-3) / 1e12 / peak},
+            "roofline_hbm": {"bound": "hbm", "kernel": "GroupNorm(+SiLU) apply, all launches of one step (statistics come "
+                                                       "from the producing conv's epilogue)",
+                             "achieved": gn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gn_gbs / pk["hbm_gbs"],
+                             "launches_per_step": gn_n, "bytes_per_step": gn_bytes, "ms_per_step": gn_ms,
+                             "peak_source": pk["source"] + " STREAM-style copy"},
             "cpu_baseline": cpu, "clocks": clk, "finite": finite,
         }
         print(json.dumps(line))

@@ -760,6 +760,24 @@ __global__ void attn_gather_dout_kernel(const T* __restrict__ dout, float* __res
   }
 }
 
+// inverse of attn_gather_dout_kernel: out[b'][l][h' dh + c] = src[p][l][c]
+template <typename T>
+__global__ void attn_scatter_out_kernel(const float* __restrict__ src, T* __restrict__ out, int n, int heads, int L, int dh,
+                                        int swap) {
+  const long long total = static_cast<long long>(n) * heads * L * dh;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % dh);
+    long long r = i / dh;
+    const int l = static_cast<int>(r % L);
+    const int pidx = static_cast<int>(r / L);
+    int bb, hh;
+    if (swap) { hh = pidx / n; bb = pidx - hh * n; }
+    else { bb = pidx / heads; hh = pidx - bb * heads; }
+    st_act<T>(out + (static_cast<long long>(bb) * L + l) * (heads * dh) + hh * dh + c, src[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // L_simple: loss = mean((noise - eps)^2), d_eps = 2 (eps - noise) / numel  (equations/ddpm/losses.py:5-13)
 // noise is recovered as (x_t - mean) / std like the reference does (diffusion_models/ddpm.py:79).
@@ -1092,32 +1110,70 @@ extern "C" long long dmme_attention_bwd_workspace(int n, int heads, int L, int d
   return (2LL * n * heads * L * L + static_cast<long long>(n) * heads * L * dh) * sizeof(float);
 }
 
+// Training-mode forward: the same strided products as the backward pass, with the softmax matrix P kept for it
+// (fp32 [n*heads][L][L]).  o_tmp: fp32 [n*heads][L][dh] scratch.
+extern "C" int dmme_attention_fwd_train(const void* q, const void* k, const void* v, long long batch_stride, int row_stride,
+                                        int head_stride, int n, int heads, int L, int dh, float scale, int head_batch_swap,
+                                        void* out, int act_dtype, float* p_out, float* o_tmp, void* stream) {
+  DMME_REQUIRE(q && k && v && out && p_out && o_tmp, DMME_E_BADARG, "attention_fwd_train: null pointer");
+  DMME_REQUIRE(n > 0 && heads > 0 && L > 0 && dh > 0, DMME_E_BADARG, "attention_fwd_train: bad sizes");
+  DMME_REQUIRE(static_cast<long long>(n) * heads <= 65535, DMME_E_SHAPE, "attention_fwd_train: more than 65535 (image, head) pairs");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long bh = static_cast<long long>(n) * heads;
+  const long long LL = static_cast<long long>(L) * L, Ld = static_cast<long long>(L) * dh;
+  int rc;
+  GemmParams g;
+  g.heads = heads; g.accumulate = 0;
+  g.a = {q, act_dtype, batch_stride, head_stride, row_stride, 1};
+  g.b = {k, act_dtype, batch_stride, head_stride, 1, row_stride};
+  g.c = p_out; g.c_dtype = DMME_F32; g.c_bo = heads * LL; g.c_h = LL; g.c_r = L; g.c_c = 1;
+  g.M = L; g.N = L; g.K = dh; g.alpha = scale;
+  if ((rc = launch_gemm(g, static_cast<int>(bh), st))) return rc;
+  softmax_rows_kernel<<<static_cast<unsigned>(ceil_div_ll(bh * L, 8)), 256, 0, st>>>(p_out, bh * L, L);
+  if ((rc = check_launch("softmax_rows_kernel"))) return rc;
+  g.a = {p_out, DMME_F32, heads * LL, LL, L, 1};
+  g.b = {v, act_dtype, batch_stride, head_stride, row_stride, 1};
+  g.c = o_tmp; g.c_bo = heads * Ld; g.c_h = Ld; g.c_r = dh; g.c_c = 1;
+  g.M = L; g.N = dh; g.K = L; g.alpha = 1.0f;
+  if ((rc = launch_gemm(g, static_cast<int>(bh), st))) return rc;
+  const long long total = bh * Ld;
+  if (act_dtype == DMME_BF16)
+    attn_scatter_out_kernel<__nv_bfloat16><<<grid_1d(total, 256), 256, 0, st>>>(o_tmp, static_cast<__nv_bfloat16*>(out), n, heads, L, dh, head_batch_swap);
+  else
+    attn_scatter_out_kernel<float><<<grid_1d(total, 256), 256, 0, st>>>(o_tmp, static_cast<float*>(out), n, heads, L, dh, head_batch_swap);
+  return check_launch("attn_scatter_out_kernel");
+}
+
 extern "C" int dmme_attention_bwd(const void* q, const void* k, const void* v, long long batch_stride, int row_stride,
                                   int head_stride, int n, int heads, int L, int dh, float scale, int head_batch_swap,
-                                  const void* dout, void* dq, void* dk, void* dv, int act_dtype, void* workspace,
-                                  long long workspace_bytes, void* stream) {
+                                  const void* dout, void* dq, void* dk, void* dv, int act_dtype, const float* p_saved,
+                                  void* workspace, long long workspace_bytes, void* stream) {
   DMME_REQUIRE(q && k && v && dout && dq && dk && dv && workspace, DMME_E_BADARG, "attention_bwd: null pointer");
   DMME_REQUIRE(n > 0 && heads > 0 && L > 0 && dh > 0, DMME_E_BADARG, "attention_bwd: bad sizes");
   DMME_REQUIRE(workspace_bytes >= dmme_attention_bwd_workspace(n, heads, L, dh), DMME_E_BADARG, "attention_bwd: workspace too small");
   DMME_REQUIRE(static_cast<long long>(n) * heads <= 65535, DMME_E_SHAPE, "attention_bwd: more than 65535 (image, head) pairs");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long bh = static_cast<long long>(n) * heads;
-  float* P = static_cast<float*>(workspace);          // [bh][L][L]
-  float* dP = P + bh * L * L;                         // [bh][L][L]
+  float* Pw = static_cast<float*>(workspace);         // [bh][L][L] (unused when the forward's P is passed in)
+  float* dP = Pw + bh * L * L;                        // [bh][L][L]
   float* dO = dP + bh * L * L;                        // [bh][L][dh]
   const long long LL = static_cast<long long>(L) * L, Ld = static_cast<long long>(L) * dh;
   int rc;
   GemmParams g;
   g.heads = heads; g.accumulate = 0;
-  // S = scale * Q K^T
-  g.a = {q, act_dtype, batch_stride, head_stride, row_stride, 1};
-  g.b = {k, act_dtype, batch_stride, head_stride, 1, row_stride};
-  g.c = P; g.c_dtype = DMME_F32; g.c_bo = heads * LL; g.c_h = LL; g.c_r = L; g.c_c = 1;
-  g.M = L; g.N = L; g.K = dh; g.alpha = scale;
-  if ((rc = launch_gemm(g, static_cast<int>(bh), st))) return rc;
   const int rows_per_block = 8;
-  softmax_rows_kernel<<<static_cast<unsigned>(ceil_div_ll(bh * L, rows_per_block)), rows_per_block * 32, 0, st>>>(P, bh * L, L);
-  if ((rc = check_launch("softmax_rows_kernel"))) return rc;
+  const float* P = p_saved;
+  if (P == nullptr) {
+    // S = scale * Q K^T, P = softmax(S) (recomputed)
+    g.a = {q, act_dtype, batch_stride, head_stride, row_stride, 1};
+    g.b = {k, act_dtype, batch_stride, head_stride, 1, row_stride};
+    g.c = Pw; g.c_dtype = DMME_F32; g.c_bo = heads * LL; g.c_h = LL; g.c_r = L; g.c_c = 1;
+    g.M = L; g.N = L; g.K = dh; g.alpha = scale;
+    if ((rc = launch_gemm(g, static_cast<int>(bh), st))) return rc;
+    softmax_rows_kernel<<<static_cast<unsigned>(ceil_div_ll(bh * L, rows_per_block)), rows_per_block * 32, 0, st>>>(Pw, bh * L, L);
+    if ((rc = check_launch("softmax_rows_kernel"))) return rc;
+    P = Pw;
+  }
   // dO in (batch, head) order
   {
     const long long total = bh * Ld;
@@ -1130,7 +1186,8 @@ extern "C" int dmme_attention_bwd(const void* q, const void* k, const void* v, l
   // dP = dO V^T
   g.a = {dO, DMME_F32, heads * Ld, Ld, dh, 1};
   g.b = {v, act_dtype, batch_stride, head_stride, 1, row_stride};
-  g.c = dP; g.alpha = 1.0f; g.M = L; g.N = L; g.K = dh;
+  g.c = dP; g.c_dtype = DMME_F32; g.c_bo = heads * LL; g.c_h = LL; g.c_r = L; g.c_c = 1;
+  g.alpha = 1.0f; g.M = L; g.N = L; g.K = dh;
   if ((rc = launch_gemm(g, static_cast<int>(bh), st))) return rc;
   attn_ds_kernel<<<static_cast<unsigned>(ceil_div_ll(bh * L, rows_per_block)), rows_per_block * 32, 0, st>>>(P, dP, bh * L, L, scale);
   if ((rc = check_launch("attn_ds_kernel"))) return rc;

@@ -29,7 +29,7 @@ EXPORTS = (
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
     "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
-    "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
+    "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
     "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_dilate2x_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
 
@@ -96,7 +96,8 @@ def load() -> C.CDLL:
                                        vp, vp, vp, vp, vp, vp, vp, vp, i, vp, i, vp]
     lib.dmme_attention_bwd_workspace.argtypes = [i, i, i, i]
     lib.dmme_attention_bwd_workspace.restype = ll
-    lib.dmme_attention_bwd.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, f, i, vp, vp, vp, vp, i, vp, ll, vp]
+    lib.dmme_attention_bwd.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, f, i, vp, vp, vp, vp, i, vp, vp, ll, vp]
+    lib.dmme_attention_fwd_train.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, f, i, vp, i, vp, vp, vp]
     lib.dmme_temb_bwd_workspace.argtypes = [i, i, i]
     lib.dmme_temb_bwd_workspace.restype = ll
     lib.dmme_temb_bwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, ll, vp]

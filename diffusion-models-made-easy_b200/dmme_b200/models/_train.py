@@ -249,7 +249,10 @@ class TrainEngine(Engine):
             nh, dh, swap = heads, c // heads, True
             hs = 3 * dh
             q, k, v = flat, flat[dh:], flat[2 * dh:]
-        ops.attention(q, k, v, n, nh, seq, dh, att.scale, seq * 3 * c, 3 * c, hs, False, 0, swap, ao, kernel=L.CONV_GENERIC)
+        # strided products with the softmax matrix kept for the backward pass
+        p_saved = self._buf(name + ".attn_p", (n * nh, seq, seq), torch.float32, dev)
+        o_tmp = self.ws.get("train.attn_otmp", (n * nh * seq * dh,), torch.float32, dev)
+        ops.attention_fwd_train(q, k, v, n, nh, seq, dh, att.scale, seq * 3 * c, 3 * c, hs, swap, ao, p_saved, o_tmp)
 
         def backward() -> None:
             g = self._grad_of(ao)
@@ -263,7 +266,7 @@ class TrainEngine(Engine):
                 dq, dk, dv = dflat, dflat[dh:], dflat[2 * dh:]
             wsz = ops.attention_bwd_workspace(n, nh, seq, dh)
             wsb = self.ws.get("train.attn_ws", (wsz // 4,), torch.float32, dev)
-            ops.attention_bwd(q, k, v, n, nh, seq, dh, att.scale, seq * 3 * c, 3 * c, hs, swap, g, dq, dk, dv, wsb)
+            ops.attention_bwd(q, k, v, n, nh, seq, dh, att.scale, seq * 3 * c, 3 * c, hs, swap, g, dq, dk, dv, wsb, p_saved)
             self._contribute(qkv, dqkv)
 
         self.tape.append(backward)

@@ -299,11 +299,21 @@ def attention_bwd_workspace(n: int, heads: int, seq: int, dh: int) -> int:
 
 def attention_bwd(q: Tensor, k: Tensor, v: Tensor, n: int, heads: int, seq: int, dh: int, scale: float, batch_stride: int,
                   row_stride: int, head_stride: int, head_batch_swap: bool, dout: Tensor, dq: Tensor, dk: Tensor,
-                  dv: Tensor, workspace: Tensor) -> None:
+                  dv: Tensor, workspace: Tensor, p_saved: Optional[Tensor] = None) -> None:
     L.check(L.load().dmme_attention_bwd(ptr(q), ptr(k), ptr(v), batch_stride, row_stride, head_stride, n, heads, seq, dh,
                                         scale, int(head_batch_swap), ptr(dout), ptr(dq), ptr(dk), ptr(dv),
-                                        L.act_code(dout.dtype), ptr(workspace),
+                                        L.act_code(dout.dtype), ptr(p_saved), ptr(workspace),
                                         workspace.numel() * workspace.element_size(), L.stream_ptr()), "attention_bwd")
+
+
+def attention_fwd_train(q: Tensor, k: Tensor, v: Tensor, n: int, heads: int, seq: int, dh: int, scale: float,
+                        batch_stride: int, row_stride: int, head_stride: int, head_batch_swap: bool, out: Tensor,
+                        p_out: Tensor, o_tmp: Tensor) -> Tensor:
+    """Attention core for training: keeps the softmax matrix ``p_out`` (fp32 [n*heads, L, L]) for the backward pass."""
+    L.check(L.load().dmme_attention_fwd_train(ptr(q), ptr(k), ptr(v), batch_stride, row_stride, head_stride, n, heads, seq,
+                                              dh, scale, int(head_batch_swap), ptr(out), L.act_code(out.dtype), ptr(p_out),
+                                              ptr(o_tmp), L.stream_ptr()), "attention_fwd_train")
+    return out
 
 
 def temb_bwd_workspace(rows: int, half: int, emb_dim: int) -> int:

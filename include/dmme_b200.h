@@ -235,12 +235,18 @@ int dmme_groupnorm_bwd(const void* grad_out, const void* src0, const void* src1,
                        float* dscale, float* dshift, int dss_ld, float* sums, int act_dtype, void* stream);
 
 /* Backward of dmme_attention_fwd for q/k/v stored as strided views of one tensor (v not transposed):
- * dq/dk/dv use the same strides as q/k/v.  dout has the layout of the forward output [n][L][heads*dh]. */
+ * dq/dk/dv use the same strides as q/k/v.  dout has the layout of the forward output [n][L][heads*dh].
+ * p_saved: the softmax matrix kept by dmme_attention_fwd_train, or NULL to recompute it. */
 long long dmme_attention_bwd_workspace(int n, int heads, int L, int dh);
 int dmme_attention_bwd(const void* q, const void* k, const void* v, long long batch_stride, int row_stride,
                        int head_stride, int n, int heads, int L, int dh, float scale, int head_batch_swap,
-                       const void* dout, void* dq, void* dk, void* dv, int act_dtype, void* workspace,
-                       long long workspace_bytes, void* stream);
+                       const void* dout, void* dq, void* dk, void* dv, int act_dtype, const float* p_saved,
+                       void* workspace, long long workspace_bytes, void* stream);
+/* Training-mode forward of the same attention core that keeps the softmax matrix for the backward pass:
+ * p_out fp32 [n*heads][L][L] (pass it to dmme_attention_bwd as p_saved), o_tmp fp32 [n*heads][L][dh] scratch. */
+int dmme_attention_fwd_train(const void* q, const void* k, const void* v, long long batch_stride, int row_stride,
+                             int head_stride, int n, int heads, int L, int dh, float scale, int head_batch_swap,
+                             void* out, int act_dtype, float* p_out, float* o_tmp, void* stream);
 
 /* Backward of dmme_temb_mlp_fwd + dmme_temb_proj_fwd.  hidden/emb: the forward's scratch / emb_out;
  * d_all [rows][total]: gradient of the batched projection output.  All parameter gradients are written. */

@@ -373,6 +373,17 @@ def test_attention_bwd(n, c, heads, L_, swap):
     ops.attention_bwd(flat, flat[step:], flat[2 * step:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, hs, swap, g.to(DEV),
                       dflat, dflat[step:], dflat[2 * step:], ws)
     assert rel_l2(dqkv.cpu(), qkv.grad) < 1e-4
+    # training-mode forward (keeps the softmax matrix) and the backward that reuses it
+    od = torch.empty(n, L_, c, device=DEV)
+    psave = torch.empty(n * heads, L_, L_, device=DEV)
+    otmp = torch.empty(n * heads * L_ * dh, device=DEV)
+    ops.attention_fwd_train(flat, flat[step:], flat[2 * step:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, hs, swap, od, psave, otmp)
+    assert rel_l2(od.cpu(), out.detach()) < 1e-5
+    dqkv2 = torch.empty_like(qd)
+    d2 = dqkv2.view(-1)
+    ops.attention_bwd(flat, flat[step:], flat[2 * step:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, hs, swap, g.to(DEV),
+                      d2, d2[step:], d2[2 * step:], ws, psave)
+    assert rel_l2(dqkv2.cpu(), qkv.grad) < 1e-4
 
 
 # ---------------------------------------------------------------------------------------------
