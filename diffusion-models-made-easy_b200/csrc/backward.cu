@@ -1074,7 +1074,7 @@ extern "C" int dmme_groupnorm_bwd(const void* grad_out, const void* src0, const 
   DMME_REQUIRE(C % groups == 0, DMME_E_SHAPE, "groupnorm_bwd: C=%d not divisible by groups=%d", C, groups);
   DMME_REQUIRE((scale == nullptr) == (shift == nullptr), DMME_E_BADARG, "groupnorm_bwd: scale and shift come together");
   DMME_REQUIRE((dscale == nullptr) == (dshift == nullptr), DMME_E_BADARG, "groupnorm_bwd: dscale and dshift come together");
-  DMME_REQUIRE(!dscale || (scale && ss_rows == n), DMME_E_BADARG, "groupnorm_bwd: dscale needs per-image scale rows");
+  DMME_REQUIRE(!dscale || scale, DMME_E_BADARG, "groupnorm_bwd: dscale without scale/shift");
   GnBwdParams p;
   p.gout = grad_out; p.src0 = src0; p.src1 = src1; p.c0 = c0; p.c1 = c1; p.n = n; p.hw = hw; p.groups = groups; p.eps = eps;
   p.gamma = gamma; p.beta = beta; p.scale = scale; p.shift = shift; p.ss_rows = ss_rows; p.ss_ld = ss_ld;

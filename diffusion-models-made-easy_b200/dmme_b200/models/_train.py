@@ -44,6 +44,8 @@ class TrainEngine(Engine):
         self._garena: Optional[Tensor] = None
         self._gcur = 0
         self.grad_sync = None          # None: single process; else dict(group=..., bucket_bytes=...)
+        self.want_input_grad = False   # set per call when the image tensor requires grad
+        self.input_grad: Optional[Tensor] = None
         self.last_buckets = []
 
     # -- buffers -------------------------------------------------------------------------------
@@ -154,7 +156,14 @@ class TrainEngine(Engine):
             if addend is not None:
                 self._contribute(addend, g)
             if in_nchw:
-                return  # the image itself needs no gradient
+                if self.want_input_grad:
+                    # d loss / d image (classifier-guidance style callers): NHWC grad -> NCHW fp32, cout' = image channels
+                    cin = conv.weight.shape[1]
+                    xd = ops.make_conv_desc(g, None, cin, ks, 1, False, None, None, False, L.OUT_NCHW_F32, act_dtype, kernel)
+                    xtc = ops.conv_uses_tc(xd)
+                    self.input_grad = self._buf(name + ".gx", (d.n, cin, d.h_in, d.w_in), torch.float32, dev)
+                    ops.conv2d_launch(xd, self._dgrad_weight(conv, 0, cin, xtc), None, self.input_grad)
+                return
             g_nchw = out_layout == L.OUT_NCHW_F32
             # data gradient of the main source
             cin = conv.weight.shape[1]
@@ -215,16 +224,23 @@ class TrainEngine(Engine):
             dgamma, dbeta = self._pgrad(norm.weight), self._pgrad(norm.bias)
             dscale = dshift = None
             per_image = scale is not None and scale.shape[0] == n
+            sc_in, sh_in, tmp_ss = scale, shift, None
             if scale is not None and ss_cols is not None:
                 o, cc = ss_cols  # cond = [shift | scale] (models/iddpm.py:116-119)
                 if per_image:
                     dshift, dscale = self._d_all[:, o:o + cc], self._d_all[:, o + cc:o + 2 * cc]
-            if scale is not None and not per_image:
-                raise NotImplementedError("training with a (1,)-shaped timestep and scale-shift norm")
+                else:
+                    # (1,)-shaped timestep: one conditioning row broadcast over the batch; per-image gradients go to a
+                    # scratch [n][2C] and are summed over the images afterwards
+                    tmp_ss = self._buf(name + ".dss", (n, 2 * cc), torch.float32, dev)
+                    dshift, dscale = tmp_ss[:, :cc], tmp_ss[:, cc:]
             sums = self._buf(name + ".sums", (n, c, 2), torch.float32, dev)
-            ops.groupnorm_bwd(g, src0, src1, norm.num_groups, norm.weight.detach(), norm.bias.detach(), silu, scale, shift,
+            ops.groupnorm_bwd(g, src0, src1, norm.num_groups, norm.weight.detach(), norm.bias.detach(), silu, sc_in, sh_in,
                               mask, norm.eps, gin0, gin1, add0[0] if add0 else None, add1[0] if add1 else None, dgamma,
                               dbeta, dscale, dshift, sums)
+            if tmp_ss is not None:
+                o, cc = ss_cols
+                ops.colsum(tmp_ss, self._d_all[0, o:o + 2 * cc])
             self._contribute(src0, gin0)
             if src1 is not None:
                 self._contribute(src1, gin1)

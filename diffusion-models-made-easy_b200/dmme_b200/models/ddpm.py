@@ -187,7 +187,7 @@ class _UNetBase(nn.Module):
             estimated noise (N, C, H, W) (IDDPM flavour: (N, 2C, H, W)), float32.  With gradients enabled the
             result carries an autograd node whose backward runs the explicit backward kernels (``_train.py``).
         """
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             if not x.is_cuda:
                 raise RuntimeError("dmme_b200.UNet runs on CUDA (sm_100a) only; there is no CPU path")
             return _UNetFunction.apply(self, x, c, *self.parameters())
@@ -202,9 +202,11 @@ class _UNetFunction(torch.autograd.Function):
         eng = unet.train_engine
         eng.force_generic = unet.precision == "fp32"
         masks = getattr(unet, "_injected_masks", None) or unet._dropout_masks(x.shape[0], x.device)
+        eng.want_input_grad = bool(x.requires_grad)
         out = eng.forward(x.detach(), c, _PRECISIONS[unet.precision], masks)
         eng.generation = getattr(eng, "generation", 0) + 1
         ctx.unet, ctx.generation = unet, eng.generation
+        ctx.x_dtype = x.dtype
         return out.clone()
 
     @staticmethod
@@ -219,7 +221,8 @@ class _UNetFunction(torch.autograd.Function):
         for p in unet.parameters():
             g = grads.get(id(p)) if p.requires_grad else None
             out.append(g.clone() if g is not None else None)
-        return (None, None, None) + tuple(out)
+        gx = eng.input_grad.clone().to(ctx.x_dtype) if eng.want_input_grad and eng.input_grad is not None else None
+        return (None, gx, None) + tuple(out)
 
 
 class UNet(_UNetBase):

@@ -226,7 +226,8 @@ int dmme_conv2d_wgrad(const dmme_conv_desc* fwd, const void* grad_out, float* dw
 
 /* Backward of dmme_groupnorm_fwd.  gin0/gin1: gradients w.r.t. src0/src1 (act dtype; NULL: not needed);
  * add0/add1: optional tensors added into gin0/gin1 (gradient accumulation of skip / residual branches);
- * dgamma/dbeta [C] written; dscale/dshift [n][dss_ld] written when given (IDDPM scale-shift, per-image rows);
+ * dgamma/dbeta [C] written; dscale/dshift [n][dss_ld] written when given (IDDPM scale-shift; always one row per image,
+ * also when the forward broadcast a single scale/shift row -- the caller then sums the rows);
  * sums: fp32 workspace [n][C][2]. */
 int dmme_groupnorm_bwd(const void* grad_out, const void* src0, const void* src1, int c0, int c1, int n, int hw,
                        int groups, float eps, const float* gamma, const float* beta, const float* scale,

@@ -600,3 +600,28 @@ def test_training_step_draws_like_the_reference_and_optimizer_step():
         losses.append(float(loss))
     assert all(math.isfinite(v) for v in losses)
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("flavour", ["ddpm", "iddpm"])
+def test_input_gradient_and_broadcast_timestep_fp32(flavour):
+    """d out / d x (what classifier-guidance style callers differentiate through, guidance/classifier.py:9-23) and a
+    (1,)-shaped timestep in a training-mode forward (one conditioning row broadcast over the batch)."""
+    from dmme_b200.models import ddpm, iddpm
+    torch.manual_seed(0)
+    m = (ddpm.UNet if flavour == "ddpm" else iddpm.UNet)(precision="fp32", dropout=0.0, **TINY)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 3, 32, 32, generator=g)
+    t = torch.tensor([42])
+    w = torch.randn(3, 3 if flavour == "ddpm" else 6, 32, 32, generator=g)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "embeddings" not in k) for k, v in sd.items()}
+    xr = x.clone().requires_grad_()
+    want = (O.unet_forward(params, xr, t, groups=2, flavour=flavour) * w).sum()
+    want.backward()
+    xd = x.to(DEV).requires_grad_()
+    got = (m(xd, t.to(DEV)) * w.to(DEV)).sum()
+    got.backward()
+    assert abs(float(got) - float(want)) < 1e-3 * abs(float(want))
+    assert rel_l2(xd.grad.cpu(), xr.grad) < 1e-3
+    _check_grads(m, {k: p.grad for k, p in params.items() if p.requires_grad}, 1e-3, 2e-2)
