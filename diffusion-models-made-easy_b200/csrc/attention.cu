@@ -24,6 +24,8 @@ constexpr int kAttnTile = 32;
 template <typename T>
 __global__ void __launch_bounds__(256) attn_generic_kernel(const AttnParams p) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   const int dh = p.dh, L = p.L;
   float* qs = sm;                                // [8][dh]
   float* tile = qs + kAttnRows * dh;             // [32][dh + 1]
@@ -157,11 +159,13 @@ extern "C" int dmme_attention_fwd(const void* q, const void* k, const void* v, l
   if (act_dtype == DMME_BF16) {
     e = cudaFuncSetAttribute(attn_generic_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attn_generic_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(p);
+    e = launch_pdl(attn_generic_kernel<__nv_bfloat16>, grid, dim3(256), smem, st, p);
+    if (e != cudaSuccess) return check_launch_err(e, "attn_generic_kernel");
   } else {
     e = cudaFuncSetAttribute(attn_generic_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attn_generic_kernel<float><<<grid, 256, smem, st>>>(p);
+    e = launch_pdl(attn_generic_kernel<float>, grid, dim3(256), smem, st, p);
+    if (e != cudaSuccess) return check_launch_err(e, "attn_generic_kernel");
   }
   return check_launch("attn_generic_kernel");
 }

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_s = tmem_slot;
   const uint32_t tmem_o = tmem_slot + 256;
+  pdl_trigger();  // after the TMEM allocation (see ptx_sm100.cuh)
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -229,8 +231,8 @@ int attn_tc_forward(const void* q, const void* k, const void* vt, int n, int d, 
     configured = true;
   }
   dim3 grid(kSeq / 128, n);
-  attn_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(p);
-  return check_launch("attn_tc_kernel");
+  cudaError_t e = launch_pdl(attn_tc_kernel, grid, dim3(kAttnThreads), kAttnSmem, stream, p);
+  return check_launch_err(e, "attn_tc_kernel");
 }
 
 }  // namespace dmme

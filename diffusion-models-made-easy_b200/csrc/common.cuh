@@ -31,8 +31,49 @@ inline int check_launch(const char* what) {
   return 0;
 }
 
+inline int check_launch_err(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  count_launch();
+  return 0;
+}
+
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while the previous kernel of the
+// stream drains; it MUST call pdl_wait() (ptx_sm100.cuh) before touching memory.  Captured by CUDA graphs as a
+// programmatic dependency edge.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its predecessor drains.
+//   pdl_wait()    -- returns once every prerequisite grid has completed and its memory is visible; a no-op when the
+//                    kernel was launched without the attribute.  Nothing the predecessor wrote (or still reads, for
+//                    buffers this kernel overwrites) may be touched before it.
+//   pdl_trigger() -- lets the dependent grid's CTAs be scheduled once every CTA of this grid has called it (or exited).
+//                    Kernels that own TMEM call it only AFTER tcgen05.alloc: a waiting dependent CTA that had taken the
+//                    columns first would block this CTA's allocation forever.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- device side: storage-type access ----------------------------------------------------------
 template <typename T>

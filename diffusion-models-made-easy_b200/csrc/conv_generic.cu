@@ -272,6 +272,8 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
 // nearest x2, NHWC; one thread per 16-byte (or single element) output vector
 template <typename T, int VEC>
 __global__ void upsample2x_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int h, int w, int c) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = c / VEC;
   const long long total = static_cast<long long>(n) * (2 * h) * (2 * w) * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -344,22 +346,23 @@ extern "C" int dmme_nhwc_to_nchw(const void* src, float* dst, int n, int c, int 
 extern "C" int dmme_upsample2x_nhwc(const void* src, void* dst, int n, int h, int w, int c, int act_dtype, void* stream) {
   DMME_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, DMME_E_BADARG, "upsample2x: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t le = cudaSuccess;
   if (act_dtype == DMME_BF16) {
     if (c % 8 == 0) {
       const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
-      upsample2x_kernel<__nv_bfloat16, 8><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n, h, w, c);
+      le = launch_pdl(upsample2x_kernel<__nv_bfloat16, 8>, dim3(grid_for(total, 256)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n, h, w, c);
     } else {
       const long long total = static_cast<long long>(n) * 4 * h * w * c;
-      upsample2x_kernel<__nv_bfloat16, 1><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n, h, w, c);
+      le = launch_pdl(upsample2x_kernel<__nv_bfloat16, 1>, dim3(grid_for(total, 256)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), n, h, w, c);
     }
   } else {
     if (c % 4 == 0) {
       const long long total = static_cast<long long>(n) * 4 * h * w * (c / 4);
-      upsample2x_kernel<float, 4><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), n, h, w, c);
+      le = launch_pdl(upsample2x_kernel<float, 4>, dim3(grid_for(total, 256)), dim3(256), 0, st, static_cast<const float*>(src), static_cast<float*>(dst), n, h, w, c);
     } else {
       const long long total = static_cast<long long>(n) * 4 * h * w * c;
-      upsample2x_kernel<float, 1><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), n, h, w, c);
+      le = launch_pdl(upsample2x_kernel<float, 1>, dim3(grid_for(total, 256)), dim3(256), 0, st, static_cast<const float*>(src), static_cast<float*>(dst), n, h, w, c);
     }
   }
-  return check_launch("upsample2x_kernel");
+  return check_launch_err(le, "upsample2x_kernel");
 }

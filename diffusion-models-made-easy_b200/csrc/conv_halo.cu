@@ -96,11 +96,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();  // after the TMEM allocation (see ptx_sm100.cuh)
 
   if (warp == kWarpProdA) {
     // =========================== halo-tile producer ===========================
     if (lane == 0) {
       int a_it = 0;
+      pdl_wait();
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int mt = u / p.n_tiles;
         const int pr0 = mt * p.rt - 1;  // first halo row (padded-row index, may be -1)
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // =========================== weight-tile producer ===========================
     if (lane == 0) {
       int b_it = 0;
+      pdl_wait();  // the packed weights may come from a pack kernel launched just before this one
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int col0 = (u % p.n_tiles) * kHaloBN;
         for (int ck = 0; ck < nck; ++ck) {
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
     const bool temb_per_image = p.temb && p.temb_rows != 1;
     int u_it = 0;
+    pdl_wait();
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
       const int mt = u / p.n_tiles, nt = u - mt * p.n_tiles;
       const int ch = nt * kHaloBN + q * 32 + lane;
@@ -333,8 +337,8 @@ static int launch_halo(const ConvHaloParams& p, cudaStream_t stream) {
   }
   const int units = p.m_tiles * p.n_tiles;
   const int grid = units < g_sm_count ? units : g_sm_count;
-  conv_halo_kernel<W, COUT><<<grid, kHaloThreads, kHaloSmem, stream>>>(p);
-  return check_launch("conv_halo_kernel");
+  cudaError_t e = launch_pdl(conv_halo_kernel<W, COUT>, dim3(grid), dim3(kHaloThreads), kHaloSmem, stream, p);
+  return check_launch_err(e, "conv_halo_kernel");
 }
 
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {

@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(256) conv_in_rows_kernel(const ConvSmallParams
   extern __shared__ __align__(16) float sm_in[];  // [CIN][rb + 2][w + 8]: image column x at padded column x + 4
   __shared__ float red[8][64][2];   // per-warp statistics partials (warp, lane pair)
   constexpr int K = 9 * CIN;
+  pdl_trigger();
+  pdl_wait();
   const int pairs = p.cout >> 1;
   const int pair = threadIdx.x % pairs, slot = threadIdx.x / pairs, slots = blockDim.x / pairs;
   const int ws = p.w + 8;
@@ -257,6 +259,8 @@ __global__ void __launch_bounds__(256) conv_in_rows_kernel(const ConvSmallParams
 // 9 x 3 x 4 weights in registers; the 3 x 10 input window is read once (8-byte loads, 256 contiguous bytes per warp);
 // the cross-lane sum is a halving butterfly (27 shuffles per 8 pixels).
 __global__ void __launch_bounds__(256) conv_out128_kernel(const ConvSmallParams p, int co_off) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -374,8 +378,8 @@ int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     const size_t smem = sizeof(float) * 3 * (rb + 2) * (d.w_in + 8);
     if (smem <= 48 * 1024 && (d.cout / 4) * (256 / (d.cout / 2)) <= 8 * 64) {
       p.stats = d.stats;  // a CTA never straddles two images
-      conv_in_rows_kernel<3><<<d.n * (d.h_in / rb), 256, smem, stream>>>(p, rb);
-      return check_launch("conv_in_rows_kernel");
+      return check_launch_err(launch_pdl(conv_in_rows_kernel<3>, dim3(d.n * (d.h_in / rb)), dim3(256), smem, stream, p, rb),
+                              "conv_in_rows_kernel");
     }
   }
   if (conv_in_supported(d)) {
@@ -400,8 +404,8 @@ int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     if (blocks > 148 * 2) blocks = 148 * 2;
     if (blocks < 1) blocks = 1;
     for (int co_off = 0; co_off < d.cout; co_off += 3) {
-      conv_out128_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, co_off);
-      int rc = check_launch("conv_out128_kernel");
+      int rc = check_launch_err(launch_pdl(conv_out128_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, p, co_off),
+                                "conv_out128_kernel");
       if (rc) return rc;
     }
     return 0;

@@ -51,19 +51,25 @@ constexpr int kConvThreads = (2 + kConvEpiWarps) * 32;
 template <int BN>
 __host__ __device__ constexpr int stage_bytes() { return kABytes + BN * kBlockK * 2; }
 
-template <int BN, int STAGES>
+// WS ("weight stationary", 1x1 convs): the whole [BN][K] weight slab of this CTA's n tile is loaded ONCE and stays in
+// shared memory; the grid is a multiple of n_tiles so the round-robin walk keeps every CTA on one n tile, and the ring
+// carries activation tiles only.  Without it a K = 256 conv re-reads 128 KB of weights per 64 KB activation tile and
+// is bound by the L2 -> SM feed (measured 73 us for the 256 -> 768 qkv projection, 353 TFLOP/s).
+template <int BN, int STAGES, bool WS>
 __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t slab_full;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;      // one accumulator stage
   constexpr uint32_t kTmemCols = 2 * kAccCols;           // double-buffered: epilogue of tile i overlaps the MMAs of tile i+1
-  constexpr int kStage = stage_bytes<BN>();
+  constexpr int kStage = WS ? kABytes : stage_bytes<BN>();
+  constexpr int kBTile = BN * kBlockK * 2;  // one k-block of weights
 
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 1024 B)
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -90,6 +96,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       mbar_init(&empty_bar[s], 1);
     }
     for (int st = 0; st < 2; ++st) { mbar_init(&acc_full[st], 1); mbar_init(&acc_empty[st], kConvEpiWarps * 32); }
+    mbar_init(&slab_full, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -105,11 +112,19 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  uint8_t* slab = ring + STAGES * kStage;  // WS only
+  pdl_trigger();  // after the TMEM allocation: a dependent kernel's CTA may now take this SM's free resources
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int it = 0;
+      pdl_wait();  // (the packed weights may come from a pack kernel launched just before this one, too)
+      if (WS) {
+        mbar_expect_tx(&slab_full, static_cast<uint32_t>(nkb) * kBTile);
+        const int wcol0 = (blockIdx.x % p.n_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(slab + kb * kBTile, &p.b, &slab_full, kb * kBlockK, wcol0);
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       DMME_TILE_COORDS(t)
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -118,7 +133,6 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], kStage);
         uint8_t* sa = ring + s * kStage;
-        uint8_t* sb = sa + kABytes;
         int which, cc, cx = x0, cy = y0, cp = 0;
         if (kb < conv_kb) {
           const int tap = kb / cchunks;
@@ -147,7 +161,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
           cc = ch * kBlockK;
         }
         tma_load_5d(sa, &p.a[which], &full_bar[s], cc, cx, cp, cy, n0);
-        tma_load_2d(sb, &p.b, &full_bar[s], kb * kBlockK, col0);
+        if (!WS) tma_load_2d(sa + kABytes, &p.b, &full_bar[s], kb * kBlockK, col0);
       }
       }
     }
@@ -156,6 +170,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
       int it = 0, t_it = 0;
+      if (WS) mbar_wait(&slab_full, 0);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
       const int stage = t_it & 1;
       mbar_wait(&acc_empty[stage], ((t_it >> 1) & 1) ^ 1);
@@ -168,7 +183,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + s * kStage);
         const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + kABytes);
+        const uint64_t bdesc = umma_desc_sw128(WS ? smem_u32(slab + kb * kBTile) : sa + kABytes);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: start-address field += 2
@@ -184,6 +199,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // which of the quarter's two warps: even / odd 32-column chunks
     int t_it = 0;
+    pdl_wait();
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
     DMME_TILE_COORDS(t)
     const int stage = t_it & 1;
@@ -195,6 +211,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const bool valid = (n < p.n) && (y < p.ho) && (x < p.wo);
     const long long pix = (static_cast<long long>(n) * p.ho + y) * p.wo + x;
     const float* trow = p.temb ? p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : n) * p.temb_ld : nullptr;
+
+    // the addend does not depend on the accumulator: its first chunk is requested before the wait, every further
+    // chunk while the previous one is converted and stored (the load latency used to serialise with each chunk)
+    const uint4* arow = (p.addend && valid) ? reinterpret_cast<const uint4*>(p.addend + pix * p.cout + col0) : nullptr;
+    uint4 apre[4];
+    if (arow) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) apre[j] = __ldg(arow + half * 4 + j);
+    }
 
     mbar_wait(&acc_full[stage], (t_it >> 1) & 1);
     tc_fence_after();
@@ -215,6 +240,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     for (int c = half * 32; c < BN; c += 64) {
       uint32_t v[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(stage * kAccCols + c), v);
+      uint4 acur[4];
+      if (arow) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acur[j] = apre[j];
+        if (c + 64 < BN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) apre[j] = __ldg(arow + (c + 64) / 8 + j);
+        }
+      }
       tmem_ld_wait();
       float f[32];
 #pragma unroll
@@ -235,11 +269,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
             f[j] += t4.x; f[j + 1] += t4.y; f[j + 2] += t4.z; f[j + 3] += t4.w;
           }
         }
-        if (p.addend) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.cout + col);
+        if (arow) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 a4 = __ldg(ap + j);
+            const uint4 a4 = acur[j];
             float lo, hi;
             unpack_bf16x2(a4.x, lo, hi); f[8 * j + 0] += lo; f[8 * j + 1] += hi;
             unpack_bf16x2(a4.y, lo, hi); f[8 * j + 2] += lo; f[8 * j + 3] += hi;
@@ -316,6 +349,368 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   }
 }
 
+// ================================================================================================================
+// Transposed variant:  D^T[M = 128 output channels][N = NP output pixels] = W[128][K] x X^T
+//
+// Same TMA-gathered operand tiles and tap schedule as conv_tc_kernel, with the operand roles swapped: the weight tile
+// is the MMA's M side, the pixel tile (NP = 128 or 256 pixels: a contiguous run of the flattened [n][y][x] space) the
+// N side, so the accumulator has TMEM lane = output channel, column = pixel.  The epilogue is then the halo kernel's:
+// thread = channel, a warp stores 32 channels x 2 B = 64 contiguous bytes per pixel (conv_tc_kernel's thread = pixel
+// layout writes sixteen bytes into each of 32 different lines per instruction: 2.1 M partial-sector L2 writes per
+// 33 MB output, measured 31 us for a 256 -> 256 1x1 conv whose MMAs take 6 us), GroupNorm statistics accumulate in
+// the thread over the pixels of an image (no shuffle butterflies), the addend is read with the same coalescing.
+// WS: 1x1 convs keep their [128][K] weight slab resident (see conv_tc_kernel).
+// ================================================================================================================
+constexpr int kTctMaxStages = 8;
+
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(lo)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
+}
+
+struct ConvTctExtra {
+  int np;           // pixels per tile (MMA N): 128 or 256
+  int stages;       // ring depth
+  int stage_bytes;  // np * 128 (+ 16 KB weight tile unless WS)
+  long long total_pix;
+  int log2_l;       // log2(ho * wo)
+  long long* trace; // debugging: per-role clock64 timestamps of CTA 0 (see dmme_debug_set_conv_trace), or null
+};
+
+// trace slots of CTA 0: [role][event index]; role 0 = producer (issue time per k-block), 1 = MMA (operands landed per
+// k-block), 2 = epilogue warp 2 (accumulator ready / tile stored per tile); 512 events per role
+__device__ __forceinline__ void trace_ev(long long* trace, int role, int idx) {
+  if (trace && blockIdx.x == 0 && idx < 512) trace[role * 512 + idx] = clock64();
+}
+
+// CMOD: channel stride of the output rows when known at compile time (128 / 256: immediate store offsets), 0 = runtime
+template <bool WS, int CMOD>
+__global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
+                                                                const ConvTctExtra x) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kTctMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kTctMaxStages];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t slab_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kAccCols = 256;
+  constexpr int kWTile = 128 * kBlockK * 2;  // [128 cout][64] bf16
+  const int NP = x.np, STAGES = x.stages, kStage = x.stage_bytes;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* ring = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* slab = ring + STAGES * kStage;  // WS only
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+#define DMME_TCT_COORDS(t)                                    \
+  const int mt = (t) / p.n_tiles;                             \
+  const int col0 = ((t) - mt * p.n_tiles) * 128;              \
+  const int tx = mt % p.tiles_x;                              \
+  const int ty = (mt / p.tiles_x) % p.tiles_y;                \
+  const int ng = mt / (p.tiles_x * p.tiles_y);                \
+  const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = ng * p.bni;
+
+  const int cchunks = p.chunks0 + p.chunks1;
+  const int conv_kb = p.taps * cchunks;
+  const int nkb = conv_kb + p.rchunks0 + p.rchunks1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int st = 0; st < 2; ++st) { mbar_init(&acc_full[st], 1); mbar_init(&acc_empty[st], kConvEpiWarps * 32); }
+    mbar_init(&slab_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a[0]);
+    if (p.chunks1) tma_prefetch_desc(&p.a[1]);
+    if (p.rchunks0) tma_prefetch_desc(&p.a[2]);
+    if (p.rchunks1) tma_prefetch_desc(&p.a[3]);
+    tma_prefetch_desc(&p.b);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 2 * kAccCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();  // after the TMEM allocation (see common.cuh)
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int it = 0;
+      pdl_wait();
+      trace_ev(x.trace, 0, 0);
+      if (WS) {
+        mbar_expect_tx(&slab_full, static_cast<uint32_t>(nkb) * kWTile);
+        const int wcol0 = (blockIdx.x % p.n_tiles) * 128;
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(slab + kb * kWTile, &p.b, &slab_full, kb * kBlockK, wcol0);
+      }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        DMME_TCT_COORDS(t)
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], kStage);
+          uint8_t* sx = ring + s * kStage;
+          int which, cc, cx = x0, cy = y0, cp = 0;
+          if (kb < conv_kb) {
+            const int tap = kb / cchunks;
+            int ch = kb - tap * cchunks;
+            which = ch < p.chunks0 ? 0 : 1;
+            if (which) ch -= p.chunks0;
+            cc = ch * kBlockK;
+            if (p.taps == 9) {
+              const int r = tap / 3, q = tap - r * 3;
+              if (p.stride == 1) {
+                cx += q - 1;
+                cy += r - 1;
+              } else {
+                const int csrc = which ? p.c1 : p.c0;
+                cc += (q != 1) ? csrc : 0;
+                cx += (q == 0) ? -1 : 0;
+                cp = (r != 1) ? 1 : 0;
+                cy += (r == 0) ? -1 : 0;
+              }
+            }
+          } else {
+            int ch = kb - conv_kb;
+            which = ch < p.rchunks0 ? 2 : 3;
+            if (which == 3) ch -= p.rchunks0;
+            cc = ch * kBlockK;
+          }
+          trace_ev(x.trace, 0, it + 1);
+          tma_load_5d(sx, &p.a[which], &full_bar[s], cc, cx, cp, cy, n0);
+          if (!WS) tma_load_2d(sx + NP * 128, &p.b, &full_bar[s], kb * kBlockK, col0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, NP);  // M = 128 output channels, N = pixels
+      int it = 0, t_it = 0;
+      if (WS) mbar_wait(&slab_full, 0);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
+        const int stage = t_it & 1;
+        mbar_wait(&acc_empty[stage], ((t_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dtm = tmem_base + stage * kAccCols;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          trace_ev(x.trace, 1, it);
+          const uint32_t sx = smem_u32(ring + s * kStage);
+          const uint64_t xdesc = umma_desc_sw128(sx);
+          const uint64_t wdesc = umma_desc_sw128(WS ? smem_u32(slab + kb * kWTile) : sx + NP * 128);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[stage]);
+      }
+    }
+  } else {
+    // =========================== epilogue: thread = output channel ===========================
+    // Eight warps share one accumulator, so the epilogue is bound by instruction issue: the common case (a chunk of
+    // 32 valid pixels of one image, channel stride known at compile time) costs 6 instructions per output -- add,
+    // convert, store with an immediate offset, widen, two statistics updates -- against 24 for the fully general form
+    // (measured 34 us -> see profiles/ for a 256 -> 256 1x1 conv at batch 256).
+    const int q = warp & 3;            // TMEM lane quarter = 32-channel block of the tile
+    const int half = (warp - 2) >> 2;  // which half of the tile's pixels
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
+    const int L = p.ho * p.wo;
+    const int total_pix = static_cast<int>(x.total_pix);
+    const bool temb_per_image = p.temb && p.temb_rows != 1;
+    const int cmod = CMOD ? CMOD : (p.out_mode == DMME_OUT_QKV ? p.cout / 3 : p.cout);
+    const int nchunks = NP >> 6;  // 32-pixel chunks per warp and tile
+    int t_it = 0;
+    pdl_wait();
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
+      const int mt = t / p.n_tiles;
+      const int cb = (t - mt * p.n_tiles) * 128 + q * 32;  // first channel of this warp's block (warp-uniform)
+      const int ch = cb + lane;                            // this thread's output channel
+      const int stage = t_it & 1;
+      float bias_c = p.bias ? __ldg(p.bias + ch) : 0.f;
+      if (p.temb && !temb_per_image) bias_c += __ldg(p.temb + ch);  // broadcast row (sampling): no per-image reload
+      // q / k / v selector, 0 unless QKV.  Derived from the warp's channel block, NOT from the lane's channel: a
+      // lane-dependent value here makes every branch on it divergent as far as ptxas can tell, and the stores of the
+      // fast path then re-materialise their uniform address descriptor with two R2UR each
+      const int which = cb / cmod;
+      const int chm = cb - which * cmod + lane;  // channel inside q / k / v
+      __nv_bfloat16* obase = which == 0 ? p.out : (which == 1 ? p.out2 : p.out3);
+      const int pix_begin = mt * NP + half * (NP >> 1);
+      float s1 = 0.f, s2 = 0.f, bt = bias_c;
+      int cur_n = -1;
+
+      auto flush_stats = [&]() {  // warp-uniform call: per-image sums of this lane's channel -> micro-group atomics
+        if (p.stats && cur_n >= 0) {
+          float a1 = s1, a2 = s2;
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+          if ((lane & 3) == 0) {
+            unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats) +
+                                     (static_cast<long long>(cur_n) * (p.cout >> 2) + (ch >> 2)) * 2;
+            atomicAdd(st, static_cast<unsigned long long>(__float2ll_rn(a1 * kFix)));
+            atomicAdd(st + 1, static_cast<unsigned long long>(__float2ll_rn(a2 * kFix)));
+          }
+        }
+        s1 = 0.f; s2 = 0.f;
+      };
+      auto enter_image = [&](int n) {  // warp-uniform
+        flush_stats();
+        cur_n = n;
+        bt = bias_c;
+        if (temb_per_image) bt += __ldg(p.temb + static_cast<long long>(n) * p.temb_ld + ch);
+      };
+      // addend values of one chunk (thread = channel: 64 contiguous bytes per pixel across the warp)
+      auto load_addend = [&](float (&av)[32], int pix0) {
+        const __nv_bfloat16* __restrict__ ap = p.addend + static_cast<long long>(pix0) * p.cout + ch;
+        if (pix0 + 32 <= total_pix) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) av[i] = __bfloat162float(__ldg(ap + i * cmod));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) av[i] = (pix0 + i < total_pix) ? __bfloat162float(__ldg(ap + i * cmod)) : 0.f;
+        }
+      };
+
+      // the addend does not depend on the accumulator: chunk 0 is requested before the accumulator is awaited, chunk
+      // c + 1 before chunk c is converted and stored
+      float av[32];
+      const bool has_add = p.addend != nullptr && pix_begin < total_pix;
+      if (has_add) load_addend(av, pix_begin);
+
+      mbar_wait(&acc_full[stage], (t_it >> 1) & 1);
+      tc_fence_after();
+      if (warp == 2 && lane == 0) trace_ev(x.trace, 2, 2 * t_it);
+
+#pragma unroll 1
+      for (int ci = 0; ci < nchunks; ++ci) {
+        const int pix0 = pix_begin + ci * 32;  // first pixel of this 32-pixel chunk (warp-uniform)
+        if (pix0 >= total_pix) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(stage * kAccCols + half * (NP >> 1) + ci * 32), v);
+        float f[32];
+        if (has_add) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = av[i];
+          if (ci + 1 < nchunks && pix0 + 32 < total_pix) load_addend(av, pix0 + 32);
+        }
+        tmem_ld_wait();
+        const bool full = pix0 + 32 <= total_pix;
+        __nv_bfloat16 r[32];
+        if (full && L >= 32) {
+          // ---- fast path: 32 valid pixels of one image ----
+          const int n = pix0 >> x.log2_l;
+          if (n != cur_n) enter_image(n);
+          if (has_add) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]) + bt;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bt;
+          }
+          if (which != 2) {
+            __nv_bfloat16* op = obase + static_cast<long long>(pix0) * cmod + chm;
+            // four independent partial sums per statistic: one serial chain of 64 dependent FADD / FFMA per chunk
+            // left the two warps of a scheduler nothing to issue
+            float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              // packed conversion (F2FP, FMA pipe) instead of two F2F (quarter-rate conversion pipe)
+              const uint32_t u = pack_bf16x2(f[i], f[i + 1]);
+#ifndef DMME_EXP_NOSTORE
+              op[i * cmod] = __ushort_as_bfloat16(static_cast<unsigned short>(u & 0xffffu));
+              op[(i + 1) * cmod] = __ushort_as_bfloat16(static_cast<unsigned short>(u >> 16));
+#else
+              if (u == 0x12345678u) op[i * cmod] = __ushort_as_bfloat16(static_cast<unsigned short>(u & 0xffffu));
+#endif
+              float lo, hi;
+              unpack_bf16x2(u, lo, hi);
+              p1[(i >> 1) & 3] += lo + hi;
+              p2[(i >> 1) & 3] = fmaf(lo, lo, p2[(i >> 1) & 3]);
+              p2[((i >> 1) + 2) & 3] = fmaf(hi, hi, p2[((i >> 1) + 2) & 3]);
+            }
+            s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+            s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+            continue;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t u = pack_bf16x2(f[i], f[i + 1]);
+            r[i] = __ushort_as_bfloat16(static_cast<unsigned short>(u & 0xffffu));
+            r[i + 1] = __ushort_as_bfloat16(static_cast<unsigned short>(u >> 16));
+            float lo, hi;
+            unpack_bf16x2(u, lo, hi);
+            s1 += lo + hi;
+            s2 = fmaf(lo, lo, s2);
+            s2 = fmaf(hi, hi, s2);
+          }
+        } else {
+          // ---- general path: ragged tail and / or several images per chunk (L = 16, 8, 4, ...) ----
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if ((i & (L - 1)) == 0 || i == 0) {  // warp-uniform
+              const int n = (pix0 + i) >> x.log2_l;
+              if (pix0 + i < total_pix && n != cur_n) enter_image(n);
+            }
+            const float val = __uint_as_float(v[i]) + bt + (has_add ? f[i] : 0.f);
+            r[i] = __float2bfloat16_rn(val);
+            if (pix0 + i < total_pix) {
+              const float rf = __bfloat162float(r[i]);
+              s1 += rf;
+              s2 = fmaf(rf, rf, s2);
+            }
+          }
+          if (which != 2) {
+            __nv_bfloat16* op = obase + static_cast<long long>(pix0) * cmod + chm;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (pix0 + i < total_pix) op[i * cmod] = r[i];
+            continue;
+          }
+        }
+        // V^T [n][C][L]: this thread's channel row, runs of 8 pixels = 16 bytes (L % 8 == 0)
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int pg = pix0 + 8 * g8;
+          if (pg < total_pix) {
+            const int n = pg >> x.log2_l;
+            const int l = pg - (n << x.log2_l);
+            uint4 o;
+            o.x = pack2(r[8 * g8 + 0], r[8 * g8 + 1]); o.y = pack2(r[8 * g8 + 2], r[8 * g8 + 3]);
+            o.z = pack2(r[8 * g8 + 4], r[8 * g8 + 5]); o.w = pack2(r[8 * g8 + 6], r[8 * g8 + 7]);
+            *reinterpret_cast<uint4*>(obase + (static_cast<long long>(n) * cmod + chm) * L + l) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[stage]);
+      if (warp == 2 && lane == 0) trace_ev(x.trace, 2, 2 * t_it + 1);
+      flush_stats();
+    }
+  }
+#undef DMME_TCT_COORDS
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kAccCols);
+  }
+}
+
 // activation map: NHWC bf16 [n][h][w][c] seen as (c', w', parity, h', n)
 static int make_act_map(CUtensorMap* out, const void* ptr, int n, int h, int w, int c, int stride, int bw, int bh,
                         int bni) {
@@ -360,12 +755,15 @@ bool conv_tc_supported(const dmme_conv_desc& d) {
   return true;
 }
 
-template <int BN, int STAGES>
+constexpr int kWsStages = 6;
+constexpr int kWsSlabMax = 128 * 1024;  // + 6 x 16 KB ring + alignment = 225 KB of the 227 KB a CTA may take
+
+template <int BN, int STAGES, bool WS>
 static int launch_conv_tc(const ConvTcParams& p, int m_tiles, cudaStream_t stream) {
-  constexpr int smem = STAGES * stage_bytes<BN>() + 1024;
+  constexpr int smem = WS ? STAGES * kABytes + kWsSlabMax + 1024 : STAGES * stage_bytes<BN>() + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d bytes): %s", smem, cudaGetErrorString(e));
       return (int)e;
@@ -384,9 +782,45 @@ static int launch_conv_tc(const ConvTcParams& p, int m_tiles, cudaStream_t strea
   q.n_tiles = p.cout / BN;
   const int total = q.m_tiles * q.n_tiles;
   // persistent: one CTA per SM (it owns the whole TMEM: two accumulator stages), tiles dealt round-robin
-  const int grid = total < sm_count ? total : sm_count;
-  conv_tc_kernel<BN, STAGES><<<grid, kConvThreads, smem, stream>>>(q);
-  return check_launch("conv_tc_kernel");
+  int grid = total < sm_count ? total : sm_count;
+  if (WS) grid -= grid % q.n_tiles;  // every CTA stays on one n tile (n is the fastest tile index)
+  cudaError_t e = launch_pdl(conv_tc_kernel<BN, STAGES, WS>, dim3(grid), dim3(kConvThreads), smem, stream, q);
+  return check_launch_err(e, "conv_tc_kernel");
+}
+
+static long long* g_conv_trace = nullptr;
+static int g_tct_mode = 1;  // 1: transposed kernel where it applies, 0: never (A/B measurements), 2: wherever supported
+static int g_sm_count_tc = 0;
+
+// pixel-tile width of the transposed kernel for this problem, 0 = use conv_tc_kernel
+static int tct_tile_pixels(const dmme_conv_desc& d) {
+  if (g_tct_mode == 0) return 0;
+  const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
+  if (d.cout % 128 || wo > 128) return 0;
+  if (d.out_layout == DMME_OUT_QKV && ((d.cout / 3) % 128 || (ho * wo) % 8)) return 0;
+  const long long total_pix = static_cast<long long>(d.n) * ho * wo;
+  const int n_tiles = d.cout / 128;
+  if (wo <= 256 && ceil_div_ll(total_pix, 256) * n_tiles >= 120) return 256;
+  if (ceil_div_ll(total_pix, 128) * n_tiles >= 100 || g_tct_mode == 2) return 128;
+  return 0;
+}
+
+template <bool WS, int CMOD>
+static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv_tct: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  int grid = total < g_sm_count_tc ? total : g_sm_count_tc;
+  if (WS) grid -= grid % p.n_tiles;
+  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD>, dim3(grid), dim3(kConvThreads), smem, stream, p, x);
+  return check_launch_err(e, "conv_tct_kernel");
 }
 
 int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
@@ -394,9 +828,17 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
-  p.bw = wo < 128 ? wo : 128;
-  p.bh = ho < 128 / p.bw ? ho : 128 / p.bw;
-  p.bni = 128 / (p.bw * p.bh);
+  if (g_sm_count_tc == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count_tc, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count_tc <= 0) g_sm_count_tc = 148;
+  }
+  const int np = tct_tile_pixels(d);
+  const int tile_px = np ? np : 128;
+  p.bw = wo < tile_px ? wo : tile_px;
+  p.bh = ho < tile_px / p.bw ? ho : tile_px / p.bw;
+  p.bni = tile_px / (p.bw * p.bh);
   p.tiles_x = wo / p.bw;
   p.tiles_y = ho / p.bh;
   const int m_tiles = p.tiles_x * p.tiles_y * ceil_div(d.n, p.bni);
@@ -427,12 +869,43 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   if (d.rc1 && (rc = make_act_map(&p.a[3], d.res1, d.n, ho, wo, d.rc1, 1, p.bw, p.bh, p.bni))) return rc;
 
   const uint64_t ktot = (uint64_t)p.taps * (d.c0 + d.c1) + d.rc0 + d.rc1;
+  if (np) {
+    // transposed kernel: 128 output channels x np pixels per unit
+    uint64_t dims[2] = {ktot, (uint64_t)d.cout};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {64u, 128u};
+    if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
+    p.m_tiles = m_tiles;
+    p.n_tiles = d.cout / 128;
+    ConvTctExtra x;
+    x.np = np;
+    x.total_pix = static_cast<long long>(d.n) * ho * wo;
+    DMME_REQUIRE(x.total_pix + 256 < (1ll << 31), DMME_E_SHAPE, "conv_tct: more than 2^31 output pixels");
+    x.trace = g_conv_trace;
+    x.log2_l = 0;
+    while ((1 << x.log2_l) < ho * wo) ++x.log2_l;
+    const int budget = 226 * 1024 - 1024;
+    const long long slab = static_cast<long long>(ktot / 64) * 128 * 128;
+    const bool ws = p.taps == 1 && slab + 2 * np * 128 <= budget && p.n_tiles <= g_sm_count_tc;
+    x.stage_bytes = np * 128 + (ws ? 0 : 128 * 128);
+    int stages = static_cast<int>((budget - (ws ? slab : 0)) / x.stage_bytes);
+    x.stages = stages > kTctMaxStages ? kTctMaxStages : stages;
+    const int smem = x.stages * x.stage_bytes + (ws ? static_cast<int>(slab) : 0) + 1024;
+    const int cmod = d.out_layout == DMME_OUT_QKV ? d.cout / 3 : d.cout;
+    if (cmod == 128) return ws ? launch_conv_tct<true, 128>(p, x, smem, stream) : launch_conv_tct<false, 128>(p, x, smem, stream);
+    if (cmod == 256) return ws ? launch_conv_tct<true, 256>(p, x, smem, stream) : launch_conv_tct<false, 256>(p, x, smem, stream);
+    return ws ? launch_conv_tct<true, 0>(p, x, smem, stream) : launch_conv_tct<false, 0>(p, x, smem, stream);
+  }
   // widest N tile that divides cout (and, for q/k/v splitting, the per-tensor width) while the persistent grid still
   // has a tile for every SM: wider tiles re-read the activation tile less often
   int unit = d.out_layout == DMME_OUT_QKV ? d.cout / 3 : d.cout;
   int bn = 64;
   if (unit % 128 == 0 && (long long)m_tiles * (d.cout / 128) >= 120) bn = 128;
   if (unit % 256 == 0 && (long long)m_tiles * (d.cout / 256) >= 120) bn = 256;
+  // 1x1 convs whose [bn][K] weight slab fits beside the activation ring keep it resident (weight stationary)
+  const bool one_by_one = p.taps == 1 && d.rc0 + d.rc1 == 0;
+  while (one_by_one && bn > 64 && ktot * bn * 2 > (uint64_t)kWsSlabMax) bn >>= 1;
+  const bool ws = one_by_one && ktot * bn * 2 <= (uint64_t)kWsSlabMax && d.cout / bn <= 148;
   {
     uint64_t dims[2] = {ktot, (uint64_t)d.cout};
     uint64_t strides[1] = {ktot * 2};
@@ -440,11 +913,24 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
   }
   // one CTA per SM: the TMA ring takes the whole shared memory (192 KB each)
+  if (ws) {
+    switch (bn) {
+      case 256: return launch_conv_tc<256, kWsStages, true>(p, m_tiles, stream);
+      case 128: return launch_conv_tc<128, kWsStages, true>(p, m_tiles, stream);
+      default: return launch_conv_tc<64, kWsStages, true>(p, m_tiles, stream);
+    }
+  }
   switch (bn) {
-    case 256: return launch_conv_tc<256, 4>(p, m_tiles, stream);
-    case 128: return launch_conv_tc<128, 6>(p, m_tiles, stream);
-    default: return launch_conv_tc<64, 8>(p, m_tiles, stream);
+    case 256: return launch_conv_tc<256, 4, false>(p, m_tiles, stream);
+    case 128: return launch_conv_tc<128, 6, false>(p, m_tiles, stream);
+    default: return launch_conv_tc<64, 8, false>(p, m_tiles, stream);
   }
 }
 
 }  // namespace dmme
+
+// A/B measurement switch: 0 = never use the transposed tcgen05 kernel, 1 = default, 2 = wherever it is supported
+extern "C" void dmme_set_conv_tct_mode(int mode) { dmme::g_tct_mode = mode; }
+extern "C" int dmme_get_conv_tct_mode(void) { return dmme::g_tct_mode; }
+// debugging: device buffer of 3 x 512 int64 that CTA 0 of the transposed kernel fills with clock64 timestamps
+extern "C" void dmme_debug_set_conv_trace(long long* buf) { dmme::g_conv_trace = buf; }

@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams q)
   per = (per + 255) / 256 * 256;
   const long long r0 = blockIdx.x * per;
   const long long r1 = r0 + per < total ? r0 + per : total;
+  pdl_trigger();
+  pdl_wait();  // statistics and activations come from the producing conv
 
   for (long long seg = r0; seg < r1;) {
     const int n = static_cast<int>(seg / nvec);
@@ -383,8 +385,8 @@ extern "C" int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, in
     long long grid = ceil_div_ll(total_vec, 256);  // at least one vector per thread
     if (grid > 148 * 4) grid = 148 * 4;            // one wave, four CTAs per SM
     q.chunks = 0;
-    gn_apply_kernel<<<static_cast<int>(grid), 256, sizeof(float) * 3 * C, st>>>(q);
-    return check_launch("gn_apply_kernel");
+    cudaError_t e = launch_pdl(gn_apply_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), sizeof(float) * 3 * C, st, q);
+    return check_launch_err(e, "gn_apply_kernel");
   }
   const bool fast = act_dtype == DMME_BF16 && C % 32 == 0 && c0 % 32 == 0 && (32 % cpg == 0) && hw <= 1024 &&
                     (hw * 4) % 32 == 0;

@@ -54,6 +54,8 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
                                  const float* __restrict__ beta, const float* __restrict__ alpha,
                                  const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr,
                                  long long numel, unsigned long long seed, unsigned long long goff) {
+  pdl_trigger();
+  pdl_wait();
   const long long t = *t_ptr;
   const float b = beta[t], a = alpha[t], ab = alpha_bar[t];
   const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
@@ -135,7 +137,11 @@ __global__ void iddpm_step_kernel(float* __restrict__ x, const float* __restrict
 }
 
 __global__ void gather_i64_kernel(const int64_t* table, const int64_t* idx, int64_t* out) { *out = table[*idx]; }
-__global__ void add_i64_kernel(int64_t* p, int64_t d) { *p += d; }
+__global__ void add_i64_kernel(int64_t* p, int64_t d) {
+  pdl_trigger();
+  pdl_wait();
+  *p += d;
+}
 
 static int ew_grid(long long work, int threads) {
   long long b = ceil_div_ll(work, threads);
@@ -152,9 +158,10 @@ extern "C" int dmme_ddpm_step(float* x, const float* eps, const float* noise, co
                               unsigned long long noise_offset, void* stream) {
   DMME_REQUIRE(x && eps && beta && alpha && alpha_bar && t_ptr && numel > 0, DMME_E_BADARG, "ddpm_step: bad arguments");
   DMME_REQUIRE(noise_offset % 4 == 0, DMME_E_BADARG, "ddpm_step: noise_offset must be a multiple of 4");
-  ddpm_step_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, eps, noise, beta, alpha, alpha_bar, t_ptr, numel, seed, noise_offset / 4);
-  return check_launch("ddpm_step_kernel");
+  return check_launch_err(launch_pdl(ddpm_step_kernel, dim3(ew_grid((numel + 3) / 4, 256)), dim3(256), 0,
+                                     static_cast<cudaStream_t>(stream), x, eps, noise, beta, alpha, alpha_bar, t_ptr, numel,
+                                     seed, noise_offset / 4),
+                          "ddpm_step_kernel");
 }
 
 extern "C" int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar, const int64_t* tau,
@@ -184,8 +191,8 @@ extern "C" int dmme_gather_i64(const int64_t* table, const int64_t* idx_ptr, int
 
 extern "C" int dmme_add_i64(int64_t* value, int64_t delta, void* stream) {
   DMME_REQUIRE(value, DMME_E_BADARG, "add_i64: null pointer");
-  add_i64_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(value, delta);
-  return check_launch("add_i64_kernel");
+  return check_launch_err(launch_pdl(add_i64_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), value, delta),
+                          "add_i64_kernel");
 }
 
 extern "C" int dmme_philox_normal(float* out, long long numel, unsigned long long seed, unsigned long long stream_id,

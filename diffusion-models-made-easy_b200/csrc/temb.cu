@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) temb_linear_kernel(const float* __restric
                                                           const float* __restrict__ w, const float* __restrict__ b,
                                                           int out_dim, int act, float* __restrict__ out) {
   extern __shared__ float es[];  // [kProjRows][in_dim]
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = blockIdx.y * kProjRows;
   for (int idx = tid; idx < kProjRows * in_dim; idx += 256) {
@@ -61,7 +63,8 @@ int launch_linear(const float* in, const int64_t* t, const float* freq, int rows
   const size_t smem = sizeof(float) * kProjRows * static_cast<size_t>(in_dim);
   DMME_REQUIRE(smem <= 48 * 1024, DMME_E_SHAPE, "%s: input width %d too large", what, in_dim);
   dim3 grid(ceil_div(out_dim, 8), ceil_div(rows, kProjRows));
-  temb_linear_kernel<<<grid, 256, smem, st>>>(in, t, freq, rows, in_dim, w, b, out_dim, act, out);
+  cudaError_t le = launch_pdl(temb_linear_kernel, grid, dim3(256), smem, st, in, t, freq, rows, in_dim, w, b, out_dim, act, out);
+  if (le != cudaSuccess) return check_launch_err(le, "temb_linear_kernel");
   return check_launch(what);
 }
 

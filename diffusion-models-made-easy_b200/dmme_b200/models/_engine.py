@@ -76,6 +76,16 @@ class Engine:
         return self._cached(("w", id(conv), tc), self._ver(conv.weight, wr),
                             lambda: ops.pack_conv_weight(conv.weight, wr, tc))
 
+    def packed_weight_identity(self, conv: nn.Conv2d) -> Tensor:
+        """[W | I]: the conv weight with an identity 1x1 residual block appended, so that ``conv(a) + x`` runs as extra
+        K chunks of the same tensor-core GEMM (bf16 x times 1.0 accumulates exactly in fp32) instead of an epilogue
+        read of x -- measured 36 vs 44 us for the 256-channel attention projection at batch 256."""
+        def build():
+            c = conv.weight.shape[0]
+            eye = torch.eye(c, device=conv.weight.device, dtype=torch.float32).view(c, c, 1, 1)
+            return ops.pack_conv_weight(conv.weight, eye, True)
+        return self._cached(("w", id(conv), "eye"), self._ver(conv.weight), build)
+
     def fused_bias(self, conv: nn.Conv2d, res: Optional[nn.Conv2d]) -> Tensor:
         if res is None:
             return conv.bias.detach()
@@ -136,10 +146,17 @@ class Engine:
     def conv(self, name: str, src0: Tensor, src1: Optional[Tensor], conv: nn.Conv2d, *, stride: int = 1,
              upsample: bool = False, res: Optional[nn.Conv2d] = None, res0: Optional[Tensor] = None,
              res1: Optional[Tensor] = None, temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
-             in_nchw: bool = False, out_layout: int = L.OUT_NHWC, act_dtype: Optional[torch.dtype] = None):
+             in_nchw: bool = False, out_layout: int = L.OUT_NHWC, act_dtype: Optional[torch.dtype] = None,
+             addend_in_gemm: bool = False):
         cout, ks = conv.weight.shape[0], conv.weight.shape[2]
         act_dtype = act_dtype or src0.dtype
         kernel = L.CONV_GENERIC if self.force_generic else L.CONV_AUTO
+        identity = False
+        if addend_in_gemm and addend is not None and res is None and not self.force_generic and \
+                act_dtype == torch.bfloat16 and cout % 64 == 0 and src0.shape[3] % 64 == 0:
+            probe = ops.make_conv_desc(src0, src1, cout, ks, stride, upsample, addend, None, in_nchw, out_layout, act_dtype, kernel)
+            if ops.conv_uses_tc(probe):
+                identity, res0, addend = True, addend, None
         if upsample and not self.force_generic and act_dtype == torch.bfloat16 and src0.shape[3] % 64 == 0 and cout % 64 == 0:
             # tensor-core path has no upsampling gather: materialise the x2 tensor once (memory-bound copy)
             n, h, w, c = src0.shape
@@ -147,7 +164,7 @@ class Engine:
             upsample = False
         d = ops.make_conv_desc(src0, src1, cout, ks, stride, upsample, res0, res1, in_nchw, out_layout, act_dtype, kernel)
         tc = ops.conv_uses_tc(d)
-        w = self.packed_weight(conv, res, tc)
+        w = self.packed_weight_identity(conv) if identity else self.packed_weight(conv, res, tc)
         b = self.fused_bias(conv, res)
         ho, wo = ops.conv_out_hw(d)
         dev = src0.device
@@ -197,7 +214,7 @@ class Engine:
             flat = qkv.view(-1)
             ops.attention(flat, flat[dh:], flat[2 * dh:], n, heads, seq, dh, att.scale, seq * 3 * c, 3 * c, 3 * dh,
                           False, 0, True, ao)
-        return self.conv(name + ".attn", ao, None, att.proj, addend=x)
+        return self.conv(name + ".attn", ao, None, att.proj, addend=x, addend_in_gemm=True)
 
     def resblock(self, name: str, blk: nn.Module, x0: Tensor, x1: Optional[Tensor], temb_all: Tensor,
                  offs: Dict[int, Tuple[int, int]], masks: Optional[Dict[str, Tensor]]) -> Tensor:

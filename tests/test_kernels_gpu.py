@@ -241,6 +241,89 @@ def test_conv_tc(cfg):
     assert err < 4e-3, f"rel-L2 {err}"
 
 
+@pytest.fixture
+def tct_everywhere():
+    """force the transposed tcgen05 kernel (thread = channel epilogue) wherever it is supported"""
+    _, L = _ops()
+    lib = L.load()
+    old = lib.dmme_get_conv_tct_mode()
+    lib.dmme_set_conv_tct_mode(2)
+    yield
+    lib.dmme_set_conv_tct_mode(old)
+
+
+TCT_CASES = [c for c in TC_CASES if c["cout"] % 128 == 0] + [
+    dict(n=70, cin=256, cout=256, h=16, w=16, k=1, addend=True),       # weight-stationary 1x1, 256-pixel tiles, 2 n tiles
+    dict(n=33, cin=512, cout=128, h=16, w=16, k=1, temb="rows"),       # K = 512 slab
+    dict(n=130, cin=256, cout=256, h=8, w=8, k=3, temb="rows"),        # 4 images per 256-pixel tile
+    dict(n=200, cin=128, cout=256, h=4, w=4, k=3, addend=True, temb="rows"),  # 2 images per 32-pixel chunk
+    dict(n=66, cin=128, cout=128, h=32, w=32, k=3, stride=2, temb="bcast"),
+]
+
+
+@pytest.mark.parametrize("cfg", TCT_CASES)
+def test_conv_tct(cfg, tct_everywhere):
+    """transposed kernel against fp32 conv on the same bf16 operands, plus its GroupNorm statistics"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(29)
+    n, cin, cout, h, w, k = (cfg[s] for s in ("n", "cin", "cout", "h", "w", "k"))
+    stride = cfg.get("stride", 1)
+    c1 = cfg.get("cin1", 0)
+    c0 = cin - c1
+    xa = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    b = torch.randn(cout, generator=g)
+    ho, wo = h // stride, w // stride
+    s0 = to_nhwc(xa[:, :c0], torch.bfloat16).to(DEV)
+    s1 = to_nhwc(xa[:, c0:], torch.bfloat16).to(DEV) if c1 else None
+    want = F.conv2d(xa, wt, b, stride=stride, padding=k // 2)
+    wres, r0, r1, bias = None, None, None, b
+    if cfg.get("res"):
+        wres = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin))
+        bres = torch.randn(cout, generator=g)
+        want = want + F.conv2d(xa, wres, bres)
+        bias = b + bres
+        r0, r1 = s0, s1
+    temb = None
+    if cfg.get("temb"):
+        temb = torch.randn(n if cfg["temb"] == "rows" else 1, cout, generator=g)
+        want = want + (temb if temb.shape[0] == n else temb.expand(n, -1))[:, :, None, None]
+        temb = temb.to(DEV)
+    addend = None
+    if cfg.get("addend"):
+        ad = bf16_round(torch.randn(n, cout, ho, wo, generator=g))
+        want = want + ad
+        addend = to_nhwc(ad, torch.bfloat16).to(DEV)
+    d = ops.make_conv_desc(s0, s1, cout, k, stride, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_TC)
+    assert ops.conv_uses_tc(d)
+    wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
+    out = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+    ops.conv2d_launch(d, wp, bias.to(DEV), out, temb, addend, stats=st)
+    torch.cuda.synchronize()
+    got = to_nchw(out.cpu())
+    err = rel_l2(got, want)
+    assert err < 4e-3, f"rel-L2 {err}"
+    sums = st.cpu().view(n, cout // 4, 2).double() / 2 ** 20
+    assert torch.allclose(sums[..., 0], got.double().reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+    assert torch.allclose(sums[..., 1], (got.double() ** 2).reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,c,h", [(3, 128, 16), (50, 256, 16), (7, 256, 4), (300, 128, 4)])
+def test_conv_tct_qkv_layout(n, c, h, tct_everywhere):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = bf16_round(torch.randn(n, c, h, h, generator=g))
+    w = bf16_round(torch.randn(3 * c, c, 1, 1, generator=g) / math.sqrt(c))
+    b = torch.randn(3 * c, generator=g)
+    (q, k, vt), tc = run_conv(x, w, b, dtype=torch.bfloat16, kernel=L.CONV_TC, out_layout=L.OUT_QKV)
+    assert tc
+    y = F.conv2d(x, w, b).flatten(2)  # n, 3c, L
+    assert rel_l2(q, y[:, :c].transpose(1, 2)) < 4e-3
+    assert rel_l2(k, y[:, c:2 * c].transpose(1, 2)) < 4e-3
+    assert rel_l2(vt, y[:, 2 * c:]) < 4e-3
+
+
 HALO_CASES = [
     dict(n=1, cin=64, cout=128, h=16, w=16),
     dict(n=4, cin=128, cout=128, h=32, w=32, temb="bcast"),
