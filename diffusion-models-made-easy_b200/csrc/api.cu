@@ -28,6 +28,8 @@ bool conv_halo_supported(const dmme_conv_desc& d);
 bool conv_halo_preferred(const dmme_conv_desc& d);
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_halo2_supported(const dmme_conv_desc& d);
+bool conv_out_tc_supported(const dmme_conv_desc& d);
+int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream);
 int conv_halo2_forward(const dmme_conv_desc& d, cudaStream_t stream);
 
 }  // namespace dmme
@@ -44,6 +46,7 @@ extern "C" int dmme_conv2d_uses_tc(const dmme_conv_desc* d) {
   if (d->kernel == DMME_CONV_GENERIC) return 0;
   if (d->kernel == DMME_CONV_HALO) return conv_halo_supported(*d) ? 1 : 0;
   if (d->kernel == DMME_CONV_HALO2) return conv_halo2_supported(*d) ? 1 : 0;
+  if (d->kernel == DMME_CONV_AUTO && conv_out_tc_supported(*d)) return 1;
   return conv_tc_supported(*d) ? 1 : 0;
 }
 
@@ -70,6 +73,7 @@ extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
       return conv_halo2_forward(*d, st);
     case DMME_CONV_AUTO:
       if (conv_tc_supported(*d)) return conv_halo_preferred(*d) ? conv_halo_forward(*d, st) : conv_tc_forward(*d, st);
+      if (conv_out_tc_supported(*d)) return conv_out_tc_forward(*d, st);
       if (conv_in_supported(*d) || conv_out_supported(*d)) return conv_small_forward(*d, st);
       return conv_generic_forward(*d, st);
     default:

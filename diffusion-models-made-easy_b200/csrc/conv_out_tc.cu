@@ -1,0 +1,254 @@
+// Output convolution (models/ddpm.py:277, GN -> SiLU -> Conv 128 -> 3, IDDPM -> 6) on tcgen05: 3x3 stride-1 conv with a
+// handful of output channels, NHWC bf16 in, NCHW fp32 (image space) out.
+//
+// With cout = 3 the weight side of the GEMM is tiny and the activation side is everything, so the roles of conv_halo.cu
+// are swapped: the halo tile of zero-padded pixel rows (same layout, same "a filter tap is a shift of the operand
+// descriptor by d rows of 128 bytes" trick) is the MMA's M side -- 128 consecutive positions of the padded-row space =
+// 128 TMEM lanes -- and the weights, padded to 16 output channels by the TMA's out-of-bounds zero fill, are the N side
+// (M = 128, N = 16, K = 16 per instruction).  All 9 x cin/64 weight tiles (2 KB each) stay in shared memory for the
+// whole kernel.  The accumulator has lane = position, column = output channel, so the epilogue is one 4/8-column
+// tcgen05.ld per thread and cout coalesced fp32 stores (consecutive lanes = consecutive x of an image row).
+// The FFMA kernel this replaces (conv_out128_kernel) needs 906 M FMAs at batch 256: 126 us against 25 us of FFMA issue.
+//
+// Work unit = RT whole padded rows (3 rows of 34 at 32x32, 7 of 18 at 16x16, 12 of 10 at 8x8), persistent CTAs, static
+// round-robin.  Warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue (one per TMEM lane quarter).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "tmap.cuh"
+
+namespace dmme {
+
+struct ConvOutTcParams {
+  CUtensorMap a;  // activations: box = one padded row [W+2 px][64 ch]
+  CUtensorMap b;  // weights [cout][K] bf16, box [16][64] (rows >= cout zero-filled)
+  int chunks;     // cin / 64
+  int n, h, w, wp;
+  int rt;          // padded rows per tile
+  int total_rows;  // n * (h + 2)
+  int units;
+  int cout;
+  const float* bias;
+  float* out;  // [n][cout][h][w] fp32
+};
+
+constexpr int kOutSlot = 24 * 1024;  // >= (1 + (rt + 2) * (W + 2)) * 128 bytes
+constexpr int kOutStages = 5;
+constexpr int kOutWTile = 16 * 128;  // [16 cout][64 ch] bf16
+constexpr int kOutThreads = 6 * 32;
+constexpr int kOutN = 16;
+
+template <int NCOL>  // accumulator columns read by the epilogue: 4 (cout <= 4) or 8
+__global__ void __launch_bounds__(kOutThreads, 1) conv_out_tc_kernel(const __grid_constant__ ConvOutTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kOutStages], a_empty[kOutStages];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t w_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* abuf = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* wbuf = abuf + kOutStages * kOutSlot;
+  const int row_bytes = p.wp * 128;
+  const int nr = p.rt + 2;
+  const int nwt = 9 * p.chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kOutStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    mbar_init(&w_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a);
+    tma_prefetch_desc(&p.b);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();  // after the TMEM allocation (see common.cuh)
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      pdl_wait();
+      // weight tile (tap, chunk) = columns [(tap * chunks + chunk) * 64, +64) of the tap-major packed [cout][K] matrix
+      mbar_expect_tx(&w_full, static_cast<uint32_t>(nwt) * kOutWTile);
+      for (int i = 0; i < nwt; ++i) tma_load_2d(wbuf + i * kOutWTile, &p.b, &w_full, i * 64, 0);
+      int it = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int pr0 = u * p.rt - 1;  // first halo row (padded-row index, may be -1)
+        for (int ck = 0; ck < p.chunks; ++ck, ++it) {
+          const int s = it % kOutStages;
+          mbar_wait(&a_empty[s], ((it / kOutStages) & 1) ^ 1);
+          mbar_expect_tx(&a_full[s], nr * row_bytes);
+          uint8_t* dst = abuf + s * kOutSlot + 128;  // 128 bytes of slack: tap (-1,-1) of position 0 reaches one row back
+          for (int i = 0; i < nr; ++i) {
+            const int pr = pr0 + i;
+            int ni, yy;
+            if (pr < 0) { ni = -1; yy = 0; }  // before the first image: whole row out of bounds -> zeros
+            else { ni = pr / (p.h + 2); yy = pr - ni * (p.h + 2) - 1; }  // yy = -1 or h: padding row -> zeros
+            tma_load_5d(dst + i * row_bytes, &p.a, &a_full[s], ck * 64, -1, 0, yy, ni);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kOutN);  // M = 128 positions, N = 16 (padded) output channels
+      mbar_wait(&w_full, 0);
+      int it = 0, u_it = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++u_it) {
+        const int stage = u_it & 1;
+        mbar_wait(&acc_empty[stage], ((u_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dtm = tmem_base + stage * kOutN;
+        for (int ck = 0; ck < p.chunks; ++ck, ++it) {
+          const int s = it % kOutStages;
+          mbar_wait(&a_full[s], (it / kOutStages) & 1);
+          tc_fence_after();
+          // position 0 of the tile = first pixel slot of the tile's first row = halo row 1
+          const uint32_t x0_addr = smem_u32(abuf + s * kOutSlot) + 128u + row_bytes;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int d = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
+            const uint64_t xdesc = umma_desc_sw128(x0_addr + static_cast<uint32_t>(d * 128));  // shifted pixel rows: M side
+            const uint64_t wdesc = umma_desc_sw128(smem_u32(wbuf + (tap * p.chunks + ck) * kOutWTile));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(dtm, xdesc + 2 * k, wdesc + 2 * k, idesc, (ck | tap | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&a_empty[s]);
+        }
+        umma_commit(&acc_full[stage]);
+      }
+    }
+  } else {
+    // =========================== epilogue: thread = position ===========================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int pos = q * 32 + lane;
+    const int rr = pos / p.wp;
+    const int xx = pos - rr * p.wp - 1;
+    const bool in_tile = rr < p.rt && xx >= 0 && xx < p.w;
+    pdl_wait();
+    float bias[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) bias[c] = (p.bias && c < p.cout) ? __ldg(p.bias + c) : 0.f;
+    const long long plane = static_cast<long long>(p.h) * p.w;
+    int u_it = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++u_it) {
+      const int stage = u_it & 1;
+      const int pr = u * p.rt + rr;
+      const int n = pr / (p.h + 2);
+      const int yy = pr - n * (p.h + 2) - 1;
+      const bool valid = in_tile && pr < p.total_rows && yy >= 0 && yy < p.h;
+      mbar_wait(&acc_full[stage], (u_it >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[NCOL];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(stage * kOutN);
+      if constexpr (NCOL == 4) tmem_ld4(taddr, v);
+      else tmem_ld8(taddr, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[stage]);
+      if (valid) {
+        float* op = p.out + (static_cast<long long>(n) * p.cout * p.h + yy) * p.w + xx;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c)
+          if (c < p.cout) op[c * plane] = __uint_as_float(v[c]) + bias[c];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+static int g_out_tc_mode = 1;
+
+bool conv_out_tc_supported(const dmme_conv_desc& d) {
+  if (g_out_tc_mode == 0) return false;
+  if (d.act_dtype != DMME_BF16 || d.in_layout != DMME_IN_NHWC || d.out_layout != DMME_OUT_NCHW_F32) return false;
+  if (d.ksize != 3 || d.stride != 1 || d.upsample || d.c1 || d.rc0 || d.rc1 || d.temb || d.addend) return false;
+  if (d.c0 <= 0 || d.c0 % 64 || d.c0 > 256) return false;  // 9 * cin/64 resident weight tiles of 2 KB
+  if (d.cout < 1 || d.cout > 8) return false;
+  if (d.w_in != 8 && d.w_in != 16 && d.w_in != 32) return false;
+  if (d.h_in != d.w_in) return false;
+  if (static_cast<long long>(d.n) * (d.h_in + 2) > (1 << 24)) return false;
+  return true;
+}
+
+template <int NCOL>
+static int launch_out_tc(const ConvOutTcParams& p, int smem, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_out_tc_kernel<NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv_out_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  cudaError_t e = launch_pdl(conv_out_tc_kernel<NCOL>, dim3(grid), dim3(kOutThreads), smem, stream, p);
+  return check_launch_err(e, "conv_out_tc_kernel");
+}
+
+int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
+  DMME_REQUIRE(conv_out_tc_supported(d), DMME_E_SHAPE, "conv_out_tc: unsupported shape/layout");
+  DMME_REQUIRE(d.src0 && d.weight && d.out, DMME_E_BADARG, "conv_out_tc: null src0/weight/out");
+  ConvOutTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.chunks = d.c0 / 64;
+  p.n = d.n; p.h = d.h_in; p.w = d.w_in; p.wp = d.w_in + 2;
+  p.rt = 128 / p.wp;
+  p.total_rows = d.n * (d.h_in + 2);
+  p.units = (p.total_rows + p.rt - 1) / p.rt;
+  p.cout = d.cout;
+  p.bias = d.bias;
+  p.out = static_cast<float*>(d.out);
+  // the halo tile is (rt + 2) padded rows behind one slack row.  The MMA's 128 positions reach up to 2 * (W + 2) + 130
+  // rows from the slot start: positions past the tile's rt rows are junk lanes that are never stored, and what they
+  // read (the next slot or the resident weights) lies inside this CTA's shared memory
+  DMME_REQUIRE((1 + (p.rt + 2) * p.wp) * 128 <= kOutSlot &&
+                   (2 * p.wp + 130) * 128 <= kOutSlot + 9 * p.chunks * kOutWTile,
+               DMME_E_SHAPE, "conv_out_tc: halo tile does not fit its shared-memory slot");
+  int rc;
+  {
+    uint64_t dims[5] = {(uint64_t)d.c0, (uint64_t)d.w_in, 1, (uint64_t)d.h_in, (uint64_t)d.n};
+    uint64_t strides[4] = {(uint64_t)d.c0 * 2, (uint64_t)d.w_in * d.c0 * 2, (uint64_t)d.w_in * d.c0 * 2,
+                           (uint64_t)d.h_in * d.w_in * d.c0 * 2};
+    uint32_t box[5] = {64u, (uint32_t)p.wp, 1u, 1u, 1u};
+    if ((rc = encode_map(&p.a, d.src0, 5, dims, strides, box))) return rc;
+  }
+  {
+    const uint64_t ktot = 9ull * d.c0;
+    uint64_t dims[2] = {ktot, (uint64_t)d.cout};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {64u, 16u};
+    if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
+  }
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  const int smem = kOutStages * kOutSlot + 9 * p.chunks * kOutWTile + 1024;
+  const int grid = p.units < sm_count ? p.units : sm_count;
+  return d.cout <= 4 ? launch_out_tc<4>(p, smem, grid, stream) : launch_out_tc<8>(p, smem, grid, stream);
+}
+
+}  // namespace dmme
+
+// A/B measurement switch: 0 = the output conv stays on the FFMA kernel, 1 = default
+extern "C" void dmme_set_conv_out_tc_mode(int mode) { dmme::g_out_tc_mode = mode; }

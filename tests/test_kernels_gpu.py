@@ -179,14 +179,33 @@ def test_conv_in_writes_groupnorm_stats():
 
 @pytest.mark.parametrize("n,h,cin,cout", [(3, 32, 128, 3), (2, 16, 128, 6), (5, 8, 64, 3), (1, 32, 256, 6)])
 def test_conv_out_nhwc_bf16_to_image(n, h, cin, cout):
-    """output_conv fast path: NHWC bf16 -> eps NCHW fp32 with 3 (DDPM) or 6 (IDDPM) channels"""
+    """output_conv FFMA path (fp32 weights): NHWC bf16 -> eps NCHW fp32 with 3 (DDPM) or 6 (IDDPM) channels"""
     _, L = _ops()
-    g = torch.Generator().manual_seed(32)
+    lib = L.load()
+    lib.dmme_set_conv_out_tc_mode(0)
+    try:
+        g = torch.Generator().manual_seed(32)
+        x = bf16_round(torch.randn(n, cin, h, h, generator=g))
+        w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+        b = torch.randn(cout, generator=g)
+        got, tc = run_conv(x, w, b, dtype=torch.bfloat16, out_layout=L.OUT_NCHW_F32)
+        assert not tc
+        assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 1e-5
+    finally:
+        lib.dmme_set_conv_out_tc_mode(1)
+
+
+@pytest.mark.parametrize("n,h,cin,cout", [(3, 32, 128, 3), (2, 16, 128, 6), (5, 8, 64, 3), (1, 32, 256, 6), (1, 8, 128, 1),
+                                          (260, 32, 128, 3), (131, 16, 192, 6), (77, 32, 128, 8)])
+def test_conv_out_tc(n, h, cin, cout):
+    """output_conv on tcgen05 (positions on the M side, bf16 weights): against fp32 conv on the same bf16 operands"""
+    _, L = _ops()
+    g = torch.Generator().manual_seed(33)
     x = bf16_round(torch.randn(n, cin, h, h, generator=g))
-    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+    w = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
     b = torch.randn(cout, generator=g)
     got, tc = run_conv(x, w, b, dtype=torch.bfloat16, out_layout=L.OUT_NCHW_F32)
-    assert not tc
+    assert tc
     assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 1e-5
 
 
