@@ -7,7 +7,8 @@ from .common.noise import gaussian, gaussian_like, uniform_int, pad
 from . import equations
 from . import models
 from . import diffusion_models
+from . import optim
 from .diffusion_models import DDPM, DDIM, IDDPM
 
 __all__ = ["DDPM", "DDIM", "IDDPM", "gaussian", "gaussian_like", "uniform_int", "pad", "equations", "models",
-           "diffusion_models"]
+           "diffusion_models", "optim"]

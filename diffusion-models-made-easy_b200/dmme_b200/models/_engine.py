@@ -69,7 +69,8 @@ class Engine:
 
     @staticmethod
     def _ver(*params: Optional[Tensor]) -> Tuple:
-        return tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+        # _dmme_gen: bumped by optim.FusedAdamEMA, whose kernels update the weights without touching torch's counter
+        return tuple((p.data_ptr(), p._version, getattr(p, "_dmme_gen", 0)) if p is not None else None for p in params)
 
     def packed_weight(self, conv: nn.Conv2d, res: Optional[nn.Conv2d], tc: bool) -> Tensor:
         wr = res.weight if res is not None else None

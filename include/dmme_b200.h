@@ -296,6 +296,23 @@ int dmme_iddpm_loss(const float* model_out, const float* x_t, const float* x_0, 
                     const float* alpha, const float* alpha_bar, int n, int c, int hw, float w_simple, float w_vlb,
                     float grad_scale, float* d_out, float* loss_out, float* partial, void* stream);
 
+/* fused optimizer tail ---------------------------------------------------------------------- */
+/*
+ * One training step's parameter update for ALL tensors in two launches: global gradient-norm clip
+ * (Lightning gradient_clip_val, configs/ddpm/cifar10.yaml:24 = torch.nn.utils.clip_grad_norm_), Adam with torch.optim.Adam's
+ * default arithmetic (lit_modules/ddpm.py:130), the caller's WarmupLR-scaled learning rate (lr_scheduler/warmup.py:10-19)
+ * and the EMA update ema = d*ema + (1-d)*w (callbacks/ema.py:169-176).
+ * table: device array of `count` entries { float* w; const float* g; float* m; float* v; float* ema (or NULL);
+ * long long numel; long long first_item; } where first_item = running sum of ceil(numel / dmme_optim_chunk()).
+ * items = total work items; partial: >= grid floats of scratch; norm_out (optional): the pre-clip global L2 norm.
+ * max_norm <= 0 disables clipping; step is the 1-based optimizer step (bias correction).
+ */
+int dmme_optim_table_entry_bytes(void);
+int dmme_optim_chunk(void);
+int dmme_adam_ema_step(const void* table, int count, long long items, double lr, double beta1, double beta2,
+                       double eps, int step, double max_norm, double ema_decay, float* partial, int grid,
+                       float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

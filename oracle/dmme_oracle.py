@@ -322,3 +322,49 @@ def ddim_generate(sd: StateDict, x_T: Tensor, alpha_bar: Tensor, tau: Tensor, gr
         if return_trajectory:
             traj.append(x.clone())
     return (x, traj) if return_trajectory else x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# optimizer tail (test infrastructure for dmme_b200.optim): Adam + WarmupLR + gradient clipping + EMA as the reference
+# composes them
+# ---------------------------------------------------------------------------------------------------------------------
+class WarmupLR(torch.optim.lr_scheduler._LRScheduler):
+    """Restatement of lr_scheduler/warmup.py:4-19: linear ramp over ``warmup`` optimizer steps, evaluated on
+    ``optimizer._step_count + 1``."""
+
+    def __init__(self, optimizer, warmup=0.0, last_epoch=-1):
+        self.warmup_steps = warmup
+        # the reference was written against torch 1.13, whose _LRScheduler counts the optimizer's steps in
+        # ``optimizer._step_count``; newer torch dropped that attribute, so the training loop below keeps it
+        if not hasattr(optimizer, "_step_count"):
+            optimizer._step_count = 0
+        super().__init__(optimizer, last_epoch)
+
+    def get_lr(self):
+        steps = self.optimizer._step_count + 1
+        if steps < self.warmup_steps:
+            return [g["initial_lr"] * (steps / self.warmup_steps) for g in self.optimizer.param_groups]
+        return [g["initial_lr"] for g in self.optimizer.param_groups]
+
+
+def optimizer_tail_reference(params, grads_per_step, lr, warmup, max_norm, decay):
+    """Run the reference's training tail on ``params`` (modified in place): per step clip_grad_norm_ (Lightning
+    gradient_clip_val, configs/ddpm/cifar10.yaml:24), Adam.step (lit_modules/ddpm.py:130), WarmupLR.step (:131-133) and
+    the EMA update of callbacks/ema.py:169-176.  Returns (ema tensors, optimizer, list of lr used per step, norms)."""
+    opt = torch.optim.Adam(params, lr=lr)
+    sched = WarmupLR(opt, warmup)
+    ema = [p.detach().clone() for p in params]
+    lrs, norms = [], []
+    for grads in grads_per_step:
+        for p, g in zip(params, grads):
+            p.grad = g.clone()
+        if max_norm:
+            norms.append(torch.nn.utils.clip_grad_norm_(params, max_norm).detach().clone())
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        opt._step_count = len(lrs)  # what torch 1.13's step wrapper did
+        sched.step()
+        with torch.no_grad():
+            torch._foreach_mul_(ema, decay)
+            torch._foreach_add_(ema, [p.detach() for p in params], alpha=(1.0 - decay))
+    return ema, opt, lrs, norms

@@ -20,6 +20,9 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--dropout", type=float, default=None)
+    ap.add_argument("--optim", default="fused", choices=["fused", "torch"],
+                    help="fused: dmme_b200.optim.FusedAdamEMA (clip + Adam + warm-up + EMA, two launches); "
+                         "torch: clip_grad_norm_ + torch.optim.Adam + foreach EMA")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -40,7 +43,13 @@ def main():
         from dmme_b200 import parallel
         parallel.broadcast_parameters(dm)
         parallel.enable_gradient_sync(dm.model)
-    opt = torch.optim.Adam(dm.parameters(), lr=2e-4)
+    params = [p for p in dm.parameters() if p.requires_grad]
+    if a.optim == "fused":
+        from dmme_b200.optim import FusedAdamEMA
+        opt = FusedAdamEMA(params, lr=2e-4, warmup=5000, max_grad_norm=1.0, ema_decay=0.9999)
+    else:
+        opt = torch.optim.Adam(params, lr=2e-4)
+        ema = [p.detach().clone() for p in params]
     torch.manual_seed(100 + rank)  # every rank trains on its own shard of the (synthetic) batch
     x0 = (torch.rand(a.batch, 3, 32, 32, device=dev) * 2 - 1)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -52,12 +61,19 @@ def main():
         ev[1].record()
         loss.backward()
         ev[2].record()
-        opt.step()
+        if a.optim == "fused":
+            opt.step()
+        else:
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            with torch.no_grad():
+                torch._foreach_mul_(ema, 0.9999)
+                torch._foreach_add_(ema, [p.detach() for p in params], alpha=1e-4)
         ev[3].record()
         torch.cuda.synchronize()
         if rank == 0:
           print(f"[{world} rank(s)] rep {r}: loss {float(loss):.5f}  fwd {ev[0].elapsed_time(ev[1]):8.2f} ms  bwd {ev[1].elapsed_time(ev[2]):8.2f} ms  "
-              f"adam {ev[2].elapsed_time(ev[3]):6.2f} ms  launches {ops.launch_count()}  "
+              f"optim({a.optim}) {ev[2].elapsed_time(ev[3]):6.2f} ms  launches {ops.launch_count()}  "
               f"mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
     if world > 1:
         w0 = next(dm.parameters()).detach().flatten()[:1000].double().sum()
