@@ -13,6 +13,8 @@
 //   glue: pixel sums (temb gradient), 2x2 sum pooling (nearest-upsample backward), in-place adds, MSE loss.
 // Tensor-core versions of the dominant products live in conv_wgrad_tc.cu; everything here is the any-shape path
 // (the reference's test fixture trains a UNet with 4/8/16/32 channels and 2 groups, tests/test_ddpm.py:7-23).
+#include <mma.h>
+
 #include "common.cuh"
 
 namespace dmme {
@@ -39,6 +41,7 @@ struct GemmParams {
   void* c; int c_dtype; long long c_bo, c_h, c_r, c_c;
   int M, N, K, heads;
   float alpha; int accumulate;
+  int bf16_mma;  // operands may be rounded to bf16 and multiplied on the tensor cores (bf16 training mode only)
 };
 
 constexpr int SG_M = 64, SG_N = 64, SG_K = 16;
@@ -108,8 +111,83 @@ __global__ void __launch_bounds__(256) gemm_strided_kernel(const GemmParams p) {
   }
 }
 
+// The same product with bf16 operands on the tensor cores (mma.sync through the wmma API, fp32 accumulate): the
+// any-stride attention products of the bf16 training path (Q K^T, P V and the four backward products per site) were
+// FFMA-bound at ~17 TFLOP/s, 28% of a training step.  Operands are converted to bf16 while they are staged in shared
+// memory (fp32 P / dS buffers included: P is rounded to bf16 in the forward kernels as well); fp32 mode never takes
+// this path.  64 x 64 tile, K step 32, 8 warps x (16 x 32) accumulators.
+constexpr int MG_K = 32;
+
+__global__ void __launch_bounds__(256) gemm_strided_mma_kernel(const GemmParams p) {
+  using namespace nvcuda;
+  __shared__ __align__(32) __nv_bfloat16 As[SG_M][MG_K + 8];
+  __shared__ __align__(32) __nv_bfloat16 Bs[MG_K][SG_N + 8];
+  __shared__ __align__(32) float Cs[SG_M][SG_N + 4];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int bo = blockIdx.z / p.heads, h = blockIdx.z - bo * p.heads;
+  const long long a0 = bo * p.a.s_bo + h * p.a.s_h, b0 = bo * p.b.s_bo + h * p.b.s_h;
+  const long long c0 = bo * p.c_bo + h * p.c_h;
+  const int m0 = blockIdx.x * SG_M, n0 = blockIdx.y * SG_N;
+  const bool a_kfast = p.a.s_c == 1;
+  const bool b_jfast = p.b.s_c == 1;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2];
+  wmma::fill_fragment(acc[0], 0.f);
+  wmma::fill_fragment(acc[1], 0.f);
+
+  for (int k0 = 0; k0 < p.K; k0 += MG_K) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int kk, ii;
+      if (a_kfast) { kk = tid & 31; ii = (tid >> 5) + 8 * j; }
+      else { ii = tid & 63; kk = (tid >> 6) + 4 * j; }
+      const int i = m0 + ii, k = k0 + kk;
+      As[ii][kk] = __float2bfloat16_rn((i < p.M && k < p.K) ? ld_any(p.a.p, a0 + i * p.a.s_r + k * p.a.s_c, p.a.dtype) : 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int kk, jj;
+      if (b_jfast) { jj = tid & 63; kk = (tid >> 6) + 4 * j; }
+      else { kk = tid & 31; jj = (tid >> 5) + 8 * j; }
+      const int jn = n0 + jj, k = k0 + kk;
+      Bs[kk][jj] = __float2bfloat16_rn((jn < p.N && k < p.K) ? ld_any(p.b.p, b0 + k * p.b.s_r + jn * p.b.s_c, p.b.dtype) : 0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < MG_K; ks += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fa;
+      wmma::load_matrix_sync(fa, &As[wm][ks], MG_K + 8);
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
+        wmma::load_matrix_sync(fb, &Bs[ks][wn + 16 * f], SG_N + 8);
+        wmma::mma_sync(acc[f], fa, fb, acc[f]);
+      }
+    }
+    __syncthreads();
+  }
+  wmma::store_matrix_sync(&Cs[wm][wn], acc[0], SG_N + 4, wmma::mem_row_major);
+  wmma::store_matrix_sync(&Cs[wm][wn + 16], acc[1], SG_N + 4, wmma::mem_row_major);
+  __syncthreads();
+  // consecutive threads walk whichever output index is contiguous in memory
+  const bool c_jfast = p.c_c == 1;
+  for (int e = tid; e < SG_M * SG_N; e += 256) {
+    const int ii = c_jfast ? e >> 6 : e & 63, jj = c_jfast ? e & 63 : e >> 6;
+    const int r = m0 + ii, cn = n0 + jj;
+    if (r >= p.M || cn >= p.N) continue;
+    const long long o = c0 + r * p.c_r + cn * p.c_c;
+    float v = p.alpha * Cs[ii][jj];
+    if (p.accumulate) v += ld_any(p.c, o, p.c_dtype);
+    st_any(p.c, o, p.c_dtype, v);
+  }
+}
+
 static int launch_gemm(const GemmParams& p, int batches, cudaStream_t st) {
   dim3 grid(ceil_div(p.M, SG_M), ceil_div(p.N, SG_N), batches);
+  if (p.bf16_mma) {
+    gemm_strided_mma_kernel<<<grid, 256, 0, st>>>(p);
+    return check_launch("gemm_strided_mma_kernel");
+  }
   gemm_strided_kernel<<<grid, 256, 0, st>>>(p);
   return check_launch("gemm_strided_kernel");
 }
@@ -122,6 +200,7 @@ static int gemm_f32(const float* a, long long a_r, long long a_c, const float* b
   p.b = {b, DMME_F32, 0, 0, b_r, b_c};
   p.c = c; p.c_dtype = DMME_F32; p.c_bo = 0; p.c_h = 0; p.c_r = ldc; p.c_c = 1;
   p.M = M; p.N = N; p.K = K; p.heads = 1; p.alpha = alpha; p.accumulate = accumulate;
+  p.bf16_mma = 0;
   return launch_gemm(p, 1, st);
 }
 
@@ -925,6 +1004,7 @@ extern "C" int dmme_gemm_strided(const void* a, int a_dtype, long long a_bo, lon
   p.b = {b, b_dtype, b_bo, b_h, b_r, b_c};
   p.c = c; p.c_dtype = c_dtype; p.c_bo = c_bo; p.c_h = c_h; p.c_r = c_r; p.c_c = c_c;
   p.M = M; p.N = N; p.K = K; p.heads = heads; p.alpha = alpha; p.accumulate = accumulate;
+  p.bf16_mma = 0;
   return launch_gemm(p, outer * heads, static_cast<cudaStream_t>(stream));
 }
 
@@ -1124,6 +1204,7 @@ extern "C" int dmme_attention_fwd_train(const void* q, const void* k, const void
   int rc;
   GemmParams g;
   g.heads = heads; g.accumulate = 0;
+  g.bf16_mma = act_dtype == DMME_BF16 ? 1 : 0;
   g.a = {q, act_dtype, batch_stride, head_stride, row_stride, 1};
   g.b = {k, act_dtype, batch_stride, head_stride, 1, row_stride};
   g.c = p_out; g.c_dtype = DMME_F32; g.c_bo = heads * LL; g.c_h = LL; g.c_r = L; g.c_c = 1;
@@ -1161,6 +1242,7 @@ extern "C" int dmme_attention_bwd(const void* q, const void* k, const void* v, l
   int rc;
   GemmParams g;
   g.heads = heads; g.accumulate = 0;
+  g.bf16_mma = act_dtype == DMME_BF16 ? 1 : 0;
   const int rows_per_block = 8;
   const float* P = p_saved;
   if (P == nullptr) {

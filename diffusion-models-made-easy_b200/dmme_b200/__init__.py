@@ -8,7 +8,8 @@ from . import equations
 from . import models
 from . import diffusion_models
 from . import optim
+from . import training
 from .diffusion_models import DDPM, DDIM, IDDPM
 
 __all__ = ["DDPM", "DDIM", "IDDPM", "gaussian", "gaussian_like", "uniform_int", "pad", "equations", "models",
-           "diffusion_models", "optim"]
+           "diffusion_models", "optim", "training"]

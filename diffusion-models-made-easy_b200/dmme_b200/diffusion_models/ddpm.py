@@ -156,7 +156,9 @@ class DDPM(nn.Module):
         alpha_bar_t = self.alpha_bar[t]
         mean, std = torch.sqrt(alpha_bar_t) * x_0, torch.sqrt(1 - alpha_bar_t)
         if noise is None:
-            x_t = torch.normal(mean, std.expand_as(mean))
+            # == torch.normal(mean, std.expand_as(mean)) draw for draw (ATen: out.normal_().mul_(std).add_(mean)) without
+            # that op's host-side `std >= 0` check, which synchronises and cannot be captured in a CUDA graph
+            x_t = torch.empty_like(mean).normal_().mul_(std).add_(mean)
         else:
             x_t = noise.to(x_0.device) * std + mean
         return x_0, t, x_t.contiguous(), mean, std

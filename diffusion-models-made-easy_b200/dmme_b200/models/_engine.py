@@ -52,6 +52,9 @@ class Engine:
         self._packed: Dict[Tuple, Tuple[Tuple, Tensor]] = {}
         self._blocks: Optional[List[Tuple[str, nn.Module]]] = None
         self.force_generic = False  # debugging / fp32 mode: never take the tcgen05 path
+        # True while a training step is captured into a CUDA graph: weight-derived buffers are rebuilt on every call, so
+        # the pack kernels become part of the graph and replays see the optimizer's latest weights
+        self.always_repack = False
         # GroupNorm statistics written by conv epilogues: one zeroed int64 arena per forward pass
         self._arena: Optional[Tensor] = None
         self._arena_cursor = 0
@@ -61,7 +64,7 @@ class Engine:
     # -- caches ------------------------------------------------------------------------------
     def _cached(self, key: Tuple, versions: Tuple, build):
         hit = self._packed.get(key)
-        if hit is not None and hit[0] == versions:
+        if hit is not None and hit[0] == versions and not self.always_repack:
             return hit[1]
         val = build()
         self._packed[key] = (versions, val)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--dropout", type=float, default=None)
+    ap.add_argument("--graph", action="store_true", help="capture forward + loss + backward in one CUDA graph and replay it")
     ap.add_argument("--optim", default="fused", choices=["fused", "torch"],
                     help="fused: dmme_b200.optim.FusedAdamEMA (clip + Adam + warm-up + EMA, two launches); "
                          "torch: clip_grad_norm_ + torch.optim.Adam + foreach EMA")
@@ -53,6 +54,22 @@ def main():
     torch.manual_seed(100 + rank)  # every rank trains on its own shard of the (synthetic) batch
     x0 = (torch.rand(a.batch, 3, 32, 32, device=dev) * 2 - 1)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    if a.graph:
+        # forward + loss + backward replayed from one CUDA graph (dmme_b200.training), optimizer eager after the replay
+        from dmme_b200.training import GraphedTrainingStep
+        step = GraphedTrainingStep(dm, None)
+        step._capture(x0)
+        for r in range(a.reps + 1):
+            ev[0].record()
+            loss = step(x0)
+            ev[2].record()
+            opt.step()
+            ev[3].record()
+            torch.cuda.synchronize()
+            if rank == 0:
+                print(f"[graph] rep {r}: loss {float(loss.detach()):.5f}  fwd+bwd {ev[0].elapsed_time(ev[2]):8.2f} ms  "
+                      f"optim({a.optim}) {ev[2].elapsed_time(ev[3]):6.2f} ms", flush=True)
+        return
     for r in range(a.reps + 1):
         opt.zero_grad(set_to_none=True)
         ops.reset_launch_count()
