@@ -21,7 +21,7 @@
 namespace dmme {
 
 struct ConvTcParams {
-  CUtensorMap a[4];  // src0, src1, res0, res1
+  CUtensorMap a[4];  // src0, src1, res0, res1 (cta_group::2 kernel: boxes of half a pixel tile)
   CUtensorMap b;     // weights [cout][K] bf16
   int chunks0, chunks1, rchunks0, rchunks1;
   int c0, c1;
@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 // WS: 1x1 convs keep their [128][K] weight slab resident (see conv_tc_kernel).
 // ================================================================================================================
 constexpr int kTctMaxStages = 8;
+constexpr int kTctProducers = 1;  // more producer lanes do not help: the k-block rate is the SS-mode MMA rate
 
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(lo)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
@@ -383,7 +384,12 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int idx) {
 }
 
 // CMOD: channel stride of the output rows when known at compile time (128 / 256: immediate store offsets), 0 = runtime
-template <bool WS, int CMOD>
+// PAIR: cta_group::2 -- the two CTAs of a cluster compute 256 output channels x NP pixels with one MMA stream (see
+//       ptx_sm100.cuh): CTA r of the pair owns channels [128 r, 128 r + 128) (its TMEM lanes, its weight tiles) and
+//       stages pixels [r NP/2, (r + 1) NP/2) of the pixel tile (the tensor maps then have half-tile boxes), so its L2 -> SM feed
+//       per k-block is 16 + 16 KB instead of 32 + 16 KB for the same 128 x NP outputs.  The 3x3 convs of the 16x16 /
+//       8x8 levels are bound by that feed (~45 B/clk/SM measured), not by the tensor pipe.
+template <bool WS, int CMOD, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
                                                                 const ConvTctExtra x) {
   extern __shared__ uint8_t smem_raw[];
@@ -403,10 +409,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
   uint8_t* ring = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* slab = ring + STAGES * kStage;  // WS only
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles;  // PAIR: n_tiles counts 256-channel tiles
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int cta0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);  // first work unit
+  const int cta_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int kTileCh = PAIR ? 256 : 128;
 #define DMME_TCT_COORDS(t)                                    \
   const int mt = (t) / p.n_tiles;                             \
-  const int col0 = ((t) - mt * p.n_tiles) * 128;              \
+  const int col0 = ((t) - mt * p.n_tiles) * kTileCh + static_cast<int>(rank) * 128; \
   const int tx = mt % p.tiles_x;                              \
   const int ty = (mt / p.tiles_x) % p.tiles_y;                \
   const int ng = mt / (p.tiles_x * p.tiles_y);                \
@@ -421,45 +431,60 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int st = 0; st < 2; ++st) { mbar_init(&acc_full[st], 1); mbar_init(&acc_empty[st], kConvEpiWarps * 32); }
+    // PAIR: the leader's acc_empty collects the epilogue threads of both CTAs
+    for (int st = 0; st < 2; ++st) { mbar_init(&acc_full[st], 1); mbar_init(&acc_empty[st], (PAIR ? 2 : 1) * kConvEpiWarps * 32); }
     mbar_init(&slab_full, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
+  constexpr int kMapBase = 0;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.a[0]);
-    if (p.chunks1) tma_prefetch_desc(&p.a[1]);
-    if (p.rchunks0) tma_prefetch_desc(&p.a[2]);
-    if (p.rchunks1) tma_prefetch_desc(&p.a[3]);
+    tma_prefetch_desc(&p.a[kMapBase + 0]);
+    if (p.chunks1) tma_prefetch_desc(&p.a[kMapBase + 1]);
+    if (p.rchunks0) tma_prefetch_desc(&p.a[kMapBase + 2]);
+    if (p.rchunks1) tma_prefetch_desc(&p.a[kMapBase + 3]);
     tma_prefetch_desc(&p.b);
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 2 * kAccCols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm(&tmem_slot, 2 * kAccCols);
+    else tmem_alloc(&tmem_slot, 2 * kAccCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before either signals the other's
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   pdl_trigger();  // after the TMEM allocation (see common.cuh)
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // kTctProducers lanes take the k-blocks round-robin (1: a single lane keeps up -- k-blocks land every ~700 clocks
+    // whether one or four lanes issue them and whether they carry 32 or 48 KB: the pace is the MMA's)
+    if (lane < kTctProducers) {
       int it = 0;
       pdl_wait();
       trace_ev(x.trace, 0, 0);
-      if (WS) {
+      if (WS && lane == 0) {
         mbar_expect_tx(&slab_full, static_cast<uint32_t>(nkb) * kWTile);
         const int wcol0 = (blockIdx.x % p.n_tiles) * 128;
         for (int kb = 0; kb < nkb; ++kb) tma_load_2d(slab + kb * kWTile, &p.b, &slab_full, kb * kBlockK, wcol0);
       }
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cta0; t < total_tiles; t += cta_step) {
         DMME_TCT_COORDS(t)
+        // PAIR: this CTA stages the second half of the pixel tile when it is the odd one: the tile is split along its
+        // slowest dimension (images when it spans several, rows otherwise)
+        const int half_n = PAIR ? (p.bni >= 2 ? static_cast<int>(rank) * (p.bni >> 1) : 0) : 0;
+        const int half_y = PAIR ? (p.bni >= 2 ? 0 : static_cast<int>(rank) * (p.bh >> 1)) : 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
+          if (it % kTctProducers != lane) continue;
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], kStage);
+          // PAIR: only the leader arms its barrier, for the bytes of both CTAs
+          if (!PAIR) mbar_expect_tx(&full_bar[s], kStage);
+          else if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStage);
           uint8_t* sx = ring + s * kStage;
-          int which, cc, cx = x0, cy = y0, cp = 0;
+          int which, cc, cx = x0, cy = y0 + half_y, cp = 0;
           if (kb < conv_kb) {
             const int tap = kb / cchunks;
             int ch = kb - tap * cchunks;
@@ -485,19 +510,25 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
             if (which == 3) ch -= p.rchunks0;
             cc = ch * kBlockK;
           }
-          trace_ev(x.trace, 0, it + 1);
-          tma_load_5d(sx, &p.a[which], &full_bar[s], cc, cx, cp, cy, n0);
-          if (!WS) tma_load_2d(sx + NP * 128, &p.b, &full_bar[s], kb * kBlockK, col0);
+          if (lane == 0) trace_ev(x.trace, 0, it + 1);
+          if (PAIR) {
+            const uint32_t lead_bar = mapa_u32(&full_bar[s], 0);
+            tma_load_5d_2sm(sx, &p.a[kMapBase + which], lead_bar, cc, cx, cp, cy, n0 + half_n);
+            tma_load_2d_2sm(sx + (NP >> 1) * 128, &p.b, lead_bar, kb * kBlockK, col0);
+          } else {
+            tma_load_5d(sx, &p.a[which], &full_bar[s], cc, cx, cp, cy, n0);
+            if (!WS) tma_load_2d(sx + NP * 128, &p.b, &full_bar[s], kb * kBlockK, col0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, NP);  // M = 128 output channels, N = pixels
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, NP);  // M = output channels (of the pair), N = pixels
       int it = 0, t_it = 0;
       if (WS) mbar_wait(&slab_full, 0);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
+      for (int t = cta0; t < total_tiles; t += cta_step, ++t_it) {
         const int stage = t_it & 1;
         mbar_wait(&acc_empty[stage], ((t_it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -510,13 +541,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
           trace_ev(x.trace, 1, it);
           const uint32_t sx = smem_u32(ring + s * kStage);
           const uint64_t xdesc = umma_desc_sw128(sx);
-          const uint64_t wdesc = umma_desc_sw128(WS ? smem_u32(slab + kb * kWTile) : sx + NP * 128);
+          const uint64_t wdesc = umma_desc_sw128(WS ? smem_u32(slab + kb * kWTile) : sx + (PAIR ? NP >> 1 : NP) * 128);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (PAIR) umma_bf16_2sm(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (PAIR) umma_commit_2sm(&empty_bar[s], 3);  // the slot is free in both CTAs
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&acc_full[stage]);
+        if (PAIR) umma_commit_2sm(&acc_full[stage], 3);
+        else umma_commit(&acc_full[stage]);
       }
     }
   } else {
@@ -536,9 +571,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
     const int nchunks = NP >> 6;  // 32-pixel chunks per warp and tile
     int t_it = 0;
     pdl_wait();
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++t_it) {
+    for (int t = cta0; t < total_tiles; t += cta_step, ++t_it) {
       const int mt = t / p.n_tiles;
-      const int cb = (t - mt * p.n_tiles) * 128 + q * 32;  // first channel of this warp's block (warp-uniform)
+      // first channel of this warp's block (warp-uniform)
+      const int cb = (t - mt * p.n_tiles) * kTileCh + static_cast<int>(rank) * 128 + q * 32;
       const int ch = cb + lane;                            // this thread's output channel
       const int stage = t_it & 1;
       float bias_c = p.bias ? __ldg(p.bias + ch) : 0.f;
@@ -696,7 +732,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[stage]);
+      if (PAIR) mbar_arrive_cluster(mapa_u32(&acc_empty[stage], 0));  // the leader's MMA thread waits for both CTAs
+      else mbar_arrive(&acc_empty[stage]);
       if (warp == 2 && lane == 0) trace_ev(x.trace, 2, 2 * t_it + 1);
       flush_stats();
     }
@@ -704,10 +741,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
 #undef DMME_TCT_COORDS
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA may leave while the other can still signal its barriers / read its tiles
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * kAccCols);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, 2 * kAccCols);
+    else tmem_dealloc(tmem_base, 2 * kAccCols);
   }
 }
 
@@ -789,6 +828,9 @@ static int launch_conv_tc(const ConvTcParams& p, int m_tiles, cudaStream_t strea
 }
 
 static long long* g_conv_trace = nullptr;
+// cta_group::2 variant: 0 never (default: measured 34.8 vs 31.9 us at 8x8 and 98 vs 93 us at 16x16 -- the mainloop is paced
+// by the SS-mode MMA, not by the operand feed the pairing halves), 1 where it applies, 2 wherever supported (tests)
+static int g_tct_pair_mode = 0;
 static int g_tct_mode = 1;  // 1: transposed kernel where it applies, 0: never (A/B measurements), 2: wherever supported
 static int g_sm_count_tc = 0;
 
@@ -800,16 +842,17 @@ static int tct_tile_pixels(const dmme_conv_desc& d) {
   if (d.out_layout == DMME_OUT_QKV && ((d.cout / 3) % 128 || (ho * wo) % 8)) return 0;
   const long long total_pix = static_cast<long long>(d.n) * ho * wo;
   const int n_tiles = d.cout / 128;
+  if (g_tct_pair_mode == 2 && d.cout % 256 == 0 && d.out_layout == DMME_OUT_NHWC) return 256;  // tests: force the pair kernel
   if (wo <= 256 && ceil_div_ll(total_pix, 256) * n_tiles >= 120) return 256;
   if (ceil_div_ll(total_pix, 128) * n_tiles >= 100 || g_tct_mode == 2) return 128;
   return 0;
 }
 
-template <bool WS, int CMOD>
+template <bool WS, int CMOD, bool PAIR = false>
 static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) {
       set_error("conv_tct: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -817,9 +860,15 @@ static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cud
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles;
+  if (PAIR) {
+    // one cluster of two CTAs (two SMs) per work unit
+    const int pairs = total < g_sm_count_tc / 2 ? total : g_sm_count_tc / 2;
+    cudaError_t e = launch_pdl_pair(conv_tct_kernel<WS, CMOD, PAIR>, dim3(2 * pairs), dim3(kConvThreads), smem, stream, p, x);
+    return check_launch_err(e, "conv_tct_kernel (cta_group::2)");
+  }
   int grid = total < g_sm_count_tc ? total : g_sm_count_tc;
   if (WS) grid -= grid % p.n_tiles;
-  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD>, dim3(grid), dim3(kConvThreads), smem, stream, p, x);
+  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD, PAIR>, dim3(grid), dim3(kConvThreads), smem, stream, p, x);
   return check_launch_err(e, "conv_tct_kernel");
 }
 
@@ -887,6 +936,24 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     const int budget = 226 * 1024 - 1024;
     const long long slab = static_cast<long long>(ktot / 64) * 128 * 128;
     const bool ws = p.taps == 1 && slab + 2 * np * 128 <= budget && p.n_tiles <= g_sm_count_tc;
+    // cta_group::2: 256 output channels x 256 pixels per CTA pair when that still gives most SM pairs a unit
+    const bool pair = g_tct_pair_mode != 0 && !ws && np == 256 && d.cout % 256 == 0 && d.out_layout == DMME_OUT_NHWC &&
+                      (static_cast<long long>(m_tiles) * (d.cout / 256) >= 56 || g_tct_pair_mode == 2);
+    if (pair) {
+      // half-tile boxes: split along the tile's slowest dimension
+      const int hbni = p.bni >= 2 ? p.bni / 2 : p.bni, hbh = p.bni >= 2 ? p.bh : p.bh / 2;
+      if ((rc = make_act_map(&p.a[0], d.src0, d.n, d.h_in, d.w_in, d.c0, d.stride, p.bw, hbh, hbni))) return rc;
+      if (d.c1 && (rc = make_act_map(&p.a[1], d.src1, d.n, d.h_in, d.w_in, d.c1, d.stride, p.bw, hbh, hbni))) return rc;
+      if (d.rc0 && (rc = make_act_map(&p.a[2], d.res0, d.n, ho, wo, d.rc0, 1, p.bw, hbh, hbni))) return rc;
+      if (d.rc1 && (rc = make_act_map(&p.a[3], d.res1, d.n, ho, wo, d.rc1, 1, p.bw, hbh, hbni))) return rc;
+      p.n_tiles = d.cout / 256;
+      x.stage_bytes = (np / 2) * 128 + 128 * 128;
+      int st = budget / x.stage_bytes;
+      x.stages = st > kTctMaxStages ? kTctMaxStages : st;
+      const int smem2 = x.stages * x.stage_bytes + 1024;
+      return d.cout == 256 ? launch_conv_tct<false, 256, true>(p, x, smem2, stream)
+                           : launch_conv_tct<false, 0, true>(p, x, smem2, stream);
+    }
     x.stage_bytes = np * 128 + (ws ? 0 : 128 * 128);
     int stages = static_cast<int>((budget - (ws ? slab : 0)) / x.stage_bytes);
     x.stages = stages > kTctMaxStages ? kTctMaxStages : stages;
@@ -934,3 +1001,5 @@ extern "C" void dmme_set_conv_tct_mode(int mode) { dmme::g_tct_mode = mode; }
 extern "C" int dmme_get_conv_tct_mode(void) { return dmme::g_tct_mode; }
 // debugging: device buffer of 3 x 512 int64 that CTA 0 of the transposed kernel fills with clock64 timestamps
 extern "C" void dmme_debug_set_conv_trace(long long* buf) { dmme::g_conv_trace = buf; }
+// A/B measurement switch for the cta_group::2 (two-SM) variant of the transposed kernel: 0 off, 1 default, 2 forced
+extern "C" void dmme_set_conv_pair_mode(int mode) { dmme::g_tct_pair_mode = mode; }

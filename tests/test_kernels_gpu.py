@@ -328,6 +328,25 @@ def test_conv_tct(cfg, tct_everywhere):
     assert torch.allclose(sums[..., 1], (got.double() ** 2).reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
 
 
+@pytest.fixture
+def pair_everywhere():
+    """force the cta_group::2 (two-SM MMA) variant of the transposed kernel wherever it is supported"""
+    _, L = _ops()
+    lib = L.load()
+    lib.dmme_set_conv_pair_mode(2)
+    yield
+    lib.dmme_set_conv_pair_mode(0)
+
+
+@pytest.mark.parametrize("cfg", [c for c in TCT_CASES if c["cout"] % 256 == 0] + [
+    dict(n=1, cin=64, cout=256, h=16, w=16, k=3),                                # a single pair
+    dict(n=75, cin=256, cout=512, h=8, w=8, k=3, temb="bcast", addend=True),     # two channel pairs, ragged last tile
+    dict(n=300, cin=256, cout=256, h=16, w=16, k=3, temb="rows"),                # several units per pair
+])
+def test_conv_tct_pair(cfg, pair_everywhere):
+    test_conv_tct.__wrapped__(cfg, None) if hasattr(test_conv_tct, "__wrapped__") else test_conv_tct(cfg, None)
+
+
 @pytest.mark.parametrize("n,c,h", [(3, 128, 16), (50, 256, 16), (7, 256, 4), (300, 128, 4)])
 def test_conv_tct_qkv_layout(n, c, h, tct_everywhere):
     _, L = _ops()
