@@ -201,3 +201,32 @@ extern "C" int dmme_philox_normal(float* out, long long numel, unsigned long lon
   philox_normal_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, numel, seed, stream_id, noise_offset / 4);
   return check_launch("philox_normal_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// denorm (common/norm.py:9-11): clip((x + 1) / 2, 0, 1), the image-space tail of GenerateImage.generate_img
+// (callbacks/generate.py:64-90) and of LitDDPM.test_step (lit_modules/ddpm.py:97-100); optionally also quantised to
+// uint8 (round(255 y)) for image logging / FID feature extraction.  One pass: 4 B read, 4 and / or 1 B written.
+// ------------------------------------------------------------------------------------------------
+namespace dmme {
+__global__ void denorm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, uint8_t* __restrict__ out_u8,
+                              long long numel) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    // torch: (x + 1) / 2 then clip(0, 1); clip propagates NaN
+    float y = __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+    y = (y != y) ? y : fminf(fmaxf(y, 0.0f), 1.0f);
+    if (out_f32) out_f32[i] = y;
+    if (out_u8) out_u8[i] = static_cast<uint8_t>(__float2int_rn(y * 255.0f));
+  }
+}
+}  // namespace dmme
+
+extern "C" int dmme_denorm(const float* x, float* out_f32, uint8_t* out_u8, long long numel, void* stream) {
+  DMME_REQUIRE(x && (out_f32 || out_u8) && numel > 0, DMME_E_BADARG, "denorm: bad arguments");
+  return check_launch_err(launch_pdl(dmme::denorm_kernel, dim3(ew_grid(numel, 256)), dim3(256), 0,
+                                     static_cast<cudaStream_t>(stream), x, out_f32, out_u8, numel),
+                          "denorm_kernel");
+}

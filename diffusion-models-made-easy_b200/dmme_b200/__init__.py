@@ -3,6 +3,7 @@ the UNet denoiser inside the DDPM / DDIM / IDDPM loops, behind the reference's P
 __version__ = "0.1.0"
 
 from .common.noise import gaussian, gaussian_like, uniform_int, pad
+from .common.norm import norm, denorm, denorm_uint8
 
 from . import equations
 from . import models
@@ -11,5 +12,5 @@ from . import optim
 from . import training
 from .diffusion_models import DDPM, DDIM, IDDPM
 
-__all__ = ["DDPM", "DDIM", "IDDPM", "gaussian", "gaussian_like", "uniform_int", "pad", "equations", "models",
+__all__ = ["DDPM", "DDIM", "IDDPM", "gaussian", "gaussian_like", "uniform_int", "pad", "norm", "denorm", "denorm_uint8", "equations", "models",
            "diffusion_models", "optim", "training"]

@@ -29,7 +29,7 @@ EXPORTS = (
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode",
-    "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
+    "dmme_denorm", "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
     "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
     "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
     "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_dilate2x_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.dmme_set_conv_tct_mode.argtypes = [i]
     lib.dmme_set_conv_out_tc_mode.argtypes = [i]
     lib.dmme_set_conv_pair_mode.argtypes = [i]
+    lib.dmme_denorm.argtypes = [vp, vp, vp, ll, vp]
     lib.dmme_adam_ema_step.argtypes = [vp, i, ll, C.c_double, C.c_double, C.c_double, C.c_double, i, C.c_double, C.c_double,
                                        vp, i, vp, vp]
     lib.dmme_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, i, vp, i, vp]

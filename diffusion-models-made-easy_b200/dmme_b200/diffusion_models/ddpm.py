@@ -88,11 +88,14 @@ class DDPM(nn.Module):
         ops.add_i64_(counter, -1)
 
     def _run_steps(self, x: Tensor, steps: int, seed: int, graph: bool,
-                   on_step: Optional[Callable[[int, Tensor], None]] = None) -> Tensor:
+                   on_step: Optional[Callable[[int, Tensor], None]] = None,
+                   pre_step: Optional[Callable[[int, Tensor], None]] = None) -> Tensor:
         dev = x.device
         counter = torch.full((1,), self._counter_start(), dtype=torch.int64, device=dev)
         if not graph:
             for k in range(steps):
+                if pre_step is not None:
+                    pre_step(k, x)
                 self._graph_step(x, counter, seed)
                 if on_step is not None:
                     on_step(k, x)
@@ -111,6 +114,8 @@ class DDPM(nn.Module):
             self._graph_step(x, counter, seed)
         # capture does not execute: state is still (x_T, T)
         for k in range(steps):
+            if pre_step is not None:
+                pre_step(k, x)
             g.replay()
             if on_step is not None:
                 on_step(k, x)
@@ -142,6 +147,43 @@ class DDPM(nn.Module):
             return self._run_steps(x, self._num_steps(), seed, graph, on_step)
         finally:
             self._noise_offset = 0
+
+    @staticmethod
+    def history_timesteps(timesteps: int, vis_length: int) -> list:
+        """The ``save_t`` list of ``GenerateImage.generate_img`` (callbacks/generate.py:73-76), same integer arithmetic."""
+        return [int(timesteps / (vis_length - 1) * i) for i in range(vis_length - 1, 0, -1)]
+
+    @torch.no_grad()
+    def generate_history(self, img_size: Tuple[int, int, int, int], vis_length: int = 20, *,
+                         x_T: Optional[Tensor] = None, seed: Optional[int] = None, graph: bool = True,
+                         uint8: bool = False) -> Tensor:
+        """The denoising sequence ``GenerateImage.generate_img`` collects (callbacks/generate.py:64-90): ``denorm(x_t)``
+        at every ``t`` in ``save_t`` *before* the step at ``t`` runs, plus ``denorm`` of the final sample, stacked as
+        ``(len, N, C, H, W)`` in [0, 1] (or uint8 0..255 with ``uint8=True``).  The chain itself is the graph-replayed
+        ``generate`` loop; each snapshot is one fused denorm launch between two replays, written straight into the
+        history tensor (the reference clones ``x_t`` and runs three elementwise kernels per snapshot)."""
+        from ..common.norm import denorm, denorm_uint8
+        dev = self.beta.device
+        if dev.type != "cuda":
+            raise RuntimeError("dmme_b200 samplers run on CUDA only; move the module with .cuda()")
+        steps, start = self._num_steps(), self._counter_start()
+        save_t = set(self.history_timesteps(start, vis_length))
+        hits = [t for t in range(start, start - steps, -1) if t in save_t]
+        hist = torch.empty((len(hits) + 1,) + tuple(img_size), dtype=torch.uint8 if uint8 else torch.float32, device=dev)
+        put = denorm_uint8 if uint8 else denorm
+        slot = {t: i for i, t in enumerate(hits)}
+
+        def tap(k: int, x: Tensor) -> None:
+            t = start - k
+            if t in slot:
+                put(x, out=hist[slot[t]])
+
+        x = gaussian(tuple(img_size), device=dev) if x_T is None else x_T.detach().to(dev).float().clone()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        x = self._run_steps(x.contiguous(), steps, seed, graph, None, tap)
+        put(x, out=hist[len(hits)])
+        return hist
 
     def _noised(self, x_0: Tensor, t: Optional[Tensor] = None, noise: Optional[Tensor] = None):
         """t ~ U{1..T-1} (randint excludes T), x_t ~ q(x_t | x_0); RNG order as the reference:

@@ -299,6 +299,14 @@ int dmme_iddpm_loss(const float* model_out, const float* x_t, const float* x_0, 
                     const float* alpha, const float* alpha_bar, int n, int c, int hw, float w_simple, float w_vlb,
                     float grad_scale, float* d_out, float* loss_out, float* partial, void* stream);
 
+/* image-space tail ------------------------------------------------------------------------- */
+/*
+ * y = clip((x + 1) / 2, 0, 1) (common/norm.py:9-11 `denorm`), written as fp32 (out_f32) and / or as uint8 round(255 y)
+ * (out_u8); either output may be NULL.  Replaces the denorm of every snapshot in GenerateImage.generate_img
+ * (callbacks/generate.py:64-90) and of LitDDPM.test_step (lit_modules/ddpm.py:97-100).  fp32 output is bit-exact.
+ */
+int dmme_denorm(const float* x, float* out_f32, uint8_t* out_u8, long long numel, void* stream);
+
 /* fused optimizer tail ---------------------------------------------------------------------- */
 /*
  * One training step's parameter update for ALL tensors in two launches: global gradient-norm clip

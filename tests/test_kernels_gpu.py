@@ -712,3 +712,46 @@ def test_philox_normal_moments_and_step_counter():
     ops.gather_i64(tau, c, out)
     torch.cuda.synchronize()
     assert int(c) == 9 and int(out) == 18
+
+
+# ---------------------------------------------------------------------------------------------
+# image-space tail: denorm / snapshot history (callbacks/generate.py, common/norm.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(3, 3, 32, 32), (1, 1, 5, 7), (64, 3, 32, 32)])
+def test_denorm_bit_exact(shape):
+    import dmme_b200
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g) * 1.5
+    x.view(-1)[:4] = torch.tensor([-1.0, 1.0, -3.0, 3.0])
+    want = torch.clip((x + 1) / 2, 0, 1)  # common/norm.py:9-11
+    got = dmme_b200.denorm(x.to(DEV)).cpu()
+    assert torch.equal(got, want)
+    u8 = dmme_b200.denorm_uint8(x.to(DEV)).cpu()
+    assert u8.dtype == torch.uint8 and torch.equal(u8, (want * 255).round().to(torch.uint8))
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_generate_history_matches_generate_taps(graph):
+    """generate_history == denorm of the chain's states at the reference's save_t (callbacks/generate.py:73-83)"""
+    import dmme_b200
+    from dmme_b200.models.ddpm import UNet
+    torch.manual_seed(0)
+    model = UNet(pos_dim=32, emb_dim=64, channels_per_depth=(64, 128), num_blocks=1, attention_depths=(2,)).eval()
+    ddpm = dmme_b200.DDPM(model, timesteps=20).to(DEV)
+    g = torch.Generator().manual_seed(2)
+    x_T = torch.randn(2, 3, 32, 32, generator=g)
+    save_t = dmme_b200.DDPM.history_timesteps(20, 5)
+    assert save_t == [int(20 / 4 * i) for i in range(4, 0, -1)] == [20, 15, 10, 5]
+    states = {20: x_T.clone()}
+
+    def after(k, x):  # state after step k = x_{T-k-1}
+        states[20 - k - 1] = x.detach().cpu().clone()
+
+    final = ddpm.generate((2, 3, 32, 32), x_T=x_T, seed=77, graph=graph, on_step=after).cpu()
+    hist = ddpm.generate_history((2, 3, 32, 32), vis_length=5, x_T=x_T, seed=77, graph=graph).cpu()
+    assert hist.shape == (5, 2, 3, 32, 32)
+    for i, t in enumerate(save_t):
+        assert torch.equal(hist[i], torch.clip((states[t] + 1) / 2, 0, 1)), t
+    assert torch.equal(hist[4], torch.clip((final + 1) / 2, 0, 1))
+    h8 = ddpm.generate_history((2, 3, 32, 32), vis_length=5, x_T=x_T, seed=77, graph=graph, uint8=True).cpu()
+    assert torch.equal(h8, (hist * 255).round().to(torch.uint8))
