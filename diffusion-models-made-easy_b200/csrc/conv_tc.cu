@@ -374,6 +374,8 @@ struct ConvTctExtra {
   int stage_bytes;  // np * 128 (+ 16 KB weight tile unless WS)
   long long total_pix;
   int log2_l;       // log2(ho * wo)
+  int subpix;       // 1: nearest x2 + 3x3 conv as four 2x2 phase convs on the low-resolution tensor (see below)
+  int log2_w;       // log2(wo) (subpix output addressing)
   long long* trace; // debugging: per-role clock64 timestamps of CTA 0 (see dmme_debug_set_conv_trace), or null
 };
 
@@ -383,6 +385,13 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int idx) {
   if (trace && blockIdx.x == 0 && idx < 512) trace[role * 512 + idx] = clock64();
 }
 
+// Sub-pixel mode (x.subpix): UpSample = nearest x2 then conv3x3 (models/ddpm.py:150-173).  On the x2 grid, output
+// (2i + a, 2j + b) only ever sees the 2x2 low-resolution neighbourhood {i - 1 + a, i + a} x {j - 1 + b, j + b}, with the
+// 3x3 taps that coincide summed: rows {0 | 1+2} for a = 0, {0+1 | 2} for a = 1, likewise for columns.  So the layer is four
+// 2x2 convolutions ("phases" (a, b)) of the LOW-resolution tensor, each writing one parity class of the output: 16
+// instead of 36 tap-MACs per low-resolution pixel (2.25x fewer FLOPs) and no materialised x2 tensor.  The packed weight
+// is [4 phases][cout][4 taps x cin] (summed in fp32, rounded to bf16 once); a work unit is (phase, pixel tile, channel
+// tile); TMA zero fill of rows / columns -1 and H, W is exactly the zero padding of the x2 grid.
 // CMOD: channel stride of the output rows when known at compile time (128 / 256: immediate store offsets), 0 = runtime
 // PAIR: cta_group::2 -- the two CTAs of a cluster compute 256 output channels x NP pixels with one MMA stream (see
 //       ptx_sm100.cuh): CTA r of the pair owns channels [128 r, 128 r + 128) (its TMEM lanes, its weight tiles) and
@@ -409,14 +418,18 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
   uint8_t* ring = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* slab = ring + STAGES * kStage;  // WS only
 
-  const int total_tiles = p.m_tiles * p.n_tiles;  // PAIR: n_tiles counts 256-channel tiles
+  const int nphase = x.subpix ? 4 : 1;
+  const int total_tiles = p.m_tiles * p.n_tiles * nphase;  // PAIR: n_tiles counts 256-channel tiles
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int cta0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);  // first work unit
   const int cta_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr int kTileCh = PAIR ? 256 : 128;
+  // unit index: channel tile fastest, then phase (the four phases of a pixel tile read the same pixels), then pixel tile
 #define DMME_TCT_COORDS(t)                                    \
-  const int mt = (t) / p.n_tiles;                             \
-  const int col0 = ((t) - mt * p.n_tiles) * kTileCh + static_cast<int>(rank) * 128; \
+  const int nt_ = (t) % p.n_tiles;                            \
+  const int sub = ((t) / p.n_tiles) % nphase; /* sub-pixel phase */ \
+  const int mt = (t) / (p.n_tiles * nphase);                  \
+  const int col0 = nt_ * kTileCh + static_cast<int>(rank) * 128; \
   const int tx = mt % p.tiles_x;                              \
   const int ty = (mt / p.tiles_x) % p.tiles_y;                \
   const int ng = mt / (p.tiles_x * p.tiles_y);                \
@@ -503,6 +516,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
                 cp = (r != 1) ? 1 : 0;
                 cy += (r == 0) ? -1 : 0;
               }
+            } else if (p.taps == 4) {  // sub-pixel phase (a, b) = (sub >> 1, sub & 1), tap (u, v) = (tap >> 1, tap & 1)
+              cy += (sub >> 1) - 1 + (tap >> 1);
+              cx += (sub & 1) - 1 + (tap & 1);
             }
           } else {
             int ch = kb - conv_kb;
@@ -510,14 +526,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
             if (which == 3) ch -= p.rchunks0;
             cc = ch * kBlockK;
           }
+          const int wrow = sub * p.cout + col0;  // the phase's block of the packed weight matrix
           if (lane == 0) trace_ev(x.trace, 0, it + 1);
           if (PAIR) {
             const uint32_t lead_bar = mapa_u32(&full_bar[s], 0);
             tma_load_5d_2sm(sx, &p.a[kMapBase + which], lead_bar, cc, cx, cp, cy, n0 + half_n);
-            tma_load_2d_2sm(sx + (NP >> 1) * 128, &p.b, lead_bar, kb * kBlockK, col0);
+            tma_load_2d_2sm(sx + (NP >> 1) * 128, &p.b, lead_bar, kb * kBlockK, wrow);
           } else {
             tma_load_5d(sx, &p.a[which], &full_bar[s], cc, cx, cp, cy, n0);
-            if (!WS) tma_load_2d(sx + NP * 128, &p.b, &full_bar[s], kb * kBlockK, col0);
+            if (!WS) tma_load_2d(sx + NP * 128, &p.b, &full_bar[s], kb * kBlockK, wrow);
           }
         }
       }
@@ -572,9 +589,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
     int t_it = 0;
     pdl_wait();
     for (int t = cta0; t < total_tiles; t += cta_step, ++t_it) {
-      const int mt = t / p.n_tiles;
+      const int mt = t / (p.n_tiles * nphase);
+      const int sub = (t / p.n_tiles) % nphase;  // sub-pixel phase
       // first channel of this warp's block (warp-uniform)
-      const int cb = (t - mt * p.n_tiles) * kTileCh + static_cast<int>(rank) * 128 + q * 32;
+      const int cb = (t % p.n_tiles) * kTileCh + static_cast<int>(rank) * 128 + q * 32;
       const int ch = cb + lane;                            // this thread's output channel
       const int stage = t_it & 1;
       float bias_c = p.bias ? __ldg(p.bias + ch) : 0.f;
@@ -656,6 +674,30 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bt;
+          }
+          if (x.subpix) {
+            // low-resolution pixel (n, i, j) -> output pixel (n, 2 i + a, 2 j + b) of the x2 tensor
+            const int rem = pix0 - (n << x.log2_l);
+            const int i0 = rem >> x.log2_w, j0 = rem & (p.wo - 1);
+            const long long obase_px = (static_cast<long long>(n) * (2 * p.ho) + 2 * i0 + (sub >> 1)) * (2 * p.wo) + 2 * j0 + (sub & 1);
+            __nv_bfloat16* op = obase + obase_px * cmod + chm;
+            const int row_step = 4 * p.wo * cmod;  // two output rows per low-resolution row
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const uint32_t u = pack_bf16x2(f[i], f[i + 1]);
+              // the chunk starts at column j0 of row i0 and may wrap over several (power-of-two wide) rows
+              const int q0 = j0 + i, q1 = j0 + i + 1;
+              op[(q0 >> x.log2_w) * row_step + ((q0 & (p.wo - 1)) - j0) * 2 * cmod] =
+                  __ushort_as_bfloat16(static_cast<unsigned short>(u & 0xffffu));
+              op[(q1 >> x.log2_w) * row_step + ((q1 & (p.wo - 1)) - j0) * 2 * cmod] =
+                  __ushort_as_bfloat16(static_cast<unsigned short>(u >> 16));
+              float lo, hi;
+              unpack_bf16x2(u, lo, hi);
+              s1 += lo + hi;
+              s2 = fmaf(lo, lo, s2);
+              s2 = fmaf(hi, hi, s2);
+            }
+            continue;
           }
           if (which != 2) {
             __nv_bfloat16* op = obase + static_cast<long long>(pix0) * cmod + chm;
@@ -777,7 +819,13 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 bool conv_tc_supported(const dmme_conv_desc& d) {
   if (d.act_dtype != DMME_BF16 || d.in_layout != DMME_IN_NHWC) return false;
   if (d.out_layout != DMME_OUT_NHWC && d.out_layout != DMME_OUT_QKV) return false;
-  if (d.upsample) return false;
+  if (d.upsample && d.upsample != 3) return false;
+  if (d.upsample == 3) {
+    // sub-pixel phases of nearest x2 + conv3x3: transposed kernel only, plain bias epilogue, whole 32-pixel chunks
+    if (d.ksize != 3 || d.stride != 1 || d.out_layout != DMME_OUT_NHWC || d.c1 || d.rc0 || d.rc1 || d.temb || d.addend)
+      return false;
+    if (d.cout % 128 || d.w_in > 128 || d.h_in * d.w_in < 32) return false;
+  }
   if (!(d.ksize == 3 || (d.ksize == 1 && d.stride == 1))) return false;
   if (d.stride != 1 && d.stride != 2) return false;
   if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.rc0 % 64 || d.rc1 % 64) return false;
@@ -836,6 +884,10 @@ static int g_sm_count_tc = 0;
 
 // pixel-tile width of the transposed kernel for this problem, 0 = use conv_tc_kernel
 static int tct_tile_pixels(const dmme_conv_desc& d) {
+  if (d.upsample == 3) {  // four phase units per (pixel tile, channel tile)
+    const long long tp = static_cast<long long>(d.n) * d.h_in * d.w_in;
+    return ceil_div_ll(tp, 256) * (d.cout / 128) * 4 >= 120 ? 256 : 128;
+  }
   if (g_tct_mode == 0) return 0;
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
   if (d.cout % 128 || wo > 128) return 0;
@@ -859,7 +911,7 @@ static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cud
     }
     configured = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * (x.subpix ? 4 : 1);
   if (PAIR) {
     // one cluster of two CTAs (two SMs) per work unit
     const int pairs = total < g_sm_count_tc / 2 ? total : g_sm_count_tc / 2;
@@ -894,7 +946,7 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   p.chunks0 = d.c0 / 64; p.chunks1 = d.c1 / 64;
   p.rchunks0 = d.rc0 / 64; p.rchunks1 = d.rc1 / 64;
   p.c0 = d.c0; p.c1 = d.c1;
-  p.taps = d.ksize * d.ksize; p.stride = d.stride;
+  p.taps = d.upsample == 3 ? 4 : d.ksize * d.ksize; p.stride = d.stride;
   p.n = d.n; p.ho = ho; p.wo = wo;
   p.cout = d.cout;
   p.bias = d.bias; p.temb = d.temb; p.temb_rows = d.temb_rows; p.temb_ld = d.temb_ld;
@@ -920,7 +972,7 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   const uint64_t ktot = (uint64_t)p.taps * (d.c0 + d.c1) + d.rc0 + d.rc1;
   if (np) {
     // transposed kernel: 128 output channels x np pixels per unit
-    uint64_t dims[2] = {ktot, (uint64_t)d.cout};
+    uint64_t dims[2] = {ktot, (uint64_t)d.cout * (d.upsample == 3 ? 4 : 1)};
     uint64_t strides[1] = {ktot * 2};
     uint32_t box[2] = {64u, 128u};
     if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
@@ -933,11 +985,14 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     x.trace = g_conv_trace;
     x.log2_l = 0;
     while ((1 << x.log2_l) < ho * wo) ++x.log2_l;
+    x.subpix = d.upsample == 3 ? 1 : 0;
+    x.log2_w = 0;
+    while ((1 << x.log2_w) < wo) ++x.log2_w;
     const int budget = 226 * 1024 - 1024;
     const long long slab = static_cast<long long>(ktot / 64) * 128 * 128;
     const bool ws = p.taps == 1 && slab + 2 * np * 128 <= budget && p.n_tiles <= g_sm_count_tc;
     // cta_group::2: 256 output channels x 256 pixels per CTA pair when that still gives most SM pairs a unit
-    const bool pair = g_tct_pair_mode != 0 && !ws && np == 256 && d.cout % 256 == 0 && d.out_layout == DMME_OUT_NHWC &&
+    const bool pair = g_tct_pair_mode != 0 && !ws && !x.subpix && np == 256 && d.cout % 256 == 0 && d.out_layout == DMME_OUT_NHWC &&
                       (static_cast<long long>(m_tiles) * (d.cout / 256) >= 56 || g_tct_pair_mode == 2);
     if (pair) {
       // half-tile boxes: split along the tile's slowest dimension

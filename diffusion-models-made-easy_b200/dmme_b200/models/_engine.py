@@ -161,6 +161,19 @@ class Engine:
             probe = ops.make_conv_desc(src0, src1, cout, ks, stride, upsample, addend, None, in_nchw, out_layout, act_dtype, kernel)
             if ops.conv_uses_tc(probe):
                 identity, res0, addend = True, addend, None
+        if upsample and not self.force_generic and act_dtype == torch.bfloat16 and src1 is None and res is None \
+                and temb is None and addend is None and out_layout == L.OUT_NHWC:
+            # nearest x2 + conv3x3 as four 2x2 phase convs on the low-resolution tensor (2.25x fewer FLOPs, no x2 tensor)
+            d = ops.make_conv_desc(src0, None, cout, ks, stride, 3, None, None, in_nchw, out_layout, act_dtype, kernel)
+            if ops.conv_uses_tc(d):
+                w = self._cached(("wup", id(conv)), self._ver(conv.weight), lambda: ops.pack_upsample_phase_weight(conv.weight))
+                ho, wo = ops.conv_out_hw(d)
+                out = self.ws.get(name, (d.n, ho, wo, cout), act_dtype, src0.device)
+                stats = self._stats_for(out, d.n, cout) if ops.conv_writes_stats(d) else None
+                if stats is None:
+                    self._stats.pop(out.data_ptr(), None)
+                ops.conv2d_launch(d, w, conv.bias.detach(), out, stats=stats)
+                return out
         if upsample and not self.force_generic and act_dtype == torch.bfloat16 and src0.shape[3] % 64 == 0 and cout % 64 == 0:
             # tensor-core path has no upsampling gather: materialise the x2 tensor once (memory-bound copy)
             n, h, w, c = src0.shape

@@ -47,6 +47,30 @@ def pack_conv_weight(w: Tensor, w_res: Optional[Tensor] = None, tc: bool = True)
     return packed
 
 
+def pack_upsample_phase_weight(w: Tensor) -> Tensor:
+    """Weights of ``nearest x2 -> conv3x3`` (UpSample, models/ddpm.py:150-173) collapsed onto the low-resolution grid:
+    bf16 ``[4 phases][cout][4 taps x cin]`` for ``make_conv_desc(upsample=3)``.  Phase (a, b) is the parity of the output
+    pixel; its 2x2 taps (u, v) sum the 3x3 taps that fall on the same low-resolution pixel: rows {0 | 1+2} for a = 0,
+    {0+1 | 2} for a = 1, likewise for columns.  Summed in fp32, rounded to bf16 once."""
+    L.require_cuda(w)
+    w = w.detach().float()
+    cout, cin, kh, kw = w.shape
+    if kh != 3 or kw != 3:
+        raise ValueError("UpSample convs are 3x3")
+    groups = (((0,), (1, 2)), ((0, 1), (2,)))  # [parity][tap] -> 3x3 indices
+    out = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=w.device)
+    for a in range(2):
+        for b in range(2):
+            for u in range(2):
+                for v in range(2):
+                    acc = 0
+                    for r in groups[a][u]:
+                        for s in groups[b][v]:
+                            acc = acc + w[:, :, r, s]
+                    out[2 * a + b, :, 2 * u + v, :] = acc
+    return out.reshape(4 * cout, 4 * cin).to(torch.bfloat16).contiguous()
+
+
 # ---------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------
@@ -91,7 +115,7 @@ def make_conv_desc(src0: Tensor, src1: Optional[Tensor], cout: int, ksize: int, 
     d.res0, d.rc0 = (ptr(res0), res0.shape[3]) if res0 is not None else (None, 0)
     d.res1, d.rc1 = (ptr(res1), res1.shape[3]) if res1 is not None else (None, 0)
     d.n, d.h_in, d.w_in = n, h, w
-    d.ksize, d.stride, d.upsample, d.cout = ksize, stride, int(upsample), cout
+    d.ksize, d.stride, d.upsample, d.cout = ksize, stride, int(upsample), cout  # upsample: 0 | 1 nearest x2 | 3 sub-pixel
     d.in_layout = L.IN_NCHW_F32 if in_nchw else L.IN_NHWC
     d.out_layout = out_layout
     if act_dtype is None:

@@ -74,7 +74,9 @@ typedef struct dmme_conv_desc {
   int ksize;                          /* 1 or 3 */
   int stride;                         /* 1 or 2 */
   int upsample;                       /* 1: nearest-neighbour x2 of the source before the conv;
-                                         2: zero-dilated x2 source (data gradient of a stride-2 conv; generic kernel) */
+                                         2: zero-dilated x2 source (data gradient of a stride-2 conv; generic kernel);
+                                         3: nearest x2 + 3x3 conv as four 2x2 phase convs of the low-resolution source
+                                            (tcgen05 path; weight = [4 phases][cout][4 taps x cin] bf16, out is x2) */
   int cout;
   const void* weight;                 /* packed by dmme_pack_conv_weight for the chosen kernel */
   const float* bias;                  /* [cout] fp32, may be NULL */

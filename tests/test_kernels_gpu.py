@@ -755,3 +755,30 @@ def test_generate_history_matches_generate_taps(graph):
     assert torch.equal(hist[4], torch.clip((final + 1) / 2, 0, 1))
     h8 = ddpm.generate_history((2, 3, 32, 32), vis_length=5, x_T=x_T, seed=77, graph=graph, uint8=True).cpu()
     assert torch.equal(h8, (hist * 255).round().to(torch.uint8))
+
+
+@pytest.mark.parametrize("n,c,cout,h", [(3, 128, 128, 16), (40, 256, 256, 8), (2, 64, 128, 32), (70, 128, 256, 16), (5, 256, 256, 8)])
+def test_conv_upsample_subpixel(n, c, cout, h):
+    """UpSample (nearest x2 -> conv3x3, models/ddpm.py:150-173) as four 2x2 phase convs on the low-resolution tensor:
+    against F.interpolate + conv2d on the same bf16 input (phase weights are summed in fp32 then rounded to bf16, so the
+    reference here uses fp32 weights and the tolerance is the bf16 weight rounding), plus the GroupNorm statistics"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(51)
+    x = bf16_round(torch.randn(n, c, h, h, generator=g))
+    w = torch.randn(cout, c, 3, 3, generator=g) / math.sqrt(9 * c)
+    b = torch.randn(cout, generator=g)
+    s0 = to_nhwc(x, torch.bfloat16).to(DEV)
+    d = ops.make_conv_desc(s0, None, cout, 3, 1, 3, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+    assert ops.conv_uses_tc(d) and ops.conv_out_hw(d) == (2 * h, 2 * h)
+    wp = ops.pack_upsample_phase_weight(w.to(DEV))
+    out = torch.full((n, 2 * h, 2 * h, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+    ops.conv2d_launch(d, wp, b.to(DEV), out, stats=st)
+    torch.cuda.synchronize()
+    got = to_nchw(out.cpu())
+    want = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    err = rel_l2(got, want)
+    assert err < 6e-3, f"rel-L2 {err}"
+    sums = st.cpu().view(n, cout // 4, 2).double() / 2 ** 20
+    assert torch.allclose(sums[..., 0], got.double().reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+    assert torch.allclose(sums[..., 1], (got.double() ** 2).reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
