@@ -122,6 +122,10 @@ bool attn_tc_supported(int act_dtype, int heads, int L, int dh, int row_stride, 
                        int v_transposed, long long v_batch_stride, int swap);
 int attn_tc_forward(const void* q, const void* k, const void* vt, int n, int d, float scale, void* out,
                     cudaStream_t stream);
+bool attn_mma_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
+                        int v_transposed, const void* q, const void* k, const void* v, const void* out);
+int attn_mma_forward(const void* q, const void* k, const void* v, long long batch_stride, int row_stride, int head_stride,
+                     int n, int heads, int L, int dh, float scale, int swap, void* out, cudaStream_t stream);
 
 }  // namespace dmme
 
@@ -145,6 +149,10 @@ extern "C" int dmme_attention_fwd(const void* q, const void* k, const void* v, l
   DMME_REQUIRE(kernel != DMME_CONV_TC || tc_ok, DMME_E_SHAPE, "attention: shape/layout not eligible for the tcgen05 kernel");
   if (tc_ok && kernel != DMME_CONV_GENERIC)
     return attn_tc_forward(q, k, v, n, dh, scale, out, static_cast<cudaStream_t>(stream));
+  if (kernel != DMME_CONV_GENERIC &&
+      attn_mma_supported(act_dtype, heads, L, dh, row_stride, head_stride, batch_stride, v_transposed, q, k, v, out))
+    return attn_mma_forward(q, k, v, batch_stride, row_stride, head_stride, n, heads, L, dh, scale, head_batch_swap, out,
+                            static_cast<cudaStream_t>(stream));
   DMME_REQUIRE(dh <= 256, DMME_E_SHAPE, "attention: head dim %d > 256 not supported", dh);
   const size_t smem = sizeof(float) * (static_cast<size_t>(kAttnRows) * dh + kAttnTile * (dh + 1) +
                                         static_cast<size_t>(kAttnRows) * L);

@@ -398,9 +398,15 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int idx) {
 //       stages pixels [r NP/2, (r + 1) NP/2) of the pixel tile (the tensor maps then have half-tile boxes), so its L2 -> SM feed
 //       per k-block is 16 + 16 KB instead of 32 + 16 KB for the same 128 x NP outputs.  The 3x3 convs of the 16x16 /
 //       8x8 levels are bound by that feed (~45 B/clk/SM measured), not by the tensor pipe.
+// Epilogue warps: 8 (two per TMEM lane quarter).  16 for the weight-stationary 1x1 convs (whose accumulator drain is the
+// kernel) was tried and is SLOWER: 576 threads leave 112 registers each, the epilogue spills (1.3 KB) and the 256 -> 256
+// projection went from 27.6 to 35.7 us, the qkv projection from 64 to 102 us.
+template <bool WS>
+__host__ __device__ constexpr int tct_epi_warps() { return 8; }
+
 template <bool WS, int CMOD, bool PAIR>
-__global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
-                                                                const ConvTctExtra x) {
+__global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
+                                                                                  const ConvTctExtra x) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kTctMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kTctMaxStages];
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
       mbar_init(&empty_bar[s], 1);
     }
     // PAIR: the leader's acc_empty collects the epilogue threads of both CTAs
-    for (int st = 0; st < 2; ++st) { mbar_init(&acc_full[st], 1); mbar_init(&acc_empty[st], (PAIR ? 2 : 1) * kConvEpiWarps * 32); }
+    for (int st = 0; st < 2; ++st) { mbar_init(&acc_full[st], 1); mbar_init(&acc_empty[st], (PAIR ? 2 : 1) * tct_epi_warps<WS>() * 32); }
     mbar_init(&slab_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -578,14 +584,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
     // convert, store with an immediate offset, widen, two statistics updates -- against 24 for the fully general form
     // (measured 34 us -> see profiles/ for a 256 -> 256 1x1 conv at batch 256).
     const int q = warp & 3;            // TMEM lane quarter = 32-channel block of the tile
-    const int half = (warp - 2) >> 2;  // which half of the tile's pixels
+    const int half = (warp - 2) >> 2;  // which part of the tile's pixels (2 or 4 parts)
+    const int ppw = NP / (tct_epi_warps<WS>() / 4);  // pixels per warp and tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
     const int L = p.ho * p.wo;
     const int total_pix = static_cast<int>(x.total_pix);
     const bool temb_per_image = p.temb && p.temb_rows != 1;
     const int cmod = CMOD ? CMOD : (p.out_mode == DMME_OUT_QKV ? p.cout / 3 : p.cout);
-    const int nchunks = NP >> 6;  // 32-pixel chunks per warp and tile
+    const int nchunks = ppw >> 5;  // 32-pixel chunks per warp and tile
     int t_it = 0;
     pdl_wait();
     for (int t = cta0; t < total_tiles; t += cta_step, ++t_it) {
@@ -603,7 +610,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
       const int which = cb / cmod;
       const int chm = cb - which * cmod + lane;  // channel inside q / k / v
       __nv_bfloat16* obase = which == 0 ? p.out : (which == 1 ? p.out2 : p.out3);
-      const int pix_begin = mt * NP + half * (NP >> 1);
+      const int pix_begin = mt * NP + half * ppw;
       float s1 = 0.f, s2 = 0.f, bt = bias_c;
       int cur_n = -1;
 
@@ -654,7 +661,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tct_kernel(const __grid_con
         const int pix0 = pix_begin + ci * 32;  // first pixel of this 32-pixel chunk (warp-uniform)
         if (pix0 >= total_pix) break;
         uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(stage * kAccCols + half * (NP >> 1) + ci * 32), v);
+        tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(stage * kAccCols + half * ppw + ci * 32), v);
         float f[32];
         if (has_add) {
 #pragma unroll
@@ -915,12 +922,12 @@ static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cud
   if (PAIR) {
     // one cluster of two CTAs (two SMs) per work unit
     const int pairs = total < g_sm_count_tc / 2 ? total : g_sm_count_tc / 2;
-    cudaError_t e = launch_pdl_pair(conv_tct_kernel<WS, CMOD, PAIR>, dim3(2 * pairs), dim3(kConvThreads), smem, stream, p, x);
+    cudaError_t e = launch_pdl_pair(conv_tct_kernel<WS, CMOD, PAIR>, dim3(2 * pairs), dim3((2 + tct_epi_warps<WS>()) * 32), smem, stream, p, x);
     return check_launch_err(e, "conv_tct_kernel (cta_group::2)");
   }
   int grid = total < g_sm_count_tc ? total : g_sm_count_tc;
   if (WS) grid -= grid % p.n_tiles;
-  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD, PAIR>, dim3(grid), dim3(kConvThreads), smem, stream, p, x);
+  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD, PAIR>, dim3(grid), dim3((2 + tct_epi_warps<WS>()) * 32), smem, stream, p, x);
   return check_launch_err(e, "conv_tct_kernel");
 }
 
@@ -1016,6 +1023,9 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     const int cmod = d.out_layout == DMME_OUT_QKV ? d.cout / 3 : d.cout;
     if (cmod == 128) return ws ? launch_conv_tct<true, 128>(p, x, smem, stream) : launch_conv_tct<false, 128>(p, x, smem, stream);
     if (cmod == 256) return ws ? launch_conv_tct<true, 256>(p, x, smem, stream) : launch_conv_tct<false, 256>(p, x, smem, stream);
+    // the IDDPM multi-head qkv projection writes one NHWC tensor of 3C channels (models/iddpm.py:38-39)
+    if (cmod == 384 && ws) return launch_conv_tct<true, 384>(p, x, smem, stream);
+    if (cmod == 768 && ws) return launch_conv_tct<true, 768>(p, x, smem, stream);
     return ws ? launch_conv_tct<true, 0>(p, x, smem, stream) : launch_conv_tct<false, 0>(p, x, smem, stream);
   }
   // widest N tile that divides cout (and, for q/k/v splitting, the per-tensor width) while the persistent grid still

@@ -28,7 +28,7 @@ EXPORTS = (
     "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
-    "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode",
+    "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
     "dmme_denorm", "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
     "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
     "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.dmme_set_conv_tct_mode.argtypes = [i]
     lib.dmme_set_conv_out_tc_mode.argtypes = [i]
     lib.dmme_set_conv_pair_mode.argtypes = [i]
+    lib.dmme_set_attn_mma_mode.argtypes = [i]
     lib.dmme_denorm.argtypes = [vp, vp, vp, ll, vp]
     lib.dmme_adam_ema_step.argtypes = [vp, i, ll, C.c_double, C.c_double, C.c_double, C.c_double, i, C.c_double, C.c_double,
                                        vp, i, vp, vp]
@@ -122,6 +123,7 @@ def load() -> C.CDLL:
     lib.dmme_set_conv_tct_mode.restype = None
     lib.dmme_set_conv_out_tc_mode.restype = None
     lib.dmme_set_conv_pair_mode.restype = None
+    lib.dmme_set_attn_mma_mode.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("dmme_abi_version",):
@@ -132,6 +134,9 @@ def load() -> C.CDLL:
     mode = os.environ.get("DMME_PAIR_MODE")  # A/B measurements only: 0 = no cta_group::2 kernels
     if mode:
         lib.dmme_set_conv_pair_mode(int(mode))
+    mode = os.environ.get("DMME_ATTN_MMA_MODE")  # A/B measurements only: 0 = multi-head attention on CUDA cores
+    if mode:
+        lib.dmme_set_attn_mma_mode(int(mode))
     mode = os.environ.get("DMME_OUT_TC_MODE")  # A/B measurements only: 0 = output conv on the FFMA kernel
     if mode:
         lib.dmme_set_conv_out_tc_mode(int(mode))

@@ -110,6 +110,8 @@ int dmme_get_conv_tct_mode(void);
 /* A/B switch for the cta_group::2 (two-SM MMA) variant of the transposed kernel: 0 = never (default: it measured no
  * faster), 1 = 256-channel 3x3 convs with enough work units, 2 = wherever it is supported */
 void dmme_set_conv_pair_mode(int mode);
+/* A/B switch: 0 = multi-head attention (models/iddpm.py:16-59) stays on the CUDA-core kernel, 1 = mma.sync kernel */
+void dmme_set_attn_mma_mode(int mode);
 /* A/B switch: 0 = the output conv (models/ddpm.py:277) stays on the FFMA kernel, 1 = tcgen05 (default) */
 void dmme_set_conv_out_tc_mode(int mode);
 

@@ -782,3 +782,37 @@ def test_conv_upsample_subpixel(n, c, cout, h):
     sums = st.cpu().view(n, cout // 4, 2).double() / 2 ** 20
     assert torch.allclose(sums[..., 0], got.double().reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
     assert torch.allclose(sums[..., 1], (got.double() ** 2).reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,c,heads,L_,swap", [(3, 256, 4, 256, True), (2, 128, 4, 256, True), (5, 256, 4, 64, True),
+                                               (2, 256, 4, 16, True), (130, 128, 4, 64, False), (1, 64, 1, 256, False),
+                                               (2, 256, 2, 128, True)])
+def test_attention_mma_multi_head(n, c, heads, L_, swap):
+    """mma.sync multi-head kernel (bf16 storage) against fp32 attention on the same bf16 operands, IDDPM channel layout
+    [head][q|k|v][dh] and the (b head) -> (head b) regrouping (models/iddpm.py:36-47)"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(12)
+    qkv = bf16_round(torch.randn(n, L_, 3 * c, generator=g))
+    dh = c // heads
+    t = qkv.reshape(n, L_, heads, 3 * dh).permute(0, 2, 1, 3).reshape(n * heads, L_, 3 * dh)
+    q, k, v = t.chunk(3, dim=2)
+    scale = c ** -0.5
+    o = torch.bmm(F.softmax(torch.bmm(q, k.transpose(1, 2) * scale), dim=2), v)
+    if swap:
+        want = o.reshape(heads, n, L_, dh).permute(1, 2, 0, 3).reshape(n, L_, c)
+    else:
+        want = o.reshape(n, heads, L_, dh).permute(0, 2, 1, 3).reshape(n, L_, c)
+    dev = qkv.to(torch.bfloat16).to(DEV).contiguous()
+    flat = dev.view(-1)
+    out = torch.full((n, L_, c), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.attention(flat, flat[dh:], flat[2 * dh:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, 3 * dh, False, 0, swap, out)
+    ref = torch.empty_like(out)
+    lib = L.load()
+    lib.dmme_set_attn_mma_mode(0)
+    try:
+        ops.attention(flat, flat[dh:], flat[2 * dh:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, 3 * dh, False, 0, swap, ref)
+    finally:
+        lib.dmme_set_attn_mma_mode(1)
+    torch.cuda.synchronize()
+    assert rel_l2(ref.float().cpu(), want) < 4e-3          # CUDA-core kernel: only the bf16 output rounding
+    assert rel_l2(out.float().cpu(), want) < 6e-3, rel_l2(out.float().cpu(), want)

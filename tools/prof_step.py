@@ -12,25 +12,42 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "diffusion-models-made-easy_b200"))
 import torch  # noqa: E402
 
-from dmme_b200 import DDPM, ops  # noqa: E402
+from dmme_b200 import DDPM, IDDPM, ops  # noqa: E402
 from dmme_b200.models import _engine  # noqa: E402
-from dmme_b200.models.ddpm import UNet  # noqa: E402
+from dmme_b200.models import ddpm as m_ddpm, iddpm as m_iddpm  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--flavour", default="ddpm", choices=["ddpm", "iddpm"])
     args = ap.parse_args()
     dev = torch.device("cuda")
     torch.manual_seed(0)
-    model = UNet().eval()
-    ddpm = DDPM(model, 1000).to(dev)
+    if args.flavour == "ddpm":
+        ddpm = DDPM(m_ddpm.UNet().eval(), 1000).to(dev)
+    else:
+        ddpm = IDDPM(m_iddpm.UNet().eval(), 1000).to(dev)
     x = torch.randn(args.batch, 3, 32, 32, device=dev)
     counter = torch.full((1,), 1000, dtype=torch.int64, device=dev)
     for _ in range(2):
         ddpm._graph_step(x, counter, 1)
     torch.cuda.synchronize()
+    # the whole step replayed from a CUDA graph (what generate() runs)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ddpm._graph_step(x, counter, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        g.replay()
+    e0.record()
+    for _ in range(20):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"# {args.flavour} sampling step, batch {args.batch}: {e0.elapsed_time(e1) / 20:.3f} ms per graph replay")
+    counter.fill_(1000)
 
     records = []
 
