@@ -125,7 +125,7 @@ int attn_tc_forward(const void* q, const void* k, const void* vt, int n, int d, 
 bool attn_mma_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
                         int v_transposed, const void* q, const void* k, const void* v, const void* out);
 int attn_mma_forward(const void* q, const void* k, const void* v, long long batch_stride, int row_stride, int head_stride,
-                     int n, int heads, int L, int dh, float scale, int swap, void* out, cudaStream_t stream);
+                     int n, int heads, int L, int dh, float scale, int swap, void* out, float* p_out, cudaStream_t stream);
 
 }  // namespace dmme
 
@@ -152,7 +152,7 @@ extern "C" int dmme_attention_fwd(const void* q, const void* k, const void* v, l
   if (kernel != DMME_CONV_GENERIC &&
       attn_mma_supported(act_dtype, heads, L, dh, row_stride, head_stride, batch_stride, v_transposed, q, k, v, out))
     return attn_mma_forward(q, k, v, batch_stride, row_stride, head_stride, n, heads, L, dh, scale, head_batch_swap, out,
-                            static_cast<cudaStream_t>(stream));
+                            nullptr, static_cast<cudaStream_t>(stream));
   DMME_REQUIRE(dh <= 256, DMME_E_SHAPE, "attention: head dim %d > 256 not supported", dh);
   const size_t smem = sizeof(float) * (static_cast<size_t>(kAttnRows) * dh + kAttnTile * (dh + 1) +
                                         static_cast<size_t>(kAttnRows) * L);

@@ -22,6 +22,7 @@ struct AttnMmaParams {
   float scale;
   int swap;
   __nv_bfloat16* out;
+  float* p_out;  // optional fp32 [n * heads][L][L]: the normalised softmax matrix, kept for the backward pass
 };
 
 constexpr int kAmRows = 64;   // query rows per CTA
@@ -120,6 +121,15 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const AttnMmaParams p) {
         if (j < L) prow[j] = __float2bfloat16_rn(t[i]);
       }
       if (lane == 0) rowinv[wr + r] = 1.0f / sum;
+      if (p.p_out) {
+        const float inv = 1.0f / sum;
+        float* prow_out = p.p_out + ((static_cast<long long>(b) * p.heads + h) * L + row0 + wr + r) * L;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = lane + 32 * i;
+          if (j < L) prow_out[j] = t[i] * inv;
+        }
+      }
     }
   }
 
@@ -187,13 +197,14 @@ bool attn_mma_supported(int act_dtype, int heads, int L, int dh, int row_stride,
 }
 
 int attn_mma_forward(const void* q, const void* k, const void* v, long long batch_stride, int row_stride, int head_stride,
-                     int n, int heads, int L, int dh, float scale, int swap, void* out, cudaStream_t stream) {
+                     int n, int heads, int L, int dh, float scale, int swap, void* out, float* p_out, cudaStream_t stream) {
   AttnMmaParams p;
   p.q = static_cast<const __nv_bfloat16*>(q); p.k = static_cast<const __nv_bfloat16*>(k);
   p.v = static_cast<const __nv_bfloat16*>(v);
   p.batch_stride = batch_stride; p.row_stride = row_stride; p.head_stride = head_stride;
   p.n = n; p.heads = heads; p.L = L; p.dh = dh; p.scale = scale; p.swap = swap;
   p.out = static_cast<__nv_bfloat16*>(out);
+  p.p_out = p_out;
   const size_t smem = static_cast<size_t>(2) * kAmRows * (dh + 8) * 2 + static_cast<size_t>(kAmRows) * (L + 8) * 4 +
                       kAmRows * 4 + 128;
   static bool configured = false;
