@@ -140,22 +140,99 @@ __global__ void __launch_bounds__(256) gemm_strided_mma_kernel(const GemmParams 
   wmma::fill_fragment(acc[0], 0.f);
   wmma::fill_fragment(acc[1], 0.f);
 
-  for (int k0 = 0; k0 < p.K; k0 += MG_K) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int kk, ii;
-      if (a_kfast) { kk = tid & 31; ii = (tid >> 5) + 8 * j; }
-      else { ii = tid & 63; kk = (tid >> 6) + 4 * j; }
-      const int i = m0 + ii, k = k0 + kk;
-      As[ii][kk] = __float2bfloat16_rn((i < p.M && k < p.K) ? ld_any(p.a.p, a0 + i * p.a.s_r + k * p.a.s_c, p.a.dtype) : 0.f);
+  // vector path: one 16-byte (bf16) or two 16-byte (fp32) loads of eight elements along the operand's contiguous
+  // dimension per thread and k-step instead of eight scalar loads (the scalar staging loop made the kernel load-bound:
+  // 8.3 ms of a 33 ms training step); needs 8-element alignment of every offset, else the scalar path below
+  const bool a_mfast = p.a.s_r == 1;
+  const bool b_kfast = p.b.s_r == 1;
+  auto aligned8 = [](const GemmOp& o, long long off0, bool row_contig) {
+    const long long other = row_contig ? o.s_c : o.s_r;
+    const int esz = o.dtype == DMME_F32 ? 4 : 2;
+    return (other % 8 == 0) && (off0 % 8 == 0) && ((reinterpret_cast<uintptr_t>(o.p) % 16) == 0) &&
+           (o.s_bo % 8 == 0) && (o.s_h % 8 == 0) && esz > 0;
+  };
+  const bool a_vec = (a_kfast || a_mfast) && p.M % 8 == 0 && p.K % 8 == 0 && aligned8(p.a, a0, a_mfast);
+  const bool b_vec = (b_jfast || b_kfast) && p.N % 8 == 0 && p.K % 8 == 0 && aligned8(p.b, b0, b_kfast);
+  auto load8 = [](const GemmOp& o, long long idx, float (&f)[8]) {
+    if (o.dtype == DMME_F32) {
+      const float4 x0 = *reinterpret_cast<const float4*>(static_cast<const float*>(o.p) + idx);
+      const float4 x1 = *reinterpret_cast<const float4*>(static_cast<const float*>(o.p) + idx + 4);
+      f[0] = x0.x; f[1] = x0.y; f[2] = x0.z; f[3] = x0.w; f[4] = x1.x; f[5] = x1.y; f[6] = x1.z; f[7] = x1.w;
+    } else {
+      const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(o.p) + idx);
+      unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
+      unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
     }
+  };
+
+  for (int k0 = 0; k0 < p.K; k0 += MG_K) {
+    if (a_vec) {
+      float f[8];
+      if (a_kfast) {  // eight consecutive k of one row
+        const int ii = tid >> 2, kk = (tid & 3) << 3;
+        const int i = m0 + ii, k = k0 + kk;
+        if (i < p.M && k < p.K) load8(p.a, a0 + i * p.a.s_r + k, f);
+        else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int kk, jj;
-      if (b_jfast) { jj = tid & 63; kk = (tid >> 6) + 4 * j; }
-      else { kk = tid & 31; jj = (tid >> 5) + 8 * j; }
-      const int jn = n0 + jj, k = k0 + kk;
-      Bs[kk][jj] = __float2bfloat16_rn((jn < p.N && k < p.K) ? ld_any(p.b.p, b0 + k * p.b.s_r + jn * p.b.s_c, p.b.dtype) : 0.f);
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(&As[ii][kk]) = u;
+      } else {  // eight consecutive rows of one k
+        const int kk = tid >> 3, ii = (tid & 7) << 3;
+        const int i = m0 + ii, k = k0 + kk;
+        if (i < p.M && k < p.K) load8(p.a, a0 + i + k * p.a.s_c, f);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) As[ii + e][kk] = __float2bfloat16_rn(f[e]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int kk, ii;
+        if (a_kfast) { kk = tid & 31; ii = (tid >> 5) + 8 * j; }
+        else { ii = tid & 63; kk = (tid >> 6) + 4 * j; }
+        const int i = m0 + ii, k = k0 + kk;
+        As[ii][kk] = __float2bfloat16_rn((i < p.M && k < p.K) ? ld_any(p.a.p, a0 + i * p.a.s_r + k * p.a.s_c, p.a.dtype) : 0.f);
+      }
+    }
+    if (b_vec) {
+      float f[8];
+      if (b_jfast) {  // eight consecutive columns of one k
+        const int kk = tid >> 3, jj = (tid & 7) << 3;
+        const int jn = n0 + jj, k = k0 + kk;
+        if (jn < p.N && k < p.K) load8(p.b, b0 + k * p.b.s_r + jn, f);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(&Bs[kk][jj]) = u;
+      } else {  // eight consecutive k of one column
+        const int jj = tid >> 2, kk = (tid & 3) << 3;
+        const int jn = n0 + jj, k = k0 + kk;
+        if (jn < p.N && k < p.K) load8(p.b, b0 + k + jn * p.b.s_c, f);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Bs[kk + e][jj] = __float2bfloat16_rn(f[e]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int kk, jj;
+        if (b_jfast) { jj = tid & 63; kk = (tid >> 6) + 4 * j; }
+        else { kk = tid & 31; jj = (tid >> 5) + 8 * j; }
+        const int jn = n0 + jj, k = k0 + kk;
+        Bs[kk][jj] = __float2bfloat16_rn((jn < p.N && k < p.K) ? ld_any(p.b.p, b0 + k * p.b.s_r + jn * p.b.s_c, p.b.dtype) : 0.f);
+      }
     }
     __syncthreads();
 #pragma unroll
