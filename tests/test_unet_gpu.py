@@ -89,6 +89,21 @@ def test_default_ddpm_unet_bf16(t):
     assert err < BF16_TOL
 
 
+@pytest.mark.parametrize("flavour,size", [("ddpm", 64), ("iddpm", 16)])
+def test_default_unet_bf16_other_resolutions(flavour, size):
+    """the default UNets at 64x64 (SURVEY C5 scale: 64x64 maps take the transposed tcgen05 kernel, the output conv the FFMA
+    kernel) and 16x16 (2x2 bottleneck): same tolerance as at 32x32"""
+    m, sd = _unet(flavour)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 3, size, size, generator=g)
+    tt = torch.tensor([300])
+    want = O.unet_forward(sd, x, tt) if flavour == "ddpm" else O.unet_forward(sd, x, tt, flavour="iddpm")
+    got = m(x.to(DEV), tt.to(DEV)).cpu()
+    err = rel_l2(got, want)
+    print(f"default {flavour} unet bf16 {size}x{size}: rel-L2 {err:.3e}")
+    assert err < BF16_TOL
+
+
 def test_default_ddpm_unet_fp32_mode():
     m, sd = _unet("ddpm", precision="fp32")
     x, tt = _c1_inputs(4)
