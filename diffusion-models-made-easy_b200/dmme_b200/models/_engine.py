@@ -55,6 +55,7 @@ class Engine:
         # True while a training step is captured into a CUDA graph: weight-derived buffers are rebuilt on every call, so
         # the pack kernels become part of the graph and replays see the optimizer's latest weights
         self.always_repack = False
+        self._side: Optional[torch.cuda.Stream] = None  # side stream of the timestep-embedding branch
         # GroupNorm statistics written by conv epilogues: one zeroed int64 arena per forward pass
         self._arena: Optional[Tensor] = None
         self._arena_cursor = 0
@@ -270,13 +271,22 @@ class Engine:
         dev = x.device
         self._begin_stats(dev)
         cond = u.condition
-        emb = ops.temb_mlp(c, cond[0].embeddings, cond[1].weight.detach(), cond[1].bias.detach(), cond[3].weight.detach(),
-                           cond[3].bias.detach(), out=self.ws.get("temb.emb", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev),
-                           scratch=self.ws.get("temb.hidden", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev))
         wcat, bcat, offs = self.temb_tables()
-        temb_all = ops.temb_proj(emb, wcat, bcat, out=self.ws.get("temb.all", (c.numel(), wcat.shape[0]), torch.float32, dev))
+        # the timestep embedding (three small launches) only depends on t: it runs on a side stream -- a parallel branch of
+        # the step's CUDA graph -- while the input conv and the first GroupNorm run, and joins before the first use
+        main = torch.cuda.current_stream(dev)
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            emb = ops.temb_mlp(c, cond[0].embeddings, cond[1].weight.detach(), cond[1].bias.detach(), cond[3].weight.detach(),
+                               cond[3].bias.detach(), out=self.ws.get("temb.emb", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev),
+                               scratch=self.ws.get("temb.hidden", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev))
+            temb_all = ops.temb_proj(emb, wcat, bcat, out=self.ws.get("temb.all", (c.numel(), wcat.shape[0]), torch.float32, dev))
 
         h = self.conv("input_conv", x, None, u.input_conv, in_nchw=True, act_dtype=act_dtype)
+        main.wait_stream(side)
         skips = [h]
         for i, m in enumerate(u.down_layers):
             name = f"down_layers.{i}"
