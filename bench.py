@@ -144,16 +144,17 @@ def conv_profile(model, x, t, reps=3):
     records = []
     orig = ops.conv2d_launch
 
-    def timed(desc, weight, bias, out, temb=None, addend=None, out2=None, out3=None, stats=None):
+    def timed(desc, weight, bias, out, temb=None, addend=None, out2=None, out3=None, stats=None, **kw):
         tc = ops.conv_uses_tc(desc)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        orig(desc, weight, bias, out, temb, addend, out2, out3, stats)
+        orig(desc, weight, bias, out, temb, addend, out2, out3, stats, **kw)
         e1.record()
         ho, wo = ops.conv_out_hw(desc)
         k = desc.ksize * desc.ksize * (desc.c0 + desc.c1) + desc.rc0 + desc.rc1
         sig = (f"{desc.ksize}x{desc.ksize} s{desc.stride} {desc.c0 + desc.c1}->{desc.cout} @{desc.h_in}x{desc.w_in}"
-               + (f" +res{desc.rc0 + desc.rc1}" if desc.rc0 + desc.rc1 else ""))
+               + (f" +res{desc.rc0 + desc.rc1}" if desc.rc0 + desc.rc1 else "")
+               + (" +GroupNorm+SiLU of the input" if kw.get("gn_ab") is not None else ""))
         records.append((tc, sig, 2.0 * desc.n * ho * wo * desc.cout * k, e0, e1))
 
     _engine.ops.conv2d_launch = timed

@@ -59,8 +59,19 @@ extern "C" int dmme_conv2d_writes_stats(const dmme_conv_desc* d) {
   return 0;
 }
 
+// fused GroupNorm of the input: the halo kernel's row-tile mode (16x16 / 32x32 maps) has the transform stage
+static bool runs_halo_rows(const dmme_conv_desc& d) {
+  const bool halo = d.kernel == DMME_CONV_HALO ? conv_halo_supported(d)
+                                               : (d.kernel == DMME_CONV_AUTO && conv_tc_supported(d) && conv_halo_preferred(d));
+  return halo && d.w_in >= 16;
+}
+
+extern "C" int dmme_conv2d_fuses_gn(const dmme_conv_desc* d) { return d && runs_halo_rows(*d) ? 1 : 0; }
+
 extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
   DMME_REQUIRE(d != nullptr, DMME_E_BADARG, "conv2d_fwd: null descriptor");
+  DMME_REQUIRE(d->gn_ab == nullptr || runs_halo_rows(*d), DMME_E_UNSUPPORTED,
+               "conv2d_fwd: a fused GroupNorm (gn_ab) needs the halo kernel; ask dmme_conv2d_fuses_gn");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (d->kernel) {
     case DMME_CONV_TC:

@@ -44,6 +44,11 @@ struct ConvHaloParams {
   const __nv_bfloat16* addend;
   __nv_bfloat16* out;
   long long* stats;
+  // fused GroupNorm(+SiLU) of the conv input (norm_act_drop_conv, models/ddpm.py:25-35): y = [silu](a * x + b) applied to
+  // the halo tile in shared memory between the TMA load and the MMAs; (a, b) per (image, channel of cat(src0, src1))
+  const float2* gn_ab;  // [n][gn_c] or null
+  int gn_c;
+  int gn_silu;
 };
 
 constexpr int kHaloBN = 128;            // output channels per unit (MMA M)
@@ -54,13 +59,16 @@ constexpr int kHaloAStages = 3;
 constexpr int kHaloBStages = 4;
 constexpr int kHaloSmem = kHaloAStages * kHaloASlot + kHaloBStages * kHaloBSlot + 1024;
 constexpr int kHaloEpiWarps = 8;
-constexpr int kHaloThreads = (kHaloEpiWarps + 3) * 32;
+constexpr int kHaloXfWarps = 8;  // GroupNorm transform warps (idle when the conv has no fused norm)
+constexpr int kHaloThreads = (kHaloEpiWarps + 3 + kHaloXfWarps) * 32;
 constexpr int kWarpProdA = kHaloEpiWarps, kWarpProdB = kHaloEpiWarps + 1, kWarpMma = kHaloEpiWarps + 2;
+constexpr int kWarpXf0 = kHaloEpiWarps + 3;
 
 template <int W, int COUT>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kHaloAStages], a_empty[kHaloAStages];
+  __shared__ __align__(8) uint64_t a_ready[kHaloAStages];  // halo tile transformed (fused GroupNorm): MMA may read it
   __shared__ __align__(8) uint64_t b_full[kHaloBStages], b_empty[kHaloBStages];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -78,7 +86,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const int nr = p.rt + 2;  // halo rows: one above and one below the tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kHaloAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_ready[s], kHaloXfWarps * 32);
+    }
     for (int s = 0; s < kHaloBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kHaloEpiWarps * 32); }
     fence_barrier_init();
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const bool is_conv = ck < cchunks;
         const int ntaps = is_conv ? 9 : 1;
         const int as = a_it % kHaloAStages;
-        mbar_wait(&a_full[as], (a_it / kHaloAStages) & 1);
+        mbar_wait(p.gn_ab ? &a_ready[as] : &a_full[as], (a_it / kHaloAStages) & 1);
         tc_fence_after();
         // position 0 of the tile = first pixel slot of the tile's first row = halo row 1
         const uint32_t x0_addr = smem_u32(abuf + as * kHaloASlot) + 128u + kRowBytes;
@@ -197,6 +209,78 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             }
           }
           __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= kWarpXf0) {
+    // =========================== fused GroupNorm(+SiLU) of the halo tile ===========================
+    // Thread = one 16-byte unit column (eight channels of the chunk: its 16 coefficients live in registers, for the two
+    // images a tile can touch) x every 16th position row.  Padding positions (x = -1, W; rows above / below an image;
+    // rows past the batch) were zero-filled by TMA and must stay zero: the reference pads AFTER norm + activation.
+    // Traffic: the tile is read and written once more through the shared-memory port (about +13% on this kernel) against
+    // a whole stand-alone pass over the tensor through HBM / L2 and its launch.
+    if (p.gn_ab != nullptr && p.imgs_per_tile == 0) {
+      const int xt = threadIdx.x - kWarpXf0 * 32;  // 0..kHaloXfWarps * 32
+      const int ul = xt & 7;                       // logical 16-byte unit = channels [8 ul, 8 ul + 8) of the chunk
+      const int r_first = xt >> 3;                 // rows r_first, r_first + 4 * kHaloXfWarps, ...
+      const int rows = nr * WP;
+      int a_it = 0;
+      pdl_wait();
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int mt = u / p.n_tiles;
+        const int pr0 = mt * p.rt - 1;
+        const int n_lo = (pr0 < 0 ? 0 : pr0) / (p.h + 2);  // first image the tile touches; it touches at most n_lo + 1 too
+        for (int ck = 0; ck < nck; ++ck, ++a_it) {
+          const int as = a_it % kHaloAStages;
+          const bool is_conv = ck < cchunks;
+          float2 c0v[8], c1v[8];
+          if (is_conv) {
+            const int cbase = ck * 64 + ul * 8;
+            const float4* g0 = reinterpret_cast<const float4*>(p.gn_ab + static_cast<long long>(n_lo) * p.gn_c + cbase);
+            const bool has1 = n_lo + 1 < p.n;
+            const float4* g1 = reinterpret_cast<const float4*>(p.gn_ab + static_cast<long long>(has1 ? n_lo + 1 : n_lo) * p.gn_c + cbase);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t0 = __ldg(g0 + j), t1 = __ldg(g1 + j);
+              c0v[2 * j] = make_float2(t0.x, t0.y); c0v[2 * j + 1] = make_float2(t0.z, t0.w);
+              c1v[2 * j] = make_float2(t1.x, t1.y); c1v[2 * j + 1] = make_float2(t1.z, t1.w);
+            }
+          }
+          mbar_wait(&a_full[as], (a_it / kHaloAStages) & 1);
+          if (is_conv) {
+            uint8_t* tile = abuf + as * kHaloASlot + 128;
+            const uint32_t tile_addr = smem_u32(tile);
+            for (int r = r_first; r < rows; r += 4 * kHaloXfWarps) {
+              const int hr = r / WP, xx = r - hr * WP;
+              const int pr = pr0 + hr;
+              if (xx == 0 || xx == WP - 1 || pr < 0 || pr >= p.total_rows) continue;
+              const int n = pr / (p.h + 2);
+              const int yy = pr - n * (p.h + 2) - 1;
+              if (yy < 0 || yy >= p.h) continue;
+              // SWIZZLE_128B: the 16-byte unit index is XORed with address bits [7, 10) of the row
+              const uint32_t phase = ((tile_addr + static_cast<uint32_t>(r) * 128u) >> 7) & 7u;
+              uint4* ptr = reinterpret_cast<uint4*>(tile + r * 128 + ((static_cast<uint32_t>(ul) ^ phase) << 4));
+              uint4 v = *ptr;
+              float f[8];
+              unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+              unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+              const bool second = n != n_lo;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 ab = second ? c1v[j] : c0v[j];
+                f[j] = fmaf(f[j], ab.x, ab.y);
+              }
+              if (p.gn_silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+              }
+              v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+              v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+              *ptr = v;
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the MMA's async-proxy reads
+          }
+          mbar_arrive(&a_ready[as]);
         }
       }
     }
@@ -390,6 +474,11 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   p.addend = static_cast<const __nv_bfloat16*>(d.addend);
   p.out = static_cast<__nv_bfloat16*>(d.out);
   p.stats = d.stats;
+  p.gn_ab = reinterpret_cast<const float2*>(d.gn_ab);
+  p.gn_c = d.c0 + d.c1;
+  p.gn_silu = d.gn_silu;
+  DMME_REQUIRE(d.gn_ab == nullptr || p.imgs_per_tile == 0, DMME_E_UNSUPPORTED,
+               "conv_halo: fused GroupNorm needs row tiles (16x16 and 32x32 maps)");
   // the MMA reads n_mma + (W+3) position rows past the first tile position; keep that inside the slot
   DMME_REQUIRE((1 + (p.rt + 2) * p.wp) * 128 <= kHaloASlot && (1 + 2 * p.wp + 1 + p.n_mma) * 128 <= kHaloASlot,
                DMME_E_SHAPE, "conv_halo: halo tile does not fit its shared-memory slot");

@@ -241,18 +241,62 @@ struct GnApplyParams {
   int chunks;  // CTAs per image
 };
 
+// y = a * x + b of channel c of image n: GroupNorm statistics (fixed-point micro-group sums of the producing conv) folded
+// with gamma / beta and the optional IDDPM scale / shift.  One function for the streaming kernel and for the coefficient
+// kernel of the conv-fused path, so both produce the same bits.
+__device__ __forceinline__ void gn_coefficients(const GnApplyParams& q, int n, int c, float& aa, float& bb) {
+  const GnParams& p = q.g;
+  const int C = p.c0 + p.c1;
+  const int cpg = C / p.groups;
+  const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * cpg);
+  const double unfix = 1.0 / static_cast<double>(1 << DMME_STATS_FRAC_BITS);
+  const int g0 = (c / cpg) * cpg;  // first channel of this channel's group
+  long long s1 = 0, s2 = 0;
+  for (int cc = g0; cc < g0 + cpg; cc += 4) {
+    const long long* st = cc < p.c0 ? q.stats0 + (static_cast<long long>(n) * (p.c0 >> 2) + (cc >> 2)) * 2
+                                    : q.stats1 + (static_cast<long long>(n) * (p.c1 >> 2) + ((cc - p.c0) >> 2)) * 2;
+    s1 += st[0];
+    s2 += st[1];
+  }
+  const float mean = static_cast<float>(static_cast<double>(s1) * unfix) * inv_cnt;
+  const float ex2 = static_cast<float>(static_cast<double>(s2) * unfix) * inv_cnt;
+  const float var = fmaxf(ex2 - mean * mean, 0.f);
+  const float rs = rsqrtf(var + p.eps);
+  const float ga = p.gamma ? p.gamma[c] : 1.f, be = p.beta ? p.beta[c] : 0.f;
+  aa = rs * ga;
+  bb = be - mean * rs * ga;
+  if (p.scale) {
+    const long long r = static_cast<long long>(p.ss_rows == 1 ? 0 : n) * p.ss_ld;
+    const float sc = 1.f + p.scale[r + c], sh = p.shift[r + c];
+    aa *= sc;
+    bb = bb * sc + sh;
+  }
+}
+
+// coefficients only, interleaved (a, b) per (image, channel): consumed by the halo conv kernel's fused GroupNorm stage
+__global__ void gn_coeff_kernel(const GnApplyParams q, float2* __restrict__ ab) {
+  pdl_trigger();
+  pdl_wait();
+  const int C = q.g.c0 + q.g.c1;
+  const long long total = static_cast<long long>(q.g.n) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long long>(n) * C);
+    float aa, bb;
+    gn_coefficients(q, n, c, aa, bb);
+    ab[i] = make_float2(aa, bb);
+  }
+}
+
 // Persistent layout: the whole tensor is one range of 16-byte vectors split evenly over the grid (one wave of CTAs, four
 // per SM); a CTA walks its range image by image and rebuilds the per-channel coefficients only when the image changes.
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams q) {
   extern __shared__ float ab[];  // a[C], b[C], m[C]
   const GnParams& p = q.g;
   const int C = p.c0 + p.c1;
-  const int cpg = C / p.groups;
   float* sa = ab;
   float* sb = ab + C;
   float* sm = ab + 2 * C;
-  const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * cpg);
-  const double unfix = 1.0 / static_cast<double>(1 << DMME_STATS_FRAC_BITS);
   const int cv = C >> 3;  // 16-byte vectors per pixel
   const long long nvec = static_cast<long long>(p.hw) * cv;      // per image
   const long long total = nvec * p.n;
@@ -269,26 +313,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams q)
     const long long v1 = (r1 - static_cast<long long>(n) * nvec) < nvec ? (r1 - static_cast<long long>(n) * nvec) : nvec;
     __syncthreads();  // the previous image's coefficients are no longer read
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g0 = (c / cpg) * cpg;  // first channel of this channel's group
-      long long s1 = 0, s2 = 0;
-      for (int cc = g0; cc < g0 + cpg; cc += 4) {
-        const long long* st = cc < p.c0 ? q.stats0 + (static_cast<long long>(n) * (p.c0 >> 2) + (cc >> 2)) * 2
-                                        : q.stats1 + (static_cast<long long>(n) * (p.c1 >> 2) + ((cc - p.c0) >> 2)) * 2;
-        s1 += st[0];
-        s2 += st[1];
-      }
-      const float mean = static_cast<float>(static_cast<double>(s1) * unfix) * inv_cnt;
-      const float ex2 = static_cast<float>(static_cast<double>(s2) * unfix) * inv_cnt;
-      const float var = fmaxf(ex2 - mean * mean, 0.f);
-      const float rs = rsqrtf(var + p.eps);
-      const float ga = p.gamma ? p.gamma[c] : 1.f, be = p.beta ? p.beta[c] : 0.f;
-      float aa = rs * ga, bb = be - mean * rs * ga;
-      if (p.scale) {
-        const long long r = static_cast<long long>(p.ss_rows == 1 ? 0 : n) * p.ss_ld;
-        const float sc = 1.f + p.scale[r + c], sh = p.shift[r + c];
-        aa *= sc;
-        bb = bb * sc + sh;
-      }
+      float aa, bb;
+      gn_coefficients(q, n, c, aa, bb);
       sa[c] = aa;
       sb[c] = bb;
       sm[c] = p.mask ? p.mask[static_cast<long long>(n) * C + c] : 1.f;
@@ -449,4 +475,27 @@ extern "C" int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, in
   if (act_dtype == DMME_BF16) gn_generic_kernel<__nv_bfloat16><<<n * groups, 256, 0, st>>>(p);
   else gn_generic_kernel<float><<<n * groups, 256, 0, st>>>(p);
   return check_launch("gn_generic_kernel");
+}
+
+// (a, b) coefficients of y = a * x + b per (image, channel), interleaved fp32 pairs [n][c0 + c1][2], from the statistics
+// the producing convolutions wrote: the input of the conv-fused GroupNorm path (dmme_conv_desc.gn_ab)
+extern "C" int dmme_groupnorm_coeff(const long long* stats0, const long long* stats1, int c0, int c1, int n, int hw,
+                                    int groups, float eps, const float* gamma, const float* beta, const float* scale,
+                                    const float* shift, int ss_rows, int ss_ld, float* ab_out, void* stream) {
+  DMME_REQUIRE(stats0 && ab_out && n > 0 && hw > 0 && c0 > 0 && c1 >= 0 && groups > 0, DMME_E_BADARG, "groupnorm_coeff: bad arguments");
+  DMME_REQUIRE(c1 == 0 || stats1, DMME_E_BADARG, "groupnorm_coeff: c1 > 0 but stats1 is null");
+  const int C = c0 + c1;
+  DMME_REQUIRE(C % groups == 0, DMME_E_SHAPE, "groupnorm_coeff: C=%d not divisible by groups=%d", C, groups);
+  const int cpg = C / groups;
+  DMME_REQUIRE(cpg % 4 == 0 && c0 % cpg == 0, DMME_E_SHAPE, "groupnorm_coeff: groups must be whole 4-channel micro-groups of one source");
+  GnApplyParams q;
+  memset(&q, 0, sizeof(q));
+  q.g.c0 = c0; q.g.c1 = c1; q.g.n = n; q.g.hw = hw; q.g.groups = groups; q.g.eps = eps;
+  q.g.gamma = gamma; q.g.beta = beta; q.g.scale = scale; q.g.shift = shift; q.g.ss_rows = ss_rows; q.g.ss_ld = ss_ld;
+  q.stats0 = stats0; q.stats1 = stats1;
+  const long long total = static_cast<long long>(n) * C;
+  const int grid = static_cast<int>(ceil_div_ll(total, 256) < 148 * 4 ? ceil_div_ll(total, 256) : 148 * 4);
+  cudaError_t e = launch_pdl(gn_coeff_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), q,
+                             reinterpret_cast<float2*>(ab_out));
+  return check_launch_err(e, "gn_coeff_kernel");
 }

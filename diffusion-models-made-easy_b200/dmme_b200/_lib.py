@@ -25,7 +25,7 @@ CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO, CONV_HALO2 = 0, 1, 2, 3, 4
 EXPORTS = (
     "dmme_abi_version", "dmme_last_error", "dmme_launch_count", "dmme_reset_launch_count",
     "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
-    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
+    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
@@ -49,6 +49,7 @@ class ConvDesc(C.Structure):
         ("addend", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p), ("out3", C.c_void_p),
         ("stats", C.c_void_p),
         ("in_layout", C.c_int), ("out_layout", C.c_int), ("act_dtype", C.c_int), ("kernel", C.c_int),
+        ("gn_ab", C.c_void_p), ("gn_silu", C.c_int),
     ]
 
 
@@ -78,6 +79,8 @@ def load() -> C.CDLL:
     lib.dmme_conv2d_uses_tc.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_conv2d_writes_stats.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_groupnorm_fwd.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, i, vp, i, vp, vp, vp]
+    lib.dmme_groupnorm_coeff.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, vp]
+    lib.dmme_conv2d_fuses_gn.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_attention_fwd.argtypes = [vp, vp, vp, ll, i, i, i, ll, i, i, i, i, f, i, vp, i, i, vp]
     lib.dmme_attention_uses_tc.argtypes = [ll, i, i, ll, i, i, i, i, i]
     lib.dmme_temb_mlp_fwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp]

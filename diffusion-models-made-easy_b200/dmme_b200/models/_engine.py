@@ -15,6 +15,7 @@ and can be captured in a CUDA graph.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -56,6 +57,8 @@ class Engine:
         # the pack kernels become part of the graph and replays see the optimizer's latest weights
         self.always_repack = False
         self._side: Optional[torch.cuda.Stream] = None  # side stream of the timestep-embedding branch
+        # GroupNorm + SiLU applied inside the halo conv kernel where it runs (DMME_FUSE_GN=0: always the stand-alone pass)
+        self.fuse_gn = os.environ.get("DMME_FUSE_GN", "1") != "0"
         # GroupNorm statistics written by conv epilogues: one zeroed int64 arena per forward pass
         self._arena: Optional[Tensor] = None
         self._arena_cursor = 0
@@ -152,7 +155,7 @@ class Engine:
              upsample: bool = False, res: Optional[nn.Conv2d] = None, res0: Optional[Tensor] = None,
              res1: Optional[Tensor] = None, temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
              in_nchw: bool = False, out_layout: int = L.OUT_NHWC, act_dtype: Optional[torch.dtype] = None,
-             addend_in_gemm: bool = False):
+             addend_in_gemm: bool = False, gn_ab: Optional[Tensor] = None, gn_silu: bool = True):
         cout, ks = conv.weight.shape[0], conv.weight.shape[2]
         act_dtype = act_dtype or src0.dtype
         kernel = L.CONV_GENERIC if self.force_generic else L.CONV_AUTO
@@ -201,8 +204,33 @@ class Engine:
         stats = self._stats_for(out, d.n, cout) if ops.conv_writes_stats(d) else None
         if stats is None:
             self._stats.pop(out.data_ptr(), None)  # the buffer may be a reused scratch with stale statistics
-        ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats)
+        ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats, gn_ab=gn_ab, gn_silu=gn_silu)
         return out
+
+    def norm_conv(self, name: str, norm: nn.GroupNorm, x0: Tensor, x1: Optional[Tensor], conv: nn.Conv2d, *,
+                  scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                  gn_name: str = "scratch.a", **conv_kw) -> Tensor:
+        """``conv(silu(norm(cat(x0, x1))))`` (norm_act_drop_conv, models/ddpm.py:25-35).  When the conv takes the halo
+        kernel and the producers left their statistics, the norm + SiLU is applied to the halo tile inside the conv kernel
+        (one small coefficient launch instead of a pass over the tensor); otherwise GroupNorm runs as its own kernel."""
+        st0 = self._stats.get(x0.data_ptr())
+        st1 = self._stats.get(x1.data_ptr()) if x1 is not None else None
+        c0 = x0.shape[3]
+        c1 = x1.shape[3] if x1 is not None else 0
+        cpg = (c0 + c1) // norm.num_groups
+        if (self.fuse_gn and mask is None and not self.force_generic and x0.dtype == torch.bfloat16 and st0 is not None
+                and (x1 is None or st1 is not None) and cpg % 4 == 0 and c0 % cpg == 0):
+            cout, ks = conv.weight.shape[0], conv.weight.shape[2]
+            probe = ops.make_conv_desc(x0, x1, cout, ks, 1, False, conv_kw.get("res0"), conv_kw.get("res1"), False,
+                                       L.OUT_NHWC, x0.dtype, L.CONV_AUTO)
+            if ops.conv_fuses_gn(probe):
+                n, h, w, _ = x0.shape
+                ab = ops.groupnorm_coeff(st0, st1, c0, c1, n, h * w, norm.num_groups, norm.weight.detach(),
+                                         norm.bias.detach(), scale, shift, norm.eps,
+                                         out=self.ws.get(gn_name + ".ab", (n, c0 + c1, 2), torch.float32, x0.device))
+                return self.conv(name, x0, x1, conv, gn_ab=ab, gn_silu=True, **conv_kw)
+        a = self.gn(gn_name, norm, x0, x1, silu=True, scale=scale, shift=shift, mask=mask)
+        return self.conv(name, a, None, conv, **conv_kw)
 
     def gn(self, name: str, norm: nn.GroupNorm, src0: Tensor, src1: Optional[Tensor], silu: bool,
            scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, mask: Optional[Tensor] = None) -> Tensor:
@@ -239,21 +267,18 @@ class Engine:
         o, width = offs[id(blk)]
         cond = temb_all[:, o:o + width]
         mask = masks.get(name) if masks else None
-        a1 = self.gn("scratch.a1", blk.conv1[0], x0, x1, silu=True)
         conv2 = blk.conv2[-1]
-        if self.flavour == "ddpm":
-            h1 = self.conv("scratch.h1", a1, None, blk.conv1[2], temb=cond)
-            a2 = self.gn("scratch.a2", blk.conv2[0], h1, None, silu=True, mask=mask)
-        else:
-            h1 = self.conv("scratch.h1", a1, None, blk.conv1[2])
-            cout = width // 2
-            a2 = self.gn("scratch.a2", blk.norm, h1, None, silu=True, shift=cond[:, :cout], scale=cond[:, cout:], mask=mask)
         has_attn = not isinstance(blk.attention, nn.Identity)
         out_name = name + (".pre" if has_attn else "")
-        if isinstance(blk.residual, nn.Identity):
-            h2 = self.conv(out_name, a2, None, conv2, addend=x0)
+        res_kw = dict(addend=x0) if isinstance(blk.residual, nn.Identity) else dict(res=blk.residual, res0=x0, res1=x1)
+        if self.flavour == "ddpm":
+            h1 = self.norm_conv("scratch.h1", blk.conv1[0], x0, x1, blk.conv1[2], gn_name="scratch.a1", temb=cond)
+            h2 = self.norm_conv(out_name, blk.conv2[0], h1, None, conv2, mask=mask, gn_name="scratch.a2", **res_kw)
         else:
-            h2 = self.conv(out_name, a2, None, conv2, res=blk.residual, res0=x0, res1=x1)
+            h1 = self.norm_conv("scratch.h1", blk.conv1[0], x0, x1, blk.conv1[2], gn_name="scratch.a1")
+            cout = width // 2
+            h2 = self.norm_conv(out_name, blk.norm, h1, None, conv2, shift=cond[:, :cout], scale=cond[:, cout:], mask=mask,
+                                gn_name="scratch.a2", **res_kw)
         if has_attn:
             h2 = self.attention_block(name, blk.attention, h2)
         return h2

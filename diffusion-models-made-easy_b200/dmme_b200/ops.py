@@ -133,6 +133,26 @@ def conv_writes_stats(desc: L.ConvDesc) -> bool:
     return bool(L.load().dmme_conv2d_writes_stats(C.byref(desc)))
 
 
+def conv_fuses_gn(desc: L.ConvDesc) -> bool:
+    """True when the kernel that would run ``desc`` can apply a fused GroupNorm(+SiLU) to its input (``gn_ab=``)."""
+    return bool(L.load().dmme_conv2d_fuses_gn(C.byref(desc)))
+
+
+def groupnorm_coeff(stats0: Tensor, stats1: Optional[Tensor], c0: int, c1: int, n: int, hw: int, groups: int,
+                    gamma: Tensor, beta: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
+                    eps: float = 1e-5, out: Optional[Tensor] = None) -> Tensor:
+    """(a, b) of ``y = a * x + b`` per (image, channel) -- GroupNorm statistics of the producing convs folded with gamma /
+    beta (+ IDDPM scale / shift) -- as fp32 ``[n, c0 + c1, 2]`` for ``conv2d_launch(gn_ab=)``."""
+    L.require_cuda(stats0, stats1, gamma, beta, out)
+    ab = _empty((n, c0 + c1, 2), torch.float32, stats0.device, out)
+    ss_rows = ss_ld = 0
+    if scale is not None:
+        ss_rows, ss_ld = scale.shape[0], scale.stride(0)
+    L.check(L.load().dmme_groupnorm_coeff(ptr(stats0), ptr(stats1), c0, c1, n, hw, groups, eps, ptr(gamma), ptr(beta),
+                                          ptr(scale), ptr(shift), ss_rows, ss_ld, ptr(ab), L.stream_ptr()), "groupnorm_coeff")
+    return ab
+
+
 def conv_out_hw(desc: L.ConvDesc) -> Tuple[int, int]:
     h = desc.h_in * (2 if desc.upsample else 1)
     w = desc.w_in * (2 if desc.upsample else 1)
@@ -142,9 +162,11 @@ def conv_out_hw(desc: L.ConvDesc) -> Tuple[int, int]:
 
 def conv2d_launch(desc: L.ConvDesc, weight: Tensor, bias: Optional[Tensor], out: Tensor,
                   temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
-                  out2: Optional[Tensor] = None, out3: Optional[Tensor] = None, stats: Optional[Tensor] = None) -> None:
+                  out2: Optional[Tensor] = None, out3: Optional[Tensor] = None, stats: Optional[Tensor] = None,
+                  gn_ab: Optional[Tensor] = None, gn_silu: bool = True) -> None:
     """Launch one fused convolution described by ``desc`` (see include/dmme_b200.h)."""
     desc.weight, desc.bias = ptr(weight), ptr(bias)
+    desc.gn_ab, desc.gn_silu = ptr(gn_ab), int(gn_silu)
     if temb is not None:
         if temb.dim() != 2 or temb.dtype != torch.float32:
             raise ValueError("temb must be a 2-D fp32 view")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMME_ABI_VERSION 2
+#define DMME_ABI_VERSION 3
 #define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
@@ -91,6 +91,12 @@ typedef struct dmme_conv_desc {
   int in_layout, out_layout;
   int act_dtype;
   int kernel;                         /* DMME_CONV_* */
+  const float* gn_ab;                 /* optional fused GroupNorm(+SiLU) of the conv INPUT (norm_act_drop_conv,
+                                         models/ddpm.py:25-35): interleaved (a, b) fp32 pairs [n][c0 + c1][2] from
+                                         dmme_groupnorm_coeff; the kernel convolves [silu](a * x + b) with zero padding
+                                         applied after the activation, as the reference does.  Halo kernel only: ask
+                                         dmme_conv2d_fuses_gn first */
+  int gn_silu;                        /* 1: SiLU after the fused norm */
 } dmme_conv_desc;
 
 /* library / device ------------------------------------------------------------------------- */
@@ -136,6 +142,8 @@ int dmme_conv2d_fwd(const dmme_conv_desc* desc, void* stream);
 int dmme_conv2d_uses_tc(const dmme_conv_desc* desc);
 /* 1 when the kernel dmme_conv2d_fwd would run for this descriptor fills desc->stats */
 int dmme_conv2d_writes_stats(const dmme_conv_desc* desc);
+/* 1 when the kernel dmme_conv2d_fwd would run for this descriptor can apply desc->gn_ab (fused GroupNorm of the input) */
+int dmme_conv2d_fuses_gn(const dmme_conv_desc* desc);
 
 /* GroupNorm (+ scale/shift) (+ SiLU) (+ channel dropout mask) -------------------------------- */
 /*
@@ -147,6 +155,10 @@ int dmme_groupnorm_fwd(const void* src0, const void* src1, int c0, int c1, int n
                        const float* gamma, const float* beta, const float* scale, const float* shift,
                        int ss_rows, int ss_ld, const float* chan_mask, int apply_silu, void* out,
                        int act_dtype, const long long* stats0, const long long* stats1, void* stream);
+/* (a, b) of y = a * x + b per (image, channel) from the producers' statistics, for dmme_conv_desc.gn_ab */
+int dmme_groupnorm_coeff(const long long* stats0, const long long* stats1, int c0, int c1, int n, int hw, int groups,
+                         float eps, const float* gamma, const float* beta, const float* scale, const float* shift,
+                         int ss_rows, int ss_ld, float* ab_out, void* stream);
 /* stats0 / stats1: optional micro-group sums of src0 / src1 written by the producing convolution
  * (dmme_conv_desc.stats).  When every source has them, GroupNorm is a single streaming pass
  * (2 B read + 2 B written per element); otherwise the kernel reduces the statistics itself. */

@@ -816,3 +816,65 @@ def test_attention_mma_multi_head(n, c, heads, L_, swap):
     torch.cuda.synchronize()
     assert rel_l2(ref.float().cpu(), want) < 4e-3          # CUDA-core kernel: only the bf16 output rounding
     assert rel_l2(out.float().cpu(), want) < 6e-3, rel_l2(out.float().cpu(), want)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n=4, c0=128, c1=0, cout=128, h=32, temb="bcast"),
+    dict(n=37, c0=128, c1=128, cout=128, h=32, res=True),            # concat source, fused 1x1 residual, several units per CTA
+    dict(n=3, c0=256, c1=0, cout=256, h=16, addend=True, temb="rows"),
+    dict(n=70, c0=256, c1=256, cout=256, h=16, silu=False),          # tiles spanning two images, plain norm
+    dict(n=150, c0=128, c1=0, cout=128, h=32),
+])
+def test_conv_halo_fused_groupnorm(cfg):
+    """GroupNorm(+SiLU) applied to the halo tile inside the conv kernel == gn_apply followed by the same conv, bit for bit
+    (same coefficient function, same fma / SiLU, zero padding after the activation)"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(61)
+    n, c0, c1, cout, h = (cfg[k] for k in ("n", "c0", "c1", "cout", "h"))
+    C = c0 + c1
+    silu = cfg.get("silu", True)
+    # producers: convs that write the tensors and their statistics
+    srcs, stats = [], []
+    for c in (c0, c1):
+        if c == 0:
+            srcs.append(None); stats.append(None)
+            continue
+        x = bf16_round(torch.randn(n, 64, h, h, generator=g))
+        w = bf16_round(torch.randn(c, 64, 3, 3, generator=g) / 8)
+        b = torch.randn(c, generator=g) * 2
+        s0 = to_nhwc(x, torch.bfloat16).to(DEV)
+        d = ops.make_conv_desc(s0, None, c, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+        out = torch.empty((n, h, h, c), dtype=torch.bfloat16, device=DEV)
+        st = torch.zeros(n * (c // 4) * 2, dtype=torch.int64, device=DEV)
+        ops.conv2d_launch(d, ops.pack_conv_weight(w.to(DEV), None, True), b.to(DEV), out, stats=st)
+        srcs.append(out); stats.append(st)
+    gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+    wt = bf16_round(torch.randn(cout, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(cout, generator=g)
+    wres = None
+    if cfg.get("res"):
+        wres = bf16_round(torch.randn(cout, C, 1, 1, generator=g) / math.sqrt(C))
+    temb = None
+    if cfg.get("temb"):
+        temb = torch.randn(n if cfg["temb"] == "rows" else 1, cout, generator=g).to(DEV)
+    addend = bf16_round(torch.randn(n, h, h, cout, generator=g)).to(torch.bfloat16).to(DEV) if cfg.get("addend") else None
+    wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
+    r0, r1 = (srcs[0], srcs[1]) if cfg.get("res") else (None, None)
+
+    # two-kernel path
+    a = ops.groupnorm(srcs[0], srcs[1], 32, gamma, beta, silu, stats0=stats[0], stats1=stats[1])
+    d = ops.make_conv_desc(a, None, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_HALO)
+    want = torch.empty((n, h, h, cout), dtype=torch.bfloat16, device=DEV)
+    st_want = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+    ops.conv2d_launch(d, wp, bias.to(DEV), want, temb, addend, stats=st_want)
+
+    # fused path: the conv reads the raw tensors
+    d = ops.make_conv_desc(srcs[0], srcs[1], cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_HALO)
+    assert ops.conv_fuses_gn(d)
+    ab = ops.groupnorm_coeff(stats[0], stats[1], c0, c1, n, h * h, 32, gamma, beta)
+    got = torch.full((n, h, h, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    st_got = torch.zeros_like(st_want)
+    ops.conv2d_launch(d, wp, bias.to(DEV), got, temb, addend, stats=st_got, gn_ab=ab, gn_silu=silu)
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    assert torch.equal(st_got, st_want)
