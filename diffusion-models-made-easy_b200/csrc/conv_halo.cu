@@ -49,13 +49,21 @@ struct ConvHaloParams {
   const float2* gn_ab;  // [n][gn_c] or null
   int gn_c;
   int gn_silu;
+  long long* trace;  // debugging: per-role clock64 timestamps of CTA 0 (dmme_debug_set_halo_trace), or null
 };
+
+// trace slots of CTA 0: [role][chunk index]; roles: 0 stage free (producer issues the loads), 1 tile landed (transform
+// starts), 2 transform done, 3 MMA warp saw the tile ready, 4 MMA warp issued the chunk's last tap, 5 accumulator full
+// (epilogue starts; index = unit), 6 epilogue done
+__device__ __forceinline__ void halo_trace(long long* trace, int role, int idx) {
+  if (trace && blockIdx.x == 0 && idx < 256) trace[role * 256 + idx] = clock64();
+}
 
 constexpr int kHaloBN = 128;            // output channels per unit (MMA M)
 constexpr int kHaloCols = 256;          // TMEM columns per accumulator stage
-constexpr int kHaloASlot = 47 * 1024;   // >= ((rt + 2) * (W+2) + 1) * 128 bytes
+constexpr int kHaloASlot = 40 * 1024;   // >= ((rt + 2) * (W+2) + 1) * 128 bytes
 constexpr int kHaloBSlot = kHaloBN * 128;
-constexpr int kHaloAStages = 3;
+constexpr int kHaloAStages = 4;
 constexpr int kHaloBStages = 4;
 constexpr int kHaloSmem = kHaloAStages * kHaloASlot + kHaloBStages * kHaloBSlot + 1024;
 constexpr int kHaloEpiWarps = 8;
@@ -130,6 +138,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           const int as = a_it % kHaloAStages;
           mbar_wait(&a_empty[as], ((a_it / kHaloAStages) & 1) ^ 1);
+          halo_trace(p.trace, 0, a_it);
           if (p.imgs_per_tile > 0) {
             // whole padded images: box = [64 ch][W+2 px][h+2 rows] from (x, y) = (-1, -1); rows outside the tile are only
             // ever read for padding-position outputs, so the two halo rows are not loaded at all
@@ -189,6 +198,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int as = a_it % kHaloAStages;
         mbar_wait(p.gn_ab ? &a_ready[as] : &a_full[as], (a_it / kHaloAStages) & 1);
         tc_fence_after();
+        if (lane == 0) halo_trace(p.trace, 3, a_it);
         // position 0 of the tile = first pixel slot of the tile's first row = halo row 1
         const uint32_t x0_addr = smem_u32(abuf + as * kHaloASlot) + 128u + kRowBytes;
         for (int tap = 0; tap < ntaps; ++tap, ++b_it) {
@@ -210,6 +220,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           __syncwarp();
         }
+        if (lane == 0) halo_trace(p.trace, 4, a_it);
       }
     }
   } else if (warp >= kWarpXf0) {
@@ -247,39 +258,57 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             }
           }
           mbar_wait(&a_full[as], (a_it / kHaloAStages) & 1);
+          if (xt == 0) halo_trace(p.trace, 1, a_it);
           if (is_conv) {
             uint8_t* tile = abuf + as * kHaloASlot + 128;
             const uint32_t tile_addr = smem_u32(tile);
-            for (int r = r_first; r < rows; r += 4 * kHaloXfWarps) {
-              const int hr = r / WP, xx = r - hr * WP;
-              const int pr = pr0 + hr;
-              if (xx == 0 || xx == WP - 1 || pr < 0 || pr >= p.total_rows) continue;
-              const int n = pr / (p.h + 2);
-              const int yy = pr - n * (p.h + 2) - 1;
-              if (yy < 0 || yy >= p.h) continue;
-              // SWIZZLE_128B: the 16-byte unit index is XORed with address bits [7, 10) of the row
-              const uint32_t phase = ((tile_addr + static_cast<uint32_t>(r) * 128u) >> 7) & 7u;
-              uint4* ptr = reinterpret_cast<uint4*>(tile + r * 128 + ((static_cast<uint32_t>(ul) ^ phase) << 4));
-              uint4 v = *ptr;
-              float f[8];
-              unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
-              unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
-              const bool second = n != n_lo;
+            // All loads of a batch are issued before the first value is used: the MMAs keep the shared-memory port
+            // nearly saturated, so one load-use round trip per row (an earlier version) made this stage latency-bound
+            // and slower than the MMAs it feeds (per-role timeline: tools/trace_halo.py).
+            constexpr int kXfBatch = 5;
+            for (int rb = r_first; rb < rows; rb += 4 * kHaloXfWarps * kXfBatch) {
+              uint4 v[kXfBatch];
+              uint32_t off[kXfBatch];
+              int sel[kXfBatch];  // 0: padding position (stays zero), 1 / 2: first / second image of the tile
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 ab = second ? c1v[j] : c0v[j];
-                f[j] = fmaf(f[j], ab.x, ab.y);
+              for (int b = 0; b < kXfBatch; ++b) {
+                const int r = rb + b * 4 * kHaloXfWarps;
+                const int hr = r / WP, xx = r - hr * WP;
+                const int pr = pr0 + hr;
+                const int n = pr / WP;  // square maps: h + 2 == W + 2
+                const int yy = pr - n * WP - 1;
+                const bool valid = r < rows && xx != 0 && xx != WP - 1 && pr >= 0 && pr < p.total_rows && yy >= 0 && yy < W;
+                sel[b] = valid ? (n != n_lo ? 2 : 1) : 0;
+                // SWIZZLE_128B: the 16-byte unit index is XORed with address bits [7, 10) of the row
+                const uint32_t phase = ((tile_addr + static_cast<uint32_t>(r) * 128u) >> 7) & 7u;
+                off[b] = static_cast<uint32_t>(r) * 128u + ((static_cast<uint32_t>(ul) ^ phase) << 4);
+                if (valid) v[b] = *reinterpret_cast<const uint4*>(tile + off[b]);
               }
-              if (p.gn_silu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+              for (int b = 0; b < kXfBatch; ++b) {
+                if (sel[b] == 0) continue;
+                float f[8];
+                unpack_bf16x2(v[b].x, f[0], f[1]); unpack_bf16x2(v[b].y, f[2], f[3]);
+                unpack_bf16x2(v[b].z, f[4], f[5]); unpack_bf16x2(v[b].w, f[6], f[7]);
+                const bool second = sel[b] == 2;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 ab = second ? c1v[j] : c0v[j];
+                  f[j] = fmaf(f[j], ab.x, ab.y);
+                }
+                if (p.gn_silu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(tile + off[b]) = o;
               }
-              v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-              v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-              *ptr = v;
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the MMA's async-proxy reads
           }
+          if (xt == 0) halo_trace(p.trace, 2, a_it);
           mbar_arrive(&a_ready[as]);
         }
       }
@@ -319,6 +348,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
       mbar_wait(&acc_full[stage], (u_it >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) halo_trace(p.trace, 5, u_it);
 #pragma unroll 1
       for (int rr = half; rr < p.rt; rr += 2) {
         const int pr = mt * p.rt + rr;
@@ -365,6 +395,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[stage]);
+      if (threadIdx.x == 0) halo_trace(p.trace, 6, u_it);
       flush_stats();
     }
   }
@@ -379,6 +410,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
 static int g_halo_mode = 1;  // 1: AUTO prefers this kernel, 0: AUTO never picks it (A/B measurements)
 static int g_sm_count = 0;
+static long long* g_halo_trace = nullptr;
 
 bool conv_halo_supported(const dmme_conv_desc& d) {
   if (g_halo_mode == 0) return false;
@@ -477,6 +509,7 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   p.gn_ab = reinterpret_cast<const float2*>(d.gn_ab);
   p.gn_c = d.c0 + d.c1;
   p.gn_silu = d.gn_silu;
+  p.trace = g_halo_trace;
   DMME_REQUIRE(d.gn_ab == nullptr || p.imgs_per_tile == 0, DMME_E_UNSUPPORTED,
                "conv_halo: fused GroupNorm needs row tiles (16x16 and 32x32 maps)");
   // the MMA reads n_mma + (W+3) position rows past the first tile position; keep that inside the slot
@@ -513,3 +546,5 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
 // A/B measurement switch: 0 = AUTO never uses the halo kernel, 1 = default
 extern "C" void dmme_set_conv_halo_mode(int mode) { dmme::g_halo_mode = mode; }
 extern "C" int dmme_get_conv_halo_mode(void) { return dmme::g_halo_mode; }
+// debugging: int64[7 * 256] device buffer receiving CTA 0's per-role timestamps (tools/trace_halo.py), null = off
+extern "C" void dmme_debug_set_halo_trace(long long* buf) { dmme::g_halo_trace = buf; }

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmme_b200.so")
+LIB_PATH = os.environ.get("DMME_LIB_PATH") or os.path.join(_HERE, "libdmme_b200.so")  # override: A/B builds only
 
 BF16, F32 = 0, 1
 IN_NHWC, IN_NCHW_F32 = 0, 1

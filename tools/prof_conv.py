@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--only", default="")
     ap.add_argument("--flush", type=int, default=1)
+    ap.add_argument("--gn", type=int, default=0, help="1: fused GroupNorm+SiLU of the input inside the halo kernel")
     args = ap.parse_args()
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
@@ -53,13 +54,18 @@ def main():
                                    L.OUT_NHWC, torch.bfloat16, kernel)
             if not ops.conv_uses_tc(d):
                 continue
+            ab = None
+            if args.gn:
+                if kname != "halo" or not ops.conv_fuses_gn(d):
+                    continue
+                ab = torch.randn(n, cin, 2, device=dev, generator=g)
             times = []
             for r in range(args.reps + 2):
                 if args.flush:
                     flush.fill_(r)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ops.conv2d_launch(d, wp, bias, out, temb, None, stats=st)
+                ops.conv2d_launch(d, wp, bias, out, temb, None, stats=st, gn_ab=ab)
                 e1.record()
                 torch.cuda.synchronize()
                 if r >= 2:
