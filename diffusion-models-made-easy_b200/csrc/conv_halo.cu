@@ -31,6 +31,7 @@ namespace dmme {
 struct ConvHaloParams {
   CUtensorMap a[4];  // src0, src1, res0, res1: box = one padded row [W+2 px][64 ch]
   CUtensorMap b;     // weights [cout][K] bf16, box [128][64]
+  CUtensorMap b_half;  // the same tensor, box [64][64]: each CTA of a multicast pair loads half of every weight tile
   int chunks0, chunks1, rchunks0, rchunks1;
   int n, h, wp;
   int rt;            // padded rows per tile
@@ -59,6 +60,22 @@ __device__ __forceinline__ void halo_trace(long long* trace, int role, int idx) 
   if (trace && blockIdx.x == 0 && idx < 256) trace[role * 256 + idx] = clock64();
 }
 
+// Chunk order inside a work unit.  The single-tap chunks of a fused 1x1 residual keep an activation stage busy for only 4
+// MMAs (~0.5k clocks against ~4.5k for a nine-tap chunk and ~5k clocks of load latency): issued back to back after the
+// conv chunks they drain the stage ring and the next unit's first tile arrives late (per-role timeline, tools/trace_halo.py:
+// a 4.5k-clock bubble per unit).  They are therefore spread between the conv chunks -- conv chunk i sits at position
+// i + ceil(i * rc / cc) -- so any window of stages-1 chunks holds a nine-tap chunk to cover the loads.
+struct HaloChunk { bool is_conv; int idx; };
+__device__ __forceinline__ HaloChunk halo_chunk_at(int j, int cc, int rc) {
+  int conv_before = 0;
+  for (int i = 0; i < cc; ++i) {
+    const int pos = i + (i * rc + cc - 1) / cc;
+    if (pos == j) return {true, i};
+    if (pos < j) ++conv_before;
+  }
+  return {false, j - conv_before};
+}
+
 constexpr int kHaloBN = 128;            // output channels per unit (MMA M)
 constexpr int kHaloCols = 256;          // TMEM columns per accumulator stage
 constexpr int kHaloASlot = 40 * 1024;   // >= ((rt + 2) * (W+2) + 1) * 128 bytes
@@ -72,7 +89,10 @@ constexpr int kHaloThreads = (kHaloEpiWarps + 3 + kHaloXfWarps) * 32;
 constexpr int kWarpProdA = kHaloEpiWarps, kWarpProdB = kHaloEpiWarps + 1, kWarpMma = kHaloEpiWarps + 2;
 constexpr int kWarpXf0 = kHaloEpiWarps + 3;
 
-template <int W, int COUT>
+// MC: clusters of two CTAs walk pairs of row tiles (same output channels) in lockstep and share the weight stream: each
+// CTA loads half of every [128][64] weight tile and multicasts it into both CTAs' stage (half the L2 -> SM weight traffic,
+// which is 2/3 of this kernel's operand feed); a stage is refilled once both CTAs' MMAs have released it.
+template <int W, int COUT, bool MC>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kHaloAStages], a_empty[kHaloAStages];
@@ -88,10 +108,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint8_t* bbuf = abuf + kHaloAStages * kHaloASlot;
 
   const int cchunks = p.chunks0 + p.chunks1;
-  const int nck = cchunks + p.rchunks0 + p.rchunks1;
+  const int rchunks = p.rchunks0 + p.rchunks1;
+  const int nck = cchunks + rchunks;
   const int units = p.m_tiles * p.n_tiles;
   constexpr int kRowBytes = WP * 128;
   const int nr = p.rt + 2;  // halo rows: one above and one below the tile
+  // schedule: CTA (pair) `sched0` takes work items sched0, sched0 + nsched, ...; item v = (row tile [pair], channel tile)
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  const int nsched = MC ? gridDim.x / 2 : gridDim.x;
+  const int sched0 = MC ? blockIdx.x / 2 : blockIdx.x;
+  const int items = MC ? ((p.m_tiles + 1) / 2) * p.n_tiles : units;
+  auto item_mt = [&](int v) { return MC ? 2 * (v / p.n_tiles) + static_cast<int>(crank) : v / p.n_tiles; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHaloAStages; ++s) {
@@ -99,7 +126,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       mbar_init(&a_empty[s], 1);
       mbar_init(&a_ready[s], kHaloXfWarps * 32);
     }
-    for (int s = 0; s < kHaloBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < kHaloBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kHaloEpiWarps * 32); }
     fence_barrier_init();
     fence_proxy_async();
@@ -109,11 +136,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (p.chunks1) tma_prefetch_desc(&p.a[1]);
     if (p.rchunks0) tma_prefetch_desc(&p.a[2]);
     if (p.rchunks1) tma_prefetch_desc(&p.a[3]);
-    tma_prefetch_desc(&p.b);
+    tma_prefetch_desc(MC ? &p.b_half : &p.b);
   }
   if (warp == kWarpMma) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's multicast loads and commits target this CTA's barriers
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   pdl_trigger();  // after the TMEM allocation (see ptx_sm100.cuh)
@@ -123,16 +151,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (lane == 0) {
       int a_it = 0;
       pdl_wait();
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int mt = u / p.n_tiles;
+      for (int u = sched0; u < items; u += nsched) {
+        const int mt = item_mt(u);
         const int pr0 = mt * p.rt - 1;  // first halo row (padded-row index, may be -1)
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           int which, cc;
-          if (ck < cchunks) {
-            which = ck < p.chunks0 ? 0 : 1;
-            cc = (which ? ck - p.chunks0 : ck) * 64;
+          const HaloChunk hc = halo_chunk_at(ck, cchunks, rchunks);
+          if (hc.is_conv) {
+            which = hc.idx < p.chunks0 ? 0 : 1;
+            cc = (which ? hc.idx - p.chunks0 : hc.idx) * 64;
           } else {
-            const int rk = ck - cchunks;
+            const int rk = hc.idx;
             which = rk < p.rchunks0 ? 2 : 3;
             cc = (which == 3 ? rk - p.rchunks0 : rk) * 64;
           }
@@ -148,10 +177,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               tma_load_5d(dst + i * (p.h + 2) * kRowBytes, &p.a[which], &a_full[as], cc, -1, 0, -1, mt * p.imgs_per_tile + i);
             continue;
           }
-          mbar_expect_tx(&a_full[as], nr * kRowBytes);
+          // the single-tap chunks of a fused 1x1 residual only read the tile's own rows: the two halo rows are not loaded
+          // (whatever the slot holds there only reaches padding-position accumulator columns)
+          const int i_lo = hc.is_conv ? 0 : 1, i_hi = hc.is_conv ? nr : nr - 1;
+          mbar_expect_tx(&a_full[as], (i_hi - i_lo) * kRowBytes);
           // slot layout: 128 bytes of slack (tap (-1,-1) of position 0 reaches one row back), then the halo rows
           uint8_t* dst = abuf + as * kHaloASlot + 128;
-          for (int i = 0; i < nr; ++i) {
+          for (int i = i_lo; i < i_hi; ++i) {
             const int pr = pr0 + i;
             int ni, yy;
             if (pr < 0) { ni = -1; yy = 0; }             // before the first image: whole row out of bounds -> zeros
@@ -166,18 +198,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (lane == 0) {
       int b_it = 0;
       pdl_wait();  // the packed weights may come from a pack kernel launched just before this one
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      for (int u = sched0; u < items; u += nsched) {
         const int col0 = (u % p.n_tiles) * kHaloBN;
         for (int ck = 0; ck < nck; ++ck) {
-          const bool is_conv = ck < cchunks;
+          const HaloChunk hc = halo_chunk_at(ck, cchunks, rchunks);
+          const bool is_conv = hc.is_conv;
           const int ntaps = is_conv ? 9 : 1;
-          const int kb0 = is_conv ? ck : 9 * cchunks + (ck - cchunks);
+          const int kb0 = is_conv ? hc.idx : 9 * cchunks + hc.idx;
           const int kbs = is_conv ? cchunks : 0;
           for (int tap = 0; tap < ntaps; ++tap, ++b_it) {
             const int bs = b_it % kHaloBStages;
             mbar_wait(&b_empty[bs], ((b_it / kHaloBStages) & 1) ^ 1);
             mbar_expect_tx(&b_full[bs], kHaloBSlot);
-            tma_load_2d(bbuf + bs * kHaloBSlot, &p.b, &b_full[bs], (kb0 + tap * kbs) * 64, col0);
+            if (MC)
+              tma_load_2d_mc(bbuf + bs * kHaloBSlot + crank * (kHaloBSlot / 2), &p.b_half, &b_full[bs], (kb0 + tap * kbs) * 64,
+                             col0 + static_cast<int>(crank) * (kHaloBN / 2), 3);
+            else
+              tma_load_2d(bbuf + bs * kHaloBSlot, &p.b, &b_full[bs], (kb0 + tap * kbs) * 64, col0);
           }
         }
       }
@@ -187,13 +224,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // the whole warp walks the loop (converged waits); one elected lane issues the MMAs and their commits
     const uint32_t idesc = umma_idesc_bf16(kHaloBN, p.n_mma);  // M = 128 output channels, N = positions of the tile
     int a_it = 0, b_it = 0, u_it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
+    for (int u = sched0; u < items; u += nsched, ++u_it) {
       const int stage = u_it & 1;
       mbar_wait(&acc_empty[stage], ((u_it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t dtm = tmem_base + stage * kHaloCols;
       for (int ck = 0; ck < nck; ++ck, ++a_it) {
-        const bool is_conv = ck < cchunks;
+        const bool is_conv = halo_chunk_at(ck, cchunks, rchunks).is_conv;
         const int ntaps = is_conv ? 9 : 1;
         const int as = a_it % kHaloAStages;
         mbar_wait(p.gn_ab ? &a_ready[as] : &a_full[as], (a_it / kHaloAStages) & 1);
@@ -212,7 +249,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (ck | tap | k) != 0 ? 1u : 0u);
-            umma_commit(&b_empty[bs]);
+            if (MC) umma_commit_mc(&b_empty[bs], 3);
+            else umma_commit(&b_empty[bs]);
             if (tap == ntaps - 1) {
               umma_commit(&a_empty[as]);
               if (ck == nck - 1) umma_commit(&acc_full[stage]);
@@ -237,16 +275,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const int rows = nr * WP;
       int a_it = 0;
       pdl_wait();
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int mt = u / p.n_tiles;
+      for (int u = sched0; u < items; u += nsched) {
+        const int mt = item_mt(u);
         const int pr0 = mt * p.rt - 1;
-        const int n_lo = (pr0 < 0 ? 0 : pr0) / (p.h + 2);  // first image the tile touches; it touches at most n_lo + 1 too
+        // first image the tile touches; it touches at most n_lo + 1 too (clamped: a pair's odd tile may lie past the batch)
+        const int n_lo = min((pr0 < 0 ? 0 : pr0) / (p.h + 2), p.n - 1);
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           const int as = a_it % kHaloAStages;
-          const bool is_conv = ck < cchunks;
+          const HaloChunk hc = halo_chunk_at(ck, cchunks, rchunks);
+          const bool is_conv = hc.is_conv;
           float2 c0v[8], c1v[8];
           if (is_conv) {
-            const int cbase = ck * 64 + ul * 8;
+            const int cbase = hc.idx * 64 + ul * 8;
             const float4* g0 = reinterpret_cast<const float4*>(p.gn_ab + static_cast<long long>(n_lo) * p.gn_c + cbase);
             const bool has1 = n_lo + 1 < p.n;
             const float4* g1 = reinterpret_cast<const float4*>(p.gn_ab + static_cast<long long>(has1 ? n_lo + 1 : n_lo) * p.gn_c + cbase);
@@ -323,8 +363,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const bool temb_per_image = p.temb && p.temb_rows != 1;
     int u_it = 0;
     pdl_wait();
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
-      const int mt = u / p.n_tiles, nt = u - mt * p.n_tiles;
+    for (int u = sched0; u < items; u += nsched, ++u_it) {
+      const int mt = item_mt(u), nt = u % p.n_tiles;
       const int ch = nt * kHaloBN + q * 32 + lane;
       const float bias_c = p.bias ? __ldg(p.bias + ch) : 0.f;
       const int stage = u_it & 1;
@@ -401,7 +441,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all();  // neither CTA may leave while the other can still write its stages / signal its barriers
+  else __syncthreads();
   if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -437,24 +478,42 @@ bool conv_halo_preferred(const dmme_conv_desc& d) {
   return true;
 }
 
-template <int W, int COUT>
-static int launch_halo(const ConvHaloParams& p, cudaStream_t stream) {
+// weight multicast across CTA pairs (clusters of two): 0 = off (default: measured 3-15% SLOWER on every signature of the
+// step -- the weight feed is not what paces this kernel and the pair runs in lockstep), 1 = launches with several work
+// items per CTA, 2 = every launch
+static int g_halo_mc = 0;
+
+template <int W, int COUT, bool MC>
+static int launch_halo_mc(const ConvHaloParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<W, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<W, COUT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) {
       set_error("conv_halo: cudaFuncSetAttribute(%d bytes): %s", kHaloSmem, cudaGetErrorString(e));
       return (int)e;
     }
     configured = true;
   }
+  if (MC) {
+    const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int pairs = items < g_sm_count / 2 ? items : g_sm_count / 2;
+    cudaError_t e = launch_pdl_pair(conv_halo_kernel<W, COUT, MC>, dim3(2 * pairs), dim3(kHaloThreads), kHaloSmem, stream, p);
+    return check_launch_err(e, "conv_halo_kernel (multicast pairs)");
+  }
   const int units = p.m_tiles * p.n_tiles;
   const int grid = units < g_sm_count ? units : g_sm_count;
-  cudaError_t e = launch_pdl(conv_halo_kernel<W, COUT>, dim3(grid), dim3(kHaloThreads), kHaloSmem, stream, p);
+  cudaError_t e = launch_pdl(conv_halo_kernel<W, COUT, MC>, dim3(grid), dim3(kHaloThreads), kHaloSmem, stream, p);
   return check_launch_err(e, "conv_halo_kernel");
+}
+
+template <int W, int COUT>
+static int launch_halo(const ConvHaloParams& p, cudaStream_t stream) {
+  // pairs pay off where CTAs walk several work items each (the 16x16 and 32x32 levels at sampling batch sizes)
+  if (g_halo_mc == 2 || (g_halo_mc == 1 && p.m_tiles * p.n_tiles >= 2 * g_sm_count)) return launch_halo_mc<W, COUT, true>(p, stream);
+  return launch_halo_mc<W, COUT, false>(p, stream);
 }
 
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
@@ -534,6 +593,8 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     uint64_t strides[1] = {ktot * 2};
     uint32_t box[2] = {64u, (uint32_t)kHaloBN};
     if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
+    uint32_t box_half[2] = {64u, (uint32_t)kHaloBN / 2};
+    if ((rc = encode_map(&p.b_half, d.weight, 2, dims, strides, box_half))) return rc;
   }
   if (d.w_in == 32) return d.cout == 128 ? launch_halo<32, 128>(p, stream) : launch_halo<32, 256>(p, stream);
   if (d.w_in == 16) return d.cout == 128 ? launch_halo<16, 128>(p, stream) : launch_halo<16, 256>(p, stream);
@@ -546,5 +607,8 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
 // A/B measurement switch: 0 = AUTO never uses the halo kernel, 1 = default
 extern "C" void dmme_set_conv_halo_mode(int mode) { dmme::g_halo_mode = mode; }
 extern "C" int dmme_get_conv_halo_mode(void) { return dmme::g_halo_mode; }
+// A/B measurement switch: 0 = default, no weight multicast (independent CTAs), 1 = clusters of two share the weight stream
+// when every CTA has several work items, 2 = pairs for every launch (tests)
+extern "C" void dmme_set_conv_halo_multicast(int mode) { dmme::g_halo_mc = mode; }
 // debugging: int64[7 * 256] device buffer receiving CTA 0's per-role timestamps (tools/trace_halo.py), null = off
 extern "C" void dmme_debug_set_halo_trace(long long* buf) { dmme::g_halo_trace = buf; }

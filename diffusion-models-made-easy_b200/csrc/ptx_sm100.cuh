@@ -202,6 +202,25 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
       "h"(cta_mask)
       : "memory");
 }
+// cta_group::1 kernels whose two cluster CTAs share an operand stream: one TMA load delivered to the same shared-memory
+// offset (and signalled on the barrier at the same offset) in every CTA of `cta_mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// ... and the matching release: arrive on the barrier at this offset in every CTA of `cta_mask` once this thread's MMAs
+// completed (each CTA's producer waits for both consumers before it overwrites the shared stage)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 // TMA loads of a CTA pair: data into this CTA's shared memory, completion bytes on the barrier at `bar_cluster_addr`
 // (the leader's)
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,

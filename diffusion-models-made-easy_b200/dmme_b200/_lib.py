@@ -27,7 +27,7 @@ EXPORTS = (
     "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
     "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
-    "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode",
+    "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode", "dmme_set_conv_halo_multicast",
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
     "dmme_denorm", "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
     "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     lib.dmme_add_i64.argtypes = [vp, C.c_int64, vp]
     lib.dmme_philox_normal.argtypes = [vp, ll, ull, ull, ull, vp]
     lib.dmme_set_conv_halo_mode.argtypes = [i]
+    lib.dmme_set_conv_halo_multicast.argtypes = [i]
+    lib.dmme_set_conv_halo_multicast.restype = None
     lib.dmme_set_conv_tct_mode.argtypes = [i]
     lib.dmme_set_conv_out_tc_mode.argtypes = [i]
     lib.dmme_set_conv_pair_mode.argtypes = [i]
@@ -140,6 +142,9 @@ def load() -> C.CDLL:
     mode = os.environ.get("DMME_ATTN_MMA_MODE")  # A/B measurements only: 0 = multi-head attention on CUDA cores
     if mode:
         lib.dmme_set_attn_mma_mode(int(mode))
+    mode = os.environ.get("DMME_HALO_MC")  # A/B measurements only: 0 = no weight multicast in the halo conv kernel
+    if mode:
+        lib.dmme_set_conv_halo_multicast(int(mode))
     mode = os.environ.get("DMME_OUT_TC_MODE")  # A/B measurements only: 0 = output conv on the FFMA kernel
     if mode:
         lib.dmme_set_conv_out_tc_mode(int(mode))

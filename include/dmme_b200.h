@@ -109,6 +109,9 @@ void dmme_reset_launch_count(void);
 /* A/B switch for measurements: 0 = AUTO never picks the halo kernel, 1 = default */
 void dmme_set_conv_halo_mode(int mode);
 int dmme_get_conv_halo_mode(void);
+/* halo kernel: clusters of two CTAs share the weight stream through TMA multicast.  0 = off (default; measured slower),
+ * 1 = launches with several work items per CTA, 2 = every launch */
+void dmme_set_conv_halo_multicast(int mode);
 /* A/B switch: 0 = AUTO/TC never use the transposed tcgen05 kernel (thread = channel epilogue), 1 = default
  * (where it has a unit for most SMs), 2 = wherever it is supported */
 void dmme_set_conv_tct_mode(int mode);

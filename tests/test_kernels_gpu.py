@@ -878,3 +878,43 @@ def test_conv_halo_fused_groupnorm(cfg):
     torch.cuda.synchronize()
     assert torch.equal(got.view(torch.int16), want.view(torch.int16))
     assert torch.equal(st_got, st_want)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n=5, c0=128, c1=0, cout=128, h=32),                       # odd number of row tiles: the pair's last tile is past the batch
+    dict(n=37, c0=128, c1=128, cout=128, h=32, res=True, gn=True),
+    dict(n=9, c0=256, c1=0, cout=256, h=16, gn=True),              # two channel tiles per row-tile pair
+    dict(n=70, c0=256, c1=256, cout=256, h=16),
+    dict(n=300, c0=128, c1=0, cout=128, h=32, gn=True),            # several items per CTA pair
+])
+def test_conv_halo_weight_multicast(cfg):
+    """clusters of two CTAs sharing the weight stream (TMA multicast) == independent CTAs, bit for bit (outputs and
+    GroupNorm statistics; same MMA order per output)"""
+    ops, L = _ops()
+    lib = L.load()
+    g = torch.Generator().manual_seed(67)
+    n, c0, c1, cout, h = (cfg[k] for k in ("n", "c0", "c1", "cout", "h"))
+    C = c0 + c1
+    s0 = to_nhwc(bf16_round(torch.randn(n, c0, h, h, generator=g)), torch.bfloat16).to(DEV)
+    s1 = to_nhwc(bf16_round(torch.randn(n, c1, h, h, generator=g)), torch.bfloat16).to(DEV) if c1 else None
+    wt = bf16_round(torch.randn(cout, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    wres = bf16_round(torch.randn(cout, C, 1, 1, generator=g) / math.sqrt(C)) if cfg.get("res") else None
+    wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    ab = torch.randn(n, C, 2, generator=g).to(DEV) if cfg.get("gn") else None
+    r0, r1 = (s0, s1) if cfg.get("res") else (None, None)
+    d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_HALO)
+    outs = []
+    try:
+        for mode in (0, 2):
+            lib.dmme_set_conv_halo_multicast(mode)
+            out = torch.full((n, h, h, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+            ops.conv2d_launch(d, wp, bias, out, stats=st, gn_ab=ab)
+            torch.cuda.synchronize()
+            outs.append((out, st))
+    finally:
+        lib.dmme_set_conv_halo_multicast(0)
+    assert torch.isfinite(outs[0][0].float()).all()
+    assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16))
+    assert torch.equal(outs[0][1], outs[1][1])

@@ -2,7 +2,7 @@
 """Per-role timeline of CTA 0 of the halo conv kernel (clock64 timestamps written by the kernel when a trace buffer is
 set): per chunk, when the stage was free and its loads issued, when the tile landed, when the fused GroupNorm transform
 finished, when the MMA warp saw it and when it had issued the chunk's last tap; per unit, epilogue start / end.
-usage: python tools/trace_halo.py [c0 c1 cout h gn(0/1) res(0/1)]"""
+usage: python tools/trace_halo.py [c0 c1 cout h gn(0/1) rc0 rc1]"""
 import ctypes as C
 import math
 import os
@@ -15,17 +15,20 @@ import torch  # noqa: E402
 from dmme_b200 import _lib as L  # noqa: E402
 from dmme_b200 import ops  # noqa: E402
 
-c0, c1, cout, h, gn, res = (int(a) for a in (sys.argv[1:7] + ["128", "0", "128", "32", "1", "0"][len(sys.argv) - 1:]))
+c0, c1, cout, h, gn, rc0, rc1 = (int(a) for a in (sys.argv[1:8] + ["128", "0", "128", "32", "1", "0", "0"][len(sys.argv) - 1:]))
+res = rc0 + rc1 > 0
 n, dev = 256, "cuda"
 cin = c0 + c1
 g = torch.Generator(device=dev).manual_seed(0)
 s0 = torch.randn(n, h, h, c0, device=dev, generator=g).bfloat16()
 s1 = torch.randn(n, h, h, c1, device=dev, generator=g).bfloat16() if c1 else None
 w = torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin)
-wr = torch.randn(cout, cin, 1, 1, device=dev, generator=g) / math.sqrt(cin) if res else None
+r0 = torch.randn(n, h, h, rc0, device=dev, generator=g).bfloat16() if rc0 else None
+r1 = torch.randn(n, h, h, rc1, device=dev, generator=g).bfloat16() if rc1 else None
+wr = torch.randn(cout, rc0 + rc1, 1, 1, device=dev, generator=g) / math.sqrt(rc0 + rc1) if res else None
 wp = ops.pack_conv_weight(w, wr, True)
 bias = torch.randn(cout, device=dev, generator=g)
-d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, s0 if res else None, s1 if res else None, False, L.OUT_NHWC,
+d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC,
                        torch.bfloat16, L.CONV_HALO)
 out = torch.empty(n, h, h, cout, device=dev, dtype=torch.bfloat16)
 ab = torch.randn(n, cin, 2, device=dev, generator=g) if gn else None
@@ -45,7 +48,7 @@ for rep in range(3):
     e1.record()
     torch.cuda.synchronize()
 lib.dmme_debug_set_halo_trace(None)
-print(f"# conv 3x3 {cin}->{cout} @{h} gn={gn} res={res}: {e0.elapsed_time(e1) * 1e3:.1f} us; clock64 ticks relative to the first event")
+print(f"# conv 3x3 {cin}->{cout} @{h} gn={gn} res={rc0 + rc1}: {e0.elapsed_time(e1) * 1e3:.1f} us; clock64 ticks relative to the first event")
 t = trace.cpu().view(7, 256)
 t0 = int(t[t > 0].min())
 nchunks = int((t[0] > 0).sum())
