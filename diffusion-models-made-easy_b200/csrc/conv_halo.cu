@@ -60,20 +60,11 @@ __device__ __forceinline__ void halo_trace(long long* trace, int role, int idx) 
   if (trace && blockIdx.x == 0 && idx < 256) trace[role * 256 + idx] = clock64();
 }
 
-// Chunk order inside a work unit.  The single-tap chunks of a fused 1x1 residual keep an activation stage busy for only 4
-// MMAs (~0.5k clocks against ~4.5k for a nine-tap chunk and ~5k clocks of load latency): issued back to back after the
-// conv chunks they drain the stage ring and the next unit's first tile arrives late (per-role timeline, tools/trace_halo.py:
-// a 4.5k-clock bubble per unit).  They are therefore spread between the conv chunks -- conv chunk i sits at position
-// i + ceil(i * rc / cc) -- so any window of stages-1 chunks holds a nine-tap chunk to cover the loads.
+// Chunk order inside a work unit: the nine-tap conv chunks, then the single-tap chunks of a fused 1x1 residual.  (Spreading
+// the residual chunks between the conv chunks to keep the stage ring covered was measured slower, tools/trace_halo.py.)
 struct HaloChunk { bool is_conv; int idx; };
-__device__ __forceinline__ HaloChunk halo_chunk_at(int j, int cc, int rc) {
-  int conv_before = 0;
-  for (int i = 0; i < cc; ++i) {
-    const int pos = i + (i * rc + cc - 1) / cc;
-    if (pos == j) return {true, i};
-    if (pos < j) ++conv_before;
-  }
-  return {false, j - conv_before};
+__device__ __forceinline__ HaloChunk halo_chunk_at(int j, int cc) {
+  return j < cc ? HaloChunk{true, j} : HaloChunk{false, j - cc};
 }
 
 constexpr int kHaloBN = 128;            // output channels per unit (MMA M)
@@ -85,9 +76,11 @@ constexpr int kHaloBStages = 4;
 constexpr int kHaloSmem = kHaloAStages * kHaloASlot + kHaloBStages * kHaloBSlot + 1024;
 constexpr int kHaloEpiWarps = 8;
 constexpr int kHaloXfWarps = 8;  // GroupNorm transform warps (idle when the conv has no fused norm)
-constexpr int kHaloThreads = (kHaloEpiWarps + 3 + kHaloXfWarps) * 32;
+constexpr int kHaloProdA = 2;     // halo-tile producer warps: one thread issues a 4 KB row box every ~300 clocks, a tile has 9-16
+constexpr int kHaloThreads = (kHaloEpiWarps + 3 + kHaloXfWarps + kHaloProdA - 1) * 32;
 constexpr int kWarpProdA = kHaloEpiWarps, kWarpProdB = kHaloEpiWarps + 1, kWarpMma = kHaloEpiWarps + 2;
 constexpr int kWarpXf0 = kHaloEpiWarps + 3;
+constexpr int kWarpProdA2 = kWarpXf0 + kHaloXfWarps;  // further halo-tile producers: the row boxes of a tile are split between the issuing threads
 
 // MC: clusters of two CTAs walk pairs of row tiles (same output channels) in lockstep and share the weight stream: each
 // CTA loads half of every [128][64] weight tile and multicasts it into both CTAs' stage (half the L2 -> SM weight traffic,
@@ -122,7 +115,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHaloAStages; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], kHaloProdA);
       mbar_init(&a_empty[s], 1);
       mbar_init(&a_ready[s], kHaloXfWarps * 32);
     }
@@ -146,8 +139,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const uint32_t tmem_base = tmem_slot;
   pdl_trigger();  // after the TMEM allocation (see ptx_sm100.cuh)
 
-  if (warp == kWarpProdA) {
-    // =========================== halo-tile producer ===========================
+  if (warp == kWarpProdA || warp >= kWarpProdA2) {
+    // =========================== halo-tile producers ===========================
+    const int prod = warp == kWarpProdA ? 0 : warp - kWarpProdA2 + 1;
+    const bool second = prod != 0;
     if (lane == 0) {
       int a_it = 0;
       pdl_wait();
@@ -156,7 +151,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int pr0 = mt * p.rt - 1;  // first halo row (padded-row index, may be -1)
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           int which, cc;
-          const HaloChunk hc = halo_chunk_at(ck, cchunks, rchunks);
+          const HaloChunk hc = halo_chunk_at(ck, cchunks);
           if (hc.is_conv) {
             which = hc.idx < p.chunks0 ? 0 : 1;
             cc = (which ? hc.idx - p.chunks0 : hc.idx) * 64;
@@ -167,8 +162,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           const int as = a_it % kHaloAStages;
           mbar_wait(&a_empty[as], ((a_it / kHaloAStages) & 1) ^ 1);
-          halo_trace(p.trace, 0, a_it);
+          if (!second) halo_trace(p.trace, 0, a_it);
           if (p.imgs_per_tile > 0) {
+            if (second) { mbar_arrive(&a_full[as]); continue; }
             // whole padded images: box = [64 ch][W+2 px][h+2 rows] from (x, y) = (-1, -1); rows outside the tile are only
             // ever read for padding-position outputs, so the two halo rows are not loaded at all
             mbar_expect_tx(&a_full[as], p.rt * kRowBytes);
@@ -179,7 +175,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           // the single-tap chunks of a fused 1x1 residual only read the tile's own rows: the two halo rows are not loaded
           // (whatever the slot holds there only reaches padding-position accumulator columns)
-          const int i_lo = hc.is_conv ? 0 : 1, i_hi = hc.is_conv ? nr : nr - 1;
+          int i_lo = hc.is_conv ? 0 : 1, i_hi = hc.is_conv ? nr : nr - 1;
+          const int i_cnt = i_hi - i_lo;
+          i_hi = i_lo + (i_cnt * (prod + 1)) / kHaloProdA;
+          i_lo = i_lo + (i_cnt * prod) / kHaloProdA;
           mbar_expect_tx(&a_full[as], (i_hi - i_lo) * kRowBytes);
           // slot layout: 128 bytes of slack (tap (-1,-1) of position 0 reaches one row back), then the halo rows
           uint8_t* dst = abuf + as * kHaloASlot + 128;
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       for (int u = sched0; u < items; u += nsched) {
         const int col0 = (u % p.n_tiles) * kHaloBN;
         for (int ck = 0; ck < nck; ++ck) {
-          const HaloChunk hc = halo_chunk_at(ck, cchunks, rchunks);
+          const HaloChunk hc = halo_chunk_at(ck, cchunks);
           const bool is_conv = hc.is_conv;
           const int ntaps = is_conv ? 9 : 1;
           const int kb0 = is_conv ? hc.idx : 9 * cchunks + hc.idx;
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       tc_fence_after();
       const uint32_t dtm = tmem_base + stage * kHaloCols;
       for (int ck = 0; ck < nck; ++ck, ++a_it) {
-        const bool is_conv = halo_chunk_at(ck, cchunks, rchunks).is_conv;
+        const bool is_conv = halo_chunk_at(ck, cchunks).is_conv;
         const int ntaps = is_conv ? 9 : 1;
         const int as = a_it % kHaloAStages;
         mbar_wait(p.gn_ab ? &a_ready[as] : &a_full[as], (a_it / kHaloAStages) & 1);
@@ -261,7 +260,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         if (lane == 0) halo_trace(p.trace, 4, a_it);
       }
     }
-  } else if (warp >= kWarpXf0) {
+  } else if (warp >= kWarpXf0 && warp < kWarpProdA2) {
     // =========================== fused GroupNorm(+SiLU) of the halo tile ===========================
     // Thread = one 16-byte unit column (eight channels of the chunk: its 16 coefficients live in registers, for the two
     // images a tile can touch) x every 16th position row.  Padding positions (x = -1, W; rows above / below an image;
@@ -282,7 +281,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int n_lo = min((pr0 < 0 ? 0 : pr0) / (p.h + 2), p.n - 1);
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           const int as = a_it % kHaloAStages;
-          const HaloChunk hc = halo_chunk_at(ck, cchunks, rchunks);
+          const HaloChunk hc = halo_chunk_at(ck, cchunks);
           const bool is_conv = hc.is_conv;
           float2 c0v[8], c1v[8];
           if (is_conv) {
@@ -466,15 +465,16 @@ bool conv_halo_supported(const dmme_conv_desc& d) {
 }
 
 
-// AUTO's choice between the two tcgen05 kernels (both are correct wherever both are supported).  Measured at batch 256
-// (tools/prof_conv.py, profiles/): both kernels are bound by the L2 -> SM operand feed (~43 B/clk/SM of the ~6300 B/clk
-// chip-wide cap); the halo kernel's 9-tap reuse of the activation tile wins at 32x32 and 16x16 (75 vs 142 us, 76 vs
-// 102 us) except when a fused 1x1 residual adds single-tap chunks (16x16: 217 vs 171 us), and the padded-position
-// overhead (36% at 8x8, 56% at 4x4) cancels the gain below 16x16 (36.8 vs 35.6 us, 26.7 vs 25.5 us).
+// AUTO's choice between the two tcgen05 kernel families (both are correct wherever both are supported), by measurement at
+// batch 256 (tools/prof_conv.py on the step's signatures, gpurun_out/r54_ab.log): the halo kernel's 9-tap reuse of the
+// activation tile wins at 32x32 and 16x16 (76 vs 86 us, 78 vs 88 us), also with a fused 1x1 residual of up to 128 channels
+// (16x16: 82 vs 90 us) -- and it can apply the GroupNorm of its input itself; wider residuals add single-tap chunks whose
+// tile loads it cannot hide (16x16 +res512: 123 vs 102 us, +res256 at 128 channels: 50 vs 39 us), and the padded-position
+// overhead (36% at 8x8, 56% at 4x4) cancels the gain below 16x16 (37 vs 31 us, 27 vs 23 us).
 bool conv_halo_preferred(const dmme_conv_desc& d) {
   if (!conv_halo_supported(d)) return false;
   if (d.w_in < 16) return false;
-  if (d.w_in == 16 && (d.rc0 + d.rc1) > 0) return false;
+  if (d.w_in == 16 && (d.rc0 + d.rc1) > 128) return false;
   return true;
 }
 

@@ -142,6 +142,9 @@ def load() -> C.CDLL:
     mode = os.environ.get("DMME_ATTN_MMA_MODE")  # A/B measurements only: 0 = multi-head attention on CUDA cores
     if mode:
         lib.dmme_set_attn_mma_mode(int(mode))
+    mode = os.environ.get("DMME_HALO_MODE")  # A/B measurements only: dmme_set_conv_halo_mode value
+    if mode:
+        lib.dmme_set_conv_halo_mode(int(mode))
     mode = os.environ.get("DMME_HALO_MC")  # A/B measurements only: 0 = no weight multicast in the halo conv kernel
     if mode:
         lib.dmme_set_conv_halo_multicast(int(mode))
