@@ -30,6 +30,7 @@ namespace dmme {
 
 struct ConvHaloParams {
   CUtensorMap a[4];  // src0, src1, res0, res1: box = one padded row [W+2 px][64 ch]
+  CUtensorMap at[4]; // the same tensors, box = the rt + 2 padded rows of a whole halo tile (tiles inside one image)
   CUtensorMap b;     // weights [cout][K] bf16, box [128][64]
   CUtensorMap b_half;  // the same tensor, box [64][64]: each CTA of a multicast pair loads half of every weight tile
   int chunks0, chunks1, rchunks0, rchunks1;
@@ -129,6 +130,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (p.chunks1) tma_prefetch_desc(&p.a[1]);
     if (p.rchunks0) tma_prefetch_desc(&p.a[2]);
     if (p.rchunks1) tma_prefetch_desc(&p.a[3]);
+    if (p.imgs_per_tile == 0) {
+      tma_prefetch_desc(&p.at[0]);
+      if (p.chunks1) tma_prefetch_desc(&p.at[1]);
+      if (p.rchunks0) tma_prefetch_desc(&p.at[2]);
+      if (p.rchunks1) tma_prefetch_desc(&p.at[3]);
+    }
     tma_prefetch_desc(MC ? &p.b_half : &p.b);
   }
   if (warp == kWarpMma) tmem_alloc(&tmem_slot, 512);
@@ -149,6 +156,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       for (int u = sched0; u < items; u += nsched) {
         const int mt = item_mt(u);
         const int pr0 = mt * p.rt - 1;  // first halo row (padded-row index, may be -1)
+        // three of four tiles lie inside one padded image: ONE box of rt + 2 rows (rows -1 / h and everything past the batch
+        // are out of bounds = zero-filled) instead of a box per row -- the issuing thread needs ~300 clocks per box
+        const int ni0 = (pr0 < 0 ? 0 : pr0) / (p.h + 2);
+        const bool one_img = p.imgs_per_tile == 0 && (pr0 + nr - 1) / (p.h + 2) == ni0;
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           int which, cc;
           const HaloChunk hc = halo_chunk_at(ck, cchunks);
@@ -173,8 +184,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               tma_load_5d(dst + i * (p.h + 2) * kRowBytes, &p.a[which], &a_full[as], cc, -1, 0, -1, mt * p.imgs_per_tile + i);
             continue;
           }
-          // the single-tap chunks of a fused 1x1 residual only read the tile's own rows: the two halo rows are not loaded
-          // (whatever the slot holds there only reaches padding-position accumulator columns)
+          if (one_img) {
+            if (second) { mbar_arrive(&a_full[as]); continue; }
+            mbar_expect_tx(&a_full[as], nr * kRowBytes);
+            tma_load_5d(abuf + as * kHaloASlot + 128, &p.at[which], &a_full[as], cc, -1, 0, pr0 - ni0 * (p.h + 2) - 1, ni0);
+            continue;
+          }
+          // tiles spanning two images: a box per padded row, split between the producers.  The single-tap chunks of a fused
+          // 1x1 residual only read the tile's own rows: the two halo rows are not loaded (whatever the slot holds there only
+          // reaches padding-position accumulator columns)
           int i_lo = hc.is_conv ? 0 : 1, i_hi = hc.is_conv ? nr : nr - 1;
           const int i_cnt = i_hi - i_lo;
           i_hi = i_lo + (i_cnt * (prod + 1)) / kHaloProdA;
@@ -575,11 +593,11 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   DMME_REQUIRE((1 + (p.rt + 2) * p.wp) * 128 <= kHaloASlot && (1 + 2 * p.wp + 1 + p.n_mma) * 128 <= kHaloASlot,
                DMME_E_SHAPE, "conv_halo: halo tile does not fit its shared-memory slot");
 
-  auto act_map = [&](CUtensorMap* m, const void* ptr, int c) -> int {
+  auto act_map = [&](CUtensorMap* m, const void* ptr, int c, int rows = 0) -> int {
     uint64_t dims[5] = {(uint64_t)c, (uint64_t)d.w_in, 1, (uint64_t)d.h_in, (uint64_t)d.n};
     uint64_t strides[4] = {(uint64_t)c * 2, (uint64_t)d.w_in * c * 2, (uint64_t)d.w_in * c * 2,
                            (uint64_t)d.h_in * d.w_in * c * 2};
-    uint32_t box[5] = {64u, (uint32_t)p.wp, 1u, p.imgs_per_tile > 0 ? (uint32_t)(d.h_in + 2) : 1u, 1u};
+    uint32_t box[5] = {64u, (uint32_t)p.wp, 1u, rows ? (uint32_t)rows : p.imgs_per_tile > 0 ? (uint32_t)(d.h_in + 2) : 1u, 1u};
     return encode_map(m, ptr, 5, dims, strides, box);
   };
   int rc;
@@ -587,6 +605,12 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   if (d.c1 && (rc = act_map(&p.a[1], d.src1, d.c1))) return rc;
   if (d.rc0 && (rc = act_map(&p.a[2], d.res0, d.rc0))) return rc;
   if (d.rc1 && (rc = act_map(&p.a[3], d.res1, d.rc1))) return rc;
+  if (p.imgs_per_tile == 0) {
+    if ((rc = act_map(&p.at[0], d.src0, d.c0, p.rt + 2))) return rc;
+    if (d.c1 && (rc = act_map(&p.at[1], d.src1, d.c1, p.rt + 2))) return rc;
+    if (d.rc0 && (rc = act_map(&p.at[2], d.res0, d.rc0, p.rt + 2))) return rc;
+    if (d.rc1 && (rc = act_map(&p.at[3], d.res1, d.rc1, p.rt + 2))) return rc;
+  }
   {
     const uint64_t ktot = 9ull * (d.c0 + d.c1) + d.rc0 + d.rc1;
     uint64_t dims[2] = {ktot, (uint64_t)d.cout};
