@@ -34,6 +34,7 @@ struct ConvHaloParams {
   CUtensorMap b;     // weights [cout][K] bf16, box [128][64]
   CUtensorMap b_half;  // the same tensor, box [64][64]: each CTA of a multicast pair loads half of every weight tile
   int chunks0, chunks1, rchunks0, rchunks1;
+  unsigned char order[32];  // chunk order of a work unit, see halo_chunk_of
   int n, h, wp;
   int rt;            // padded rows per tile
   int n_mma;         // MMA N: rt * wp rounded up to a multiple of 16
@@ -61,12 +62,14 @@ __device__ __forceinline__ void halo_trace(long long* trace, int role, int idx) 
   if (trace && blockIdx.x == 0 && idx < 256) trace[role * 256 + idx] = clock64();
 }
 
-// Chunk order inside a work unit: the nine-tap conv chunks, then the single-tap chunks of a fused 1x1 residual.  (Spreading
-// the residual chunks between the conv chunks to keep the stage ring covered was measured slower, tools/trace_halo.py.)
+// Chunk order inside a work unit (ConvHaloParams::order, built on the host: bit 7 = nine-tap conv chunk, low bits = its
+// index).  The single-tap chunks of a fused 1x1 residual keep an activation stage busy for only 4 MMAs (~0.6k clocks against
+// ~4.5k for a nine-tap chunk): issued back to back they fill the whole stage ring, and the next unit's first conv tile is
+// loaded -- and, with a fused GroupNorm, transformed -- with nothing left to overlap it (per-role timeline,
+// tools/trace_halo.py).  They are therefore spread between the conv chunks: conv chunk i sits at position
+// i + ceil(i * rc / cc).
 struct HaloChunk { bool is_conv; int idx; };
-__device__ __forceinline__ HaloChunk halo_chunk_at(int j, int cc) {
-  return j < cc ? HaloChunk{true, j} : HaloChunk{false, j - cc};
-}
+__device__ __forceinline__ HaloChunk halo_chunk_of(unsigned char code) { return HaloChunk{(code & 0x80) != 0, code & 0x7f}; }
 
 constexpr int kHaloBN = 128;            // output channels per unit (MMA M)
 constexpr int kHaloCols = 256;          // TMEM columns per accumulator stage
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const bool one_img = p.imgs_per_tile == 0 && (pr0 + nr - 1) / (p.h + 2) == ni0;
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           int which, cc;
-          const HaloChunk hc = halo_chunk_at(ck, cchunks);
+          const HaloChunk hc = halo_chunk_of(p.order[ck]);
           if (hc.is_conv) {
             which = hc.idx < p.chunks0 ? 0 : 1;
             cc = (which ? hc.idx - p.chunks0 : hc.idx) * 64;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       for (int u = sched0; u < items; u += nsched) {
         const int col0 = (u % p.n_tiles) * kHaloBN;
         for (int ck = 0; ck < nck; ++ck) {
-          const HaloChunk hc = halo_chunk_at(ck, cchunks);
+          const HaloChunk hc = halo_chunk_of(p.order[ck]);
           const bool is_conv = hc.is_conv;
           const int ntaps = is_conv ? 9 : 1;
           const int kb0 = is_conv ? hc.idx : 9 * cchunks + hc.idx;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       tc_fence_after();
       const uint32_t dtm = tmem_base + stage * kHaloCols;
       for (int ck = 0; ck < nck; ++ck, ++a_it) {
-        const bool is_conv = halo_chunk_at(ck, cchunks).is_conv;
+        const bool is_conv = halo_chunk_of(p.order[ck]).is_conv;
         const int ntaps = is_conv ? 9 : 1;
         const int as = a_it % kHaloAStages;
         mbar_wait(p.gn_ab ? &a_ready[as] : &a_full[as], (a_it / kHaloAStages) & 1);
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int n_lo = min((pr0 < 0 ? 0 : pr0) / (p.h + 2), p.n - 1);
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           const int as = a_it % kHaloAStages;
-          const HaloChunk hc = halo_chunk_at(ck, cchunks);
+          const HaloChunk hc = halo_chunk_of(p.order[ck]);
           const bool is_conv = hc.is_conv;
           float2 c0v[8], c1v[8];
           if (is_conv) {
@@ -544,6 +547,17 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.chunks0 = d.c0 / 64; p.chunks1 = d.c1 / 64; p.rchunks0 = d.rc0 / 64; p.rchunks1 = d.rc1 / 64;
   p.n = d.n; p.h = d.h_in; p.wp = d.w_in + 2;
+  {
+    const int cc = p.chunks0 + p.chunks1, rc = p.rchunks0 + p.rchunks1;
+    DMME_REQUIRE(cc + rc <= 32, DMME_E_SHAPE, "conv_halo: more than 32 channel chunks per work unit");
+    int pos = 0, r = 0;
+    for (int i = 0; i < cc; ++i) {
+      const int r_before = g_halo_mode & 16 ? 0 : (i * rc + cc - 1) / cc;  // bit 4 (A/B): residual chunks after the conv chunks
+      while (r < r_before) p.order[pos++] = static_cast<unsigned char>(r++);
+      p.order[pos++] = static_cast<unsigned char>(0x80 | i);
+    }
+    while (r < rc) p.order[pos++] = static_cast<unsigned char>(r++);
+  }
   p.total_rows = d.n * (d.h_in + 2);
   p.n_tiles = d.cout / kHaloBN;
   if (g_sm_count == 0) {
