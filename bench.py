@@ -258,12 +258,13 @@ def run_gpu(args):
     seed = 20261018 + rank
 
     # ---- warm-up (eager: packs weights, sizes workspace) + launch count per step ----
+    ddpm._graph_step(x, counter, seed)  # first call: also packs the weights (one pack launch per conv site)
+    torch.cuda.synchronize()
     ops.reset_launch_count()
     ddpm._graph_step(x, counter, seed)
     torch.cuda.synchronize()
     launches_per_step = ops.launch_count()
-    for _ in range(2):
-        ddpm._graph_step(x, counter, seed)
+    ddpm._graph_step(x, counter, seed)
     torch.cuda.synchronize()
 
     # ---- capture one step ----
@@ -342,7 +343,9 @@ def run_gpu(args):
         gn_groups, (gn_n, gn_bytes, gn_ms) = gn_profile(model, x, counter)
         gn_gbs = gn_bytes / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0
         # dominant GroupNorm launch signature (largest share of the pass) -- the HBM-bound kernel of the step
-        gd_sig, (gd_n, gd_bytes, gd_ms) = max(gn_groups.items(), key=lambda kv: kv[1][2])
+        # the GroupNorm launch signature that actually streams through HBM: the largest tensor (the others fit the 126 MB L2
+        # and are latency-bound launches of a few MB; most GroupNorms of the step now run inside the halo conv kernel)
+        gd_sig, (gd_n, gd_bytes, gd_ms) = max(gn_groups.items(), key=lambda kv: kv[1][1] / kv[1][0])
         gd_gbs = gd_bytes / (gd_ms * 1e-3) / 1e9 if gd_ms > 0 else 0.0
         step_flop = FLOP_PER_IMAGE * B
         cpu = None
@@ -376,8 +379,8 @@ def run_gpu(args):
                                                    "achieved": all_tc, "frac": all_tc / peak},
                          "step_tensor_frac": step_flop / (ms_dev * 1e-3) / 1e12 / peak},
             "roofline_hbm": {"bound": "hbm", "kernel": f"gn_apply_kernel, launch {gd_sig} x{B} images ({gd_n} launches per step, "
-                                                       "largest share of the GroupNorm pass; statistics come from the "
-                                                       "producing conv's epilogue)",
+                                                       "the largest stand-alone GroupNorm tensor; statistics come from "
+                                                       "the producing conv's epilogue)",
                              "achieved": gd_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gd_gbs / pk["hbm_gbs"],
                              "traffic": traffic_for(gd_sig), "launches_per_step": gd_n,
                              "bytes_per_launch": gd_bytes / gd_n, "us_per_launch": 1e3 * gd_ms / gd_n,
