@@ -24,7 +24,8 @@ struct AttnTcParams {
 };
 
 constexpr int kSeq = 256;
-constexpr int kAttnThreads = 192;
+constexpr int kAttnSmWarps = 8;            // softmax / epilogue warps: two per TMEM lane quarter, each half of the columns
+constexpr int kAttnThreads = (2 + kAttnSmWarps) * 32;
 constexpr int kStageA = 128 * 128;        // 128 rows x 64 bf16
 constexpr int kStageB = 256 * 128;        // up to 256 rows x 64 bf16
 constexpr int kAttnStage = kStageA + kStageB;
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   __shared__ __align__(8) uint64_t empty_bar[kAttnStages];
   __shared__ __align__(8) uint64_t s_full, p_ready, o_full;
   __shared__ uint32_t tmem_slot;
+  __shared__ float row_part[2][128];  // per-row partial max, then partial sum, of the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&s_full, 1);
-    mbar_init(&p_ready, 128);
+    mbar_init(&p_ready, kAttnSmWarps * 32);
     mbar_init(&o_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -122,26 +124,35 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       umma_commit(&o_full);
     }
   } else {
+    // thread = (query row, half of the key columns): the two warps of a TMEM lane quarter split the 256 scores of a row,
+    // exchange their partial row maximum / sum through shared memory, and later split the d output columns the same way
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    constexpr int kHalfSeq = kSeq / 2;
+    const int c_lo = half * kHalfSeq;
     mbar_wait(&s_full, 0);
     tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < kSeq; c += 32) {
+    for (int c = c_lo; c < c_lo + kHalfSeq; c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_off + c, v);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
     }
+    row_part[half][row] = mx;
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+    mx = fmaxf(mx, row_part[half ^ 1][row]);
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");  // both halves have read before the sums overwrite
     float sum = 0.f;
     const float sl = p.scale_log2e;
     const float mxs = mx * sl;
     uint8_t* prow = pbuf + row * 128;
 #pragma unroll 1
-    for (int c = 0; c < kSeq; c += 32) {
+    for (int c = c_lo; c < c_lo + kHalfSeq; c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_off + c, v);
       tmem_ld_wait();
@@ -163,16 +174,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
         *reinterpret_cast<uint4*>(pc + (((u0 + jj) ^ (row & 7)) << 4)) = o;
       }
     }
+    row_part[half][row] = sum;
     tc_fence_before();
     fence_proxy_async();  // P was written through the generic proxy; the MMA reads it through the async proxy
     mbar_arrive(&p_ready);
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+    // the same summation order in both halves: the two threads of a row scale by the same bits
+    sum = row_part[0][row] + row_part[1][row];
 
     mbar_wait(&o_full, 0);
     tc_fence_after();
     const float inv = 1.0f / sum;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(img) * kSeq + q0 + row) * d;
+    const int dh2 = d >> 1;
 #pragma unroll 1
-    for (int c = 0; c < d; c += 32) {
+    for (int c = half * dh2; c < (half + 1) * dh2; c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_o + lane_off + c, v);
       tmem_ld_wait();
