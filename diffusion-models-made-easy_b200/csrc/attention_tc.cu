@@ -29,7 +29,7 @@ constexpr int kAttnThreads = (2 + kAttnSmWarps) * 32;
 constexpr int kStageA = 128 * 128;        // 128 rows x 64 bf16
 constexpr int kStageB = 256 * 128;        // up to 256 rows x 64 bf16
 constexpr int kAttnStage = kStageA + kStageB;
-constexpr int kAttnStages = 2;
+constexpr int kAttnStages = 3;           // 3 x 48 KB ring + 64 KB P = 209 KB: the Q/K phase is load-latency bound with two
 constexpr int kPBytes = 128 * kSeq * 2;   // P: 4 chunks of [128][64] bf16
 constexpr int kAttnSmem = kAttnStages * kAttnStage + kPBytes + 1024;
 

@@ -490,12 +490,13 @@ bool conv_halo_supported(const dmme_conv_desc& d) {
 // batch 256 (tools/prof_conv.py on the step's signatures, gpurun_out/r54_ab.log): the halo kernel's 9-tap reuse of the
 // activation tile wins at 32x32 and 16x16 (76 vs 86 us, 78 vs 88 us), also with a fused 1x1 residual of up to 128 channels
 // (16x16: 82 vs 90 us) -- and it can apply the GroupNorm of its input itself; wider residuals add single-tap chunks whose
-// tile loads it cannot hide (16x16 +res512: 123 vs 102 us, +res256 at 128 channels: 50 vs 39 us), and the padded-position
+// tile loads it cannot hide (16x16 256->256 +res512: 123 vs 102 us; 128->128 +res256 is 46 us with its GroupNorm inside
+// against 40 + 12 us), and the padded-position
 // overhead (36% at 8x8, 56% at 4x4) cancels the gain below 16x16 (37 vs 31 us, 27 vs 23 us).
 bool conv_halo_preferred(const dmme_conv_desc& d) {
   if (!conv_halo_supported(d)) return false;
   if (d.w_in < 16) return false;
-  if (d.w_in == 16 && (d.rc0 + d.rc1) > 128) return false;
+  if (d.w_in == 16 && (d.rc0 + d.rc1) > 128 && !(d.cout == 128 && d.rc0 + d.rc1 <= 256)) return false;
   return true;
 }
 
@@ -580,15 +581,16 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     }
     p.rt = p.imgs_per_tile * (d.h_in + 2);
   } else {
-    // rows per tile: as many as fit 256 accumulator columns (7 rows of 34, 14 of 18), or half of that when the launch
-    // would otherwise leave SMs idle / quantise badly (cost ~ waves x (MMA width + fixed overhead))
+    // rows per tile: at most what fits 256 accumulator columns (7 rows of 34, 14 of 18); fewer rows when that fills the
+    // last wave better (cost ~ waves x (MMA width + per-unit overhead; 96 columns' worth by measurement: with 48 the 32x32
+    // level went to 6-row tiles and lost 4%)): at batch 256 the 128-channel 16x16 convs
+    // take 11 rows (419 units = 2.8 waves) instead of 14 (330 units = 2.2 waves, a third wave for a fifth of the SMs)
     long long best_cost = -1;
-    for (int cols = kHaloCols; cols >= kHaloCols / 2; cols /= 2) {
-      const int rt = cols / p.wp;
-      if (rt < 1) continue;
+    const int rt_max = kHaloCols / p.wp;
+    for (int rt = rt_max; rt >= 1 && 2 * rt >= rt_max; --rt) {
       const int n_mma = ((rt * p.wp + 15) / 16) * 16;
       const long long units = static_cast<long long>((p.total_rows + rt - 1) / rt) * p.n_tiles;
-      const long long cost = ((units + g_sm_count - 1) / g_sm_count) * (n_mma + 48);
+      const long long cost = ((units + g_sm_count - 1) / g_sm_count) * (n_mma + 96);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.rt = rt; p.n_mma = n_mma; }
     }
   }
