@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const AttnMmaParams p) {
 }
 
 static int g_attn_mma_mode = 1;
+bool attn_tensor_core_multi_head_enabled() { return g_attn_mma_mode != 0; }
 
 bool attn_mma_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
                         int v_transposed, const void* q, const void* k, const void* v, const void* out) {

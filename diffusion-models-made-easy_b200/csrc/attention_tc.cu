@@ -212,6 +212,235 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Multi-head variant for the IDDPM flavour (MultiHeadAttention, models/iddpm.py:16-59) at 256 tokens and 64-channel heads:
+// q | k | v of head h are the channel ranges [3 dh h, +dh), [+dh, +2 dh), [+2 dh, +3 dh) of one packed [n][L][3C] tensor, so
+// all three operands come from the same tensor map with different boxes.  One CTA per (image, head, 128 queries):
+//   S = Q K^T   one 64-channel k-block, four M=128 N=256 K=16 MMAs, both operands K-major
+//   P           the single-head kernel's softmax (eight warps), bf16 into shared memory
+//   O = P V     V is NOT transposed here: a [64 keys][64 channels] box is the canonical MN-major SWIZZLE_128B layout of the
+//               B operand (N = channels contiguous, K = keys in rows), as in conv_wgrad_tc.cu -- K step = 16 rows = 2 KB
+// and the output goes to the reference's "(b head) -> (head b)" position (models/iddpm.py:44-46).
+// ----------------------------------------------------------------------------------------------
+struct AttnTcMhParams {
+  CUtensorMap q, k, v;  // the packed qkv tensor, boxes [64 ch][128 rows], [64][256], [64][64]
+  int n, heads;
+  float scale_log2e;
+  int swap;
+  __nv_bfloat16* out;   // [n][256][heads * 64]
+};
+
+constexpr int kMhDh = 64;
+constexpr uint32_t kMhIdescO = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (uint32_t(kMhDh >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+
+__device__ __forceinline__ uint64_t attn_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);
+  d |= uint64_t((8192u >> 4) & 0x3FFFu) << 16;   // LBO: next 64-channel block (N = 64: a single block, never used)
+  d |= uint64_t(1024 >> 4) << 32;                // SBO: 8 key rows * 128 B
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __grid_constant__ AttnTcMhParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t qk_full, v_full[kSeq / 64];
+  __shared__ __align__(8) uint64_t s_full, p_ready, o_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float row_part[2][128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* qbuf = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // [128][64] bf16
+  uint8_t* kbuf = qbuf + kStageA;                                       // [256][64]
+  uint8_t* vbuf = kbuf + kStageB;                                       // 4 x [64 keys][64 ch]
+  uint8_t* pbuf = vbuf + kSeq * 128;                                    // P: 4 chunks of [128][64]
+
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y, img = blockIdx.z;
+  const int ch0 = head * 3 * kMhDh;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&qk_full, 1);
+    for (int j = 0; j < kSeq / 64; ++j) mbar_init(&v_full[j], 1);
+    mbar_init(&s_full, 1);
+    mbar_init(&p_ready, kAttnSmWarps * 32);
+    mbar_init(&o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q);
+    tma_prefetch_desc(&p.k);
+    tma_prefetch_desc(&p.v);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot;
+  const uint32_t tmem_o = tmem_slot + 256;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // every operand of the tile fits shared memory at once: all loads are issued up front
+      mbar_expect_tx(&qk_full, kStageA + kStageB);
+      tma_load_3d(qbuf, &p.q, &qk_full, ch0, q0, img);
+      tma_load_3d(kbuf, &p.k, &qk_full, ch0 + kMhDh, 0, img);
+      for (int jc = 0; jc < kSeq / 64; ++jc) {
+        mbar_expect_tx(&v_full[jc], 64 * 128);
+        tma_load_3d(vbuf + jc * 64 * 128, &p.v, &v_full[jc], ch0 + 2 * kMhDh, jc * 64, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, kSeq);
+      mbar_wait(&qk_full, 0);
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_sw128(smem_u32(qbuf)), bdesc = umma_desc_sw128(smem_u32(kbuf));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&s_full);
+      mbar_wait(&p_ready, 0);
+      tc_fence_after();
+      for (int jc = 0; jc < kSeq / 64; ++jc) {
+        mbar_wait(&v_full[jc], 0);
+        tc_fence_after();
+        const uint64_t pdesc = umma_desc_sw128(smem_u32(pbuf + jc * kStageA));
+        const uint32_t vaddr = smem_u32(vbuf + jc * 64 * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_o, pdesc + 2 * k, attn_desc_mn_sw128(vaddr + k * 2048), kMhIdescO, (jc | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&o_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    constexpr int kHalfSeq = kSeq / 2;
+    const int c_lo = half * kHalfSeq;
+    mbar_wait(&s_full, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = c_lo; c < c_lo + kHalfSeq; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_s + lane_off + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    row_part[half][row] = mx;
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+    mx = fmaxf(mx, row_part[half ^ 1][row]);
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+    float sum = 0.f;
+    const float sl = p.scale_log2e;
+    const float mxs = mx * sl;
+    uint8_t* prow = pbuf + row * 128;
+#pragma unroll 1
+    for (int c = c_lo; c < c_lo + kHalfSeq; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_s + lane_off + c, v);
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        e[j] = exp2f(fmaf(__uint_as_float(v[j]), sl, -mxs));
+        sum += e[j];
+      }
+      uint8_t* pc = prow + (c >> 6) * kStageA;
+      const int u0 = (c & 63) >> 3;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 o;
+        o.x = pack_bf16x2(e[8 * jj + 0], e[8 * jj + 1]);
+        o.y = pack_bf16x2(e[8 * jj + 2], e[8 * jj + 3]);
+        o.z = pack_bf16x2(e[8 * jj + 4], e[8 * jj + 5]);
+        o.w = pack_bf16x2(e[8 * jj + 6], e[8 * jj + 7]);
+        *reinterpret_cast<uint4*>(pc + (((u0 + jj) ^ (row & 7)) << 4)) = o;
+      }
+    }
+    row_part[half][row] = sum;
+    tc_fence_before();
+    fence_proxy_async();
+    mbar_arrive(&p_ready);
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+    sum = row_part[0][row] + row_part[1][row];
+
+    mbar_wait(&o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    int bo = img, ho = head;
+    if (p.swap) {
+      const int flat = img * p.heads + head;  // "(b head)" index reinterpreted as "(head b)" (models/iddpm.py:44-46)
+      bo = flat % p.n;
+      ho = flat / p.n;
+    }
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(bo) * kSeq + q0 + row) * (p.heads * kMhDh) + ho * kMhDh + half * 32;
+    uint32_t v[32];
+    tmem_ld32(tmem_o + lane_off + half * 32, v);
+    tmem_ld_wait();
+    uint4* dp = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]) * inv, __uint_as_float(v[8 * jj + 1]) * inv);
+      o.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv);
+      o.z = pack_bf16x2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv);
+      o.w = pack_bf16x2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv);
+      dp[jj] = o;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_slot, 512);
+  }
+}
+
+constexpr int kAttnMhSmem = kStageA + kStageB + kSeq * 128 + kPBytes + 1024;
+
+bool attn_tc_mh_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
+                          int v_transposed, const void* q, const void* k, const void* v, const void* out) {
+  if (act_dtype != DMME_BF16 || v_transposed || L != kSeq || dh != kMhDh || heads < 1) return false;
+  if (head_stride != 3 * dh || row_stride != heads * 3 * dh || batch_stride != static_cast<long long>(L) * row_stride) return false;
+  const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(q);
+  if (static_cast<const __nv_bfloat16*>(k) != qb + dh || static_cast<const __nv_bfloat16*>(v) != qb + 2 * dh) return false;
+  return (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+}
+
+int attn_tc_mh_forward(const void* qkv, int n, int heads, float scale, int swap, void* out, cudaStream_t stream) {
+  AttnTcMhParams p;
+  memset(&p, 0, sizeof(p));
+  const int c3 = heads * 3 * kMhDh;
+  uint64_t dims[3] = {(uint64_t)c3, (uint64_t)kSeq, (uint64_t)n};
+  uint64_t strides[2] = {(uint64_t)c3 * 2, (uint64_t)kSeq * c3 * 2};
+  uint32_t boxq[3] = {64u, 128u, 1u}, boxk[3] = {64u, 256u, 1u}, boxv[3] = {64u, 64u, 1u};
+  int rc;
+  if ((rc = encode_map(&p.q, qkv, 3, dims, strides, boxq))) return rc;
+  if ((rc = encode_map(&p.k, qkv, 3, dims, strides, boxk))) return rc;
+  if ((rc = encode_map(&p.v, qkv, 3, dims, strides, boxv))) return rc;
+  p.n = n; p.heads = heads; p.swap = swap;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMhSmem);
+    if (e != cudaSuccess) { set_error("attn_tc_mh: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  dim3 grid(kSeq / 128, heads, n);
+  cudaError_t e = launch_pdl(attn_tc_mh_kernel, grid, dim3(kAttnThreads), kAttnMhSmem, stream, p);
+  return check_launch_err(e, "attn_tc_mh_kernel");
+}
+
 bool attn_tc_supported(int act_dtype, int heads, int L, int dh, int row_stride, long long batch_stride,
                        int v_transposed, long long v_batch_stride, int swap) {
   return act_dtype == DMME_BF16 && heads == 1 && L == kSeq && dh % 64 == 0 && dh >= 64 && dh <= 256 &&
