@@ -230,8 +230,10 @@ struct AttnTcMhParams {
   __nv_bfloat16* out;   // [n][256][heads * 64]
 };
 
-constexpr int kMhDh = 64;
-constexpr uint32_t kMhIdescO = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (uint32_t(kMhDh >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+// P V instruction descriptor: A (P) K-major, B (V) MN-major, M = 128 queries, N = head channels
+__host__ __device__ constexpr uint32_t attn_mh_idesc_o(int dh) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (uint32_t(dh >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+}
 
 __device__ __forceinline__ uint64_t attn_desc_mn_sw128(uint32_t saddr) {
   uint64_t d = 0;
@@ -243,7 +245,12 @@ __device__ __forceinline__ uint64_t attn_desc_mn_sw128(uint32_t saddr) {
   return d;
 }
 
+// DH = 64: boxes q [64][128 rows], k [64][256], v [64][64 keys].  DH = 32: a 64-channel box at the head's first channel holds
+// [q | k] and one at +32 holds [k | v]: Q and K are the two 64-byte halves of the rows of ONE [64][256] box (K-major
+// descriptors step 32 bytes inside a 128-byte row anyway), V is the second half of the rows of the [k | v] boxes.
+template <int DH>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __grid_constant__ AttnTcMhParams p) {
+  constexpr int kMhDh = DH;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t qk_full, v_full[kSeq / 64];
   __shared__ __align__(8) uint64_t s_full, p_ready, o_full;
@@ -287,12 +294,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) {
       // every operand of the tile fits shared memory at once: all loads are issued up front
-      mbar_expect_tx(&qk_full, kStageA + kStageB);
-      tma_load_3d(qbuf, &p.q, &qk_full, ch0, q0, img);
-      tma_load_3d(kbuf, &p.k, &qk_full, ch0 + kMhDh, 0, img);
+      if constexpr (DH == 64) {
+        mbar_expect_tx(&qk_full, kStageA + kStageB);
+        tma_load_3d(qbuf, &p.q, &qk_full, ch0, q0, img);
+        tma_load_3d(kbuf, &p.k, &qk_full, ch0 + kMhDh, 0, img);
+      } else {
+        mbar_expect_tx(&qk_full, kStageB);
+        tma_load_3d(kbuf, &p.k, &qk_full, ch0, 0, img);  // [q | k] of all 256 tokens
+      }
       for (int jc = 0; jc < kSeq / 64; ++jc) {
         mbar_expect_tx(&v_full[jc], 64 * 128);
-        tma_load_3d(vbuf + jc * 64 * 128, &p.v, &v_full[jc], ch0 + 2 * kMhDh, jc * 64, img);
+        tma_load_3d(vbuf + jc * 64 * 128, &p.v, &v_full[jc], DH == 64 ? ch0 + 2 * kMhDh : ch0 + kMhDh, jc * 64, img);
       }
     }
   } else if (warp == 1) {
@@ -300,9 +312,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __gri
       const uint32_t idesc_s = umma_idesc_bf16(128, kSeq);
       mbar_wait(&qk_full, 0);
       tc_fence_after();
-      const uint64_t adesc = umma_desc_sw128(smem_u32(qbuf)), bdesc = umma_desc_sw128(smem_u32(kbuf));
+      // DH = 32: Q = first 64 bytes of rows q0.. of the [q | k] box, K = second 64 bytes of all its rows
+      const uint64_t adesc = umma_desc_sw128(DH == 64 ? smem_u32(qbuf) : smem_u32(kbuf) + static_cast<uint32_t>(q0) * 128u);
+      const uint64_t bdesc = umma_desc_sw128(DH == 64 ? smem_u32(kbuf) : smem_u32(kbuf) + 64u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+      for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
       umma_commit(&s_full);
       mbar_wait(&p_ready, 0);
       tc_fence_after();
@@ -310,10 +324,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __gri
         mbar_wait(&v_full[jc], 0);
         tc_fence_after();
         const uint64_t pdesc = umma_desc_sw128(smem_u32(pbuf + jc * kStageA));
-        const uint32_t vaddr = smem_u32(vbuf + jc * 64 * 128);
+        const uint32_t vaddr = smem_u32(vbuf + jc * 64 * 128) + (DH == 64 ? 0u : 64u);  // DH = 32: V = second half of [k | v]
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_o, pdesc + 2 * k, attn_desc_mn_sw128(vaddr + k * 2048), kMhIdescO, (jc | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem_o, pdesc + 2 * k, attn_desc_mn_sw128(vaddr + k * 2048), attn_mh_idesc_o(DH), (jc | k) != 0 ? 1u : 0u);
       }
       umma_commit(&o_full);
     }
@@ -382,13 +396,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __gri
       bo = flat % p.n;
       ho = flat / p.n;
     }
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(bo) * kSeq + q0 + row) * (p.heads * kMhDh) + ho * kMhDh + half * 32;
-    uint32_t v[32];
-    tmem_ld32(tmem_o + lane_off + half * 32, v);
+    constexpr int kCols = DH / 2;  // output channels per thread
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(bo) * kSeq + q0 + row) * (p.heads * kMhDh) + ho * kMhDh + half * kCols;
+    uint32_t v[kCols];
+    if constexpr (DH == 64) tmem_ld32(tmem_o + lane_off + half * kCols, v);
+    else tmem_ld16(tmem_o + lane_off + half * kCols, v);
     tmem_ld_wait();
     uint4* dp = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
+    for (int jj = 0; jj < kCols / 8; ++jj) {
       uint4 o;
       o.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]) * inv, __uint_as_float(v[8 * jj + 1]) * inv);
       o.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv);
@@ -409,17 +425,18 @@ constexpr int kAttnMhSmem = kStageA + kStageB + kSeq * 128 + kPBytes + 1024;
 
 bool attn_tc_mh_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
                           int v_transposed, const void* q, const void* k, const void* v, const void* out) {
-  if (act_dtype != DMME_BF16 || v_transposed || L != kSeq || dh != kMhDh || heads < 1) return false;
+  if (act_dtype != DMME_BF16 || v_transposed || L != kSeq || (dh != 64 && dh != 32) || heads < 1) return false;
   if (head_stride != 3 * dh || row_stride != heads * 3 * dh || batch_stride != static_cast<long long>(L) * row_stride) return false;
   const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(q);
   if (static_cast<const __nv_bfloat16*>(k) != qb + dh || static_cast<const __nv_bfloat16*>(v) != qb + 2 * dh) return false;
   return (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
 }
 
-int attn_tc_mh_forward(const void* qkv, int n, int heads, float scale, int swap, void* out, cudaStream_t stream) {
+template <int DH>
+static int attn_tc_mh_launch(const void* qkv, int n, int heads, float scale, int swap, void* out, cudaStream_t stream) {
   AttnTcMhParams p;
   memset(&p, 0, sizeof(p));
-  const int c3 = heads * 3 * kMhDh;
+  const int c3 = heads * 3 * DH;
   uint64_t dims[3] = {(uint64_t)c3, (uint64_t)kSeq, (uint64_t)n};
   uint64_t strides[2] = {(uint64_t)c3 * 2, (uint64_t)kSeq * c3 * 2};
   uint32_t boxq[3] = {64u, 128u, 1u}, boxk[3] = {64u, 256u, 1u}, boxv[3] = {64u, 64u, 1u};
@@ -432,13 +449,18 @@ int attn_tc_mh_forward(const void* qkv, int n, int heads, float scale, int swap,
   p.out = static_cast<__nv_bfloat16*>(out);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMhSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_mh_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMhSmem);
     if (e != cudaSuccess) { set_error("attn_tc_mh: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
   dim3 grid(kSeq / 128, heads, n);
-  cudaError_t e = launch_pdl(attn_tc_mh_kernel, grid, dim3(kAttnThreads), kAttnMhSmem, stream, p);
+  cudaError_t e = launch_pdl(attn_tc_mh_kernel<DH>, grid, dim3(kAttnThreads), kAttnMhSmem, stream, p);
   return check_launch_err(e, "attn_tc_mh_kernel");
+}
+
+int attn_tc_mh_forward(const void* qkv, int n, int heads, int dh, float scale, int swap, void* out, cudaStream_t stream) {
+  return dh == 64 ? attn_tc_mh_launch<64>(qkv, n, heads, scale, swap, out, stream)
+                  : attn_tc_mh_launch<32>(qkv, n, heads, scale, swap, out, stream);
 }
 
 bool attn_tc_supported(int act_dtype, int heads, int L, int dh, int row_stride, long long batch_stride,
