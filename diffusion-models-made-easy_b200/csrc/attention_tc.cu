@@ -249,7 +249,7 @@ __device__ __forceinline__ uint64_t attn_desc_mn_sw128(uint32_t saddr) {
 // [q | k] and one at +32 holds [k | v]: Q and K are the two 64-byte halves of the rows of ONE [64][256] box (K-major
 // descriptors step 32 bytes inside a 128-byte row anyway), V is the second half of the rows of the [k | v] boxes.
 template <int DH>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __grid_constant__ AttnTcMhParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_mh_kernel(const __grid_constant__ AttnTcMhParams p) {
   constexpr int kMhDh = DH;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t qk_full, v_full[kSeq / 64];
@@ -261,8 +261,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __gri
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* qbuf = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // [128][64] bf16
   uint8_t* kbuf = qbuf + kStageA;                                       // [256][64]
-  uint8_t* vbuf = kbuf + kStageB;                                       // 4 x [64 keys][64 ch]
-  uint8_t* pbuf = vbuf + kSeq * 128;                                    // P: 4 chunks of [128][64]
+  // Two CTAs share an SM (their serial phases overlap): 97 KB of shared memory and 256 TMEM columns each.  P (64 KB)
+  // overwrites Q | K (48 KB, dead once S is complete) and 16 KB more; O reuses the first columns of S (dead once every
+  // softmax thread has read its row, which is what p_ready says).
+  uint8_t* pbuf = qbuf;                                                 // P: 4 chunks of [128][64]
+  uint8_t* vbuf = qbuf + kPBytes;                                       // 4 x [64 keys][64 ch]
 
   const int q0 = blockIdx.x * 128;
   const int head = blockIdx.y, img = blockIdx.z;
@@ -282,12 +285,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __gri
     tma_prefetch_desc(&p.k);
     tma_prefetch_desc(&p.v);
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  if (warp == 1) tmem_alloc(&tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_s = tmem_slot;
-  const uint32_t tmem_o = tmem_slot + 256;
+  const uint32_t tmem_o = tmem_slot;
   pdl_trigger();
   pdl_wait();
 
@@ -417,11 +420,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_mh_kernel(const __gri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_slot, 512);
+    tmem_dealloc(tmem_slot, 256);
   }
 }
 
-constexpr int kAttnMhSmem = kStageA + kStageB + kSeq * 128 + kPBytes + 1024;
+constexpr int kAttnMhSmem = kPBytes + kSeq * 128 + 1024;  // P (over Q | K) + V + alignment slack: two CTAs per SM
 
 bool attn_tc_mh_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
                           int v_transposed, const void* q, const void* k, const void* v, const void* out) {
