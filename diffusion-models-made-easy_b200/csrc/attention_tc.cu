@@ -424,11 +424,220 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_mh_kernel(const __gri
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// The same for the 64-token sites (8x8 maps, 64-channel heads): one CTA takes TWO images of one head -- 128 query rows and
+// 128 key rows that are contiguous in the packed tensor -- computes the 128 x 128 score tile and keeps its two diagonal
+// 64 x 64 blocks: the thread of (row, half) owns the keys of image `half`, and where that is not the row's own image it
+// contributes nothing to the row maximum / sum and writes zeros into P, so the off-diagonal products vanish in P V.
+// ----------------------------------------------------------------------------------------------
+struct AttnTcMh64Params {
+  CUtensorMap qk, v;   // the packed qkv tensor as [n * 64 rows][3C]: boxes [64 ch][128 rows] and [64 ch][64 rows]
+  int n, heads;
+  float scale_log2e;
+  int swap;
+  __nv_bfloat16* out;  // [n][64][heads * 64]
+};
+
+constexpr int kMh64Smem = 2 * kStageA + 2 * 64 * 128 + 1024;  // P (2 chunks, over Q | K) + V (2 chunks)
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_mh64_kernel(const __grid_constant__ AttnTcMh64Params p) {
+  constexpr int kDh = 64, kL = 64, kKeys = 2 * kL;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t qk_full, v_full[2];
+  __shared__ __align__(8) uint64_t s_full, p_ready, o_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float row_part[2][128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* qbuf = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // [128][64] bf16
+  uint8_t* kbuf = qbuf + kStageA;                                       // [128][64]
+  uint8_t* pbuf = qbuf;                                                 // P: 2 chunks of [128][64], over Q | K
+  uint8_t* vbuf = qbuf + 2 * kStageA;                                   // 2 x [64 keys][64 ch]
+
+  const int head = blockIdx.y, pair = blockIdx.z;
+  const int ch0 = head * 3 * kDh;
+  const int row0 = pair * kKeys;  // first token row of the pair in the [n * 64][3C] view
+
+  if (threadIdx.x == 0) {
+    mbar_init(&qk_full, 1);
+    mbar_init(&v_full[0], 1);
+    mbar_init(&v_full[1], 1);
+    mbar_init(&s_full, 1);
+    mbar_init(&p_ready, kAttnSmWarps * 32);
+    mbar_init(&o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.qk);
+    tma_prefetch_desc(&p.v);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot;
+  const uint32_t tmem_o = tmem_slot;  // O reuses the score columns once every softmax thread has read its row
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&qk_full, 2 * kStageA);
+      tma_load_2d(qbuf, &p.qk, &qk_full, ch0, row0);
+      tma_load_2d(kbuf, &p.qk, &qk_full, ch0 + kDh, row0);
+      for (int jc = 0; jc < 2; ++jc) {
+        mbar_expect_tx(&v_full[jc], 64 * 128);
+        tma_load_2d(vbuf + jc * 64 * 128, &p.v, &v_full[jc], ch0 + 2 * kDh, row0 + jc * 64);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, kKeys);
+      mbar_wait(&qk_full, 0);
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_sw128(smem_u32(qbuf)), bdesc = umma_desc_sw128(smem_u32(kbuf));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&s_full);
+      mbar_wait(&p_ready, 0);
+      tc_fence_after();
+      for (int jc = 0; jc < 2; ++jc) {
+        mbar_wait(&v_full[jc], 0);
+        tc_fence_after();
+        const uint64_t pdesc = umma_desc_sw128(smem_u32(pbuf + jc * kStageA));
+        const uint32_t vaddr = smem_u32(vbuf + jc * 64 * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_o, pdesc + 2 * k, attn_desc_mn_sw128(vaddr + k * 2048), attn_mh_idesc_o(kDh), (jc | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&o_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;      // key block = image `half` of the pair
+    const int row = q * 32 + lane;         // query row: image row >> 6 of the pair, token row & 63
+    const bool own = (row >> 6) == half;   // warp-uniform (a warp's 32 rows lie in one image)
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int c_lo = half * kL;
+    mbar_wait(&s_full, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+    if (own) {
+#pragma unroll 1
+      for (int c = c_lo; c < c_lo + kL; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+    }
+    float sum = 0.f;
+    const float sl = p.scale_log2e;
+    const float mxs = mx * sl;
+    uint8_t* prow = pbuf + half * kStageA + row * 128;
+#pragma unroll 1
+    for (int c = c_lo; c < c_lo + kL; c += 32) {
+      float e[32];
+      if (own) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          e[j] = exp2f(fmaf(__uint_as_float(v[j]), sl, -mxs));
+          sum += e[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) e[j] = 0.f;
+      }
+      const int u0 = (c & 63) >> 3;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 o;
+        o.x = pack_bf16x2(e[8 * jj + 0], e[8 * jj + 1]);
+        o.y = pack_bf16x2(e[8 * jj + 2], e[8 * jj + 3]);
+        o.z = pack_bf16x2(e[8 * jj + 4], e[8 * jj + 5]);
+        o.w = pack_bf16x2(e[8 * jj + 6], e[8 * jj + 7]);
+        *reinterpret_cast<uint4*>(prow + (((u0 + jj) ^ (row & 7)) << 4)) = o;
+      }
+    }
+    row_part[half][row] = sum;
+    tc_fence_before();
+    fence_proxy_async();
+    mbar_arrive(&p_ready);
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+    sum = row_part[0][row] + row_part[1][row];  // one of the two is the row's sum, the other 0
+
+    mbar_wait(&o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    const int img = 2 * pair + (row >> 6);
+    if (img < p.n) {
+      int bo = img, ho = head;
+      if (p.swap) {
+        const int flat = img * p.heads + head;  // "(b head)" index reinterpreted as "(head b)" (models/iddpm.py:44-46)
+        bo = flat % p.n;
+        ho = flat / p.n;
+      }
+      // both threads of a row write 32 of its 64 output channels
+      __nv_bfloat16* orow = p.out + (static_cast<long long>(bo) * kL + (row & 63)) * (p.heads * kDh) + ho * kDh + half * 32;
+      uint32_t v[32];
+      tmem_ld32(tmem_o + lane_off + half * 32, v);
+      tmem_ld_wait();
+      uint4* dp = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]) * inv, __uint_as_float(v[8 * jj + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]) * inv, __uint_as_float(v[8 * jj + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[8 * jj + 4]) * inv, __uint_as_float(v[8 * jj + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[8 * jj + 6]) * inv, __uint_as_float(v[8 * jj + 7]) * inv);
+        dp[jj] = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_slot, 128);
+  }
+}
+
+int attn_tc_mh64_forward(const void* qkv, int n, int heads, float scale, int swap, void* out, cudaStream_t stream) {
+  AttnTcMh64Params p;
+  memset(&p, 0, sizeof(p));
+  const int c3 = heads * 3 * 64;
+  uint64_t dims[2] = {(uint64_t)c3, (uint64_t)n * 64};
+  uint64_t strides[1] = {(uint64_t)c3 * 2};
+  uint32_t boxqk[2] = {64u, 128u}, boxv[2] = {64u, 64u};
+  int rc;
+  if ((rc = encode_map(&p.qk, qkv, 2, dims, strides, boxqk))) return rc;
+  if ((rc = encode_map(&p.v, qkv, 2, dims, strides, boxv))) return rc;
+  p.n = n; p.heads = heads; p.swap = swap;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_mh64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMh64Smem);
+    if (e != cudaSuccess) { set_error("attn_tc_mh64: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  dim3 grid(1, heads, (n + 1) / 2);
+  cudaError_t e = launch_pdl(attn_tc_mh64_kernel, grid, dim3(kAttnThreads), kMh64Smem, stream, p);
+  return check_launch_err(e, "attn_tc_mh64_kernel");
+}
+
 constexpr int kAttnMhSmem = kPBytes + kSeq * 128 + 1024;  // P (over Q | K) + V + alignment slack: two CTAs per SM
 
 bool attn_tc_mh_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
                           int v_transposed, const void* q, const void* k, const void* v, const void* out) {
-  if (act_dtype != DMME_BF16 || v_transposed || L != kSeq || (dh != 64 && dh != 32) || heads < 1) return false;
+  if (act_dtype != DMME_BF16 || v_transposed || heads < 1) return false;
+  if (!((L == kSeq && (dh == 64 || dh == 32)) || (L == 64 && dh == 64))) return false;
   if (head_stride != 3 * dh || row_stride != heads * 3 * dh || batch_stride != static_cast<long long>(L) * row_stride) return false;
   const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(q);
   if (static_cast<const __nv_bfloat16*>(k) != qb + dh || static_cast<const __nv_bfloat16*>(v) != qb + 2 * dh) return false;
@@ -461,7 +670,8 @@ static int attn_tc_mh_launch(const void* qkv, int n, int heads, float scale, int
   return check_launch_err(e, "attn_tc_mh_kernel");
 }
 
-int attn_tc_mh_forward(const void* qkv, int n, int heads, int dh, float scale, int swap, void* out, cudaStream_t stream) {
+int attn_tc_mh_forward(const void* qkv, int n, int heads, int L, int dh, float scale, int swap, void* out, cudaStream_t stream) {
+  if (L == 64) return attn_tc_mh64_forward(qkv, n, heads, scale, swap, out, stream);
   return dh == 64 ? attn_tc_mh_launch<64>(qkv, n, heads, scale, swap, out, stream)
                   : attn_tc_mh_launch<32>(qkv, n, heads, scale, swap, out, stream);
 }
