@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """The honest GPU competitor: the reference's algorithm -- the oracle restatement, plain torch ops (cuDNN /
 cuBLAS kernels, eager mode) -- timed on the same B200 for the bench workload: one DDPM sampling step on 256 images, fp32
-(TF32 off / on) and under bf16 autocast.  Measurement only; nothing in the product path imports the oracle.
-usage: python tools/ref_gpu_eager.py [--batch 256] [--reps 5]"""
+(TF32 off / on) and under bf16 autocast.  Measurement only (it lives under tests/ because only tests/, smoke() and bench.py may use the oracle); nothing in the product path imports it.
+usage: python tests/ref_gpu_eager.py [--batch 256] [--reps 5]"""
 import argparse
 import os
 import sys
