@@ -785,10 +785,12 @@ def test_conv_upsample_subpixel(n, c, cout, h):
 
 
 @pytest.mark.parametrize("n,c,heads,L_,swap", [(3, 256, 4, 256, True), (2, 128, 4, 256, True), (5, 256, 4, 64, True),
+                                               (1, 256, 4, 64, False), (7, 128, 2, 64, True), (9, 64, 2, 256, False),
                                                (2, 256, 4, 16, True), (130, 128, 4, 64, False), (1, 64, 1, 256, False),
                                                (2, 256, 2, 128, True)])
 def test_attention_mma_multi_head(n, c, heads, L_, swap):
-    """mma.sync multi-head kernel (bf16 storage) against fp32 attention on the same bf16 operands, IDDPM channel layout
+    """multi-head kernels (tcgen05 at 256 tokens and at 64 tokens with 64-channel heads, mma.sync elsewhere; bf16 storage)
+    against fp32 attention on the same bf16 operands, IDDPM channel layout
     [head][q|k|v][dh] and the (b head) -> (head b) regrouping (models/iddpm.py:36-47)"""
     ops, L = _ops()
     g = torch.Generator().manual_seed(12)
@@ -804,7 +806,8 @@ def test_attention_mma_multi_head(n, c, heads, L_, swap):
         want = o.reshape(n, heads, L_, dh).permute(0, 2, 1, 3).reshape(n, L_, c)
     dev = qkv.to(torch.bfloat16).to(DEV).contiguous()
     flat = dev.view(-1)
-    out = torch.full((n, L_, c), float("nan"), dtype=torch.bfloat16, device=DEV)
+    guarded = torch.full((n + 2, L_, c), float("nan"), dtype=torch.bfloat16, device=DEV)  # one canary image on either side
+    out = guarded[1:-1]
     ops.attention(flat, flat[dh:], flat[2 * dh:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, 3 * dh, False, 0, swap, out)
     ref = torch.empty_like(out)
     lib = L.load()
@@ -816,6 +819,7 @@ def test_attention_mma_multi_head(n, c, heads, L_, swap):
     torch.cuda.synchronize()
     assert rel_l2(ref.float().cpu(), want) < 4e-3          # CUDA-core kernel: only the bf16 output rounding
     assert rel_l2(out.float().cpu(), want) < 6e-3, rel_l2(out.float().cpu(), want)
+    assert torch.isnan(guarded[0]).all() and torch.isnan(guarded[-1]).all()  # nothing written outside the output
 
 
 @pytest.mark.parametrize("cfg", [
