@@ -127,7 +127,8 @@ bool attn_mma_supported(int act_dtype, int heads, int L, int dh, int row_stride,
 bool attn_tensor_core_multi_head_enabled();
 bool attn_tc_mh_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
                           int v_transposed, const void* q, const void* k, const void* v, const void* out);
-int attn_tc_mh_forward(const void* qkv, int n, int heads, int L, int dh, float scale, int swap, void* out, cudaStream_t stream);
+int attn_tc_mh_forward(const void* qkv, int n, int heads, int L, int dh, float scale, int swap, void* out, float* p_out,
+                       cudaStream_t stream);
 int attn_mma_forward(const void* q, const void* k, const void* v, long long batch_stride, int row_stride, int head_stride,
                      int n, int heads, int L, int dh, float scale, int swap, void* out, float* p_out, cudaStream_t stream);
 
@@ -156,7 +157,7 @@ extern "C" int dmme_attention_fwd(const void* q, const void* k, const void* v, l
   // packed multi-head qkv at 256 tokens / 64- or 32-channel heads (the IDDPM UNet's 16x16 attention sites): tcgen05
   if (kernel != DMME_CONV_GENERIC && attn_tensor_core_multi_head_enabled() &&
       attn_tc_mh_supported(act_dtype, heads, L, dh, row_stride, head_stride, batch_stride, v_transposed, q, k, v, out))
-    return attn_tc_mh_forward(q, n, heads, L, dh, scale, head_batch_swap, out, static_cast<cudaStream_t>(stream));
+    return attn_tc_mh_forward(q, n, heads, L, dh, scale, head_batch_swap, out, nullptr, static_cast<cudaStream_t>(stream));
   if (kernel != DMME_CONV_GENERIC &&
       attn_mma_supported(act_dtype, heads, L, dh, row_stride, head_stride, batch_stride, v_transposed, q, k, v, out))
     return attn_mma_forward(q, k, v, batch_stride, row_stride, head_stride, n, heads, L, dh, scale, head_batch_swap, out,

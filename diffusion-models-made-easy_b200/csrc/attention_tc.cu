@@ -228,6 +228,7 @@ struct AttnTcMhParams {
   float scale_log2e;
   int swap;
   __nv_bfloat16* out;   // [n][256][heads * 64]
+  float* p_out;         // optional fp32 [n * heads][256][256]: the normalised softmax matrix, kept for the backward pass
 };
 
 // P V instruction descriptor: A (P) K-major, B (V) MN-major, M = 128 queries, N = head channels
@@ -384,11 +385,38 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_mh_kernel(const __gri
       }
     }
     row_part[half][row] = sum;
-    tc_fence_before();
-    fence_proxy_async();
-    mbar_arrive(&p_ready);
-    asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
-    sum = row_part[0][row] + row_part[1][row];
+    if (p.p_out == nullptr) {
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(&p_ready);
+      asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+      sum = row_part[0][row] + row_part[1][row];
+    } else {
+      // training forward: the normalised probabilities go to global memory before the scores are released (O reuses their
+      // TMEM columns): a third pass over this thread's half of the row, now that the whole row's sum is known
+      asm volatile("bar.sync 1, %0;" ::"n"(kAttnSmWarps * 32) : "memory");
+      sum = row_part[0][row] + row_part[1][row];
+      const float inv_p = 1.0f / sum;
+      float* gp = p.p_out + ((static_cast<long long>(img) * p.heads + head) * kSeq + q0 + row) * kSeq;
+#pragma unroll 1
+      for (int c = c_lo; c < c_lo + kHalfSeq; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = exp2f(fmaf(__uint_as_float(v[j + 0]), sl, -mxs)) * inv_p;
+          o.y = exp2f(fmaf(__uint_as_float(v[j + 1]), sl, -mxs)) * inv_p;
+          o.z = exp2f(fmaf(__uint_as_float(v[j + 2]), sl, -mxs)) * inv_p;
+          o.w = exp2f(fmaf(__uint_as_float(v[j + 3]), sl, -mxs)) * inv_p;
+          *reinterpret_cast<float4*>(gp + c + j) = o;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(&p_ready);
+    }
 
     mbar_wait(&o_full, 0);
     tc_fence_after();
@@ -436,6 +464,7 @@ struct AttnTcMh64Params {
   float scale_log2e;
   int swap;
   __nv_bfloat16* out;  // [n][64][heads * 64]
+  float* p_out;        // optional fp32 [n * heads][64][64]: the normalised softmax matrix, kept for the backward pass
 };
 
 constexpr int kMh64Smem = 2 * kStageA + 2 * 64 * 128 + 1024;  // P (2 chunks, over Q | K) + V (2 chunks)
@@ -566,6 +595,27 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_mh64_kernel(const __g
       }
     }
     row_part[half][row] = sum;
+    if (p.p_out != nullptr && own && 2 * pair + (row >> 6) < p.n) {
+      // training forward: this thread holds the whole row (its image's 64 keys): normalised probabilities to global memory
+      // before the scores are released
+      const float inv_p = 1.0f / sum;
+      float* gp = p.p_out + ((static_cast<long long>(2 * pair + (row >> 6)) * p.heads + head) * kL + (row & 63)) * kL;
+#pragma unroll 1
+      for (int c = c_lo; c < c_lo + kL; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = exp2f(fmaf(__uint_as_float(v[j + 0]), sl, -mxs)) * inv_p;
+          o.y = exp2f(fmaf(__uint_as_float(v[j + 1]), sl, -mxs)) * inv_p;
+          o.z = exp2f(fmaf(__uint_as_float(v[j + 2]), sl, -mxs)) * inv_p;
+          o.w = exp2f(fmaf(__uint_as_float(v[j + 3]), sl, -mxs)) * inv_p;
+          *reinterpret_cast<float4*>(gp + (c - c_lo) + j) = o;
+        }
+      }
+    }
     tc_fence_before();
     fence_proxy_async();
     mbar_arrive(&p_ready);
@@ -608,7 +658,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_mh64_kernel(const __g
   }
 }
 
-int attn_tc_mh64_forward(const void* qkv, int n, int heads, float scale, int swap, void* out, cudaStream_t stream) {
+int attn_tc_mh64_forward(const void* qkv, int n, int heads, float scale, int swap, void* out, float* p_out,
+                         cudaStream_t stream) {
   AttnTcMh64Params p;
   memset(&p, 0, sizeof(p));
   const int c3 = heads * 3 * 64;
@@ -621,6 +672,7 @@ int attn_tc_mh64_forward(const void* qkv, int n, int heads, float scale, int swa
   p.n = n; p.heads = heads; p.swap = swap;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out);
+  p.p_out = p_out;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_mh64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMh64Smem);
@@ -645,7 +697,8 @@ bool attn_tc_mh_supported(int act_dtype, int heads, int L, int dh, int row_strid
 }
 
 template <int DH>
-static int attn_tc_mh_launch(const void* qkv, int n, int heads, float scale, int swap, void* out, cudaStream_t stream) {
+static int attn_tc_mh_launch(const void* qkv, int n, int heads, float scale, int swap, void* out, float* p_out,
+                             cudaStream_t stream) {
   AttnTcMhParams p;
   memset(&p, 0, sizeof(p));
   const int c3 = heads * 3 * DH;
@@ -659,6 +712,7 @@ static int attn_tc_mh_launch(const void* qkv, int n, int heads, float scale, int
   p.n = n; p.heads = heads; p.swap = swap;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out);
+  p.p_out = p_out;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_mh_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMhSmem);
@@ -670,10 +724,11 @@ static int attn_tc_mh_launch(const void* qkv, int n, int heads, float scale, int
   return check_launch_err(e, "attn_tc_mh_kernel");
 }
 
-int attn_tc_mh_forward(const void* qkv, int n, int heads, int L, int dh, float scale, int swap, void* out, cudaStream_t stream) {
-  if (L == 64) return attn_tc_mh64_forward(qkv, n, heads, scale, swap, out, stream);
-  return dh == 64 ? attn_tc_mh_launch<64>(qkv, n, heads, scale, swap, out, stream)
-                  : attn_tc_mh_launch<32>(qkv, n, heads, scale, swap, out, stream);
+int attn_tc_mh_forward(const void* qkv, int n, int heads, int L, int dh, float scale, int swap, void* out, float* p_out,
+                       cudaStream_t stream) {
+  if (L == 64) return attn_tc_mh64_forward(qkv, n, heads, scale, swap, out, p_out, stream);
+  return dh == 64 ? attn_tc_mh_launch<64>(qkv, n, heads, scale, swap, out, p_out, stream)
+                  : attn_tc_mh_launch<32>(qkv, n, heads, scale, swap, out, p_out, stream);
 }
 
 bool attn_tc_supported(int act_dtype, int heads, int L, int dh, int row_stride, long long batch_stride,

@@ -19,6 +19,11 @@
 
 namespace dmme {
 
+bool attn_tensor_core_multi_head_enabled();
+bool attn_tc_mh_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
+                          int v_transposed, const void* q, const void* k, const void* v, const void* out);
+int attn_tc_mh_forward(const void* qkv, int n, int heads, int L, int dh, float scale, int swap, void* out, float* p_out,
+                       cudaStream_t stream);
 bool attn_mma_supported(int act_dtype, int heads, int L, int dh, int row_stride, int head_stride, long long batch_stride,
                         int v_transposed, const void* q, const void* k, const void* v, const void* out);
 int attn_mma_forward(const void* q, const void* k, const void* v, long long batch_stride, int row_stride, int head_stride,
@@ -1281,7 +1286,11 @@ extern "C" int dmme_attention_fwd_train(const void* q, const void* k, const void
   DMME_REQUIRE(n > 0 && heads > 0 && L > 0 && dh > 0, DMME_E_BADARG, "attention_fwd_train: bad sizes");
   DMME_REQUIRE(static_cast<long long>(n) * heads <= 65535, DMME_E_SHAPE, "attention_fwd_train: more than 65535 (image, head) pairs");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // bf16 mode: the fused mma.sync kernel (attention_mma.cu) also writes the normalised P the backward pass needs
+  // bf16 mode: the fused kernels also write the normalised P the backward pass needs -- tcgen05 at 256 tokens and at 64
+  // tokens with 64-channel heads (attention_tc.cu), mma.sync elsewhere (attention_mma.cu)
+  if (attn_tensor_core_multi_head_enabled() &&
+      attn_tc_mh_supported(act_dtype, heads, L, dh, row_stride, head_stride, batch_stride, 0, q, k, v, out))
+    return attn_tc_mh_forward(q, n, heads, L, dh, scale, head_batch_swap, out, p_out, st);
   if (attn_mma_supported(act_dtype, heads, L, dh, row_stride, head_stride, batch_stride, 0, q, k, v, out))
     return attn_mma_forward(q, k, v, batch_stride, row_stride, head_stride, n, heads, L, dh, scale, head_batch_swap, out,
                             p_out, st);

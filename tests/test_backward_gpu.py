@@ -386,6 +386,29 @@ def test_attention_bwd(n, c, heads, L_, swap):
     assert rel_l2(dqkv2.cpu(), qkv.grad) < 1e-4
 
 
+@pytest.mark.parametrize("n,c,heads,L_", [(3, 256, 4, 256), (2, 128, 4, 256), (5, 256, 4, 64), (1, 64, 1, 256), (2, 128, 4, 64)])
+def test_attention_fwd_train_bf16_keeps_softmax(n, c, heads, L_):
+    """bf16 training forward of the multi-head layout (tcgen05 kernels at 256 tokens and at 64 tokens with 64-channel heads,
+    mma.sync elsewhere): the kept fp32 softmax matrix and the output against fp32 attention on the same bf16 operands"""
+    ops, L = _ops()
+    dh = c // heads
+    g = torch.Generator().manual_seed(21)
+    qkv = torch.randn(n, L_, 3 * c, generator=g).to(torch.bfloat16)
+    t = qkv.float().reshape(n, L_, heads, 3, dh).permute(3, 0, 2, 1, 4).reshape(3, n * heads, L_, dh)
+    scale = c ** -0.5
+    prob = torch.softmax(t[0] @ (t[1] * scale).transpose(1, 2), dim=2)
+    want = (prob @ t[2]).reshape(heads, n, L_, dh).permute(1, 2, 0, 3).reshape(n, L_, c)
+    dev = qkv.to(DEV).contiguous()
+    flat = dev.view(-1)
+    od = torch.full((n, L_, c), float("nan"), dtype=torch.bfloat16, device=DEV)
+    psave = torch.full((n * heads, L_, L_), float("nan"), device=DEV)
+    otmp = torch.empty(n * heads * L_ * dh, device=DEV)
+    ops.attention_fwd_train(flat, flat[dh:], flat[2 * dh:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, 3 * dh, True, od, psave, otmp)
+    torch.cuda.synchronize()
+    assert rel_l2(psave.cpu(), prob) < 1e-4, rel_l2(psave.cpu(), prob)
+    assert rel_l2(od.float().cpu(), want) < 6e-3, rel_l2(od.float().cpu(), want)
+
+
 # ---------------------------------------------------------------------------------------------
 # conditioning MLP backward
 # ---------------------------------------------------------------------------------------------
