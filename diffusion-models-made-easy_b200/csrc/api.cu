@@ -27,16 +27,23 @@ int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_halo_supported(const dmme_conv_desc& d);
 bool conv_halo_preferred(const dmme_conv_desc& d);
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream);
-bool conv_halo2_supported(const dmme_conv_desc& d);
 bool conv_out_tc_supported(const dmme_conv_desc& d);
 int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream);
-int conv_halo2_forward(const dmme_conv_desc& d, cudaStream_t stream);
 
 }  // namespace dmme
 
 using namespace dmme;
 
 extern "C" int dmme_abi_version(void) { return DMME_ABI_VERSION; }
+// 1 when the library was built with -DDMME_EXPERIMENTAL (the cta_group::2 conv and the weight-multicast halo variants:
+// parity-green negative results kept out of the shipped build)
+extern "C" int dmme_has_experimental(void) {
+#ifdef DMME_EXPERIMENTAL
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" const char* dmme_last_error(void) { return g_err; }
 extern "C" long long dmme_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void dmme_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
@@ -45,7 +52,6 @@ extern "C" int dmme_conv2d_uses_tc(const dmme_conv_desc* d) {
   if (!d) return 0;
   if (d->kernel == DMME_CONV_GENERIC) return 0;
   if (d->kernel == DMME_CONV_HALO) return conv_halo_supported(*d) ? 1 : 0;
-  if (d->kernel == DMME_CONV_HALO2) return conv_halo2_supported(*d) ? 1 : 0;
   if (d->kernel == DMME_CONV_AUTO && conv_out_tc_supported(*d)) return 1;
   return conv_tc_supported(*d) ? 1 : 0;
 }
@@ -53,7 +59,6 @@ extern "C" int dmme_conv2d_uses_tc(const dmme_conv_desc* d) {
 extern "C" int dmme_conv2d_writes_stats(const dmme_conv_desc* d) {
   if (!d || d->kernel == DMME_CONV_GENERIC || d->out_layout != DMME_OUT_NHWC || d->cout % 4) return 0;
   if (d->kernel == DMME_CONV_HALO) return conv_halo_supported(*d) ? 1 : 0;
-  if (d->kernel == DMME_CONV_HALO2) return conv_halo2_supported(*d) ? 1 : 0;
   if (conv_tc_supported(*d)) return 1;
   if (d->kernel == DMME_CONV_AUTO && conv_in_supported(*d) && (static_cast<long long>(d->h_in) * d->w_in) % 64 == 0) return 1;
   return 0;
@@ -80,8 +85,6 @@ extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
       return conv_generic_forward(*d, st);
     case DMME_CONV_HALO:
       return conv_halo_forward(*d, st);
-    case DMME_CONV_HALO2:
-      return conv_halo2_forward(*d, st);
     case DMME_CONV_AUTO:
       if (conv_tc_supported(*d)) return conv_halo_preferred(*d) ? conv_halo_forward(*d, st) : conv_tc_forward(*d, st);
       if (conv_out_tc_supported(*d)) return conv_out_tc_forward(*d, st);

@@ -208,7 +208,8 @@ int attn_mma_forward(const void* q, const void* k, const void* v, long long batc
   p.p_out = p_out;
   const size_t smem = static_cast<size_t>(2) * kAmRows * (dh + 8) * 2 + static_cast<size_t>(kAmRows) * (L + 8) * 4 +
                       kAmRows * 4 + 128;
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) { set_error("attn_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -673,7 +673,8 @@ int attn_tc_mh64_forward(const void* qkv, int n, int heads, float scale, int swa
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.p_out = p_out;
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_mh64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMh64Smem);
     if (e != cudaSuccess) { set_error("attn_tc_mh64: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -713,7 +714,8 @@ static int attn_tc_mh_launch(const void* qkv, int n, int heads, float scale, int
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.p_out = p_out;
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_mh_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMhSmem);
     if (e != cudaSuccess) { set_error("attn_tc_mh: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -759,7 +761,8 @@ int attn_tc_forward(const void* q, const void* k, const void* vt, int n, int d, 
   p.n = n; p.d = d;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out);
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) { set_error("attn_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

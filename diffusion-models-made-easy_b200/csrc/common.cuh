@@ -81,6 +81,28 @@ inline cudaError_t launch_pdl_pair(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// one-time per-DEVICE setup (cudaFuncSetAttribute applies to the current device only): `static DeviceOnce once_;`
+struct DeviceOnce {
+  bool done[64] = {};
+  bool& here() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return done[d & 63];
+  }
+};
+// SM count of the current device (cached per device ordinal)
+inline int device_sm_count() {
+  static int cache[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  int& c = cache[d & 63];
+  if (c == 0) {
+    cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, d);
+    if (c <= 0) c = 148;
+  }
+  return c;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -507,11 +507,9 @@ static int g_halo_mc = 0;
 
 template <int W, int COUT, bool MC>
 static int launch_halo_mc(const ConvHaloParams& p, cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<W, COUT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) {
       set_error("conv_halo: cudaFuncSetAttribute(%d bytes): %s", kHaloSmem, cudaGetErrorString(e));
@@ -534,7 +532,9 @@ static int launch_halo_mc(const ConvHaloParams& p, cudaStream_t stream) {
 template <int W, int COUT>
 static int launch_halo(const ConvHaloParams& p, cudaStream_t stream) {
   // pairs pay off where CTAs walk several work items each (the 16x16 and 32x32 levels at sampling batch sizes)
+#ifdef DMME_EXPERIMENTAL  // weight multicast measured 3-15% slower: built only with -DDMME_EXPERIMENTAL
   if (g_halo_mc == 2 || (g_halo_mc == 1 && p.m_tiles * p.n_tiles >= 2 * g_sm_count)) return launch_halo_mc<W, COUT, true>(p, stream);
+#endif
   return launch_halo_mc<W, COUT, false>(p, stream);
 }
 
@@ -561,12 +561,7 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   }
   p.total_rows = d.n * (d.h_in + 2);
   p.n_tiles = d.cout / kHaloBN;
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
+  g_sm_count = device_sm_count();
   const int img_pos = (d.h_in + 2) * p.wp;
   p.imgs_per_tile = 0;
   if (img_pos <= kHaloCols) {

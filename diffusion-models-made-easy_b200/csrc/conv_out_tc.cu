@@ -189,7 +189,8 @@ bool conv_out_tc_supported(const dmme_conv_desc& d) {
 
 template <int NCOL>
 static int launch_out_tc(const ConvOutTcParams& p, int smem, int grid, cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_out_tc_kernel<NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) {
@@ -236,13 +237,7 @@ int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     uint32_t box[2] = {64u, 16u};
     if ((rc = encode_map(&p.b, d.weight, 2, dims, strides, box))) return rc;
   }
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (sm_count <= 0) sm_count = 148;
-  }
+  const int sm_count = device_sm_count();
   const int smem = kOutStages * kOutSlot + 9 * p.chunks * kOutWTile + 1024;
   const int grid = p.units < sm_count ? p.units : sm_count;
   return d.cout <= 4 ? launch_out_tc<4>(p, smem, grid, stream) : launch_out_tc<8>(p, smem, grid, stream);

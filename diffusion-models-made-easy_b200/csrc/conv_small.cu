@@ -385,7 +385,8 @@ int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   if (conv_in_supported(d)) {
     const int cg = d.cout / 8, ppi = 256 / cg;
     const size_t smem = sizeof(float) * (static_cast<size_t>(27) * d.cout + d.cout + static_cast<size_t>(ppi) * (d.cout / 4) * 2);
-    static bool configured = false;
+    static DeviceOnce once_;
+  bool& configured = once_.here();
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       if (e != cudaSuccess) { set_error("conv_in: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

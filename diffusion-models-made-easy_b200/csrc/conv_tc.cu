@@ -855,7 +855,8 @@ constexpr int kWsSlabMax = 128 * 1024;  // + 6 x 16 KB ring + alignment = 225 KB
 template <int BN, int STAGES, bool WS>
 static int launch_conv_tc(const ConvTcParams& p, int m_tiles, cudaStream_t stream) {
   constexpr int smem = WS ? STAGES * kABytes + kWsSlabMax + 1024 : STAGES * stage_bytes<BN>() + 1024;
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -864,13 +865,7 @@ static int launch_conv_tc(const ConvTcParams& p, int m_tiles, cudaStream_t strea
     }
     configured = true;
   }
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (sm_count <= 0) sm_count = 148;
-  }
+  const int sm_count = device_sm_count();
   ConvTcParams q = p;
   q.m_tiles = m_tiles;
   q.n_tiles = p.cout / BN;
@@ -909,7 +904,8 @@ static int tct_tile_pixels(const dmme_conv_desc& d) {
 
 template <bool WS, int CMOD, bool PAIR = false>
 static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) {
@@ -936,12 +932,7 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
-  if (g_sm_count_tc == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count_tc, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count_tc <= 0) g_sm_count_tc = 148;
-  }
+  g_sm_count_tc = device_sm_count();
   const int np = tct_tile_pixels(d);
   const int tile_px = np ? np : 128;
   p.bw = wo < tile_px ? wo : tile_px;
@@ -1001,6 +992,7 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     // cta_group::2: 256 output channels x 256 pixels per CTA pair when that still gives most SM pairs a unit
     const bool pair = g_tct_pair_mode != 0 && !ws && !x.subpix && np == 256 && d.cout % 256 == 0 && d.out_layout == DMME_OUT_NHWC &&
                       (static_cast<long long>(m_tiles) * (d.cout / 256) >= 56 || g_tct_pair_mode == 2);
+#ifdef DMME_EXPERIMENTAL
     if (pair) {
       // half-tile boxes: split along the tile's slowest dimension
       const int hbni = p.bni >= 2 ? p.bni / 2 : p.bni, hbh = p.bni >= 2 ? p.bh : p.bh / 2;
@@ -1016,6 +1008,9 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
       return d.cout == 256 ? launch_conv_tct<false, 256, true>(p, x, smem2, stream)
                            : launch_conv_tct<false, 0, true>(p, x, smem2, stream);
     }
+#else
+    (void)pair;  // the cta_group::2 variant measured no faster: built only with -DDMME_EXPERIMENTAL
+#endif
     x.stage_bytes = np * 128 + (ws ? 0 : 128 * 128);
     int stages = static_cast<int>((budget - (ws ? slab : 0)) / x.stage_bytes);
     x.stages = stages > kTctMaxStages ? kTctMaxStages : stages;

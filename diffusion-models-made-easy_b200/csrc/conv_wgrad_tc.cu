@@ -234,7 +234,8 @@ template <int N>
 static int launch_wgrad_tc(const WgradTcParams& p, int items, int slices, cudaStream_t stream) {
   constexpr int stages = N == 128 ? 3 : 4;
   constexpr int smem = stages * (2 * kWgTileBytes + 3 * (N / 64) * kWgTileBytes) + 1024;
-  static bool configured = false;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {

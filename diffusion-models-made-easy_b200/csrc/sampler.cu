@@ -20,6 +20,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+// schedule-table index: negative values wrap like torch indexing (table[-1] is the last entry), anything still outside
+// [0, len) is clamped -- a replayed CUDA graph cannot raise; the eager wrappers raise IndexError on the host instead
+__device__ __forceinline__ long long table_index(long long t, int len) {
+  if (t < 0) t += len;
+  return t < 0 ? 0 : (t >= len ? len - 1 : t);
+}
 __device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x) + 0.5f) * 2.3283064365386963e-10f; }
 // four standard normals for element group g of stream sid
 __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long sid, unsigned long long g) {
@@ -52,12 +58,13 @@ __global__ void philox_normal_kernel(float* __restrict__ out, long long numel, u
 // ---- DDPM ancestral step ---------------------------------------------------------------------
 __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
                                  const float* __restrict__ beta, const float* __restrict__ alpha,
-                                 const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr,
+                                 const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr, int table_len,
                                  long long numel, unsigned long long seed, unsigned long long goff) {
   pdl_trigger();
   pdl_wait();
   const long long t = *t_ptr;
-  const float b = beta[t], a = alpha[t], ab = alpha_bar[t];
+  const long long ti = table_index(t, table_len);
+  const float b = beta[ti], a = alpha[ti], ab = alpha_bar[ti];
   const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
   const float c2 = __fdiv_rn(b, __fsqrt_rn(__fsub_rn(1.0f, ab)));
   const float sd = __fsqrt_rn(b);
@@ -85,10 +92,10 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
 // ---- DDIM step, as written in the reference --------------------------------------------------
 __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
                                  const float* __restrict__ alpha_bar, const int64_t* __restrict__ tau,
-                                 const int64_t* __restrict__ i_ptr, long long numel) {
+                                 const int64_t* __restrict__ i_ptr, int table_len, int tau_len, long long numel) {
   const long long i = *i_ptr;
-  const float ab_i = alpha_bar[tau[i]];
-  const float ab_p = alpha_bar[tau[i - 1]];
+  const float ab_i = alpha_bar[table_index(tau[table_index(i, tau_len)], table_len)];
+  const float ab_p = alpha_bar[table_index(tau[table_index(i - 1, tau_len)], table_len)];
   const float s1 = __fsqrt_rn(__fsub_rn(1.0f, ab_i));
   const float sp = __fsqrt_rn(ab_p);
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < numel;
@@ -101,10 +108,11 @@ __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict_
 // ---- IDDPM learned-variance step -------------------------------------------------------------
 __global__ void iddpm_step_kernel(float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ noise,
                                   const float* __restrict__ beta, const float* __restrict__ alpha,
-                                  const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr, int n, int c,
-                                  int hw, unsigned long long seed, unsigned long long goff) {
+                                  const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr, int table_len,
+                                  int n, int c, int hw, unsigned long long seed, unsigned long long goff) {
   const long long t = *t_ptr;
-  const float b = beta[t], a = alpha[t], ab = alpha_bar[t], abp = alpha_bar[t - 1];
+  const long long ti = table_index(t, table_len), tp = table_index(t - 1, table_len);
+  const float b = beta[ti], a = alpha[ti], ab = alpha_bar[ti], abp = alpha_bar[tp];
   const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
   const float c2 = __fdiv_rn(b, __fsqrt_rn(__fsub_rn(1.0f, ab)));
   const float bt = __fmul_rn(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)), b);
@@ -154,32 +162,35 @@ static int ew_grid(long long work, int threads) {
 using namespace dmme;
 
 extern "C" int dmme_ddpm_step(float* x, const float* eps, const float* noise, const float* beta, const float* alpha,
-                              const float* alpha_bar, const int64_t* t_ptr, long long numel, unsigned long long seed,
-                              unsigned long long noise_offset, void* stream) {
-  DMME_REQUIRE(x && eps && beta && alpha && alpha_bar && t_ptr && numel > 0, DMME_E_BADARG, "ddpm_step: bad arguments");
+                              const float* alpha_bar, const int64_t* t_ptr, int table_len, long long numel,
+                              unsigned long long seed, unsigned long long noise_offset, void* stream) {
+  DMME_REQUIRE(x && eps && beta && alpha && alpha_bar && t_ptr && numel > 0 && table_len > 0, DMME_E_BADARG,
+               "ddpm_step: bad arguments");
   DMME_REQUIRE(noise_offset % 4 == 0, DMME_E_BADARG, "ddpm_step: noise_offset must be a multiple of 4");
   return check_launch_err(launch_pdl(ddpm_step_kernel, dim3(ew_grid((numel + 3) / 4, 256)), dim3(256), 0,
-                                     static_cast<cudaStream_t>(stream), x, eps, noise, beta, alpha, alpha_bar, t_ptr, numel,
-                                     seed, noise_offset / 4),
+                                     static_cast<cudaStream_t>(stream), x, eps, noise, beta, alpha, alpha_bar, t_ptr,
+                                     table_len, numel, seed, noise_offset / 4),
                           "ddpm_step_kernel");
 }
 
 extern "C" int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar, const int64_t* tau,
-                              const int64_t* i_ptr, long long numel, void* stream) {
-  DMME_REQUIRE(x && eps && alpha_bar && tau && i_ptr && numel > 0, DMME_E_BADARG, "ddim_step: bad arguments");
-  ddim_step_kernel<<<ew_grid(numel, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, alpha_bar, tau, i_ptr, numel);
+                              const int64_t* i_ptr, int table_len, int tau_len, long long numel, void* stream) {
+  DMME_REQUIRE(x && eps && alpha_bar && tau && i_ptr && numel > 0 && table_len > 0 && tau_len > 0, DMME_E_BADARG,
+               "ddim_step: bad arguments");
+  ddim_step_kernel<<<ew_grid(numel, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, alpha_bar, tau, i_ptr, table_len,
+                                                                                     tau_len, numel);
   return check_launch("ddim_step_kernel");
 }
 
 extern "C" int dmme_iddpm_step(float* x, const float* model_out, const float* noise, const float* beta,
-                               const float* alpha, const float* alpha_bar, const int64_t* t_ptr, int n, int c, int hw,
-                               unsigned long long seed, unsigned long long noise_offset, void* stream) {
-  DMME_REQUIRE(x && model_out && beta && alpha && alpha_bar && t_ptr && n > 0 && c > 0 && hw > 0, DMME_E_BADARG,
+                               const float* alpha, const float* alpha_bar, const int64_t* t_ptr, int table_len, int n, int c,
+                               int hw, unsigned long long seed, unsigned long long noise_offset, void* stream) {
+  DMME_REQUIRE(x && model_out && beta && alpha && alpha_bar && t_ptr && table_len > 0 && n > 0 && c > 0 && hw > 0, DMME_E_BADARG,
                "iddpm_step: bad arguments");
   DMME_REQUIRE(noise_offset % 4 == 0, DMME_E_BADARG, "iddpm_step: noise_offset must be a multiple of 4");
   const long long numel = static_cast<long long>(n) * c * hw;
   iddpm_step_kernel<<<ew_grid((numel + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, model_out, noise, beta, alpha, alpha_bar, t_ptr, n, c, hw, seed, noise_offset / 4);
+      x, model_out, noise, beta, alpha, alpha_bar, t_ptr, table_len, n, c, hw, seed, noise_offset / 4);
   return check_launch("iddpm_step_kernel");
 }
 

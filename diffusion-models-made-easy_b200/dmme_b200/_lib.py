@@ -19,11 +19,11 @@ LIB_PATH = os.environ.get("DMME_LIB_PATH") or os.path.join(_HERE, "libdmme_b200.
 BF16, F32 = 0, 1
 IN_NHWC, IN_NCHW_F32 = 0, 1
 OUT_NHWC, OUT_NCHW_F32, OUT_QKV = 0, 1, 2
-CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO, CONV_HALO2 = 0, 1, 2, 3, 4
+CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO = 0, 1, 2, 3
 
 # every symbol include/dmme_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = (
-    "dmme_abi_version", "dmme_last_error", "dmme_launch_count", "dmme_reset_launch_count",
+    "dmme_abi_version", "dmme_has_experimental", "dmme_last_error", "dmme_launch_count", "dmme_reset_launch_count",
     "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
     "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
@@ -85,9 +85,9 @@ def load() -> C.CDLL:
     lib.dmme_attention_uses_tc.argtypes = [ll, i, i, ll, i, i, i, i, i]
     lib.dmme_temb_mlp_fwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp]
     lib.dmme_temb_proj_fwd.argtypes = [vp, i, i, vp, vp, i, vp, vp]
-    lib.dmme_ddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, ull, ull, vp]
-    lib.dmme_ddim_step.argtypes = [vp, vp, vp, vp, vp, ll, vp]
-    lib.dmme_iddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, ull, ull, vp]
+    lib.dmme_ddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, ll, ull, ull, vp]
+    lib.dmme_ddim_step.argtypes = [vp, vp, vp, vp, vp, i, i, ll, vp]
+    lib.dmme_iddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, ull, ull, vp]
     lib.dmme_gather_i64.argtypes = [vp, vp, vp, vp]
     lib.dmme_add_i64.argtypes = [vp, C.c_int64, vp]
     lib.dmme_philox_normal.argtypes = [vp, ll, ull, ull, ull, vp]
@@ -169,8 +169,19 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def stream_ptr() -> int:
-    """The CUDA stream every launch goes to: torch's current stream (see callbacks/ema.py:273-296)."""
+    """The CUDA stream every launch goes to: torch's current stream of the CURRENT device (see callbacks/ema.py:273-296).
+    The module-level entry points (UNet.forward, DDPM.sampling_step / generate / training_step, FusedAdamEMA.step) make the
+    tensors' device current first (``on_device``), so a model on cuda:1 launches on cuda:1's stream whatever device the
+    caller had selected."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(t: torch.Tensor):
+    """Context manager: make ``t``'s CUDA device the current one (kernel launches, streams and the C side's per-device
+    kernel attributes all follow the current device)."""
+    if not t.is_cuda:
+        raise RuntimeError("dmme_b200 kernels need CUDA tensors; there is no CPU path")
+    return torch.cuda.device(t.device)
 
 
 def act_code(dtype: torch.dtype) -> int:
@@ -187,3 +198,6 @@ def require_cuda(*tensors: Optional[torch.Tensor]) -> None:
             raise RuntimeError("dmme_b200 kernels need CUDA tensors; there is no CPU path")
         if t is not None and not t.is_contiguous():
             raise RuntimeError("dmme_b200 kernels need contiguous tensors")
+        if t is not None and t.device.index != torch.cuda.current_device():
+            raise RuntimeError(f"dmme_b200: tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}; "
+                               "call through the module entry points or wrap the call in torch.cuda.device(tensor.device)")

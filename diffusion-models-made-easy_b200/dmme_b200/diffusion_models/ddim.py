@@ -41,11 +41,12 @@ class DDIM(DDPM):
 
     def sampling_step(self, x_tau_i: Tensor, i: Tensor, noise: Optional[Tensor] = None) -> Tensor:
         r"""Mean of :math:`p_\theta(x_{\tau_{i-1}}|x_{\tau_i})`; ``i`` has shape (1,)."""
-        i = self._check_step_index(i)
-        x = x_tau_i.detach().float().contiguous().clone()
-        t_model = ops.gather_i64(self.tau, i, torch.empty(1, dtype=torch.int64, device=x.device))
-        eps = self.model.forward_raw(x, t_model)
-        return ops.ddim_step_(x, eps, self.alpha_bar, self.tau, i)
+        i = self._check_step_index(i, self.tau.shape[0])
+        with torch.cuda.device(self.beta.device):
+            x = x_tau_i.detach().to(self.beta.device).float().contiguous().clone()
+            t_model = ops.gather_i64(self.tau, i, torch.empty(1, dtype=torch.int64, device=x.device))
+            eps = self._model_out(x, t_model)
+            return ops.ddim_step_(x, eps, self.alpha_bar, self.tau, i)
 
     def _counter_start(self) -> int:
         return self.sub_timesteps
@@ -54,8 +55,11 @@ class DDIM(DDPM):
         return self.sub_timesteps
 
     def _graph_step(self, x: Tensor, counter: Tensor, seed: int) -> None:
-        t_model = self.model.engine.ws.get("ddim.t", (1,), torch.int64, x.device)
+        t_model = self.__dict__.get("_t_model")
+        if t_model is None or t_model.device != x.device:
+            t_model = torch.empty(1, dtype=torch.int64, device=x.device)  # stable address across graph replays
+            self.__dict__["_t_model"] = t_model
         ops.gather_i64(self.tau, counter, t_model)
-        eps = self.model.forward_raw(x, t_model)
+        eps = self._model_out(x, t_model)
         ops.ddim_step_(x, eps, self.alpha_bar, self.tau, counter)
         ops.add_i64_(counter, -1)

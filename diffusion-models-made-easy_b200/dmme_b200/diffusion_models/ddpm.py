@@ -49,11 +49,26 @@ class DDPM(nn.Module):
         """Applies the internal model: :math:`\\epsilon_\\theta(x, t)`."""
         return self.model(x, t)
 
-    def _check_step_index(self, t: Tensor) -> Tensor:
+    def _check_step_index(self, t: Tensor, table_len: Optional[int] = None) -> Tensor:
         if t.numel() != 1:
             # the reference itself fails here (torch.where broadcast, ddpm.py:110; SURVEY quirk 1)
             raise ValueError("sampling_step takes a step tensor of shape (1,), as DDPM.generate passes it")
+        # eager entry point: validate on the host like the reference's `self.beta[t]` (negative indices wrap, anything past
+        # the table raises IndexError); the graph-replayed chain owns its counter and needs no check
+        n = int(table_len if table_len is not None else self.beta.shape[0])
+        tv = int(t.reshape(-1)[0].item())
+        if not -n <= tv < n:
+            raise IndexError(f"index {tv} is out of bounds for dimension 0 with size {n}")
         return t.reshape(1).to(device=self.beta.device, dtype=torch.int64).contiguous()
+
+    def _model_out(self, x: Tensor, t: Tensor) -> Tensor:
+        """eps (or (eps, v)) of the wrapped model: the dmme_b200 UNet's raw executor output, or -- for any other
+        ``nn.Module`` (a guidance wrapper, the reference UNet, ...) as the reference allows -- ``self.model(x, t)``."""
+        raw = getattr(self.model, "forward_raw", None)
+        if raw is not None:
+            return raw(x, t)
+        with torch.no_grad():
+            return self.model(x, t).detach().float().contiguous()
 
     def _update_(self, x: Tensor, model_out: Tensor, noise: Optional[Tensor], t: Tensor, seed: int) -> Tensor:
         return ops.ddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed,
@@ -68,11 +83,12 @@ class DDPM(nn.Module):
             noise: optional standard-normal tensor shaped like ``x_t`` (default: ``torch.randn_like``)
         """
         t = self._check_step_index(t)
-        x = x_t.detach().float().contiguous().clone()
-        out = self.model.forward_raw(x, t)
-        if noise is None:
-            noise = torch.randn_like(x)
-        return self._update_(x, out, noise.contiguous(), t, 0)
+        with torch.cuda.device(self.beta.device):
+            x = x_t.detach().to(self.beta.device).float().contiguous().clone()
+            out = self._model_out(x, t)
+            if noise is None:
+                noise = torch.randn_like(x)
+            return self._update_(x, out, noise.to(x.device).float().contiguous(), t, 0)
 
     # ------------------------------------------------------------------------------------------
     def _counter_start(self) -> int:
@@ -83,7 +99,7 @@ class DDPM(nn.Module):
 
     def _graph_step(self, x: Tensor, counter: Tensor, seed: int) -> None:
         """One denoising step on device-resident state; everything launched here is graph-capturable."""
-        out = self.model.forward_raw(x, counter)
+        out = self._model_out(x, counter)
         self._update_(x, out, None, counter, seed)
         ops.add_i64_(counter, -1)
 
@@ -144,7 +160,8 @@ class DDPM(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         self._noise_offset = int(noise_offset)
         try:
-            return self._run_steps(x, self._num_steps(), seed, graph, on_step)
+            with torch.cuda.device(dev):
+                return self._run_steps(x, self._num_steps(), seed, graph, on_step)
         finally:
             self._noise_offset = 0
 
@@ -181,8 +198,9 @@ class DDPM(nn.Module):
         x = gaussian(tuple(img_size), device=dev) if x_T is None else x_T.detach().to(dev).float().clone()
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        x = self._run_steps(x.contiguous(), steps, seed, graph, None, tap)
-        put(x, out=hist[len(hits)])
+        with torch.cuda.device(dev):
+            x = self._run_steps(x.contiguous(), steps, seed, graph, None, tap)
+            put(x, out=hist[len(hits)])
         return hist
 
     def _noised(self, x_0: Tensor, t: Optional[Tensor] = None, noise: Optional[Tensor] = None):
@@ -214,10 +232,11 @@ class DDPM(nn.Module):
         Returns:
             loss, :math:`L_\text{simple}` (0-dim tensor; ``loss.backward()`` runs the explicit backward kernels)
         """
-        x_0, t, x_t, mean, std = self._noised(x_0, t, noise)
-        noise_in_x_t = self.model(x_t, t)
-        noise = ((x_t - mean) / std).contiguous()
-        return _SimpleLoss.apply(noise_in_x_t, noise)
+        with torch.cuda.device(x_0.device if x_0.is_cuda else self.beta.device):
+            x_0, t, x_t, mean, std = self._noised(x_0, t, noise)
+            noise_in_x_t = self.model(x_t, t)
+            noise = ((x_t - mean) / std).contiguous()
+            return _SimpleLoss.apply(noise_in_x_t, noise)
 
 
 class _SimpleLoss(torch.autograd.Function):

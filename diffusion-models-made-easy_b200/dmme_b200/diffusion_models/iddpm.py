@@ -56,15 +56,18 @@ class IDDPM(DDPM):
         r"""Hybrid loss :math:`L_\text{simple} + \gamma L_\text{vlb}` (or :math:`L_\text{vlb}` alone for
         ``loss_type="vlb"``), diffusion_models/iddpm.py:62-116.  The whole loss tail (learned-variance
         interpolation, discrete NLL at t = 1, KL elsewhere, MSE) and its gradient run as one fused kernel."""
-        x_0, t, x_t, _, _ = self._noised(x_0, t, noise)
-        model_out = self.model(x_t, t)
         if self.loss_type == "hybrid":
             w_simple, w_vlb = 1.0, float(self.gamma)
         elif self.loss_type == "vlb":
             w_simple, w_vlb = 0.0, 1.0
         else:
-            return None  # the reference falls off the end of training_step for any other loss_type
-        return _HybridLoss.apply(model_out, x_t, x_0, t, self.beta, self.alpha, self.alpha_bar, w_simple, w_vlb)
+            w_simple = None  # the reference falls off the end of training_step for any other loss_type (after the forward)
+        with torch.cuda.device(x_0.device if x_0.is_cuda else self.beta.device):
+            x_0, t, x_t, _, _ = self._noised(x_0, t, noise)
+            model_out = self.model(x_t, t)
+            if w_simple is None:
+                return None
+            return _HybridLoss.apply(model_out, x_t, x_0, t, self.beta, self.alpha, self.alpha_bar, w_simple, w_vlb)
 
 
 class _HybridLoss(torch.autograd.Function):

@@ -169,7 +169,7 @@ class _UNetBase(nn.Module):
         autograd graph is recorded; use ``forward`` (with gradients enabled) for training."""
         if not x.is_cuda:
             raise RuntimeError("dmme_b200.UNet runs on CUDA (sm_100a) only; there is no CPU path")
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(x.device):
             if masks is None:
                 masks = self._dropout_masks(x.shape[0], x.device)
             eng = self.engine
@@ -190,7 +190,8 @@ class _UNetBase(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             if not x.is_cuda:
                 raise RuntimeError("dmme_b200.UNet runs on CUDA (sm_100a) only; there is no CPU path")
-            return _UNetFunction.apply(self, x, c, *self.parameters())
+            with torch.cuda.device(x.device):
+                return _UNetFunction.apply(self, x, c, *self.parameters())
         return self.forward_raw(x, c).clone()
 
 
@@ -216,7 +217,8 @@ class _UNetFunction(torch.autograd.Function):
         if eng.generation != ctx.generation:
             raise RuntimeError("dmme_b200: backward() of a UNet call whose saved activations were overwritten by a later "
                                "forward; run backward before the next training forward of the same module")
-        grads = eng.backward(d_out.contiguous())
+        with torch.cuda.device(d_out.device):
+            grads = eng.backward(d_out.contiguous())
         out = []
         for p in unet.parameters():
             g = grads.get(id(p)) if p.requires_grad else None

@@ -242,13 +242,14 @@ def ddpm_step_(x: Tensor, eps: Tensor, noise: Optional[Tensor], beta: Tensor, al
                t: Tensor, seed: int = 0, noise_offset: int = 0) -> Tensor:
     L.require_cuda(x, eps, noise, beta, alpha, alpha_bar, t)
     L.check(L.load().dmme_ddpm_step(ptr(x), ptr(eps), ptr(noise), ptr(beta), ptr(alpha), ptr(alpha_bar), ptr(t),
-                                    x.numel(), seed, noise_offset, L.stream_ptr()), "ddpm_step")
+                                    beta.numel(), x.numel(), seed, noise_offset, L.stream_ptr()), "ddpm_step")
     return x
 
 
 def ddim_step_(x: Tensor, eps: Tensor, alpha_bar: Tensor, tau: Tensor, i: Tensor) -> Tensor:
     L.require_cuda(x, eps, alpha_bar, tau, i)
-    L.check(L.load().dmme_ddim_step(ptr(x), ptr(eps), ptr(alpha_bar), ptr(tau), ptr(i), x.numel(), L.stream_ptr()),
+    L.check(L.load().dmme_ddim_step(ptr(x), ptr(eps), ptr(alpha_bar), ptr(tau), ptr(i), alpha_bar.numel(), tau.numel(),
+                                    x.numel(), L.stream_ptr()),
             "ddim_step")
     return x
 
@@ -258,7 +259,7 @@ def iddpm_step_(x: Tensor, model_out: Tensor, noise: Optional[Tensor], beta: Ten
     L.require_cuda(x, model_out, noise, beta, alpha, alpha_bar, t)
     n, c, h, w = x.shape
     L.check(L.load().dmme_iddpm_step(ptr(x), ptr(model_out), ptr(noise), ptr(beta), ptr(alpha), ptr(alpha_bar), ptr(t),
-                                     n, c, h * w, seed, noise_offset, L.stream_ptr()), "iddpm_step")
+                                     beta.numel(), n, c, h * w, seed, noise_offset, L.stream_ptr()), "iddpm_step")
     return x
 
 

@@ -82,6 +82,9 @@ class FusedAdamEMA:
     # ------------------------------------------------------------------------------------------
     def _refresh_table(self) -> None:
         ptrs = [p.grad.data_ptr() if p.grad is not None else 0 for p in self.params]
+        if not any(ptrs):
+            # e.g. zero_grad(set_to_none=True) after a graph-captured backward rebinds p.grad away from the captured buffers
+            raise RuntimeError("FusedAdamEMA.step(): no parameter has a gradient -- nothing would be updated")
         if ptrs == self._grad_ptrs:
             return
         t = self._table_host.view(-1, 7)
@@ -104,13 +107,15 @@ class FusedAdamEMA:
     @torch.no_grad()
     def step(self) -> None:
         """One optimizer step on the current ``p.grad`` values (parameters without a gradient are left untouched)."""
-        self.step_count += 1
         self._refresh_table()
+        self.step_count += 1
         lr = warmup_lr(self.lr, self.step_count, self.warmup)
-        L.check(L.load().dmme_adam_ema_step(self._table_dev.data_ptr(), len(self.params), self._items, lr, self.betas[0],
-                                            self.betas[1], self.eps, self.step_count, self.max_grad_norm,
-                                            self.ema_decay if self.ema_decay is not None else 0.0, self._partial.data_ptr(),
-                                            self._grid, self._norm.data_ptr(), L.stream_ptr()), "adam_ema_step")
+        with torch.cuda.device(self._table_dev.device):
+            L.check(L.load().dmme_adam_ema_step(self._table_dev.data_ptr(), len(self.params), self._items, lr,
+                                                self.betas[0], self.betas[1], self.eps, self.step_count, self.max_grad_norm,
+                                                self.ema_decay if self.ema_decay is not None else 0.0,
+                                                self._partial.data_ptr(), self._grid, self._norm.data_ptr(), L.stream_ptr()),
+                    "adam_ema_step")
         # the kernels write the weights through raw pointers: tell the executors' packed-weight caches (models/_engine.py
         # keys them on (data_ptr, _version, _dmme_gen)) that every parameter changed
         for p in self.params:

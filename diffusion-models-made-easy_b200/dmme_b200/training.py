@@ -32,6 +32,7 @@ class GraphedTrainingStep:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._x: Optional[Tensor] = None
         self._loss: Optional[Tensor] = None
+        self._grads = []  # (parameter, gradient buffer inside the graph's private pool) of the captured backward
 
     def _params(self):
         return [p for p in self.diffusion.parameters() if p.requires_grad]
@@ -61,6 +62,7 @@ class GraphedTrainingStep:
                 self._loss.backward()
         finally:
             eng.always_repack = False
+        self._grads = [(p, p.grad) for p in self._params() if p.grad is not None]
 
     def __call__(self, x_0: Tensor) -> Tensor:
         if not x_0.is_cuda:
@@ -69,6 +71,11 @@ class GraphedTrainingStep:
             self._capture(x_0)
         self._x.copy_(x_0, non_blocking=True)
         self._graph.replay()
+        # the replay writes into the buffers captured above whatever p.grad points to now: a caller-side
+        # zero_grad(set_to_none=True) (or anything else that rebinds p.grad) must not silently disconnect the optimizer
+        for p, g in self._grads:
+            if p.grad is not g:
+                p.grad = g
         if self.optimizer is not None:
             self.optimizer.step()
         return self._loss

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMME_ABI_VERSION 3
+#define DMME_ABI_VERSION 4
 #define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
@@ -51,10 +51,8 @@ enum {
   DMME_CONV_AUTO = 0,    /* tcgen05 when the shape allows, generic otherwise */
   DMME_CONV_GENERIC = 1, /* FFMA implicit GEMM, any shape, fp32 math */
   DMME_CONV_TC = 2,      /* tcgen05/TMEM + TMA implicit GEMM, one A tile per filter tap (any supported shape) */
-  DMME_CONV_HALO = 3,    /* tcgen05 3x3 stride-1 kernel that keeps the activation halo tile in shared memory for all
+  DMME_CONV_HALO = 3     /* tcgen05 3x3 stride-1 kernel that keeps the activation halo tile in shared memory for all
                             nine taps */
-  DMME_CONV_HALO2 = 4    /* the same with one weight tile feeding two position tiles (all 512 TMEM columns): the 32x32
-                            and 16x16 levels; AUTO prefers it where it measured fastest */
 };
 
 /*
@@ -101,6 +99,9 @@ typedef struct dmme_conv_desc {
 
 /* library / device ------------------------------------------------------------------------- */
 int dmme_abi_version(void);
+/* 1 when built with -DDMME_EXPERIMENTAL: the cta_group::2 transposed conv (dmme_set_conv_pair_mode) and the
+ * weight-multicast halo conv (dmme_set_conv_halo_multicast) exist; 0 (the shipped build): those switches do nothing */
+int dmme_has_experimental(void);
 const char* dmme_last_error(void);
 /* number of kernel launches issued through this library since the last reset (process-wide) */
 long long dmme_launch_count(void);
@@ -199,8 +200,10 @@ int dmme_temb_proj_fwd(const float* emb, int rows, int emb_dim, const float* wca
 
 /* sampler updates (image space, NCHW fp32, elementwise) ------------------------------------- */
 /*
- * tables: fp32 device arrays of length T+1 (beta, alpha, alpha_bar as registered by
- * DDPM.__init__ diffusion_models/ddpm.py:41-51); t_ptr: int64 device scalar holding the current t.
+ * tables: fp32 device arrays of length table_len = T+1 (beta, alpha, alpha_bar as registered by
+ * DDPM.__init__ diffusion_models/ddpm.py:41-51); t_ptr: int64 device scalar holding the current t.  Table indices
+ * (t, t-1, tau[i], tau[i-1]) wrap when negative like the reference's torch indexing and are clamped to the table
+ * otherwise (the reference raises IndexError for t > T; the Python wrappers do that on the host in eager mode).
  * noise: fp32 tensor of standard normals (NULL: draw Philox4x32-10 normals from (seed, *t_ptr, element index)).
  * noise_offset: index of x[0] inside the whole (unsharded) sample batch, a multiple of 4 -- a rank that owns images
  * [i0, i1) passes i0 * C*H*W and draws exactly the noise the single-GPU run draws for those images.
@@ -208,17 +211,17 @@ int dmme_temb_proj_fwd(const float* emb, int rows, int emb_dim, const float* wca
  *        (diffusion_models/ddpm.py:83-111, equations/ddpm/ddpm.py:44-72)
  */
 int dmme_ddpm_step(float* x, const float* eps, const float* noise, const float* beta, const float* alpha,
-                   const float* alpha_bar, const int64_t* t_ptr, long long numel, unsigned long long seed,
+                   const float* alpha_bar, const int64_t* t_ptr, int table_len, long long numel, unsigned long long seed,
                    unsigned long long noise_offset, void* stream);
 /* ddim (as written in equations/ddim/ddim.py:52-57): x0 = (x - sqrt(1-abar_i) eps)/sqrt(abar_prev); x <- sqrt(abar_prev) x0
  * i_ptr: int64 device scalar with the sub-sequence index i; tau: int64 [S+1]. */
 int dmme_ddim_step(float* x, const float* eps, const float* alpha_bar, const int64_t* tau, const int64_t* i_ptr,
-                   long long numel, void* stream);
+                   int table_len, int tau_len, long long numel, void* stream);
 /* iddpm learned variance (diffusion_models/iddpm.py:118-164, equations/iddpm/losses.py:34-37):
  * model_out NCHW fp32 [n][2*c][hw]: first c channels eps, last c channels v. */
 int dmme_iddpm_step(float* x, const float* model_out, const float* noise, const float* beta, const float* alpha,
-                    const float* alpha_bar, const int64_t* t_ptr, int n, int c, int hw, unsigned long long seed,
-                    unsigned long long noise_offset, void* stream);
+                    const float* alpha_bar, const int64_t* t_ptr, int table_len, int n, int c, int hw,
+                    unsigned long long seed, unsigned long long noise_offset, void* stream);
 /* writes tau[*i_ptr] into *t_out (DDIM: the model is evaluated at tau_i) */
 int dmme_gather_i64(const int64_t* table, const int64_t* idx_ptr, int64_t* out, void* stream);
 /* *value += delta: advances the device-resident step counter between graph replays

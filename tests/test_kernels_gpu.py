@@ -344,6 +344,8 @@ def pair_everywhere():
     dict(n=300, cin=256, cout=256, h=16, w=16, k=3, temb="rows"),                # several units per pair
 ])
 def test_conv_tct_pair(cfg, pair_everywhere):
+    if not _ops()[1].load().dmme_has_experimental():
+        pytest.skip("cta_group::2 variant is compiled only with -DDMME_EXPERIMENTAL (measured no faster, DESIGN.md)")
     test_conv_tct.__wrapped__(cfg, None) if hasattr(test_conv_tct, "__wrapped__") else test_conv_tct(cfg, None)
 
 
@@ -379,15 +381,18 @@ HALO_CASES = [
 
 def _halo_params():
     out = [pytest.param(c, "halo", id=f"halo-{i}") for i, c in enumerate(HALO_CASES)]
-    out += [pytest.param(c, "halo2", id=f"halo2-{i}") for i, c in enumerate(HALO_CASES) if c["w"] >= 16]
-    out.append(pytest.param(dict(n=256, cin=128, cout=128, h=32, w=32, temb="bcast", addend=True), "halo2", id="halo2-batch256"))
-    out.append(pytest.param(dict(n=97, cin=256, cout=256, h=16, w=16, temb="rows"), "halo2", id="halo2-odd-batch"))
+    # the tilings bench.py times (rows per tile are chosen by wave fill FROM THE BATCH): per-GPU batches 256 / 128 / 64 / 32
+    # of BASELINE config #2 (256 images split over 1 / 2 / 4 / 8 GPUs) at the 16x16 and 32x32 levels
+    for nb in (256, 128, 64, 32):
+        out.append(pytest.param(dict(n=nb, cin=256, cout=256, h=16, w=16, temb="bcast"), "halo", id=f"halo-timed-16x16-c256-n{nb}"))
+        out.append(pytest.param(dict(n=nb, cin=256, cout=128, h=16, w=16, addend=False), "halo", id=f"halo-timed-16x16-c128-n{nb}"))
+        out.append(pytest.param(dict(n=nb, cin=128, cout=128, h=32, w=32, temb="bcast", addend=True), "halo", id=f"halo-timed-32x32-n{nb}"))
     return out
 
 
 @pytest.mark.parametrize("cfg,which", _halo_params())
 def test_conv_halo(cfg, which):
-    """halo-reuse persistent tcgen05 kernels (one / two position tiles per weight tile) against fp32 conv on the same
+    """halo-reuse persistent tcgen05 kernel against fp32 conv on the same
     bf16 operands, plus their GroupNorm stats"""
     ops, L = _ops()
     g = torch.Generator().manual_seed(23)
@@ -420,7 +425,7 @@ def test_conv_halo(cfg, which):
         want = want + ad
         addend = to_nhwc(ad, torch.bfloat16).to(DEV)
     d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16,
-                           L.CONV_HALO if which == "halo" else L.CONV_HALO2)
+                           L.CONV_HALO)
     assert ops.conv_uses_tc(d)
     wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
     out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=DEV)
@@ -828,6 +833,13 @@ def test_attention_mma_multi_head(n, c, heads, L_, swap):
     dict(n=3, c0=256, c1=0, cout=256, h=16, addend=True, temb="rows"),
     dict(n=70, c0=256, c1=256, cout=256, h=16, silu=False),          # tiles spanning two images, plain norm
     dict(n=150, c0=128, c1=0, cout=128, h=32),
+    # the tilings bench.py times: 13 / 11 rows per tile at 16x16 only appear at batch 256; per-GPU shards 128 / 64 / 32
+    dict(n=256, c0=256, c1=0, cout=256, h=16, temb="bcast"),
+    dict(n=256, c0=256, c1=0, cout=128, h=16),
+    dict(n=128, c0=256, c1=256, cout=256, h=16),
+    dict(n=64, c0=256, c1=0, cout=256, h=16, addend=True),
+    dict(n=32, c0=128, c1=128, cout=128, h=32, res=True),
+    dict(n=32, c0=256, c1=0, cout=256, h=16, temb="bcast"),
 ])
 def test_conv_halo_fused_groupnorm(cfg):
     """GroupNorm(+SiLU) applied to the halo tile inside the conv kernel == gn_apply followed by the same conv, bit for bit
@@ -894,6 +906,8 @@ def test_conv_halo_fused_groupnorm(cfg):
 def test_conv_halo_weight_multicast(cfg):
     """clusters of two CTAs sharing the weight stream (TMA multicast) == independent CTAs, bit for bit (outputs and
     GroupNorm statistics; same MMA order per output)"""
+    if not _ops()[1].load().dmme_has_experimental():
+        pytest.skip("weight-multicast variant is compiled only with -DDMME_EXPERIMENTAL (measured slower, DESIGN.md)")
     ops, L = _ops()
     lib = L.load()
     g = torch.Generator().manual_seed(67)

@@ -56,7 +56,7 @@ def main():
         out = torch.empty(n, h, h, cout, device=dev, dtype=torch.bfloat16)
         st = torch.zeros(n * cout // 4 * 2, dtype=torch.int64, device=dev)
         flop = 2.0 * n * h * h * cout * (9 * cin + rc0 + rc1)
-        for kname, kernel in (("halo", L.CONV_HALO), ("halo2", L.CONV_HALO2), ("tc", L.CONV_TC)):
+        for kname, kernel in (("halo", L.CONV_HALO), ("tc", L.CONV_TC)):
             if args.only and args.only != kname:
                 continue
             d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False,
