@@ -6,7 +6,9 @@ GPU work).  ``GraphedTrainingStep`` captures forward + loss + backward once into
 input buffer; the optimizer (``optim.FusedAdamEMA``: two launches whose scalars change every step) runs eagerly after the
 replay.  Random draws inside the captured region (timesteps, noise, dropout masks) come from torch's CUDA generator,
 which advances its Philox offset per replay, so every step sees fresh draws exactly as in eager mode.
-Single-process only: the bucketed gradient all-reduce of ``parallel.enable_gradient_sync`` is not captured.
+Data parallel (``parallel.enable_gradient_sync``): the bucketed NCCL all-reduces of the flat gradient arena are issued from
+inside the backward pass and are captured with it (NCCL >= 2.9.6 collectives are graph-capturable); each replay then runs
+backward kernels and all-reduces concurrently on the captured stream fork, with no host work per bucket.
 """
 from __future__ import annotations
 
@@ -42,8 +44,7 @@ class GraphedTrainingStep:
             p.grad = None
 
     def _capture(self, x_0: Tensor) -> None:
-        if getattr(self.diffusion.model.train_engine, "grad_sync", None) is not None:
-            raise RuntimeError("GraphedTrainingStep does not capture the data-parallel gradient all-reduce")
+        synced = getattr(self.diffusion.model.train_engine, "grad_sync", None) is not None
         self._x = x_0.detach().clone()
         side = torch.cuda.Stream(device=x_0.device)
         side.wait_stream(torch.cuda.current_stream(x_0.device))
@@ -57,7 +58,9 @@ class GraphedTrainingStep:
         eng = self.diffusion.model.train_engine
         eng.always_repack = True  # the bf16 weight packing must be replayed too: the weights change between replays
         try:
-            with torch.cuda.graph(self._graph):
+            # thread-local capture mode with collectives inside: NCCL's watchdog thread polls CUDA events concurrently, which
+            # the default (global) mode would treat as a capture violation
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local" if synced else "global"):
                 self._loss = self.diffusion.training_step(self._x)
                 self._loss.backward()
         finally:

@@ -299,14 +299,20 @@ def vlb_loss(eps_hat: Tensor, var: Tensor, x_t: Tensor, t: Tensor, x_0: Tensor, 
 # --------------------------------------------------------------------------------------------
 @torch.no_grad()
 def ddpm_generate(sd: StateDict, x_T: Tensor, noises: Sequence[Tensor], tables: Sequence[Tensor], timesteps: int,
-                  groups: int = 32) -> Tensor:
-    """DDPM.generate (src/dmme/diffusion_models/ddpm.py:113-133): t runs T..1 with t of shape (1,)."""
+                  groups: int = 32, steps: Optional[int] = None, return_trajectory: bool = False):
+    """DDPM.generate (src/dmme/diffusion_models/ddpm.py:113-133): t runs T..1 with t of shape (1,).
+    ``steps``: stop after that many steps (a prefix of the chain); ``return_trajectory``: also return every x_{t-1}."""
     x = x_T
+    traj = []
     for k, t in enumerate(range(timesteps, 0, -1)):
+        if steps is not None and k >= steps:
+            break
         tt = torch.tensor([t])
         eps = unet_forward(sd, x, tt, groups)
         x = ddpm_step(x, tt, eps, noises[k], tables)
-    return x
+        if return_trajectory:
+            traj.append(x.clone())
+    return (x, traj) if return_trajectory else x
 
 
 @torch.no_grad()

@@ -606,6 +606,26 @@ def test_mid_training_step(flavour, precision):
         _check_grads(m, want, 5e-2)
 
 
+def test_default_iddpm_training_step_bf16():
+    """BASELINE config #4 at full size: the default 36.2 M-parameter IDDPM UNet (256 / 512-channel weight gradients, 11
+    multi-head attention sites with their kept softmax matrices, cosine schedule, hybrid loss), batch 8, dropout 0,
+    bf16 tensor-core path -- loss and every parameter gradient against autograd through the fp32 CPU oracle."""
+    from dmme_b200 import IDDPM
+    m, sd = _model("iddpm", "bf16", 0.0)
+    T = 1000
+    dm = IDDPM(m, timesteps=T).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(8, 3, 32, 32, generator=g) * 2 - 1
+    z = torch.randn(8, 3, 32, 32, generator=g)
+    t = torch.tensor([2, 17, 250, 500, 640, 800, 999, 3])
+    want_loss, want = _oracle_training("iddpm", sd, x0, t, z, O.cosine_tables(T), 32)
+    loss = dm.training_step(x0.to(DEV), t=t.to(DEV), noise=z.to(DEV))
+    loss.backward()
+    print(f"default iddpm training step: loss {float(loss):.6f} (oracle {want_loss:.6f})")
+    assert abs(float(loss) - want_loss) < 2e-2 * abs(want_loss), (float(loss), want_loss)
+    _check_grads(m, want, 5e-2)
+
+
 def test_training_step_draws_like_the_reference_and_optimizer_step():
     """training_step(x_0) without injection: t from randint(1, T), loss finite, Adam step changes the weights and the
     packed bf16 weights are rebuilt (the next forward differs)."""

@@ -194,3 +194,88 @@ def test_ddpm_generate_graph_equals_eager_and_is_seeded():
     assert torch.isfinite(a).all()
     out = d.generate((2, 3, 32, 32))  # reference smoke test: tests/test_ddpm.py:45-60
     assert out.shape == (2, 3, 32, 32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the configurations bench.py times (BASELINE config #2: 256 images split over 1 / 2 / 4 / 8 GPUs)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [256, 128, 64, 32])
+def test_default_ddpm_unet_bf16_timed_batches(batch):
+    """per-GPU batches of the strong-scaling bench: shard r of n owns images [r * 256 / n, (r + 1) * 256 / n) of the
+    seed-1234 x_T (SURVEY par. 8d).  The conv kernels pick their tilings from the batch (rows per halo tile by wave fill,
+    pixel-tile width by unit count), so every timed batch gets its own whole-UNet parity check -- here on the LAST shard."""
+    m, sd = _unet("ddpm")
+    x_all, _ = _c1_inputs(256)
+    world = 256 // batch
+    x = x_all[(world - 1) * batch:].contiguous()
+    tt = torch.tensor([1000])
+    want = O.unet_forward(sd, x, tt)
+    got = m(x.to(DEV), tt.to(DEV)).cpu()
+    err = rel_l2(got, want)
+    worst = max(rel_l2(got[i], want[i]) for i in range(batch))
+    print(f"default ddpm unet bf16 batch {batch}: rel-L2 {err:.3e}, worst image {worst:.3e}")
+    assert err < BF16_TOL and worst < BF16_TOL
+
+
+def _philox_noises(ops, shape, seed, ts, noise_offset=0):
+    """the normals ddpm_step_kernel draws in-kernel at step t (stream id = t), reproduced for the oracle"""
+    return [ops.philox_normal(shape, seed, t, DEV, noise_offset=noise_offset).cpu() for t in ts]
+
+
+def test_ddpm_ancestral_chain_default_bf16():
+    """BASELINE config #2, multi-step: the first 20 steps (t = 1000 .. 981) of the graph-replayed ancestral chain with
+    in-kernel Philox noise against the oracle's DDPM.generate fed the same noise; rel-L2 <= 1e-2 after EVERY step."""
+    from dmme_b200 import DDPM, ops
+    m, sd = _unet("ddpm")
+    d = DDPM(m).to(DEV)
+    x_T, _ = _c1_inputs(4)
+    seed, steps = 4242, 20
+    ts = list(range(1000, 1000 - steps, -1))
+    noises = _philox_noises(ops, x_T.shape, seed, ts)
+    _, traj = O.ddpm_generate(sd, x_T, noises, O.linear_tables(1000), 1000, steps=steps, return_trajectory=True)
+    seen = []
+    with torch.cuda.device(0):
+        d._run_steps(x_T.to(DEV).clone(), steps, seed, True, lambda k, x: seen.append(x.cpu().clone()))
+    errs = [rel_l2(a, b) for a, b in zip(seen, traj)]
+    print("ddpm ancestral chain (T=1000, first 20 steps) rel-L2: first %.3e  max %.3e  last %.3e" % (errs[0], max(errs), errs[-1]))
+    assert len(seen) == steps and max(errs) < BF16_TOL
+
+
+def test_ddpm_ancestral_chain_full_short_schedule_bf16():
+    """a COMPLETE ancestral chain (T = 20: every step down to t = 1, whose noise is drawn and discarded as in
+    diffusion_models/ddpm.py:107-110) through DDPM.generate's CUDA-graph path, against the oracle on the same noise."""
+    from dmme_b200 import DDPM, ops
+    m, sd = _unet("ddpm")
+    d = DDPM(m, timesteps=20).to(DEV)
+    x_T, _ = _c1_inputs(4)
+    seed = 777
+    ts = list(range(20, 0, -1))
+    noises = _philox_noises(ops, x_T.shape, seed, ts)
+    want, traj = O.ddpm_generate(sd, x_T, noises, O.linear_tables(20), 20, return_trajectory=True)
+    seen = []
+    got = d.generate(x_T.shape, x_T=x_T.to(DEV), seed=seed, on_step=lambda k, x: seen.append(x.cpu().clone())).cpu()
+    errs = [rel_l2(a, b) for a, b in zip(seen, traj)]
+    print("ddpm ancestral chain (T=20, complete) rel-L2: first %.3e  max %.3e  last %.3e" % (errs[0], max(errs), errs[-1]))
+    assert len(seen) == 20 and max(errs) < BF16_TOL
+    assert rel_l2(got, want) < BF16_TOL
+
+
+def test_ddpm_graph_step_timed_batch_matches_oracle_subset():
+    """the exact object bench.py replays -- DDPM._graph_step captured at batch 256 -- for three steps; DDPM's UNet has no
+    cross-sample coupling (SURVEY par. 8e), so the oracle runs on a 16-image subset (first / last images and the images
+    around the halo kernel's tile boundaries) with the Philox noise of those images."""
+    from dmme_b200 import DDPM, ops
+    m, sd = _unet("ddpm")
+    d = DDPM(m).to(DEV)
+    x_T, _ = _c1_inputs(256)
+    seed, steps = 99, 3
+    pick = torch.tensor([0, 1, 2, 3, 36, 37, 73, 74, 127, 128, 129, 200, 252, 253, 254, 255])
+    ts = list(range(1000, 1000 - steps, -1))
+    noises = [z[pick] for z in _philox_noises(ops, x_T.shape, seed, ts)]
+    _, traj = O.ddpm_generate(sd, x_T[pick], noises, O.linear_tables(1000), 1000, steps=steps, return_trajectory=True)
+    seen = []
+    with torch.cuda.device(0):
+        d._run_steps(x_T.to(DEV).clone(), steps, seed, True, lambda k, x: seen.append(x[pick.to(DEV)].cpu().clone()))
+    errs = [rel_l2(a, b) for a, b in zip(seen, traj)]
+    print("ddpm graph step at batch 256, 16-image subset, rel-L2 per step:", ["%.3e" % e for e in errs])
+    assert max(errs) < BF16_TOL
