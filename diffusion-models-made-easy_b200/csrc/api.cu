@@ -28,6 +28,7 @@ bool conv_halo_supported(const dmme_conv_desc& d);
 bool conv_halo_preferred(const dmme_conv_desc& d);
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_out_tc_supported(const dmme_conv_desc& d);
+long long conv_splitk_workspace(const dmme_conv_desc& d);
 int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream);
 
 }  // namespace dmme
@@ -73,10 +74,23 @@ static bool runs_halo_rows(const dmme_conv_desc& d) {
 
 extern "C" int dmme_conv2d_fuses_gn(const dmme_conv_desc* d) { return d && runs_halo_rows(*d) ? 1 : 0; }
 
+// split-K is a choice of the AUTO / TC dispatch below 16x16-and-up halo territory: the same conditions as the dispatch
+static bool takes_conv_tc(const dmme_conv_desc& d) {
+  if (d.kernel == DMME_CONV_TC) return conv_tc_supported(d);
+  return d.kernel == DMME_CONV_AUTO && conv_tc_supported(d) && !conv_halo_preferred(d);
+}
+
+extern "C" long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* d) {
+  if (!d || !takes_conv_tc(*d)) return 0;
+  return conv_splitk_workspace(*d);
+}
+
 extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
   DMME_REQUIRE(d != nullptr, DMME_E_BADARG, "conv2d_fwd: null descriptor");
   DMME_REQUIRE(d->gn_ab == nullptr || runs_halo_rows(*d), DMME_E_UNSUPPORTED,
                "conv2d_fwd: a fused GroupNorm (gn_ab) needs the halo kernel; ask dmme_conv2d_fuses_gn");
+  DMME_REQUIRE((d->out_norm[0].out == nullptr && d->out_norm[1].out == nullptr) || (takes_conv_tc(*d) && d->splitk_ws != nullptr),
+               DMME_E_UNSUPPORTED, "conv2d_fwd: out_norm needs the split-K path; ask dmme_conv2d_splitk_workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (d->kernel) {
     case DMME_CONV_TC:

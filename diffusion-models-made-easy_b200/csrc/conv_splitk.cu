@@ -1,0 +1,160 @@
+// Finishing pass of the split-K convolutions (conv_tc.cu, conv_tct_kernel<.., SPLIT>).
+//
+// The split-K GEMM leaves `split` fp32 partial tensors [pixel][cout].  One CTA owns one (image, 32-channel slab): it sums
+// the slices, adds bias + timestep embedding + addend (ResBlock.forward models/ddpm.py:129,131), stores the raw bf16
+// output and its GroupNorm micro-group statistics exactly like the conv epilogues do -- and, because it holds whole
+// images, finishes the GroupNorm(+SiLU) of up to two consumers in the same launch (norm_act_drop_conv
+// models/ddpm.py:25-35: the next conv of the chain, and the up-path ResBlock that later reads this tensor as the skip
+// half of its concat).  At the 4x4 / 8x8 levels this replaces conv + gn_apply (+ gn_coeff) launches by GEMM + finish.
+#include "common.cuh"
+
+namespace dmme {
+
+struct NormOut {
+  __nv_bfloat16* out;
+  const float* gamma; const float* beta;
+  const float* scale; const float* shift;
+  int ss_rows, ss_ld, cpg, silu;
+  float eps;
+};
+
+struct SplitFinishParams {
+  const float* partial;
+  long long split_stride;
+  int split;
+  int n, hw, cout;
+  const float* bias;
+  const float* temb;
+  int temb_rows, temb_ld;
+  const __nv_bfloat16* addend;
+  __nv_bfloat16* out;
+  long long* stats;
+  NormOut no[2];
+};
+
+constexpr int kFinishWarps = 8;
+
+__global__ void __launch_bounds__(kFinishWarps * 32) splitk_finish_kernel(const SplitFinishParams p) {
+  __shared__ float red1[kFinishWarps][32], red2[kFinishWarps][32];
+  __shared__ float ch1[32], ch2[32];
+  const int slabs = p.cout >> 5;
+  const int n = blockIdx.x / slabs;
+  const int slab = blockIdx.x - n * slabs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = slab * 32 + lane;  // this thread's channel: a warp covers 32 contiguous channels of one pixel
+  pdl_trigger();
+  pdl_wait();  // the partial tiles come from the split-K GEMM launched just before
+
+  float add = p.bias ? __ldg(p.bias + c) : 0.f;
+  if (p.temb) add += __ldg(p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : n) * p.temb_ld + c);
+  const long long img0 = static_cast<long long>(n) * p.hw;
+
+  // ---- pass 1: sum the K slices, epilogue terms, raw bf16 store, per-channel sums of the STORED values ----
+  float s1 = 0.f, s2 = 0.f;
+  for (int px = warp; px < p.hw; px += kFinishWarps) {
+    const long long o = (img0 + px) * p.cout + c;
+    // fixed summation order (deterministic); eight independent loads in flight per round trip
+    float v = add;
+    const float* __restrict__ pp = p.partial + o;
+    int s = 0;
+    for (; s + 8 <= p.split; s += 8) {
+      float a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = __ldg(pp + (s + j) * p.split_stride);
+      v += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    }
+    for (; s + 2 <= p.split; s += 2) {
+      const float a0 = __ldg(pp + s * p.split_stride), a1 = __ldg(pp + (s + 1) * p.split_stride);
+      v += a0 + a1;
+    }
+    if (s < p.split) v += __ldg(pp + s * p.split_stride);
+    if (p.addend) v += __bfloat162float(p.addend[o]);
+    const __nv_bfloat16 r = __float2bfloat16_rn(v);
+    p.out[o] = r;
+    const float rf = __bfloat162float(r);
+    s1 += rf;
+    s2 = fmaf(rf, rf, s2);
+  }
+  red1[warp][lane] = s1;
+  red2[warp][lane] = s2;
+  __syncthreads();
+  if (warp == 0) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFinishWarps; ++w) { t1 += red1[w][lane]; t2 += red2[w][lane]; }
+    ch1[lane] = t1;
+    ch2[lane] = t2;
+    if (p.stats) {
+      // [n][cout/4][2] fixed-point micro-group sums, the format every conv epilogue writes (dmme_conv_desc.stats)
+      float m1 = t1, m2 = t2;
+      m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+      m1 += __shfl_xor_sync(0xffffffffu, m1, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+      if ((lane & 3) == 0) {
+        const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
+        unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats) +
+                                 (static_cast<long long>(n) * (p.cout >> 2) + (c >> 2)) * 2;
+        atomicAdd(st, static_cast<unsigned long long>(__float2ll_rn(m1 * kFix)));
+        atomicAdd(st + 1, static_cast<unsigned long long>(__float2ll_rn(m2 * kFix)));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: the consumers' GroupNorm(+SiLU) of the stored tensor ----
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const NormOut& q = p.no[k];
+    if (q.out == nullptr) continue;  // uniform
+    const int g0 = (lane / q.cpg) * q.cpg;
+    float t1 = 0.f, t2 = 0.f;
+    for (int j = 0; j < q.cpg; ++j) { t1 += ch1[g0 + j]; t2 += ch2[g0 + j]; }
+    const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * q.cpg);
+    const float mean = t1 * inv_cnt;
+    const float var = fmaxf(t2 * inv_cnt - mean * mean, 0.f);
+    const float rs = rsqrtf(var + q.eps);
+    const float ga = q.gamma ? __ldg(q.gamma + c) : 1.f, be = q.beta ? __ldg(q.beta + c) : 0.f;
+    float aa = rs * ga, bb = be - mean * rs * ga;
+    if (q.scale) {
+      const long long r = static_cast<long long>(q.ss_rows == 1 ? 0 : n) * q.ss_ld;
+      const float sc = 1.f + __ldg(q.scale + r + c), sh = __ldg(q.shift + r + c);
+      aa *= sc;
+      bb = bb * sc + sh;
+    }
+    for (int px = warp; px < p.hw; px += kFinishWarps) {
+      const long long o = (img0 + px) * p.cout + c;
+      float y = fmaf(__bfloat162float(p.out[o]), aa, bb);  // this thread's own store of pass 1
+      if (q.silu) y = silu_f(y);
+      q.out[o] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream) {
+  SplitFinishParams p;
+  memset(&p, 0, sizeof(p));
+  const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
+  p.partial = static_cast<const float*>(d.splitk_ws);
+  p.split = split;
+  p.n = d.n; p.hw = ho * wo; p.cout = d.cout;
+  p.split_stride = static_cast<long long>(d.n) * p.hw * d.cout;
+  p.bias = d.bias; p.temb = d.temb; p.temb_rows = d.temb_rows; p.temb_ld = d.temb_ld;
+  p.addend = static_cast<const __nv_bfloat16*>(d.addend);
+  p.out = static_cast<__nv_bfloat16*>(d.out);
+  p.stats = d.stats;
+  for (int k = 0; k < 2; ++k) {
+    const dmme_out_norm& s = d.out_norm[k];
+    if (s.out == nullptr) continue;
+    DMME_REQUIRE(s.cpg >= 1 && s.cpg <= 32 && 32 % s.cpg == 0, DMME_E_SHAPE,
+                 "conv split-K finish: out_norm channels per group must divide 32 (got %d)", s.cpg);
+    DMME_REQUIRE(s.out != d.out, DMME_E_BADARG, "conv split-K finish: out_norm[%d].out aliases out", k);
+    p.no[k].out = static_cast<__nv_bfloat16*>(s.out);
+    p.no[k].gamma = s.gamma; p.no[k].beta = s.beta; p.no[k].scale = s.scale; p.no[k].shift = s.shift;
+    p.no[k].ss_rows = s.ss_rows; p.no[k].ss_ld = s.ss_ld; p.no[k].cpg = s.cpg; p.no[k].silu = s.silu; p.no[k].eps = s.eps;
+    DMME_REQUIRE(s.scale == nullptr || s.shift != nullptr, DMME_E_BADARG, "conv split-K finish: scale without shift");
+  }
+  const int grid = d.n * (d.cout / 32);
+  return check_launch_err(launch_pdl(splitk_finish_kernel, dim3(grid), dim3(kFinishWarps * 32), 0, stream, p),
+                          "splitk_finish_kernel");
+}
+
+}  // namespace dmme

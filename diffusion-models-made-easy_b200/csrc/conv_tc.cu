@@ -377,6 +377,12 @@ struct ConvTctExtra {
   int subpix;       // 1: nearest x2 + 3x3 conv as four 2x2 phase convs on the low-resolution tensor (see below)
   int log2_w;       // log2(wo) (subpix output addressing)
   long long* trace; // debugging: per-role clock64 timestamps of CTA 0 (see dmme_debug_set_conv_trace), or null
+  // split-K (SPLIT kernels): a work unit is (pixel tile, channel tile, K slice s of `split`); it accumulates k-blocks
+  // [s * nkb / split, (s + 1) * nkb / split) and stores its fp32 tile to partial[s][pixel][cout] (no epilogue terms: the
+  // finishing pass conv_splitk.cu adds them after summing the slices)
+  int split;
+  float* partial;
+  long long split_stride;  // elements between two K slices = total_pix * cout
 };
 
 // trace slots of CTA 0: [role][event index]; role 0 = producer (issue time per k-block), 1 = MMA (operands landed per
@@ -404,7 +410,7 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int idx) {
 template <bool WS>
 __host__ __device__ constexpr int tct_epi_warps() { return 8; }
 
-template <bool WS, int CMOD, bool PAIR>
+template <bool WS, int CMOD, bool PAIR, bool SPLIT = false>
 __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
                                                                                   const ConvTctExtra x) {
   extern __shared__ uint8_t smem_raw[];
@@ -425,16 +431,22 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
   uint8_t* slab = ring + STAGES * kStage;  // WS only
 
   const int nphase = x.subpix ? 4 : 1;
-  const int total_tiles = p.m_tiles * p.n_tiles * nphase;  // PAIR: n_tiles counts 256-channel tiles
+  const int nsplit = SPLIT ? x.split : 1;
+  const int total_tiles = p.m_tiles * p.n_tiles * nphase * nsplit;  // PAIR: n_tiles counts 256-channel tiles
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int cta0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);  // first work unit
   const int cta_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr int kTileCh = PAIR ? 256 : 128;
   // unit index: channel tile fastest, then phase (the four phases of a pixel tile read the same pixels), then pixel tile
+  // SPLIT: the K slice is the fastest unit index (the slices of one tile run concurrently on neighbouring CTAs)
 #define DMME_TCT_COORDS(t)                                    \
-  const int nt_ = (t) % p.n_tiles;                            \
-  const int sub = ((t) / p.n_tiles) % nphase; /* sub-pixel phase */ \
-  const int mt = (t) / (p.n_tiles * nphase);                  \
+  const int tu_ = SPLIT ? (t) / nsplit : (t);                 \
+  const int ks_ = SPLIT ? (t) - tu_ * nsplit : 0;             \
+  const int kb_lo = SPLIT ? (ks_ * nkb) / nsplit : 0;         \
+  const int kb_hi = SPLIT ? ((ks_ + 1) * nkb) / nsplit : nkb; \
+  const int nt_ = tu_ % p.n_tiles;                            \
+  const int sub = (tu_ / p.n_tiles) % nphase; /* sub-pixel phase */ \
+  const int mt = tu_ / (p.n_tiles * nphase);                  \
   const int col0 = nt_ * kTileCh + static_cast<int>(rank) * 128; \
   const int tx = mt % p.tiles_x;                              \
   const int ty = (mt / p.tiles_x) % p.tiles_y;                \
@@ -494,7 +506,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
         // slowest dimension (images when it spans several, rows otherwise)
         const int half_n = PAIR ? (p.bni >= 2 ? static_cast<int>(rank) * (p.bni >> 1) : 0) : 0;
         const int half_y = PAIR ? (p.bni >= 2 ? 0 : static_cast<int>(rank) * (p.bh >> 1)) : 0;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           if (it % kTctProducers != lane) continue;
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -553,10 +565,12 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
       if (WS) mbar_wait(&slab_full, 0);
       for (int t = cta0; t < total_tiles; t += cta_step, ++t_it) {
         const int stage = t_it & 1;
+        const int ksm = SPLIT ? t % nsplit : 0;
+        const int kb_lo = SPLIT ? (ksm * nkb) / nsplit : 0, kb_hi = SPLIT ? ((ksm + 1) * nkb) / nsplit : nkb;
         mbar_wait(&acc_empty[stage], ((t_it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t dtm = tmem_base + stage * kAccCols;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -568,7 +582,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             if (PAIR) umma_bf16_2sm(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
           }
           if (PAIR) umma_commit_2sm(&empty_bar[s], 3);  // the slot is free in both CTAs
           else umma_commit(&empty_bar[s]);
@@ -596,10 +610,12 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
     int t_it = 0;
     pdl_wait();
     for (int t = cta0; t < total_tiles; t += cta_step, ++t_it) {
-      const int mt = t / (p.n_tiles * nphase);
-      const int sub = (t / p.n_tiles) % nphase;  // sub-pixel phase
+      const int tu = SPLIT ? t / nsplit : t;
+      const int ks = SPLIT ? t - tu * nsplit : 0;  // K slice (SPLIT)
+      const int mt = tu / (p.n_tiles * nphase);
+      const int sub = (tu / p.n_tiles) % nphase;  // sub-pixel phase
       // first channel of this warp's block (warp-uniform)
-      const int cb = (t % p.n_tiles) * kTileCh + static_cast<int>(rank) * 128 + q * 32;
+      const int cb = (tu % p.n_tiles) * kTileCh + static_cast<int>(rank) * 128 + q * 32;
       const int ch = cb + lane;                            // this thread's output channel
       const int stage = t_it & 1;
       float bias_c = p.bias ? __ldg(p.bias + ch) : 0.f;
@@ -656,8 +672,29 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
       tc_fence_after();
       if (warp == 2 && lane == 0) trace_ev(x.trace, 2, 2 * t_it);
 
+      if constexpr (SPLIT) {
+        // fp32 partial tile of this K slice: thread = channel, a warp stores 128 contiguous bytes per pixel
+        float* __restrict__ pp = x.partial + ks * x.split_stride + ch;
 #pragma unroll 1
-      for (int ci = 0; ci < nchunks; ++ci) {
+        for (int ci = 0; ci < nchunks; ++ci) {
+          const int pix0 = pix_begin + ci * 32;
+          if (pix0 >= total_pix) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(stage * kAccCols + half * ppw + ci * 32), v);
+          tmem_ld_wait();
+          float* po = pp + static_cast<long long>(pix0) * p.cout;
+          if (pix0 + 32 <= total_pix) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) po[static_cast<long long>(i) * p.cout] = __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (pix0 + i < total_pix) po[static_cast<long long>(i) * p.cout] = __uint_as_float(v[i]);
+          }
+        }
+      }
+#pragma unroll 1
+      for (int ci = 0; ci < (SPLIT ? 0 : nchunks); ++ci) {
         const int pix0 = pix_begin + ci * 32;  // first pixel of this 32-pixel chunk (warp-uniform)
         if (pix0 >= total_pix) break;
         uint32_t v[32];
@@ -902,19 +939,72 @@ static int tct_tile_pixels(const dmme_conv_desc& d) {
   return 0;
 }
 
-template <bool WS, int CMOD, bool PAIR = false>
+// ---- split-K plan ----------------------------------------------------------------------------------------------------
+// The 4x4 / 8x8 levels (and every level at the small per-GPU batches of the strong-scaling run) have fewer pixel x channel
+// tiles than SMs, and one CTA then walks the whole K loop alone at the ~45 B/clk a single SM ingests from L2 (measured:
+// 19 us for 36 k-blocks whether 16 or 128 CTAs run).  Splitting K makes every (tile, K slice) a work unit; a finishing
+// pass sums the slices and -- because it sees whole images -- also applies the consumers' GroupNorm(+SiLU).
+static int g_splitk_mode = 1;
+struct SplitPlan { int np, split; };
+
+static SplitPlan splitk_plan(const dmme_conv_desc& d) {
+  SplitPlan none{0, 1};
+  if (g_splitk_mode == 0 || !conv_tc_supported(d)) return none;
+  if (d.ksize != 3 || d.upsample || d.out_layout != DMME_OUT_NHWC || d.cout % 128) return none;
+  const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
+  if (wo > 128 || (ho * wo) > 256) return none;  // whole images per finishing CTA; the 16x16 level and below
+  const long long total_pix = static_cast<long long>(d.n) * ho * wo;
+  if (total_pix * d.cout > (1ll << 26)) return none;
+  const int sm = device_sm_count();
+  const int nkb = 9 * ((d.c0 + d.c1) / 64) + (d.rc0 + d.rc1) / 64;
+  const int n_tiles = d.cout / 128;
+  auto unit_clocks = [](int kb, int bytes_per_kb) { return kb * (bytes_per_kb / 48.0) + 2500.0; };
+  // what runs without the workspace: the transposed kernel where it has a unit for most SMs, else 128 px x 64 ch tiles
+  double base_cost;
+  {
+    const int np0 = tct_tile_pixels(d);
+    if (np0) base_cost = static_cast<double>(ceil_div_ll(ceil_div_ll(total_pix, np0) * n_tiles, sm)) * unit_clocks(nkb, np0 * 128 + 16384);
+    else base_cost = static_cast<double>(ceil_div_ll(ceil_div_ll(total_pix, 128) * (d.cout / 64), sm)) * unit_clocks(nkb, 24576);
+  }
+  SplitPlan best = none;
+  double best_cost = 0.8 * base_cost + 6000.0;  // + the stand-alone GroupNorm launch the finishing pass replaces
+  if (g_splitk_mode == 2) best_cost = 1e30;      // tests: split wherever the kernel supports it
+  for (int np = 128; np <= 256; np *= 2) {
+    if (np == 256 && wo > 256) continue;
+    const long long base_units = ceil_div_ll(total_pix, np) * n_tiles;
+    for (int split = 2; split <= 16 && 2 * split <= nkb; ++split) {
+      const long long units = base_units * split;
+      if (units > 2 * sm) break;
+      const double gemm = static_cast<double>(ceil_div_ll(units, sm)) * unit_clocks(ceil_div(nkb, split), np * 128 + 16384);
+      const double finish = 4000.0 + static_cast<double>(split) * total_pix * d.cout * 4.0 / (sm * 64.0);
+      if (gemm + finish < best_cost) { best_cost = gemm + finish; best = SplitPlan{np, split}; }
+    }
+  }
+  return best;
+}
+
+long long conv_splitk_workspace(const dmme_conv_desc& d) {
+  const SplitPlan plan = splitk_plan(d);
+  if (plan.split <= 1) return 0;
+  const long long total_pix = static_cast<long long>(d.n) * (d.h_in / d.stride) * (d.w_in / d.stride);
+  return static_cast<long long>(plan.split) * total_pix * d.cout * 4;
+}
+
+int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream);  // conv_splitk.cu
+
+template <bool WS, int CMOD, bool PAIR = false, bool SPLIT = false>
 static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
   static DeviceOnce once_;
   bool& configured = once_.here();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD, PAIR, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) {
       set_error("conv_tct: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     configured = true;
   }
-  const int total = p.m_tiles * p.n_tiles * (x.subpix ? 4 : 1);
+  const int total = p.m_tiles * p.n_tiles * (x.subpix ? 4 : 1) * (SPLIT ? x.split : 1);
   if (PAIR) {
     // one cluster of two CTAs (two SMs) per work unit
     const int pairs = total < g_sm_count_tc / 2 ? total : g_sm_count_tc / 2;
@@ -923,8 +1013,8 @@ static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cud
   }
   int grid = total < g_sm_count_tc ? total : g_sm_count_tc;
   if (WS) grid -= grid % p.n_tiles;
-  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD, PAIR>, dim3(grid), dim3((2 + tct_epi_warps<WS>()) * 32), smem, stream, p, x);
-  return check_launch_err(e, "conv_tct_kernel");
+  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD, PAIR, SPLIT>, dim3(grid), dim3((2 + tct_epi_warps<WS>()) * 32), smem, stream, p, x);
+  return check_launch_err(e, SPLIT ? "conv_tct_kernel (split-K)" : "conv_tct_kernel");
 }
 
 int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
@@ -933,7 +1023,15 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
   g_sm_count_tc = device_sm_count();
-  const int np = tct_tile_pixels(d);
+  SplitPlan plan{0, 1};
+  if (d.splitk_ws != nullptr) {
+    plan = splitk_plan(d);
+    if (plan.split > 1 && d.splitk_ws_bytes < static_cast<long long>(plan.split) * d.n * ho * wo * d.cout * 4) plan = SplitPlan{0, 1};
+  }
+  const bool has_out_norm = d.out_norm[0].out != nullptr || d.out_norm[1].out != nullptr;
+  DMME_REQUIRE(!has_out_norm || plan.split > 1, DMME_E_UNSUPPORTED,
+               "conv_tc: out_norm needs the split-K path (ask dmme_conv2d_splitk_workspace and pass splitk_ws)");
+  const int np = plan.split > 1 ? plan.np : tct_tile_pixels(d);
   const int tile_px = np ? np : 128;
   p.bw = wo < tile_px ? wo : tile_px;
   p.bh = ho < tile_px / p.bw ? ho : tile_px / p.bw;
@@ -986,7 +1084,20 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     x.subpix = d.upsample == 3 ? 1 : 0;
     x.log2_w = 0;
     while ((1 << x.log2_w) < wo) ++x.log2_w;
+    x.split = 1; x.partial = nullptr; x.split_stride = 0;
     const int budget = 226 * 1024 - 1024;
+    if (plan.split > 1) {
+      x.split = plan.split;
+      x.partial = static_cast<float*>(d.splitk_ws);
+      x.split_stride = x.total_pix * d.cout;
+      p.bias = nullptr; p.temb = nullptr; p.addend = nullptr; p.stats = nullptr;  // applied by the finishing pass
+      x.stage_bytes = np * 128 + 128 * 128;
+      const int st = budget / x.stage_bytes;
+      x.stages = st > kTctMaxStages ? kTctMaxStages : st;
+      const int smem_s = x.stages * x.stage_bytes + 1024;
+      if ((rc = launch_conv_tct<false, 0, false, true>(p, x, smem_s, stream))) return rc;
+      return conv_splitk_finish(d, plan.split, stream);
+    }
     const long long slab = static_cast<long long>(ktot / 64) * 128 * 128;
     const bool ws = p.taps == 1 && slab + 2 * np * 128 <= budget && p.n_tiles <= g_sm_count_tc;
     // cta_group::2: 256 output channels x 256 pixels per CTA pair when that still gives most SM pairs a unit
@@ -1058,6 +1169,8 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
 
 // A/B measurement switch: 0 = never use the transposed tcgen05 kernel, 1 = default, 2 = wherever it is supported
 extern "C" void dmme_set_conv_tct_mode(int mode) { dmme::g_tct_mode = mode; }
+// A/B measurement switch: 0 = never split K, 1 = default (cost model), 2 = wherever supported (tests)
+extern "C" void dmme_set_conv_splitk_mode(int mode) { dmme::g_splitk_mode = mode; }
 extern "C" int dmme_get_conv_tct_mode(void) { return dmme::g_tct_mode; }
 // debugging: device buffer of 3 x 512 int64 that CTA 0 of the transposed kernel fills with clock64 timestamps
 extern "C" void dmme_debug_set_conv_trace(long long* buf) { dmme::g_conv_trace = buf; }

@@ -25,7 +25,7 @@ CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO = 0, 1, 2, 3
 EXPORTS = (
     "dmme_abi_version", "dmme_has_experimental", "dmme_last_error", "dmme_launch_count", "dmme_reset_launch_count",
     "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
-    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
+    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_conv2d_splitk_workspace", "dmme_set_conv_splitk_mode", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode", "dmme_set_conv_halo_multicast",
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
@@ -34,6 +34,15 @@ EXPORTS = (
     "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
     "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_dilate2x_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
+
+
+class OutNorm(C.Structure):
+    """Mirror of ``struct dmme_out_norm``."""
+
+    _fields_ = [
+        ("out", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("ss_rows", C.c_int), ("ss_ld", C.c_int), ("cpg", C.c_int), ("silu", C.c_int), ("eps", C.c_float),
+    ]
 
 
 class ConvDesc(C.Structure):
@@ -50,6 +59,7 @@ class ConvDesc(C.Structure):
         ("stats", C.c_void_p),
         ("in_layout", C.c_int), ("out_layout", C.c_int), ("act_dtype", C.c_int), ("kernel", C.c_int),
         ("gn_ab", C.c_void_p), ("gn_silu", C.c_int),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_longlong), ("out_norm", OutNorm * 2),
     ]
 
 
@@ -81,6 +91,10 @@ def load() -> C.CDLL:
     lib.dmme_groupnorm_fwd.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, i, vp, i, vp, vp, vp]
     lib.dmme_groupnorm_coeff.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, vp]
     lib.dmme_conv2d_fuses_gn.argtypes = [C.POINTER(ConvDesc)]
+    lib.dmme_conv2d_splitk_workspace.argtypes = [C.POINTER(ConvDesc)]
+    lib.dmme_conv2d_splitk_workspace.restype = ll
+    lib.dmme_set_conv_splitk_mode.argtypes = [i]
+    lib.dmme_set_conv_splitk_mode.restype = None
     lib.dmme_attention_fwd.argtypes = [vp, vp, vp, ll, i, i, i, ll, i, i, i, i, f, i, vp, i, i, vp]
     lib.dmme_attention_uses_tc.argtypes = [ll, i, i, ll, i, i, i, i, i]
     lib.dmme_temb_mlp_fwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp]
@@ -136,6 +150,9 @@ def load() -> C.CDLL:
     mode = os.environ.get("DMME_TCT_MODE")  # A/B measurements only: 0 = never use the transposed tcgen05 conv kernel
     if mode:
         lib.dmme_set_conv_tct_mode(int(mode))
+    mode = os.environ.get("DMME_SPLITK_MODE")  # A/B measurements only: 0 = never split K
+    if mode:
+        lib.dmme_set_conv_splitk_mode(int(mode))
     mode = os.environ.get("DMME_PAIR_MODE")  # A/B measurements only: 0 = no cta_group::2 kernels
     if mode:
         lib.dmme_set_conv_pair_mode(int(mode))

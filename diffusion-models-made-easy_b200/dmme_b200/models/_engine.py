@@ -64,6 +64,13 @@ class Engine:
         self._arena_cursor = 0
         self._arena_need = 0
         self._stats: Dict[int, Tensor] = {}
+        # split-K convs (4x4 / 8x8 levels, small batches): shared fp32 partial-tile workspace, the GroupNorm(+SiLU) outputs
+        # their finishing pass wrote for the consumers {(raw tensor ptr, id(norm module)): normalised tensor}, and the
+        # static producer -> consumers plan of the topology
+        self._splitk_ws: Optional[Tensor] = None
+        self._normed: Dict[Tuple[int, int], Tensor] = {}
+        self._consumers: Optional[Dict[str, List[Tuple]]] = None
+        self.fuse_out_norm = os.environ.get("DMME_FUSE_OUT_NORM", "1") != "0"
 
     # -- caches ------------------------------------------------------------------------------
     def _cached(self, key: Tuple, versions: Tuple, build):
@@ -129,6 +136,56 @@ class Engine:
             o += l.weight.shape[0]
         return w, b, offs
 
+    # -- who normalises what ---------------------------------------------------------------------
+    def consumers(self) -> Dict[str, List[Tuple]]:
+        """producer tensor name -> [(GroupNorm module, first channel inside that norm, channels of that norm, silu)]: the
+        norms that read a block / down-sampling output -- the next ResBlock's conv1 norm (part 0 of a concat on the up
+        path), the attention norm of its own block, and the up-path ResBlock that later pops it as a skip (part 1)."""
+        if self._consumers is not None:
+            return self._consumers
+        u = self.unet
+        plan: Dict[str, List[Tuple]] = {}
+
+        def out_name(name, m):
+            return name + ".attn" if not isinstance(m.attention, nn.Identity) else name
+
+        seq = []  # (name, module, is_resblock, section)
+        for sec, lst in (("down", u.down_layers), ("mid", u.middle_layers), ("up", u.up_layers)):
+            pre = {"down": "down_layers", "mid": "middle_layers", "up": "up_layers"}[sec]
+            for i, m in enumerate(lst):
+                seq.append((f"{pre}.{i}", m, hasattr(m, "conv1"), sec))
+        # channels of every produced tensor
+        chan = {"input_conv": u.input_conv.weight.shape[0]}
+        skips = ["input_conv"]
+        prev = "input_conv"
+        for name, m, is_rb, sec in seq:
+            if is_rb:
+                cout = m.conv1[2].weight.shape[0]
+                norm = m.conv1[0]
+                if sec == "up":
+                    sk = skips.pop()
+                    total = chan[prev] + chan[sk]
+                    plan.setdefault(prev, []).append((norm, 0, total, True))
+                    plan.setdefault(sk, []).append((norm, chan[prev], total, True))
+                else:
+                    plan.setdefault(prev, []).append((norm, 0, chan[prev], True))
+                if not isinstance(m.attention, nn.Identity):
+                    plan.setdefault(name + ".pre", []).append((m.attention.norm, 0, cout, False))
+                    chan[name + ".pre"] = cout
+                prev = out_name(name, m)
+                chan[prev] = cout
+            else:
+                conv = m.conv if hasattr(m, "conv") else m
+                prev_c = conv.weight.shape[0]
+                prev = name
+                chan[prev] = prev_c
+            if sec == "down":
+                skips.append(prev)
+        plan.setdefault(prev, []).append((u.output_conv[0], 0, chan[prev], True))
+        # the chain consumer first: when a tensor has more than two readers the skip reader falls back to its own pass
+        self._consumers = plan
+        return plan
+
     # -- GroupNorm statistics arena ------------------------------------------------------------
     def _begin_stats(self, device) -> None:
         if self._arena is None or self._arena.device != device or self._arena.numel() < self._arena_need:
@@ -138,6 +195,7 @@ class Engine:
         self._arena_cursor = 0
         self._arena_need = 0
         self._stats.clear()
+        self._normed.clear()
 
     def _stats_for(self, out: Tensor, n: int, cout: int) -> Optional[Tensor]:
         size = n * (cout // 4) * 2
@@ -155,7 +213,10 @@ class Engine:
              upsample: bool = False, res: Optional[nn.Conv2d] = None, res0: Optional[Tensor] = None,
              res1: Optional[Tensor] = None, temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
              in_nchw: bool = False, out_layout: int = L.OUT_NHWC, act_dtype: Optional[torch.dtype] = None,
-             addend_in_gemm: bool = False, gn_ab: Optional[Tensor] = None, gn_silu: bool = True):
+             addend_in_gemm: bool = False, gn_ab: Optional[Tensor] = None, gn_silu: bool = True,
+             consumers: Optional[List[Tuple]] = None):
+        """``consumers``: [(norm module, first channel, channels of that norm, silu[, scale, shift])] reading this conv's
+        output; when the conv runs split-K its finishing pass writes their GroupNorm(+SiLU) too (``self._normed``)."""
         cout, ks = conv.weight.shape[0], conv.weight.shape[2]
         act_dtype = act_dtype or src0.dtype
         kernel = L.CONV_GENERIC if self.force_generic else L.CONV_AUTO
@@ -204,6 +265,23 @@ class Engine:
         stats = self._stats_for(out, d.n, cout) if ops.conv_writes_stats(d) else None
         if stats is None:
             self._stats.pop(out.data_ptr(), None)  # the buffer may be a reused scratch with stale statistics
+        ws_bytes = ops.conv_splitk_workspace(d) if (gn_ab is None and act_dtype == torch.bfloat16 and not self.force_generic) else 0
+        if ws_bytes:
+            if self._splitk_ws is None or self._splitk_ws.device != dev or self._splitk_ws.numel() * 4 < ws_bytes:
+                self._splitk_ws = torch.empty(max(ws_bytes // 4, 1 << 22), dtype=torch.float32, device=dev)
+            norms = []
+            for k, spec in enumerate((consumers or [])[:2] if self.fuse_out_norm else []):
+                norm, off, total, silu = spec[:4]
+                scale, shift = (spec[4], spec[5]) if len(spec) > 4 else (None, None)
+                cpg = total // norm.num_groups
+                if cpg < 1 or 32 % cpg or off % cpg or cout % cpg:
+                    continue
+                y = self.ws.get(f"{name}.normed{k}", (d.n, ho, wo, cout), act_dtype, dev)
+                norms.append(ops.out_norm(y, norm.weight.detach()[off:off + cout], norm.bias.detach()[off:off + cout], cpg,
+                                          silu, norm.eps, scale, shift))
+                self._normed[(out.data_ptr(), id(norm))] = y
+            ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats, splitk_ws=self._splitk_ws, out_norms=norms)
+            return out
         ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats, gn_ab=gn_ab, gn_silu=gn_silu)
         return out
 
@@ -213,11 +291,23 @@ class Engine:
         """``conv(silu(norm(cat(x0, x1))))`` (norm_act_drop_conv, models/ddpm.py:25-35).  When the conv takes the halo
         kernel and the producers left their statistics, the norm + SiLU is applied to the halo tile inside the conv kernel
         (one small coefficient launch instead of a pass over the tensor); otherwise GroupNorm runs as its own kernel."""
-        st0 = self._stats.get(x0.data_ptr())
-        st1 = self._stats.get(x1.data_ptr()) if x1 is not None else None
         c0 = x0.shape[3]
         c1 = x1.shape[3] if x1 is not None else 0
         cpg = (c0 + c1) // norm.num_groups
+        if mask is None and self._normed:
+            # parts already normalised by the split-K finishing pass of their producer; a part that is not gets its own
+            # stand-alone pass (groups never straddle the two parts of a concat)
+            n0 = self._normed.get((x0.data_ptr(), id(norm)))
+            n1 = self._normed.get((x1.data_ptr(), id(norm))) if x1 is not None else None
+            if n0 is not None or n1 is not None:
+                if n0 is None and c0 % cpg == 0:
+                    n0 = self.gn_part(gn_name + ".p0", norm, x0, 0, cpg, scale, shift)
+                if x1 is not None and n1 is None and n0 is not None and c1 % cpg == 0:
+                    n1 = self.gn_part(gn_name + ".p1", norm, x1, c0, cpg, scale, shift)
+                if n0 is not None and (x1 is None or n1 is not None):
+                    return self.conv(name, n0, n1, conv, **conv_kw)
+        st0 = self._stats.get(x0.data_ptr())
+        st1 = self._stats.get(x1.data_ptr()) if x1 is not None else None
         if (self.fuse_gn and mask is None and not self.force_generic and x0.dtype == torch.bfloat16 and st0 is not None
                 and (x1 is None or st1 is not None) and cpg % 4 == 0 and c0 % cpg == 0):
             cout, ks = conv.weight.shape[0], conv.weight.shape[2]
@@ -231,6 +321,16 @@ class Engine:
                 return self.conv(name, x0, x1, conv, gn_ab=ab, gn_silu=True, **conv_kw)
         a = self.gn(gn_name, norm, x0, x1, silu=True, scale=scale, shift=shift, mask=mask)
         return self.conv(name, a, None, conv, **conv_kw)
+
+    def gn_part(self, name: str, norm: nn.GroupNorm, src: Tensor, off: int, cpg: int, scale: Optional[Tensor] = None,
+                shift: Optional[Tensor] = None) -> Tensor:
+        """GroupNorm + SiLU of ONE part of a concat (channels [off, off + c) of ``norm``): its groups lie inside the part."""
+        n, h, w, c = src.shape
+        out = self.ws.get(name, (n, h, w, c), src.dtype, src.device)
+        sc = scale[:, off:off + c] if scale is not None else None
+        sh = shift[:, off:off + c] if shift is not None else None
+        return ops.groupnorm(src, None, c // cpg, norm.weight.detach()[off:off + c], norm.bias.detach()[off:off + c], True,
+                             sc, sh, None, norm.eps, out, self._stats.get(src.data_ptr()), None)
 
     def gn(self, name: str, norm: nn.GroupNorm, src0: Tensor, src1: Optional[Tensor], silu: bool,
            scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, mask: Optional[Tensor] = None) -> Tensor:
@@ -246,7 +346,9 @@ class Engine:
     def attention_block(self, name: str, att: nn.Module, x: Tensor) -> Tensor:
         n, h, w, c = x.shape
         seq = h * w
-        a = self.gn("scratch.attn_norm", att.norm, x, None, silu=False)
+        a = self._normed.get((x.data_ptr(), id(att.norm)))
+        if a is None:
+            a = self.gn("scratch.attn_norm", att.norm, x, None, silu=False)
         heads = getattr(att, "num_heads", None)
         ao = self.ws.get("scratch.attn_out", (n, h, w, c), x.dtype, x.device)
         if heads is None:
@@ -271,13 +373,18 @@ class Engine:
         has_attn = not isinstance(blk.attention, nn.Identity)
         out_name = name + (".pre" if has_attn else "")
         res_kw = dict(addend=x0) if isinstance(blk.residual, nn.Identity) else dict(res=blk.residual, res0=x0, res1=x1)
+        res_kw["consumers"] = self.consumers().get(out_name)
         if self.flavour == "ddpm":
-            h1 = self.norm_conv("scratch.h1", blk.conv1[0], x0, x1, blk.conv1[2], gn_name="scratch.a1", temb=cond)
+            c_mid = blk.conv1[2].weight.shape[0]
+            h1 = self.norm_conv("scratch.h1", blk.conv1[0], x0, x1, blk.conv1[2], gn_name="scratch.a1", temb=cond,
+                                consumers=None if mask is not None else [(blk.conv2[0], 0, c_mid, True)])
             h2 = self.norm_conv(out_name, blk.conv2[0], h1, None, conv2, mask=mask, gn_name="scratch.a2", **res_kw)
         else:
-            h1 = self.norm_conv("scratch.h1", blk.conv1[0], x0, x1, blk.conv1[2], gn_name="scratch.a1")
             cout = width // 2
-            h2 = self.norm_conv(out_name, blk.norm, h1, None, conv2, shift=cond[:, :cout], scale=cond[:, cout:], mask=mask,
+            shift, scale = cond[:, :cout], cond[:, cout:]
+            h1 = self.norm_conv("scratch.h1", blk.conv1[0], x0, x1, blk.conv1[2], gn_name="scratch.a1",
+                                consumers=None if mask is not None else [(blk.norm, 0, cout, True, scale, shift)])
+            h2 = self.norm_conv(out_name, blk.norm, h1, None, conv2, shift=shift, scale=scale, mask=mask,
                                 gn_name="scratch.a2", **res_kw)
         if has_attn:
             h2 = self.attention_block(name, blk.attention, h2)
@@ -310,6 +417,7 @@ class Engine:
                                scratch=self.ws.get("temb.hidden", (c.numel(), cond[3].weight.shape[0]), torch.float32, dev))
             temb_all = ops.temb_proj(emb, wcat, bcat, out=self.ws.get("temb.all", (c.numel(), wcat.shape[0]), torch.float32, dev))
 
+        plan = self.consumers()
         h = self.conv("input_conv", x, None, u.input_conv, in_nchw=True, act_dtype=act_dtype)
         main.wait_stream(side)
         skips = [h]
@@ -318,7 +426,7 @@ class Engine:
             if hasattr(m, "conv1"):
                 h = self.resblock(name, m, h, None, temb_all, offs, masks)
             else:
-                h = self.conv(name, h, None, m, stride=2)
+                h = self.conv(name, h, None, m, stride=2, consumers=plan.get(name))
             skips.append(h)
         for i, m in enumerate(u.middle_layers):
             h = self.resblock(f"middle_layers.{i}", m, h, None, temb_all, offs, masks)

@@ -153,6 +153,27 @@ def groupnorm_coeff(stats0: Tensor, stats1: Optional[Tensor], c0: int, c1: int, 
     return ab
 
 
+def conv_splitk_workspace(desc: L.ConvDesc) -> int:
+    """Bytes of fp32 workspace with which ``conv2d_launch(splitk_ws=)`` runs ``desc`` split-K (0: it would not split).
+    Only the split-K path honours ``out_norms=``."""
+    return int(L.load().dmme_conv2d_splitk_workspace(C.byref(desc)))
+
+
+def out_norm(out: Tensor, gamma: Tensor, beta: Tensor, cpg: int, silu: bool, eps: float = 1e-5,
+             scale: Optional[Tensor] = None, shift: Optional[Tensor] = None) -> L.OutNorm:
+    """One ``dmme_out_norm``: the GroupNorm(+SiLU) a consumer applies to this conv's output, written by the split-K
+    finishing pass.  ``gamma`` / ``beta`` (and ``scale`` / ``shift``, 2-D fp32 views) start at this tensor's first channel
+    inside the consumer's norm; ``cpg`` is the consumer's group width."""
+    o = L.OutNorm()
+    o.out, o.gamma, o.beta = ptr(out), ptr(gamma), ptr(beta)
+    o.cpg, o.silu, o.eps = int(cpg), int(silu), float(eps)
+    if scale is not None:
+        if scale.dim() != 2 or shift is None or shift.dim() != 2 or scale.stride(0) != shift.stride(0):
+            raise ValueError("scale/shift must be 2-D fp32 views with equal row stride")
+        o.scale, o.shift, o.ss_rows, o.ss_ld = ptr(scale), ptr(shift), scale.shape[0], scale.stride(0)
+    return o
+
+
 def conv_out_hw(desc: L.ConvDesc) -> Tuple[int, int]:
     h = desc.h_in * (2 if desc.upsample else 1)
     w = desc.w_in * (2 if desc.upsample else 1)
@@ -163,9 +184,14 @@ def conv_out_hw(desc: L.ConvDesc) -> Tuple[int, int]:
 def conv2d_launch(desc: L.ConvDesc, weight: Tensor, bias: Optional[Tensor], out: Tensor,
                   temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
                   out2: Optional[Tensor] = None, out3: Optional[Tensor] = None, stats: Optional[Tensor] = None,
-                  gn_ab: Optional[Tensor] = None, gn_silu: bool = True) -> None:
+                  gn_ab: Optional[Tensor] = None, gn_silu: bool = True, splitk_ws: Optional[Tensor] = None,
+                  out_norms=()) -> None:
     """Launch one fused convolution described by ``desc`` (see include/dmme_b200.h)."""
     desc.weight, desc.bias = ptr(weight), ptr(bias)
+    desc.splitk_ws = ptr(splitk_ws)
+    desc.splitk_ws_bytes = splitk_ws.numel() * splitk_ws.element_size() if splitk_ws is not None else 0
+    for k in range(2):
+        desc.out_norm[k] = out_norms[k] if k < len(out_norms) else L.OutNorm()
     desc.gn_ab, desc.gn_silu = ptr(gn_ab), int(gn_silu)
     if temb is not None:
         if temb.dim() != 2 or temb.dtype != torch.float32:

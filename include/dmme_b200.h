@@ -63,6 +63,24 @@ enum {
  * in-place adds of ResBlock.forward models/ddpm.py:129,131, the skip torch.cat models/ddpm.py:310,
  * nn.Upsample models/ddpm.py:161 and the attention residual models/ddpm.py:75.
  */
+/*
+ * Fused GroupNorm(+SiLU) of the conv OUTPUT for one consumer (split-K path only, see dmme_conv_desc.splitk_ws): besides the
+ * raw tensor `out`, the finishing pass writes  y = [silu]( [(1 + scale)] * GN(out) * gamma + beta [+ shift] )  -- the
+ * operand the consumer's conv reads (norm_act_drop_conv models/ddpm.py:25-35, Attention.norm models/ddpm.py:73, the
+ * scale-shift norm models/iddpm.py:119).  When the consumer normalises a channel concat (models/ddpm.py:310) this tensor
+ * is one part of it: gamma / beta / scale / shift then point at this part's first channel and cpg is the CONSUMER's group
+ * width (groups never straddle the two parts).
+ */
+typedef struct dmme_out_norm {
+  void* out;                          /* NHWC act_dtype tensor of the output shape; NULL: unused */
+  const float* gamma; const float* beta;
+  const float* scale; const float* shift; /* optional [ss_rows][ss_ld] fp32, rows = 1 (broadcast) or n */
+  int ss_rows, ss_ld;
+  int cpg;                            /* channels per group of the consumer's GroupNorm (1..32, divides 32) */
+  int silu;
+  float eps;
+} dmme_out_norm;
+
 typedef struct dmme_conv_desc {
   const void* src0; const void* src1; /* NHWC activations (or NCHW fp32 image when in_layout says so) */
   int c0, c1;                         /* channels of src0 / src1 (c1 = 0: no concat) */
@@ -95,6 +113,13 @@ typedef struct dmme_conv_desc {
                                          applied after the activation, as the reference does.  Halo kernel only: ask
                                          dmme_conv2d_fuses_gn first */
   int gn_silu;                        /* 1: SiLU after the fused norm */
+  void* splitk_ws;                    /* optional fp32 workspace of dmme_conv2d_splitk_workspace(desc) bytes.  With it, a
+                                         3x3 conv whose grid would leave most SMs idle (the 4x4 / 8x8 levels, small
+                                         batches) runs split-K: every (pixel tile, channel tile, K slice) is a work unit
+                                         that stores its fp32 partial tile, and a finishing pass sums the slices, adds
+                                         bias / temb / addend, writes `out` and `stats` and applies out_norm[] */
+  long long splitk_ws_bytes;
+  dmme_out_norm out_norm[2];          /* optional fused GroupNorm(+SiLU) of the output for up to two consumers */
 } dmme_conv_desc;
 
 /* library / device ------------------------------------------------------------------------- */
@@ -148,6 +173,12 @@ int dmme_conv2d_uses_tc(const dmme_conv_desc* desc);
 int dmme_conv2d_writes_stats(const dmme_conv_desc* desc);
 /* 1 when the kernel dmme_conv2d_fwd would run for this descriptor can apply desc->gn_ab (fused GroupNorm of the input) */
 int dmme_conv2d_fuses_gn(const dmme_conv_desc* desc);
+/* bytes of fp32 workspace (desc->splitk_ws) with which dmme_conv2d_fwd runs this descriptor split-K, 0 when it would not
+ * (enough work units without splitting, or a shape / layout the split-K kernel does not take).  desc->out_norm[] is only
+ * honoured on the split-K path. */
+long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* desc);
+/* A/B switch: 0 = never split K, 1 = default (by the cost model), 2 = wherever the split-K kernel supports the shape */
+void dmme_set_conv_splitk_mode(int mode);
 
 /* GroupNorm (+ scale/shift) (+ SiLU) (+ channel dropout mask) -------------------------------- */
 /*

@@ -936,3 +936,129 @@ def test_conv_halo_weight_multicast(cfg):
     assert torch.isfinite(outs[0][0].float()).all()
     assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16))
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# split-K convolution + finishing pass with the consumers' GroupNorm(+SiLU) (4x4 / 8x8 levels, small per-GPU batches)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def splitk_everywhere():
+    _, L = _ops()
+    lib = L.load()
+    lib.dmme_set_conv_splitk_mode(2)
+    yield
+    lib.dmme_set_conv_splitk_mode(1)
+
+
+SPLITK_CASES = [
+    dict(n=32, cin=256, cout=256, h=4, temb="bcast", norms=[(8, True)]),                       # 4x4 at the 8-GPU shard batch
+    dict(n=32, cin=256, cout=256, h=8, addend=True, norms=[(8, True), (16, True)]),            # 8x8, chain + skip consumer
+    dict(n=256, cin=512, cin1=256, cout=256, h=4, res=True, temb="bcast", norms=[(16, True)]),  # up path: concat + fused residual
+    dict(n=4, cin=256, cout=256, h=4, temb="rows", norms=[(8, False)]),                        # fewer pixels than one tile; plain norm
+    dict(n=7, cin=128, cout=128, h=8, norms=[(4, True)], scale_shift=True),                    # ragged batch, IDDPM scale / shift
+    dict(n=32, cin=256, cout=256, h=16, stride=2, norms=[(8, True), (16, True)]),              # stride-2 down-sampling conv 16 -> 8
+    dict(n=64, cin=256, cout=256, h=8, norms=[]),                                              # no consumer norm: raw + stats only
+    dict(n=128, cin=256, cout=256, h=4, temb="bcast", addend=True, norms=[(8, True)]),
+]
+
+
+@pytest.mark.parametrize("cfg", SPLITK_CASES)
+def test_conv_splitk_with_output_norms(cfg, splitk_everywhere):
+    """split-K tcgen05 conv (K slices as work units, fp32 partial tiles) + finishing pass == fp32 conv on the same bf16
+    operands; raw output, its GroupNorm statistics, and the fused GroupNorm(+SiLU) outputs for up to two consumers"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(91)
+    n, cin, cout, h = (cfg[s] for s in ("n", "cin", "cout", "h"))
+    stride = cfg.get("stride", 1)
+    c1 = cfg.get("cin1", 0)
+    c0 = cin - c1
+    ho = h // stride
+    xa = bf16_round(torch.randn(n, cin, h, h, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9))
+    b = torch.randn(cout, generator=g)
+    s0 = to_nhwc(xa[:, :c0], torch.bfloat16).to(DEV)
+    s1 = to_nhwc(xa[:, c0:], torch.bfloat16).to(DEV) if c1 else None
+    want = F.conv2d(xa, wt, b, stride=stride, padding=1)
+    wres, r0, r1, bias = None, None, None, b
+    if cfg.get("res"):
+        wres = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin))
+        bres = torch.randn(cout, generator=g)
+        want = want + F.conv2d(xa, wres, bres)
+        bias = b + bres
+        r0, r1 = s0, s1
+    temb = None
+    if cfg.get("temb"):
+        temb = torch.randn(n if cfg["temb"] == "rows" else 1, cout, generator=g)
+        want = want + (temb if temb.shape[0] == n else temb.expand(n, -1))[:, :, None, None]
+        temb = temb.to(DEV)
+    addend = None
+    if cfg.get("addend"):
+        ad = bf16_round(torch.randn(n, cout, ho, ho, generator=g))
+        want = want + ad
+        addend = to_nhwc(ad, torch.bfloat16).to(DEV)
+    d = ops.make_conv_desc(s0, s1, cout, 3, stride, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+    ws_bytes = ops.conv_splitk_workspace(d)
+    assert ws_bytes > 0, "the forced split-K mode must accept this shape"
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=DEV)
+    wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
+    out = torch.empty((n, ho, ho, cout), dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+    norms, specs = [], []
+    for cpg, silu in cfg["norms"]:
+        gamma, beta = torch.randn(cout, generator=g), torch.randn(cout, generator=g)
+        sc = sh = None
+        if cfg.get("scale_shift"):
+            sc, sh = torch.randn(n, cout, generator=g) * 0.3, torch.randn(n, cout, generator=g)
+        y = torch.full((n, ho, ho, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+        # dmme_out_norm holds raw pointers: the device tensors must outlive the launch
+        dev_t = [t.to(DEV) if t is not None else None for t in (gamma, beta, sc, sh)]
+        norms.append(ops.out_norm(y, dev_t[0], dev_t[1], cpg, silu, 1e-5, dev_t[2], dev_t[3]))
+        specs.append((y, gamma, beta, cpg, silu, sc, sh, dev_t))
+    ops.conv2d_launch(d, wp, bias.to(DEV), out, temb, addend, stats=st, splitk_ws=ws, out_norms=norms)
+    torch.cuda.synchronize()
+    got = to_nchw(out.cpu())
+    err = rel_l2(got, want)
+    assert err < 4e-3, f"raw output rel-L2 {err}"
+    sums = st.cpu().view(n, cout // 4, 2).double() / 2 ** 20
+    assert torch.allclose(sums[..., 0], got.double().reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+    assert torch.allclose(sums[..., 1], (got.double() ** 2).reshape(n, cout // 4, -1).sum(-1), rtol=1e-5, atol=2e-2)
+    for y, gamma, beta, cpg, silu, sc, sh, _ in specs:
+        ref = F.group_norm(got, cout // cpg, gamma, beta, 1e-5)  # the norm of the tensor AS STORED (bf16-rounded)
+        if sc is not None:
+            ref = ref * (1 + sc[:, :, None, None]) + sh[:, :, None, None]
+        if silu:
+            ref = F.silu(ref)
+        e = rel_l2(to_nchw(y.cpu()), ref)
+        assert e < 6e-3, f"fused output norm (cpg {cpg}, silu {silu}) rel-L2 {e}"
+
+
+def test_conv_splitk_default_plan_matches_unsplit():
+    """the cost model's own choice at the strong-scaling shard batches: wherever it splits, the result equals the unsplit
+    kernels' (same operands, fp32 accumulation in a different order) and out_norm is refused without the workspace"""
+    ops, L = _ops()
+    lib = L.load()
+    g = torch.Generator().manual_seed(93)
+    split_seen = 0
+    for n, c, h in ((32, 256, 4), (32, 256, 8), (64, 256, 4), (128, 256, 8), (256, 256, 4), (256, 256, 8)):
+        x = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16).to(DEV)
+        w = torch.randn(c, c, 3, 3, generator=g) / math.sqrt(9 * c)
+        wp = ops.pack_conv_weight(w.to(DEV), None, True)
+        bias = torch.randn(c, generator=g).to(DEV)
+        d = ops.make_conv_desc(x, None, c, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+        ws_bytes = ops.conv_splitk_workspace(d)
+        a = torch.empty((n, h, h, c), dtype=torch.bfloat16, device=DEV)
+        ops.conv2d_launch(d, wp, bias, a)  # no workspace: the unsplit kernels
+        if not ws_bytes:
+            continue
+        split_seen += 1
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=DEV)
+        b = torch.empty_like(a)
+        d2 = ops.make_conv_desc(x, None, c, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+        ops.conv2d_launch(d2, wp, bias, b, splitk_ws=ws)
+        torch.cuda.synchronize()
+        assert rel_l2(b.float().cpu(), a.float().cpu()) < 3e-3
+    assert split_seen >= 3
+    y = torch.empty_like(a)
+    d3 = ops.make_conv_desc(x, None, c, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+    with pytest.raises(RuntimeError, match="split-K"):
+        ops.conv2d_launch(d3, wp, bias, a, out_norms=[ops.out_norm(y, bias, bias, 8, True)])
