@@ -80,6 +80,10 @@ static bool takes_conv_tc(const dmme_conv_desc& d) {
   return d.kernel == DMME_CONV_AUTO && conv_tc_supported(d) && !conv_halo_preferred(d);
 }
 
+extern "C" int dmme_conv2d_fuses_sampler(const dmme_conv_desc* d) {
+  return d && d->kernel == DMME_CONV_AUTO && !conv_tc_supported(*d) && conv_out_tc_supported(*d) ? 1 : 0;
+}
+
 extern "C" long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* d) {
   if (!d || !takes_conv_tc(*d)) return 0;
   return conv_splitk_workspace(*d);
@@ -91,6 +95,8 @@ extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
                "conv2d_fwd: a fused GroupNorm (gn_ab) needs the halo kernel; ask dmme_conv2d_fuses_gn");
   DMME_REQUIRE((d->out_norm[0].out == nullptr && d->out_norm[1].out == nullptr) || (takes_conv_tc(*d) && d->splitk_ws != nullptr),
                DMME_E_UNSUPPORTED, "conv2d_fwd: out_norm needs the split-K path; ask dmme_conv2d_splitk_workspace");
+  DMME_REQUIRE(d->sampler == nullptr || d->sampler->kind == DMME_SAMPLER_NONE || dmme_conv2d_fuses_sampler(d), DMME_E_UNSUPPORTED,
+               "conv2d_fwd: a fused sampler update needs the tcgen05 output-conv kernel; ask dmme_conv2d_fuses_sampler");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (d->kernel) {
     case DMME_CONV_TC:

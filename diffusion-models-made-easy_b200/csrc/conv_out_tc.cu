@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "sampler.cuh"
 #include "tmap.cuh"
 
 namespace dmme {
@@ -30,7 +31,15 @@ struct ConvOutTcParams {
   int units;
   int cout;
   const float* bias;
-  float* out;  // [n][cout][h][w] fp32
+  float* out;  // [n][cout][h][w] fp32, or null when the sampler update below consumes eps in the epilogue
+  // fused sampler update (dmme_sampler_epilogue): x_t <- x_{t-1} in place from the eps / v still in registers
+  int samp_kind;
+  float* x;
+  const float* noise;
+  const float* beta; const float* alpha; const float* alpha_bar;
+  const int64_t* t_ptr; const int64_t* tau;
+  int table_len, tau_len;
+  unsigned long long seed, goff;  // goff: Philox group (4 elements) of x[0] inside the whole sample batch
 };
 
 constexpr int kOutSlot = 24 * 1024;  // >= (1 + (rt + 2) * (W + 2)) * 128 bytes
@@ -140,6 +149,15 @@ __global__ void __launch_bounds__(kOutThreads, 1) conv_out_tc_kernel(const __gri
 #pragma unroll
     for (int c = 0; c < NCOL; ++c) bias[c] = (p.bias && c < p.cout) ? __ldg(p.bias + c) : 0.f;
     const long long plane = static_cast<long long>(p.h) * p.w;
+    // per-step scalars of the fused sampler update: read once, after the grid dependency resolved (the step counter and
+    // x_t were written by earlier kernels of the stream)
+    DdpmScalars sd{};
+    DdimScalars si{};
+    IddpmScalars sv{};
+    if (p.samp_kind == DMME_SAMPLER_DDPM) sd = ddpm_scalars(p.beta, p.alpha, p.alpha_bar, p.t_ptr, p.table_len);
+    else if (p.samp_kind == DMME_SAMPLER_DDIM) si = ddim_scalars(p.alpha_bar, p.tau, p.t_ptr, p.table_len, p.tau_len);
+    else if (p.samp_kind == DMME_SAMPLER_IDDPM) sv = iddpm_scalars(p.beta, p.alpha, p.alpha_bar, p.t_ptr, p.table_len);
+    const int img_c = p.samp_kind == DMME_SAMPLER_IDDPM ? p.cout >> 1 : p.cout;  // channels of x_t
     int u_it = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++u_it) {
       const int stage = u_it & 1;
@@ -157,10 +175,52 @@ __global__ void __launch_bounds__(kOutThreads, 1) conv_out_tc_kernel(const __gri
       tc_fence_before();
       mbar_arrive(&acc_empty[stage]);
       if (valid) {
-        float* op = p.out + (static_cast<long long>(n) * p.cout * p.h + yy) * p.w + xx;
+        if (p.out) {
+          float* op = p.out + (static_cast<long long>(n) * p.cout * p.h + yy) * p.w + xx;
 #pragma unroll
-        for (int c = 0; c < NCOL; ++c)
-          if (c < p.cout) op[c * plane] = __uint_as_float(v[c]) + bias[c];
+          for (int c = 0; c < NCOL; ++c)
+            if (c < p.cout) op[c * plane] = __uint_as_float(v[c]) + bias[c];
+        }
+        if (p.samp_kind != DMME_SAMPLER_NONE) {
+          // element e of x_t (NCHW): the noise of element e is lane e % 4 of Philox group e / 4, exactly what the
+          // stand-alone kernels draw (a thread owns one pixel of every channel, so it computes a group per channel and
+          // uses one of its four normals)
+          const long long e0 = (static_cast<long long>(n) * img_c * p.h + yy) * p.w + xx;
+#pragma unroll
+          for (int c = 0; c < NCOL; ++c) {
+            if (c < img_c) {
+              const long long e = e0 + c * plane;
+              const float eps = __uint_as_float(v[c]) + bias[c];
+              const float xi = p.x[e];
+              float z = 0.f;
+              const bool need_z = p.samp_kind == DMME_SAMPLER_DDPM ? !sd.last : (p.samp_kind == DMME_SAMPLER_IDDPM ? !sv.last : false);
+              if (need_z) {
+                if (p.noise) {
+                  z = p.noise[e];
+                } else {
+                  const unsigned long long t = static_cast<unsigned long long>(p.samp_kind == DMME_SAMPLER_DDPM ? sd.t : sv.t);
+                  const float4 z4 = philox_normal4(p.seed, t, p.goff + static_cast<unsigned long long>(e >> 2));
+                  const int j = static_cast<int>(e & 3);
+                  z = j == 0 ? z4.x : (j == 1 ? z4.y : (j == 2 ? z4.z : z4.w));
+                }
+              } else if (p.noise && p.samp_kind != DMME_SAMPLER_DDIM) {
+                z = p.noise[e];  // t == 1: drawn and discarded, like the reference; the value does not matter
+              }
+              float r;
+              if (p.samp_kind == DMME_SAMPLER_DDPM) r = ddpm_update(xi, eps, z, sd);
+              else if (p.samp_kind == DMME_SAMPLER_DDIM) r = ddim_update(xi, eps, si);
+              else {
+                // v = channel img_c + c of the network output; NCOL = 8 covers cout <= 8
+                float vv = 0.f;
+#pragma unroll
+                for (int k = 0; k < NCOL; ++k)
+                  if (k == img_c + c) vv = __uint_as_float(v[k]) + bias[k];
+                r = iddpm_update(xi, eps, vv, z, sv);
+              }
+              p.x[e] = r;
+            }
+          }
+        }
       }
     }
   }
@@ -179,6 +239,7 @@ bool conv_out_tc_supported(const dmme_conv_desc& d) {
   if (g_out_tc_mode == 0) return false;
   if (d.act_dtype != DMME_BF16 || d.in_layout != DMME_IN_NHWC || d.out_layout != DMME_OUT_NCHW_F32) return false;
   if (d.ksize != 3 || d.stride != 1 || d.upsample || d.c1 || d.rc0 || d.rc1 || d.temb || d.addend) return false;
+  if (d.sampler && d.sampler->kind == DMME_SAMPLER_IDDPM && (d.cout & 1)) return false;
   if (d.c0 <= 0 || d.c0 % 64 || d.c0 > 256) return false;  // 9 * cin/64 resident weight tiles of 2 KB
   if (d.cout < 1 || d.cout > 8) return false;
   if (d.w_in != 8 && d.w_in != 16 && d.w_in != 32) return false;
@@ -205,7 +266,7 @@ static int launch_out_tc(const ConvOutTcParams& p, int smem, int grid, cudaStrea
 
 int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   DMME_REQUIRE(conv_out_tc_supported(d), DMME_E_SHAPE, "conv_out_tc: unsupported shape/layout");
-  DMME_REQUIRE(d.src0 && d.weight && d.out, DMME_E_BADARG, "conv_out_tc: null src0/weight/out");
+  DMME_REQUIRE(d.src0 && d.weight && (d.out || d.sampler), DMME_E_BADARG, "conv_out_tc: null src0/weight/out");
   ConvOutTcParams p;
   memset(&p, 0, sizeof(p));
   p.chunks = d.c0 / 64;
@@ -216,6 +277,18 @@ int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   p.cout = d.cout;
   p.bias = d.bias;
   p.out = static_cast<float*>(d.out);
+  if (d.sampler && d.sampler->kind != DMME_SAMPLER_NONE) {
+    const dmme_sampler_epilogue& s = *d.sampler;
+    DMME_REQUIRE(s.kind >= DMME_SAMPLER_DDPM && s.kind <= DMME_SAMPLER_IDDPM, DMME_E_BADARG, "conv_out_tc: unknown sampler kind %d", s.kind);
+    DMME_REQUIRE(s.x && s.alpha_bar && s.t_ptr && s.table_len > 0, DMME_E_BADARG, "conv_out_tc: sampler epilogue needs x, alpha_bar, t_ptr");
+    DMME_REQUIRE(s.kind == DMME_SAMPLER_DDIM ? (s.tau && s.tau_len > 0) : (s.beta && s.alpha), DMME_E_BADARG,
+                 "conv_out_tc: sampler epilogue tables missing");
+    DMME_REQUIRE(s.noise_offset % 4 == 0 && (static_cast<long long>(d.h_in) * d.w_in) % 4 == 0, DMME_E_BADARG,
+                 "conv_out_tc: noise_offset / image size must be multiples of 4");
+    p.samp_kind = s.kind; p.x = s.x; p.noise = s.noise;
+    p.beta = s.beta; p.alpha = s.alpha; p.alpha_bar = s.alpha_bar; p.t_ptr = s.t_ptr; p.tau = s.tau;
+    p.table_len = s.table_len; p.tau_len = s.tau_len; p.seed = s.seed; p.goff = s.noise_offset / 4;
+  }
   // the halo tile is (rt + 2) padded rows behind one slack row.  The MMA's 128 positions reach up to 2 * (W + 2) + 130
   // rows from the slot start: positions past the tile's rt rows are junk lanes that are never stored, and what they
   // read (the next slot or the resident weights) lies inside this CTA's shared memory

@@ -32,8 +32,14 @@ struct SplitFinishParams {
   NormOut no[2];
 };
 
-constexpr int kFinishWarps = 8;
+constexpr int kFinishWarps = 16;
+constexpr int kMaxSplit = 16;  // conv_tc.cu splitk_plan never splits further
 
+// PPT: pixels per thread (hw <= 16 * PPT).  A warp covers the 32 channels of one pixel (128 contiguous bytes of every K
+// slice); its pixels are px = warp, warp + 16, ...  All K slices of a pixel are requested before the first is used (one
+// L2 round trip per pixel instead of one per slice pair: the pass is pure latency), and the finished values stay in
+// registers for the GroupNorm pass.
+template <int PPT>
 __global__ void __launch_bounds__(kFinishWarps * 32) splitk_finish_kernel(const SplitFinishParams p) {
   __shared__ float red1[kFinishWarps][32], red2[kFinishWarps][32];
   __shared__ float ch1[32], ch2[32];
@@ -41,7 +47,7 @@ __global__ void __launch_bounds__(kFinishWarps * 32) splitk_finish_kernel(const 
   const int n = blockIdx.x / slabs;
   const int slab = blockIdx.x - n * slabs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = slab * 32 + lane;  // this thread's channel: a warp covers 32 contiguous channels of one pixel
+  const int c = slab * 32 + lane;  // this thread's channel
   pdl_trigger();
   pdl_wait();  // the partial tiles come from the split-K GEMM launched just before
 
@@ -49,31 +55,30 @@ __global__ void __launch_bounds__(kFinishWarps * 32) splitk_finish_kernel(const 
   if (p.temb) add += __ldg(p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : n) * p.temb_ld + c);
   const long long img0 = static_cast<long long>(n) * p.hw;
 
-  // ---- pass 1: sum the K slices, epilogue terms, raw bf16 store, per-channel sums of the STORED values ----
+  // ---- pass 1: sum the K slices (fixed order: deterministic), epilogue terms, raw bf16 store, sums of the STORED values
+  float rf[PPT];
   float s1 = 0.f, s2 = 0.f;
-  for (int px = warp; px < p.hw; px += kFinishWarps) {
-    const long long o = (img0 + px) * p.cout + c;
-    // fixed summation order (deterministic); eight independent loads in flight per round trip
-    float v = add;
-    const float* __restrict__ pp = p.partial + o;
-    int s = 0;
-    for (; s + 8 <= p.split; s += 8) {
-      float a[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = __ldg(pp + (s + j) * p.split_stride);
-      v += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  for (int i = 0; i < PPT; ++i) {
+    const int px = warp + i * kFinishWarps;
+    rf[i] = 0.f;
+    if (px < p.hw) {
+      const long long o = (img0 + px) * p.cout + c;
+      const float* __restrict__ pp = p.partial + o;
+      float a[kMaxSplit];
+#pragma unroll
+      for (int j = 0; j < kMaxSplit; ++j) a[j] = j < p.split ? __ldg(pp + j * p.split_stride) : 0.f;
+      const float ad = p.addend ? __bfloat162float(p.addend[o]) : 0.f;
+      float v = add;
+#pragma unroll
+      for (int j = 0; j < kMaxSplit; j += 4) v += (a[j] + a[j + 1]) + (a[j + 2] + a[j + 3]);
+      v += ad;
+      const __nv_bfloat16 r = __float2bfloat16_rn(v);
+      p.out[o] = r;
+      rf[i] = __bfloat162float(r);
+      s1 += rf[i];
+      s2 = fmaf(rf[i], rf[i], s2);
     }
-    for (; s + 2 <= p.split; s += 2) {
-      const float a0 = __ldg(pp + s * p.split_stride), a1 = __ldg(pp + (s + 1) * p.split_stride);
-      v += a0 + a1;
-    }
-    if (s < p.split) v += __ldg(pp + s * p.split_stride);
-    if (p.addend) v += __bfloat162float(p.addend[o]);
-    const __nv_bfloat16 r = __float2bfloat16_rn(v);
-    p.out[o] = r;
-    const float rf = __bfloat162float(r);
-    s1 += rf;
-    s2 = fmaf(rf, rf, s2);
   }
   red1[warp][lane] = s1;
   red2[warp][lane] = s2;
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(kFinishWarps * 32) splitk_finish_kernel(const 
       }
     }
   }
+  if (p.no[0].out == nullptr && p.no[1].out == nullptr) return;
   __syncthreads();
 
   // ---- pass 2: the consumers' GroupNorm(+SiLU) of the stored tensor ----
@@ -120,11 +126,14 @@ __global__ void __launch_bounds__(kFinishWarps * 32) splitk_finish_kernel(const 
       aa *= sc;
       bb = bb * sc + sh;
     }
-    for (int px = warp; px < p.hw; px += kFinishWarps) {
-      const long long o = (img0 + px) * p.cout + c;
-      float y = fmaf(__bfloat162float(p.out[o]), aa, bb);  // this thread's own store of pass 1
-      if (q.silu) y = silu_f(y);
-      q.out[o] = __float2bfloat16_rn(y);
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int px = warp + i * kFinishWarps;
+      if (px < p.hw) {
+        float y = fmaf(rf[i], aa, bb);
+        if (q.silu) y = silu_f(y);
+        q.out[(img0 + px) * p.cout + c] = __float2bfloat16_rn(y);
+      }
     }
   }
 }
@@ -152,9 +161,13 @@ int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream) 
     p.no[k].ss_rows = s.ss_rows; p.no[k].ss_ld = s.ss_ld; p.no[k].cpg = s.cpg; p.no[k].silu = s.silu; p.no[k].eps = s.eps;
     DMME_REQUIRE(s.scale == nullptr || s.shift != nullptr, DMME_E_BADARG, "conv split-K finish: scale without shift");
   }
-  const int grid = d.n * (d.cout / 32);
-  return check_launch_err(launch_pdl(splitk_finish_kernel, dim3(grid), dim3(kFinishWarps * 32), 0, stream, p),
-                          "splitk_finish_kernel");
+  DMME_REQUIRE(split >= 2 && split <= kMaxSplit && p.hw <= 256, DMME_E_SHAPE, "conv split-K finish: split %d / %d pixels per image", split, p.hw);
+  const dim3 grid(d.n * (d.cout / 32)), block(kFinishWarps * 32);
+  cudaError_t e;
+  if (p.hw <= 16) e = launch_pdl(splitk_finish_kernel<1>, grid, block, 0, stream, p);
+  else if (p.hw <= 64) e = launch_pdl(splitk_finish_kernel<4>, grid, block, 0, stream, p);
+  else e = launch_pdl(splitk_finish_kernel<16>, grid, block, 0, stream, p);
+  return check_launch_err(e, "splitk_finish_kernel");
 }
 
 }  // namespace dmme

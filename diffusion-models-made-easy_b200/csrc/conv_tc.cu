@@ -952,7 +952,7 @@ static SplitPlan splitk_plan(const dmme_conv_desc& d) {
   if (g_splitk_mode == 0 || !conv_tc_supported(d)) return none;
   if (d.ksize != 3 || d.upsample || d.out_layout != DMME_OUT_NHWC || d.cout % 128) return none;
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
-  if (wo > 128 || (ho * wo) > 256) return none;  // whole images per finishing CTA; the 16x16 level and below
+  if (wo > 8 || (ho * wo) > 64) return none;  // the 8x8 level and below (measured: at 16x16 GEMM + finish only ties the unsplit conv + norm)
   const long long total_pix = static_cast<long long>(d.n) * ho * wo;
   if (total_pix * d.cout > (1ll << 26)) return none;
   const int sm = device_sm_count();

@@ -4,44 +4,9 @@
 // bit-identical to torch on the CPU.  Schedule scalars are read from device tables at index *t_ptr,
 // so a captured CUDA graph of one step can be replayed for every t with no host work.
 #include "common.cuh"
+#include "sampler.cuh"
 
 namespace dmme {
-
-// ---- Philox4x32-10 -----------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-// schedule-table index: negative values wrap like torch indexing (table[-1] is the last entry), anything still outside
-// [0, len) is clamped -- a replayed CUDA graph cannot raise; the eager wrappers raise IndexError on the host instead
-__device__ __forceinline__ long long table_index(long long t, int len) {
-  if (t < 0) t += len;
-  return t < 0 ? 0 : (t >= len ? len - 1 : t);
-}
-__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x) + 0.5f) * 2.3283064365386963e-10f; }
-// four standard normals for element group g of stream sid
-__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long sid, unsigned long long g) {
-  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32),
-                                           static_cast<uint32_t>(sid), static_cast<uint32_t>(sid >> 32)),
-                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-  float4 z;
-  float s, c;
-  float rad = sqrtf(-2.0f * logf(u01(r.x)));
-  sincospif(2.0f * u01(r.y), &s, &c);
-  z.x = rad * c; z.y = rad * s;
-  rad = sqrtf(-2.0f * logf(u01(r.z)));
-  sincospif(2.0f * u01(r.w), &s, &c);
-  z.z = rad * c; z.w = rad * s;
-  return z;
-}
 
 __global__ void philox_normal_kernel(float* __restrict__ out, long long numel, unsigned long long seed,
                                      unsigned long long sid, unsigned long long goff) {
@@ -62,13 +27,9 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
                                  long long numel, unsigned long long seed, unsigned long long goff) {
   pdl_trigger();
   pdl_wait();
-  const long long t = *t_ptr;
-  const long long ti = table_index(t, table_len);
-  const float b = beta[ti], a = alpha[ti], ab = alpha_bar[ti];
-  const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
-  const float c2 = __fdiv_rn(b, __fsqrt_rn(__fsub_rn(1.0f, ab)));
-  const float sd = __fsqrt_rn(b);
-  const bool last = (t == 1);
+  const DdpmScalars sc = ddpm_scalars(beta, alpha, alpha_bar, t_ptr, table_len);
+  const long long t = sc.t;
+  const bool last = sc.last;
   const long long groups = (numel + 3) / 4;
   for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups;
        g += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -81,9 +42,7 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
     for (int j = 0; j < 4; ++j) {
       const long long i = g * 4 + j;
       if (i < numel) {
-        const float mean = __fmul_rn(c1, __fsub_rn(x[i], __fmul_rn(c2, eps[i])));
-        const float z = noise ? noise[i] : zz[j];
-        x[i] = last ? mean : __fadd_rn(__fmul_rn(z, sd), mean);
+        x[i] = ddpm_update(x[i], eps[i], noise ? noise[i] : zz[j], sc);
       }
     }
   }
@@ -93,15 +52,10 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
 __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
                                  const float* __restrict__ alpha_bar, const int64_t* __restrict__ tau,
                                  const int64_t* __restrict__ i_ptr, int table_len, int tau_len, long long numel) {
-  const long long i = *i_ptr;
-  const float ab_i = alpha_bar[table_index(tau[table_index(i, tau_len)], table_len)];
-  const float ab_p = alpha_bar[table_index(tau[table_index(i - 1, tau_len)], table_len)];
-  const float s1 = __fsqrt_rn(__fsub_rn(1.0f, ab_i));
-  const float sp = __fsqrt_rn(ab_p);
+  const DdimScalars sc = ddim_scalars(alpha_bar, tau, i_ptr, table_len, tau_len);
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < numel;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float x0 = __fdiv_rn(__fsub_rn(x[e], __fmul_rn(s1, eps[e])), sp);
-    x[e] = __fmul_rn(sp, x0);
+    x[e] = ddim_update(x[e], eps[e], sc);
   }
 }
 
@@ -110,14 +64,9 @@ __global__ void iddpm_step_kernel(float* __restrict__ x, const float* __restrict
                                   const float* __restrict__ beta, const float* __restrict__ alpha,
                                   const float* __restrict__ alpha_bar, const int64_t* __restrict__ t_ptr, int table_len,
                                   int n, int c, int hw, unsigned long long seed, unsigned long long goff) {
-  const long long t = *t_ptr;
-  const long long ti = table_index(t, table_len), tp = table_index(t - 1, table_len);
-  const float b = beta[ti], a = alpha[ti], ab = alpha_bar[ti], abp = alpha_bar[tp];
-  const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(a));
-  const float c2 = __fdiv_rn(b, __fsqrt_rn(__fsub_rn(1.0f, ab)));
-  const float bt = __fmul_rn(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)), b);
-  const float log_b = logf(b), log_bt = logf(fmaxf(bt, 1e-12f));
-  const bool last = (t == 1);
+  const IddpmScalars sc = iddpm_scalars(beta, alpha, alpha_bar, t_ptr, table_len);
+  const long long t = sc.t;
+  const bool last = sc.last;
   const long long numel = static_cast<long long>(n) * c * hw;
   const long long groups = (numel + 3) / 4;
   for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups;
@@ -135,10 +84,7 @@ __global__ void iddpm_step_kernel(float* __restrict__ x, const float* __restrict
         const long long ch = nc % c, ni = nc / c;
         const float e = mo[(ni * 2 * c + ch) * hw + l];
         const float v = mo[(ni * 2 * c + c + ch) * hw + l];
-        const float var = expf(__fadd_rn(__fmul_rn(v, log_b), __fmul_rn(__fsub_rn(1.0f, v), log_bt)));
-        const float mean = __fmul_rn(c1, __fsub_rn(x[i], __fmul_rn(c2, e)));
-        const float z = noise ? noise[i] : zz[j];
-        x[i] = last ? mean : __fadd_rn(__fmul_rn(z, __fsqrt_rn(var)), mean);
+        x[i] = iddpm_update(x[i], e, v, noise ? noise[i] : zz[j], sc);
       }
     }
   }

@@ -25,7 +25,7 @@ CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO = 0, 1, 2, 3
 EXPORTS = (
     "dmme_abi_version", "dmme_has_experimental", "dmme_last_error", "dmme_launch_count", "dmme_reset_launch_count",
     "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
-    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_conv2d_splitk_workspace", "dmme_set_conv_splitk_mode", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
+    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_conv2d_splitk_workspace", "dmme_conv2d_fuses_sampler", "dmme_set_conv_splitk_mode", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode", "dmme_set_conv_halo_multicast",
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
@@ -45,6 +45,20 @@ class OutNorm(C.Structure):
     ]
 
 
+SAMPLER_NONE, SAMPLER_DDPM, SAMPLER_DDIM, SAMPLER_IDDPM = 0, 1, 2, 3
+
+
+class SamplerEpilogue(C.Structure):
+    """Mirror of ``struct dmme_sampler_epilogue``."""
+
+    _fields_ = [
+        ("kind", C.c_int), ("x", C.c_void_p), ("noise", C.c_void_p),
+        ("beta", C.c_void_p), ("alpha", C.c_void_p), ("alpha_bar", C.c_void_p),
+        ("t_ptr", C.c_void_p), ("tau", C.c_void_p), ("table_len", C.c_int), ("tau_len", C.c_int),
+        ("seed", C.c_ulonglong), ("noise_offset", C.c_ulonglong),
+    ]
+
+
 class ConvDesc(C.Structure):
     """Mirror of ``struct dmme_conv_desc``."""
 
@@ -60,6 +74,7 @@ class ConvDesc(C.Structure):
         ("in_layout", C.c_int), ("out_layout", C.c_int), ("act_dtype", C.c_int), ("kernel", C.c_int),
         ("gn_ab", C.c_void_p), ("gn_silu", C.c_int),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_longlong), ("out_norm", OutNorm * 2),
+        ("sampler", C.POINTER(SamplerEpilogue)),
     ]
 
 
@@ -91,6 +106,7 @@ def load() -> C.CDLL:
     lib.dmme_groupnorm_fwd.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, i, vp, i, vp, vp, vp]
     lib.dmme_groupnorm_coeff.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp, i, i, vp, vp]
     lib.dmme_conv2d_fuses_gn.argtypes = [C.POINTER(ConvDesc)]
+    lib.dmme_conv2d_fuses_sampler.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_conv2d_splitk_workspace.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_conv2d_splitk_workspace.restype = ll
     lib.dmme_set_conv_splitk_mode.argtypes = [i]

@@ -45,8 +45,15 @@ class DDIM(DDPM):
         with torch.cuda.device(self.beta.device):
             x = x_tau_i.detach().to(self.beta.device).float().contiguous().clone()
             t_model = ops.gather_i64(self.tau, i, torch.empty(1, dtype=torch.int64, device=x.device))
-            eps = self._model_out(x, t_model)
-            return ops.ddim_step_(x, eps, self.alpha_bar, self.tau, i)
+            return self._denoise_(x, t_model, i, None, 0)
+
+    _sampler_kind = 2  # dmme_b200._lib.SAMPLER_DDIM
+
+    def _update_(self, x: Tensor, model_out: Tensor, noise: Optional[Tensor], i: Tensor, seed: int) -> Tensor:
+        return ops.ddim_step_(x, model_out, self.alpha_bar, self.tau, i)
+
+    def _sampler_epilogue(self, x: Tensor, noise: Optional[Tensor], i: Tensor, seed: int):
+        return ops.sampler_epilogue(self._sampler_kind, x, i, self.alpha_bar, None, None, self.tau)
 
     def _counter_start(self) -> int:
         return self.sub_timesteps
@@ -60,6 +67,5 @@ class DDIM(DDPM):
             t_model = torch.empty(1, dtype=torch.int64, device=x.device)  # stable address across graph replays
             self.__dict__["_t_model"] = t_model
         ops.gather_i64(self.tau, counter, t_model)
-        eps = self._model_out(x, t_model)
-        ops.ddim_step_(x, eps, self.alpha_bar, self.tau, counter)
+        self._denoise_(x, t_model, counter, None, seed)
         ops.add_i64_(counter, -1)

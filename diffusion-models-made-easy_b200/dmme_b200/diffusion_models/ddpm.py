@@ -74,6 +74,25 @@ class DDPM(nn.Module):
         return ops.ddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed,
                               getattr(self, "_noise_offset", 0))
 
+    _sampler_kind = 1  # dmme_b200._lib.SAMPLER_DDPM
+
+    def _sampler_epilogue(self, x: Tensor, noise: Optional[Tensor], t: Tensor, seed: int):
+        """The same update as ``_update_`` as an epilogue of the UNet's output conv (eps never leaves the registers)."""
+        return ops.sampler_epilogue(self._sampler_kind, x, t, self.alpha_bar, self.beta, self.alpha, None, noise, seed,
+                                    getattr(self, "_noise_offset", 0))
+
+    def _denoise_(self, x: Tensor, t_model: Tensor, t: Tensor, noise: Optional[Tensor], seed: int) -> Tensor:
+        """x_t -> x_{t-1} in place: the network at ``t_model`` followed by this sampler's update at step ``t``."""
+        raw = getattr(self.model, "forward_raw", None)
+        if raw is not None and x.shape[1] * x.shape[2] * x.shape[3] % 4 == 0:
+            spec = self._sampler_epilogue(x, noise, t, seed)  # keeps raw pointers: alive until the launch below returned
+            out = raw(x, t_model, sampler=spec)
+            if self.model.engine.sampler_applied:
+                return x
+        else:
+            out = self._model_out(x, t_model)
+        return self._update_(x, out, noise, t, seed)
+
     def sampling_step(self, x_t: Tensor, t: Tensor, noise: Optional[Tensor] = None) -> Tensor:
         r"""Denoise by sampling from :math:`p_\theta(x_{t-1}|x_t)`.
 
@@ -85,10 +104,9 @@ class DDPM(nn.Module):
         t = self._check_step_index(t)
         with torch.cuda.device(self.beta.device):
             x = x_t.detach().to(self.beta.device).float().contiguous().clone()
-            out = self._model_out(x, t)
             if noise is None:
                 noise = torch.randn_like(x)
-            return self._update_(x, out, noise.to(x.device).float().contiguous(), t, 0)
+            return self._denoise_(x, t, t, noise.to(x.device).float().contiguous(), 0)
 
     # ------------------------------------------------------------------------------------------
     def _counter_start(self) -> int:
@@ -99,8 +117,7 @@ class DDPM(nn.Module):
 
     def _graph_step(self, x: Tensor, counter: Tensor, seed: int) -> None:
         """One denoising step on device-resident state; everything launched here is graph-capturable."""
-        out = self._model_out(x, counter)
-        self._update_(x, out, None, counter, seed)
+        self._denoise_(x, counter, counter, None, seed)
         ops.add_i64_(counter, -1)
 
     def _run_steps(self, x: Tensor, steps: int, seed: int, graph: bool,

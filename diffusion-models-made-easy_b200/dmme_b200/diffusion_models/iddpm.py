@@ -44,6 +44,8 @@ class IDDPM(DDPM):
         return ops.iddpm_step_(x, model_out, noise, self.beta, self.alpha, self.alpha_bar, t, seed,
                                getattr(self, "_noise_offset", 0))
 
+    _sampler_kind = 3  # dmme_b200._lib.SAMPLER_IDDPM
+
     def forward_model(self, x_t: Tensor, t: Tensor, beta_t: Tensor, alpha_bar_t: Tensor,
                       alpha_bar_t_minus_one: Tensor) -> NoiseVariance:
         """(noise, variance) with the interpolated learned variance (diffusion_models/iddpm.py:150-164)."""

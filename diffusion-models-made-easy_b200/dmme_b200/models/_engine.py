@@ -71,6 +71,10 @@ class Engine:
         self._normed: Dict[Tuple[int, int], Tensor] = {}
         self._consumers: Optional[Dict[str, List[Tuple]]] = None
         self.fuse_out_norm = os.environ.get("DMME_FUSE_OUT_NORM", "1") != "0"
+        # sampler update applied by the output conv's epilogue (eps stays in registers); sampler_applied reports whether the
+        # last forward did it (the callers run the stand-alone update kernel otherwise)
+        self.fuse_sampler = os.environ.get("DMME_FUSE_SAMPLER", "1") != "0"
+        self.sampler_applied = False
 
     # -- caches ------------------------------------------------------------------------------
     def _cached(self, key: Tuple, versions: Tuple, build):
@@ -214,7 +218,7 @@ class Engine:
              res1: Optional[Tensor] = None, temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
              in_nchw: bool = False, out_layout: int = L.OUT_NHWC, act_dtype: Optional[torch.dtype] = None,
              addend_in_gemm: bool = False, gn_ab: Optional[Tensor] = None, gn_silu: bool = True,
-             consumers: Optional[List[Tuple]] = None):
+             consumers: Optional[List[Tuple]] = None, sampler=None):
         """``consumers``: [(norm module, first channel, channels of that norm, silu[, scale, shift])] reading this conv's
         output; when the conv runs split-K its finishing pass writes their GroupNorm(+SiLU) too (``self._normed``)."""
         cout, ks = conv.weight.shape[0], conv.weight.shape[2]
@@ -252,6 +256,11 @@ class Engine:
         dev = src0.device
         if out_layout == L.OUT_NCHW_F32:
             out = self.ws.get(name, (d.n, cout, ho, wo), torch.float32, dev)
+            if sampler is not None and self.fuse_sampler and temb is None and addend is None and ops.conv_fuses_sampler(d):
+                d.out = None  # eps is consumed in the epilogue and never written
+                ops.conv2d_launch(d, w, b, None, sampler=sampler)
+                self.sampler_applied = True
+                return out
             ops.conv2d_launch(d, w, b, out, temb, addend)
             return out
         if out_layout == L.OUT_QKV:
@@ -391,8 +400,12 @@ class Engine:
         return h2
 
     # -- whole network -------------------------------------------------------------------------
-    def forward(self, x: Tensor, c: Tensor, act_dtype: torch.dtype, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    def forward(self, x: Tensor, c: Tensor, act_dtype: torch.dtype, masks: Optional[Dict[str, Tensor]] = None,
+                sampler=None) -> Tensor:
+        """``sampler``: an ``ops.sampler_epilogue`` to apply in the output conv's epilogue when the kernel supports it
+        (``self.sampler_applied`` tells; the returned eps buffer is then NOT written)."""
         u = self.unet
+        self.sampler_applied = False
         L.require_cuda(x, c)
         if x.dtype != torch.float32:
             x = x.float()
@@ -437,4 +450,4 @@ class Engine:
             else:
                 h = self.conv(name, h, None, m.conv, upsample=True)
         a = self.gn("scratch.out_norm", u.output_conv[0], h, None, silu=True)
-        return self.conv("output_conv", a, None, u.output_conv[2], out_layout=L.OUT_NCHW_F32)
+        return self.conv("output_conv", a, None, u.output_conv[2], out_layout=L.OUT_NCHW_F32, sampler=sampler)

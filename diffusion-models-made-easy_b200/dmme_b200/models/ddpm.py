@@ -164,9 +164,11 @@ class _UNetBase(nn.Module):
             object.__setattr__(self, "_train_engine_obj", eng)
         return eng
 
-    def forward_raw(self, x: Tensor, c: Tensor, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    def forward_raw(self, x: Tensor, c: Tensor, masks: Optional[Dict[str, Tensor]] = None, sampler=None) -> Tensor:
         """Inference forward: returns the executor's own output buffer (overwritten by the next call).  No
-        autograd graph is recorded; use ``forward`` (with gradients enabled) for training."""
+        autograd graph is recorded; use ``forward`` (with gradients enabled) for training.
+        ``sampler``: optional ``ops.sampler_epilogue``; when ``self.engine.sampler_applied`` is True afterwards, the output
+        conv applied that update to ``x_t`` in its epilogue and the returned buffer was not written."""
         if not x.is_cuda:
             raise RuntimeError("dmme_b200.UNet runs on CUDA (sm_100a) only; there is no CPU path")
         with torch.no_grad(), torch.cuda.device(x.device):
@@ -174,7 +176,7 @@ class _UNetBase(nn.Module):
                 masks = self._dropout_masks(x.shape[0], x.device)
             eng = self.engine
             eng.force_generic = self.precision == "fp32"
-            return eng.forward(x.contiguous(), c.contiguous(), _PRECISIONS[self.precision], masks)
+            return eng.forward(x.contiguous(), c.contiguous(), _PRECISIONS[self.precision], masks, sampler)
 
     def forward(self, x: Tensor, c: Tensor) -> Tensor:
         r"""Predicts noise from x.

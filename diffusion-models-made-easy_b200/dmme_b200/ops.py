@@ -153,6 +153,26 @@ def groupnorm_coeff(stats0: Tensor, stats1: Optional[Tensor], c0: int, c1: int, 
     return ab
 
 
+def conv_fuses_sampler(desc: L.ConvDesc) -> bool:
+    """True when the kernel that would run ``desc`` can apply a sampler update in its epilogue (``sampler=``)."""
+    return bool(L.load().dmme_conv2d_fuses_sampler(C.byref(desc)))
+
+
+def sampler_epilogue(kind: int, x: Tensor, t: Tensor, alpha_bar: Tensor, beta: Optional[Tensor] = None,
+                     alpha: Optional[Tensor] = None, tau: Optional[Tensor] = None, noise: Optional[Tensor] = None,
+                     seed: int = 0, noise_offset: int = 0) -> L.SamplerEpilogue:
+    """One ``dmme_sampler_epilogue``: the DDPM / DDIM / IDDPM update of ``x`` (in place) applied by the output conv.
+    The struct holds raw pointers: the caller keeps the tensors alive until the launch has been issued."""
+    L.require_cuda(x, t, alpha_bar, beta, alpha, tau, noise)
+    s = L.SamplerEpilogue()
+    s.kind, s.x, s.noise = int(kind), ptr(x), ptr(noise)
+    s.beta, s.alpha, s.alpha_bar = ptr(beta), ptr(alpha), ptr(alpha_bar)
+    s.t_ptr, s.tau = ptr(t), ptr(tau)
+    s.table_len, s.tau_len = alpha_bar.numel(), tau.numel() if tau is not None else 0
+    s.seed, s.noise_offset = int(seed) & (2 ** 64 - 1), int(noise_offset)
+    return s
+
+
 def conv_splitk_workspace(desc: L.ConvDesc) -> int:
     """Bytes of fp32 workspace with which ``conv2d_launch(splitk_ws=)`` runs ``desc`` split-K (0: it would not split).
     Only the split-K path honours ``out_norms=``."""
@@ -185,9 +205,10 @@ def conv2d_launch(desc: L.ConvDesc, weight: Tensor, bias: Optional[Tensor], out:
                   temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
                   out2: Optional[Tensor] = None, out3: Optional[Tensor] = None, stats: Optional[Tensor] = None,
                   gn_ab: Optional[Tensor] = None, gn_silu: bool = True, splitk_ws: Optional[Tensor] = None,
-                  out_norms=()) -> None:
+                  out_norms=(), sampler: Optional[L.SamplerEpilogue] = None) -> None:
     """Launch one fused convolution described by ``desc`` (see include/dmme_b200.h)."""
     desc.weight, desc.bias = ptr(weight), ptr(bias)
+    desc.sampler = C.pointer(sampler) if sampler is not None else None
     desc.splitk_ws = ptr(splitk_ws)
     desc.splitk_ws_bytes = splitk_ws.numel() * splitk_ws.element_size() if splitk_ws is not None else 0
     for k in range(2):

@@ -81,6 +81,26 @@ typedef struct dmme_out_norm {
   float eps;
 } dmme_out_norm;
 
+/*
+ * Sampler update fused into the OUTPUT conv's epilogue (models/ddpm.py:277 followed by the tail of
+ * DDPM.sampling_step diffusion_models/ddpm.py:94-110, DDIM.sampling_step diffusion_models/ddim.py:55-77 or
+ * IDDPM.sampling_step diffusion_models/iddpm.py:118-164): eps (and v) never leave the registers, x_t is updated in
+ * place, the noise is drawn in the epilogue (Philox4x32-10 keyed by (seed, t, element index), the same draws as
+ * dmme_ddpm_step) or read from `noise`.  Same arithmetic, same bits as the stand-alone dmme_*_step kernels.
+ * Output-conv tcgen05 kernel only: ask dmme_conv2d_fuses_sampler.
+ */
+enum { DMME_SAMPLER_NONE = 0, DMME_SAMPLER_DDPM = 1, DMME_SAMPLER_DDIM = 2, DMME_SAMPLER_IDDPM = 3 };
+typedef struct dmme_sampler_epilogue {
+  int kind;                           /* DMME_SAMPLER_* */
+  float* x;                           /* x_t, NCHW fp32 [n][C][h][w], updated in place (C = cout, IDDPM: cout / 2) */
+  const float* noise;                 /* optional injected standard normals shaped like x (NULL: in-kernel Philox) */
+  const float* beta; const float* alpha; const float* alpha_bar; /* schedule tables of length table_len */
+  const int64_t* t_ptr;               /* device scalar: t (DDPM / IDDPM) or the sub-sequence index i (DDIM) */
+  const int64_t* tau;                 /* DDIM: int64 [tau_len] */
+  int table_len, tau_len;
+  unsigned long long seed, noise_offset;
+} dmme_sampler_epilogue;
+
 typedef struct dmme_conv_desc {
   const void* src0; const void* src1; /* NHWC activations (or NCHW fp32 image when in_layout says so) */
   int c0, c1;                         /* channels of src0 / src1 (c1 = 0: no concat) */
@@ -120,6 +140,8 @@ typedef struct dmme_conv_desc {
                                          bias / temb / addend, writes `out` and `stats` and applies out_norm[] */
   long long splitk_ws_bytes;
   dmme_out_norm out_norm[2];          /* optional fused GroupNorm(+SiLU) of the output for up to two consumers */
+  const dmme_sampler_epilogue* sampler; /* optional fused sampler update (output conv); `out` may then be NULL: eps is
+                                         not written at all */
 } dmme_conv_desc;
 
 /* library / device ------------------------------------------------------------------------- */
@@ -173,6 +195,8 @@ int dmme_conv2d_uses_tc(const dmme_conv_desc* desc);
 int dmme_conv2d_writes_stats(const dmme_conv_desc* desc);
 /* 1 when the kernel dmme_conv2d_fwd would run for this descriptor can apply desc->gn_ab (fused GroupNorm of the input) */
 int dmme_conv2d_fuses_gn(const dmme_conv_desc* desc);
+/* 1 when the kernel dmme_conv2d_fwd would run for this descriptor can apply desc->sampler in its epilogue */
+int dmme_conv2d_fuses_sampler(const dmme_conv_desc* desc);
 /* bytes of fp32 workspace (desc->splitk_ws) with which dmme_conv2d_fwd runs this descriptor split-K, 0 when it would not
  * (enough work units without splitting, or a shape / layout the split-K kernel does not take).  desc->out_norm[] is only
  * honoured on the split-K path. */

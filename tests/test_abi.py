@@ -53,7 +53,7 @@ def test_conv_desc_struct_matches_header_field_order():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(void|float|int|long long|dmme_out_norm)\s*\*?\s*", "", decl)
+        decl = re.sub(r"^(const\s+)?(void|float|int|long long|dmme_out_norm|dmme_sampler_epilogue)\s*\*?\s*", "", decl)
         names += [re.sub(r"\[\d+\]$", "", n.strip().lstrip("*").strip()) for n in decl.split(",")]
     assert names == [f[0] for f in _lib.ConvDesc._fields_]
     # the nested dmme_out_norm mirrors its header declaration too, and both structs have the C compiler's size
@@ -67,7 +67,8 @@ def test_conv_desc_struct_matches_header_field_order():
             names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
     assert names == [f[0] for f in _lib.OutNorm._fields_]
     import ctypes
-    assert ctypes.sizeof(_lib.OutNorm) == 64 and ctypes.sizeof(_lib.ConvDesc) == 200 + 2 * 64
+    assert ctypes.sizeof(_lib.OutNorm) == 64 and ctypes.sizeof(_lib.ConvDesc) == 200 + 2 * 64 + 8
+    assert ctypes.sizeof(_lib.SamplerEpilogue) == 88
 
 
 def test_cpu_tensors_are_refused_loudly():

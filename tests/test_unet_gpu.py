@@ -279,3 +279,35 @@ def test_ddpm_graph_step_timed_batch_matches_oracle_subset():
     errs = [rel_l2(a, b) for a, b in zip(seen, traj)]
     print("ddpm graph step at batch 256, 16-image subset, rel-L2 per step:", ["%.3e" % e for e in errs])
     assert max(errs) < BF16_TOL
+
+
+@pytest.mark.parametrize("kind", ["ddpm_philox", "ddpm_injected", "ddpm_last_step", "ddim", "iddpm_philox", "iddpm_injected"])
+def test_sampler_update_in_output_conv_epilogue_is_bit_exact(kind):
+    """the sampler update applied by the output conv's epilogue (eps / v still in registers, x_t updated in place, noise
+    drawn in the epilogue) == output conv writing eps + the stand-alone dmme_*_step kernel, bit for bit"""
+    from dmme_b200 import DDIM, DDPM, IDDPM
+    flavour = "iddpm" if kind.startswith("iddpm") else "ddpm"
+    m, _ = _unet(flavour)
+    d = {"ddpm": DDPM, "ddim": DDIM, "iddpm": IDDPM}[kind.split("_")[0]](m).to(DEV)
+    g = torch.Generator().manual_seed(31)
+    x0 = torch.randn(5, 3, 32, 32, generator=g).to(DEV)
+    z = torch.randn(5, 3, 32, 32, generator=g).to(DEV) if kind.endswith("injected") else None
+    if kind == "ddim":
+        i = torch.tensor([37], device=DEV)
+        t_model = d.tau[i].clone()
+        t = i
+    else:
+        t = torch.tensor([1 if kind == "ddpm_last_step" else 640], device=DEV)
+        t_model = t
+    outs = []
+    with torch.cuda.device(0):
+        for fuse in (True, False):
+            m.engine.fuse_sampler = fuse
+            x = x0.clone()
+            d._denoise_(x, t_model, t, z, 1234)
+            assert m.engine.sampler_applied == fuse
+            outs.append(x.clone())
+    m.engine.fuse_sampler = True
+    assert torch.isfinite(outs[0]).all()
+    assert not torch.equal(outs[0], x0)
+    assert torch.equal(outs[0], outs[1])
