@@ -40,6 +40,16 @@ __device__ __forceinline__ float dsilu_f(float z) {
   const float s = 1.0f / (1.0f + expf(-z));
   return s * (1.0f + z * (1.0f - s));
 }
+// bf16 paths: sigmoid(z) = 0.5 + 0.5 tanh(z / 2) with tanh.approx (one MUFU, rel. error 2^-11, far below the bf16 rounding
+// of the gradient it multiplies).  exp + full-precision division cost ~25 instructions per call and made the GroupNorm
+// backward slab kernel -- which evaluates it twice per element at 8 warps per SM -- instruction-bound (210 us for a 100 MB
+// layer).
+__device__ __forceinline__ float dsilu_fast(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  const float s = fmaf(0.5f, t, 0.5f);
+  return s * fmaf(z, 1.0f - s, 1.0f);
+}
 
 // ------------------------------------------------------------------------------------------------
 // strided batched product  C[b](i,j) = alpha * sum_k A[b](i,k) B[b](k,j)  (+ C[b](i,j) when accumulate)
@@ -513,6 +523,69 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
   }
 }
 
+// Weight gradient of the OUTPUT conv (models/ddpm.py:277: 128 -> 3 / 6 channels, 3x3): grad_out is the fp32 NCHW image-space
+// gradient, a handful of channels wide, so the generic 64 x 64 tiling above wastes 90% of its tile (1.7 ms per step).
+// Here thread = input channel, one CTA per image: the image's grad_out (cout planes with a zero halo) sits in shared
+// memory, every activation value is loaded once (coalesced, 2 B) and feeds 9 taps x cout FMAs against broadcast
+// shared-memory reads; the CTA writes its [cout][kp] partial (slice = image) for wgrad_reduce_kernel.
+//   dW[co][ci][r][s] = sum over input pixels (y, x) of a[y][x][ci] * g[co][y - r + 1][x - s + 1]
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const WgradParams p) {
+  extern __shared__ float gs[];  // [COUT][h + 2][w + 4]: zero halo, rows padded to a multiple of 4 floats
+  const int h = p.h_in, w = p.w_in, ws = w + 4, plane = (h + 2) * ws;
+  const int n = blockIdx.x;
+  const int ci = threadIdx.x;  // blockDim.x == c0
+  for (int i = threadIdx.x; i < COUT * plane; i += blockDim.x) gs[i] = 0.f;
+  __syncthreads();
+  const float* g = static_cast<const float*>(p.g) + static_cast<long long>(n) * COUT * h * w;
+  for (int i = threadIdx.x; i < COUT * h * w; i += blockDim.x) {
+    const int co = i / (h * w), rem = i - co * h * w, y = rem / w, x = rem - y * w;
+    gs[co * plane + (y + 1) * ws + x + 1] = g[i];
+  }
+  __syncthreads();
+  float acc[9][COUT];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[t][co] = 0.f;
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(p.src0) + static_cast<long long>(n) * h * w * p.c0 + ci;
+  for (int y = 0; y < h; ++y) {
+    for (int x = 0; x < w; ++x) {
+      const float av = __bfloat162float(a[static_cast<long long>(y * w + x) * p.c0]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        // output row y - r + 1 -> halo row y - r + 2; output columns x - s + 1 -> halo columns x + 2 - s, s = 0..2
+        const float* row = gs + (y - r + 2) * ws + x;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          const float g2 = row[co * plane + 2], g1 = row[co * plane + 1], g0 = row[co * plane];
+          acc[r * 3 + 0][co] = fmaf(av, g2, acc[r * 3 + 0][co]);
+          acc[r * 3 + 1][co] = fmaf(av, g1, acc[r * 3 + 1][co]);
+          acc[r * 3 + 2][co] = fmaf(av, g0, acc[r * 3 + 2][co]);
+        }
+      }
+    }
+  }
+  float* part = p.partial + static_cast<long long>(n) * COUT * p.kp;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) part[static_cast<long long>(co) * p.kp + t * p.c0 + ci] = acc[t][co];
+  // bias column k = 9 c0: sum of grad_out over the image
+  if (threadIdx.x < COUT) {
+    float t = 0.f;
+    const float* gp = g + static_cast<long long>(threadIdx.x) * h * w;
+    for (int i = 0; i < h * w; ++i) t += gp[i];
+    part[static_cast<long long>(threadIdx.x) * p.kp + 9 * p.c0] = t;
+  }
+}
+
+static bool conv_out_wgrad_supported(const dmme_conv_desc& d) {
+  return d.kernel != DMME_CONV_GENERIC && d.act_dtype == DMME_BF16 && d.out_layout == DMME_OUT_NCHW_F32 &&
+         d.in_layout == DMME_IN_NHWC && d.ksize == 3 && d.stride == 1 && !d.upsample && d.c1 == 0 && d.rc0 + d.rc1 == 0 &&
+         (d.cout == 3 || d.cout == 6) && d.c0 >= 32 && d.c0 <= 256 && d.c0 % 32 == 0 && d.h_in <= 32 && d.w_in <= 32;
+}
+
 // partial [slices][cout][kp] -> dW OIHW [cout][cin][taps], dWres [cout][rc], dbias [cout]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slices, int cout, int kp, int cin, int taps, int rc,
                                     float* __restrict__ dw, float* __restrict__ dwres, float* __restrict__ dbias) {
@@ -780,7 +853,7 @@ __global__ void __launch_bounds__(256, MAXV > 4 ? 1 : 2) gn_bwd_slab_kernel(cons
     for (int j = 0; j < 8; ++j) {
       xh[j] = fmaf(xf[j], ha[j], hb[j]);
       float gval = gf[j] * mk[j];
-      if (p.silu) gval *= dsilu_f(fmaf(xf[j], za[j], zb[j]));
+      if (p.silu) gval *= dsilu_fast(fmaf(xf[j], za[j], zb[j]));
       gz[j] = gval;
     }
   };
@@ -1173,6 +1246,7 @@ extern "C" long long dmme_conv2d_wgrad_workspace(const dmme_conv_desc* d) {
     // partials + the per-image pixel sums of grad_out for the bias gradient
     return (static_cast<long long>(tslices) * d->cout * kp + static_cast<long long>(d->n) * d->cout) * sizeof(float);
   }
+  if (conv_out_wgrad_supported(*d)) slices = slices > d->n ? slices : d->n;  // one slice per image
   return static_cast<long long>(slices) * d->cout * kp * sizeof(float);
 }
 
@@ -1217,6 +1291,16 @@ extern "C" int dmme_conv2d_wgrad(const dmme_conv_desc* d, const void* grad_out, 
   p.ksize = d->ksize; p.stride = d->stride; p.upsample = d->upsample; p.in_nchw = d->in_layout == DMME_IN_NCHW_F32;
   p.cout = d->cout; p.kp = kp; p.partial = static_cast<float*>(workspace); p.pix_per_slice = pps;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (conv_out_wgrad_supported(*d)) {
+    const int smem = d->cout * (d->h_in + 2) * (d->w_in + 4) * static_cast<int>(sizeof(float));
+    if (d->cout == 3) conv_out_wgrad_kernel<3><<<d->n, d->c0, smem, st>>>(p);
+    else conv_out_wgrad_kernel<6><<<d->n, d->c0, smem, st>>>(p);
+    int rc = check_launch("conv_out_wgrad_kernel");
+    if (rc) return rc;
+    const long long total = static_cast<long long>(d->cout) * kp;
+    wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(p.partial, d->n, d->cout, kp, d->c0, 9, 0, dweight, nullptr, dbias);
+    return check_launch("wgrad_reduce_kernel");
+  }
   dim3 grid(ceil_div(kp, SG_N), ceil_div(d->cout, SG_M), slices);
   if (d->act_dtype == DMME_BF16) conv_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
   else conv_wgrad_kernel<float><<<grid, 256, 0, st>>>(p);
