@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) attn_generic_kernel(const AttnParams p) {
   const float inv = 1.0f / sum;
 
   // ---- P V ----
-  constexpr int kMaxCPerLane = 8;  // dh <= 256
+  constexpr int kMaxCPerLane = 16;  // dh <= 512 (the LSUN-256 UNet attends over 512 channels, configs/ddpm/lsun_bedroom.yaml:82-90)
   float acc[kMaxCPerLane];
 #pragma unroll
   for (int i = 0; i < kMaxCPerLane; ++i) acc[i] = 0.f;
@@ -162,7 +162,7 @@ extern "C" int dmme_attention_fwd(const void* q, const void* k, const void* v, l
       attn_mma_supported(act_dtype, heads, L, dh, row_stride, head_stride, batch_stride, v_transposed, q, k, v, out))
     return attn_mma_forward(q, k, v, batch_stride, row_stride, head_stride, n, heads, L, dh, scale, head_batch_swap, out,
                             nullptr, static_cast<cudaStream_t>(stream));
-  DMME_REQUIRE(dh <= 256, DMME_E_SHAPE, "attention: head dim %d > 256 not supported", dh);
+  DMME_REQUIRE(dh <= 512, DMME_E_SHAPE, "attention: head dim %d > 512 not supported", dh);
   const size_t smem = sizeof(float) * (static_cast<size_t>(kAttnRows) * dh + kAttnTile * (dh + 1) +
                                         static_cast<size_t>(kAttnRows) * L);
   DMME_REQUIRE(smem <= 200 * 1024, DMME_E_SHAPE, "attention: sequence length %d too long for the generic kernel", L);

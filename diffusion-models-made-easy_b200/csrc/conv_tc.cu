@@ -929,7 +929,7 @@ static int tct_tile_pixels(const dmme_conv_desc& d) {
   }
   if (g_tct_mode == 0) return 0;
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
-  if (d.cout % 128 || wo > 128) return 0;
+  if (d.cout % 128 || wo > 256) return 0;  // a tile is at least one run of 128 / 256 pixels of a row
   if (d.out_layout == DMME_OUT_QKV && ((d.cout / 3) % 128 || (ho * wo) % 8)) return 0;
   const long long total_pix = static_cast<long long>(d.n) * ho * wo;
   const int n_tiles = d.cout / 128;

@@ -277,6 +277,13 @@ TCT_CASES = [c for c in TC_CASES if c["cout"] % 128 == 0] + [
     dict(n=130, cin=256, cout=256, h=8, w=8, k=3, temb="rows"),        # 4 images per 256-pixel tile
     dict(n=200, cin=128, cout=256, h=4, w=4, k=3, addend=True, temb="rows"),  # 2 images per 32-pixel chunk
     dict(n=66, cin=128, cout=128, h=32, w=32, k=3, stride=2, temb="bcast"),
+    # LSUN-256 shapes (configs/ddpm/lsun_bedroom.yaml:78-90, batch 2): 256 / 128 / 64 pixel wide maps
+    dict(n=2, cin=128, cout=128, h=256, w=256, k=3, temb="bcast"),
+    dict(n=2, cin=256, cout=128, h=256, w=256, k=3, cin1=128, res=True),
+    dict(n=2, cin=128, cout=128, h=256, w=256, k=3, stride=2),
+    dict(n=2, cin=128, cout=128, h=128, w=128, k=3, addend=True),
+    dict(n=2, cin=128, cout=256, h=64, w=64, k=3, temb="rows"),
+    dict(n=1, cin=128, cout=128, h=256, w=256, k=1, addend=True),
 ]
 
 

@@ -311,3 +311,38 @@ def test_sampler_update_in_output_conv_epilogue_is_bit_exact(kind):
     assert torch.isfinite(outs[0]).all()
     assert not torch.equal(outs[0], x0)
     assert torch.equal(outs[0], outs[1])
+
+
+LSUN = dict(dropout=0.0, channels_per_depth=(128, 128, 256, 256, 512, 512), attention_depths=(5,))
+
+
+def test_lsun_unet_bf16_256x256():
+    """SURVEY par. 8f-3: the LSUN-256 UNet of configs/ddpm/lsun_bedroom.yaml:78-90 (6 depths, 128..512 channels, 256x256
+    maps down to 8x8, attention at depth 5, dropout 0 => `conv2.2` keys) at that config's batch 2, against the oracle"""
+    m, sd = _unet("ddpm", **LSUN)
+    assert "down_layers.0.conv2.2.weight" in sd and sum(v.numel() for k, v in sd.items() if "embeddings" not in k) > 90e6
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 256, 256, generator=g)
+    tt = torch.tensor([777])
+    want = O.unet_forward(sd, x, tt)
+    got = m(x.to(DEV), tt.to(DEV)).cpu()
+    err = rel_l2(got, want)
+    print(f"lsun unet bf16 256x256 batch 2: rel-L2 {err:.3e}")
+    assert err < BF16_TOL
+
+
+def test_lsun_ddpm_sampling_steps_256x256():
+    """three graph-replayed ancestral steps of the LSUN-256 model (T = 1000 .. 998) against the oracle on the same noise"""
+    from dmme_b200 import DDPM, ops
+    m, sd = _unet("ddpm", **LSUN)
+    d = DDPM(m).to(DEV)
+    x_T = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(6))
+    seed, steps = 11, 3
+    noises = _philox_noises(ops, x_T.shape, seed, [1000, 999, 998])
+    _, traj = O.ddpm_generate(sd, x_T, noises, O.linear_tables(1000), 1000, steps=steps, return_trajectory=True)
+    seen = []
+    with torch.cuda.device(0):
+        d._run_steps(x_T.to(DEV).clone(), steps, seed, True, lambda k, x: seen.append(x.cpu().clone()))
+    errs = [rel_l2(a, b) for a, b in zip(seen, traj)]
+    print("lsun ddpm steps rel-L2:", ["%.3e" % e for e in errs])
+    assert max(errs) < BF16_TOL
