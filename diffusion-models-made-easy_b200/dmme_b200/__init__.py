@@ -10,7 +10,8 @@ from . import models
 from . import diffusion_models
 from . import optim
 from . import training
+from . import guidance
 from .diffusion_models import DDPM, DDIM, IDDPM
 
 __all__ = ["DDPM", "DDIM", "IDDPM", "gaussian", "gaussian_like", "uniform_int", "pad", "norm", "denorm", "denorm_uint8", "equations", "models",
-           "diffusion_models", "optim", "training"]
+           "diffusion_models", "optim", "training", "guidance"]

@@ -331,6 +331,38 @@ def ddim_generate(sd: StateDict, x_T: Tensor, alpha_bar: Tensor, tau: Tensor, gr
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# classifier guidance (src/dmme/guidance/classifier.py) -- the reference module is unimportable (it needs dmme.ddpm / dmme.ddim,
+# which do not exist), so this restatement follows the file as written and is NOT pinned against a run of the reference:
+# PARITY UNPINNED for this part
+# ---------------------------------------------------------------------------------------------------------------------
+def classifier_grad(classifier, y: Tensor, x_t: Tensor, t: Tensor) -> Tensor:
+    """classifier.py:9-23: grad of log_softmax(classifier(x_t, t))[:, y].sum() w.r.t. x_t (a (B, B) selection, as written)."""
+    x = x_t.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        log_probs = F.log_softmax(classifier(x, t.float()), dim=1)
+        (g,) = torch.autograd.grad(log_probs[:, y].sum(), x)
+    return g
+
+
+def guided_ddpm_sample(model, classifier, y: Tensor, x_t: Tensor, t: Tensor, noise: Tensor, tables: Sequence[Tensor],
+                       scale: float = 10.0) -> Tensor:
+    """classifier.py:26-36: ancestral step (per-sample t), then x += scale * classifier_grad at the new x."""
+    beta, alpha, alpha_bar = tables
+    with torch.no_grad():
+        x = ddpm_mean(x_t, model(x_t, t), _col(beta, t), _col(alpha, t), _col(alpha_bar, t)) + torch.sqrt(_col(beta, t)) * noise
+    return x + scale * classifier_grad(classifier, y, x, t)
+
+
+def guided_ddim_sample(model, classifier, y: Tensor, x_t: Tensor, t: Tensor, alpha_bar: Tensor, scale: float = 10.0) -> Tensor:
+    """classifier.py:39-63: eps_hat = eps - sqrt(1 - abar_t) scale grad, then the eta = 0 DDIM update written there."""
+    ab_p, ab_t = _col(alpha_bar, t - 1), _col(alpha_bar, t)
+    g = classifier_grad(classifier, y, x_t, t)
+    with torch.no_grad():
+        eps = model(x_t, t) - torch.sqrt(1 - ab_t) * scale * g
+        return torch.sqrt(ab_p) * (x_t - torch.sqrt(1 - ab_t) * eps) / torch.sqrt(ab_t) + torch.sqrt(1 - ab_p) * eps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # optimizer tail (test infrastructure for dmme_b200.optim): Adam + WarmupLR + gradient clipping + EMA as the reference
 # composes them
 # ---------------------------------------------------------------------------------------------------------------------
