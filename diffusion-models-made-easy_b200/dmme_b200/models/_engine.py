@@ -74,6 +74,10 @@ class Engine:
         # sampler update applied by the output conv's epilogue (eps stays in registers); sampler_applied reports whether the
         # last forward did it (the callers run the stand-alone update kernel otherwise)
         self.fuse_sampler = os.environ.get("DMME_FUSE_SAMPLER", "1") != "0"
+        # consecutive ResBlocks of the 8x8 / 4x4 levels in one persistent launch (csrc/conv_chain.cu); DMME_CHAIN=0: per-conv
+        # launches as at the higher resolutions
+        self.use_chain = os.environ.get("DMME_CHAIN", "1") != "0"
+        self._layers: Optional[List[Tuple[str, nn.Module, str, str]]] = None
         self.sampler_applied = False
 
     # -- caches ------------------------------------------------------------------------------
@@ -399,6 +403,155 @@ class Engine:
             h2 = self.attention_block(name, blk.attention, h2)
         return h2
 
+    # -- chains of low-resolution ResBlocks --------------------------------------------------------
+    def layer_seq(self) -> List[Tuple[str, nn.Module, str, str]]:
+        """[(state_dict prefix, module, kind, section)] of UNet.forward's walk (models/ddpm.py:295-313); kind = "res"
+        (ResBlock) | "down" (stride-2 conv) | "up" (UpSample)."""
+        if self._layers is None:
+            u = self.unet
+            seq = []
+            for sec, pre, lst in (("down", "down_layers", u.down_layers), ("mid", "middle_layers", u.middle_layers),
+                                  ("up", "up_layers", u.up_layers)):
+                for i, m in enumerate(lst):
+                    kind = "res" if hasattr(m, "conv1") else ("down" if sec == "down" else "up")
+                    seq.append((f"{pre}.{i}", m, kind, sec))
+            self._layers = seq
+        return self._layers
+
+    def chain_run(self, seq, i: int, h: Tensor, skips: List[Tensor], masks) -> int:
+        """How many consecutive ResBlocks starting at seq[i] the chain kernel takes (0: none).  A run ends after a block
+        with attention, at a resolution change, and wherever a GroupNorm's groups do not fit the epilogue's shuffles."""
+        if not self.use_chain or self.force_generic or masks or h.dtype != torch.bfloat16:
+            return 0
+        n, hh, ww, c_in = h.shape
+        cout = ops.CHAIN_COUT
+        if not ops.conv_chain_supported(n, hh, ww, cout):
+            return 0
+        run, pops, pushed = 0, 0, False
+        while i + run < len(seq) and run < ops.CHAIN_MAX_OPS // 2:
+            name, blk, kind, sec = seq[i + run]
+            if kind != "res":
+                break
+            conv1, conv2 = blk.conv1[2], blk.conv2[-1]
+            c1 = 0
+            if sec == "up":
+                # the skip this block pops must exist before the launch (pushed by a block outside this run)
+                if pushed or pops + 1 > len(skips):
+                    break
+                pops += 1
+                c1 = skips[-pops].shape[3]
+            norm1, norm2 = blk.conv1[0], (blk.conv2[0] if self.flavour == "ddpm" else blk.norm)
+            ok = (c_in == cout and c1 % 64 == 0 and conv1.weight.shape[0] == cout and conv2.weight.shape[0] == cout
+                  and conv1.weight.shape[1] == c_in + c1 and conv1.weight.shape[2] == 3 and conv2.weight.shape[2] == 3
+                  and (c_in + c1) % norm1.num_groups == 0 and cout % norm2.num_groups == 0)
+            if ok:
+                cpg1, cpg2 = (c_in + c1) // norm1.num_groups, cout // norm2.num_groups
+                ok = 32 % cpg1 == 0 and c_in % cpg1 == 0 and 32 % cpg2 == 0
+            if ok and isinstance(blk.residual, nn.Identity):
+                ok = c1 == 0
+            elif ok:
+                ok = blk.residual.weight.shape[1] == c_in + c1
+            if not ok:
+                break
+            pushed = pushed or sec == "down"
+            run += 1
+            if not isinstance(blk.attention, nn.Identity):
+                break
+        return run
+
+    def norm_inputs(self, name: str, norm: nn.GroupNorm, x0: Tensor, x1: Optional[Tensor]) -> Tuple[Tensor, Optional[Tensor]]:
+        """The GroupNorm + SiLU'd operand(s) of a conv1 (no scale / shift): what a producer's fused pass already wrote, or
+        a stand-alone pass now."""
+        c0 = x0.shape[3]
+        n0 = self._normed.get((x0.data_ptr(), id(norm)))
+        if x1 is None:
+            return (n0 if n0 is not None else self.gn(name + ".n0", norm, x0, None, silu=True)), None
+        c1 = x1.shape[3]
+        cpg = (c0 + c1) // norm.num_groups
+        n1 = self._normed.get((x1.data_ptr(), id(norm)))
+        if c0 % cpg == 0 and c1 % cpg == 0:
+            if n0 is None:
+                n0 = self.gn_part(name + ".n0", norm, x0, 0, cpg)
+            if n1 is None:
+                n1 = self.gn_part(name + ".n1", norm, x1, c0, cpg)
+            return n0, n1
+        return self.gn(name + ".n01", norm, x0, x1, silu=True), None
+
+    def chain_blocks(self, blocks, h: Tensor, skips: List[Tensor], temb_all: Tensor, offs: Dict[int, Tuple[int, int]]) -> Tensor:
+        """``blocks`` consecutive ResBlocks (same resolution, 256 channels) as ONE launch of the chain kernel: per block
+        op A = conv1 (+temb) whose epilogue leaves conv2's normalised operand in shared memory, op B = conv2 (+residual)
+        whose epilogue stores the raw block output and the GroupNorm(+SiLU) its consumers apply -- the next block's, kept
+        in shared memory, and e.g. the up-path skip reader's or the attention norm's, to global memory."""
+        n, hh, ww, _ = h.shape
+        dev, dt = h.device, h.dtype
+        cout = ops.CHAIN_COUT
+        chain = []
+        x_raw, resident = h, False
+        for bi, (name, blk, _, sec) in enumerate(blocks):
+            o, width = offs[id(blk)]
+            cond = temb_all[:, o:o + width]
+            conv1, conv2 = blk.conv1[2], blk.conv2[-1]
+            has_attn = not isinstance(blk.attention, nn.Identity)
+            out_name = name + (".pre" if has_attn else "")
+            x1 = skips.pop() if sec == "up" else None
+            norm1 = blk.conv1[0]
+            if resident:
+                s0 = None
+                s1 = None
+                if x1 is not None:
+                    s1 = self._normed.get((x1.data_ptr(), id(norm1)))
+                    if s1 is None:
+                        s1 = self.gn_part(name + ".n1", norm1, x1, cout, (cout + x1.shape[3]) // norm1.num_groups)
+            else:
+                s0, s1 = self.norm_inputs(name, norm1, x_raw, x1)
+            if self.flavour == "ddpm":
+                norm2, temb, scale, shift = blk.conv2[0], cond, None, None
+            else:
+                norm2, temb = blk.norm, None
+                shift, scale = cond[:, :cout], cond[:, cout:]
+            on_a = ops.out_norm(None, norm2.weight.detach(), norm2.bias.detach(), cout // norm2.num_groups, True, norm2.eps,
+                                scale, shift)
+            chain.append(ops.chain_op(s0, s1, self.packed_weight(conv1, None, True), conv1.bias.detach(), c0=cout, temb=temb,
+                                      out_norms=[on_a], keep=0))
+            out = self.ws.get(out_name, (n, hh, ww, cout), dt, dev)
+            stats = self._stats_for(out, n, cout)
+            if stats is None:
+                self._stats.pop(out.data_ptr(), None)
+            if isinstance(blk.residual, nn.Identity):
+                kw = dict(addend=x_raw)
+                w2, b2 = self.packed_weight(conv2, None, True), conv2.bias.detach()
+            else:
+                kw = dict(res0=x_raw, res1=x1)
+                w2, b2 = self.packed_weight(conv2, blk.residual, True), self.fused_bias(conv2, blk.residual)
+            nxt_norm = blocks[bi + 1][1].conv1[0] if bi + 1 < len(blocks) else None
+            norms, keep = [], -1
+            for k, spec in enumerate((self.consumers().get(out_name) or [])[:2]):
+                norm, off, total, silu = spec[:4]
+                cpg = total // norm.num_groups
+                if cpg < 1 or 32 % cpg or off % cpg or cout % cpg:
+                    continue
+                gam, bet = norm.weight.detach()[off:off + cout], norm.bias.detach()[off:off + cout]
+                if norm is nxt_norm and off == 0:
+                    keep = len(norms)
+                    norms.append(ops.out_norm(None, gam, bet, cpg, silu, norm.eps))
+                else:
+                    y = self.ws.get(f"{out_name}.normed{k}", (n, hh, ww, cout), dt, dev)
+                    norms.append(ops.out_norm(y, gam, bet, cpg, silu, norm.eps))
+                    self._normed[(out.data_ptr(), id(norm))] = y
+            if nxt_norm is not None and keep < 0:
+                raise RuntimeError(f"dmme_b200: chain planning lost the consumer of {out_name}")
+            chain.append(ops.chain_op(None, None, w2, b2, c0=cout, out=out, stats=stats, out_norms=norms, keep=keep, **kw))
+            x_raw, resident = out, keep >= 0
+            if sec == "down":
+                skips.append(out)
+        ops.conv_chain(chain, n, hh, ww)
+        last_name, last = blocks[-1][0], blocks[-1][1]
+        if not isinstance(last.attention, nn.Identity):
+            x_raw = self.attention_block(last_name, last.attention, x_raw)
+            if blocks[-1][3] == "down":
+                skips[-1] = x_raw
+        return x_raw
+
     # -- whole network -------------------------------------------------------------------------
     def forward(self, x: Tensor, c: Tensor, act_dtype: torch.dtype, masks: Optional[Dict[str, Tensor]] = None,
                 sampler=None) -> Tensor:
@@ -434,20 +587,23 @@ class Engine:
         h = self.conv("input_conv", x, None, u.input_conv, in_nchw=True, act_dtype=act_dtype)
         main.wait_stream(side)
         skips = [h]
-        for i, m in enumerate(u.down_layers):
-            name = f"down_layers.{i}"
-            if hasattr(m, "conv1"):
-                h = self.resblock(name, m, h, None, temb_all, offs, masks)
-            else:
+        seq = self.layer_seq()
+        i = 0
+        while i < len(seq):
+            name, m, kind, sec = seq[i]
+            if kind == "res":
+                run = self.chain_run(seq, i, h, skips, masks)
+                if run:
+                    h = self.chain_blocks(seq[i:i + run], h, skips, temb_all, offs)
+                    i += run
+                    continue
+                h = self.resblock(name, m, h, skips.pop() if sec == "up" else None, temb_all, offs, masks)
+            elif kind == "down":
                 h = self.conv(name, h, None, m, stride=2, consumers=plan.get(name))
-            skips.append(h)
-        for i, m in enumerate(u.middle_layers):
-            h = self.resblock(f"middle_layers.{i}", m, h, None, temb_all, offs, masks)
-        for i, m in enumerate(u.up_layers):
-            name = f"up_layers.{i}"
-            if hasattr(m, "conv1"):
-                h = self.resblock(name, m, h, skips.pop(), temb_all, offs, masks)
             else:
                 h = self.conv(name, h, None, m.conv, upsample=True)
+            if sec == "down":
+                skips.append(h)
+            i += 1
         a = self.gn("scratch.out_norm", u.output_conv[0], h, None, silu=True)
         return self.conv("output_conv", a, None, u.output_conv[2], out_layout=L.OUT_NCHW_F32, sampler=sampler)

@@ -226,6 +226,43 @@ def conv2d_launch(desc: L.ConvDesc, weight: Tensor, bias: Optional[Tensor], out:
     L.check(L.load().dmme_conv2d_fwd(C.byref(desc), L.stream_ptr()), "conv2d_fwd")
 
 
+CHAIN_COUT = 256      # output channels of every conv of a chain (csrc/conv_chain.cu)
+CHAIN_MAX_OPS = 16
+
+
+def chain_op(src0: Optional[Tensor], src1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], *,
+             c0: Optional[int] = None, res0: Optional[Tensor] = None, res1: Optional[Tensor] = None,
+             temb: Optional[Tensor] = None, addend: Optional[Tensor] = None, out: Optional[Tensor] = None,
+             stats: Optional[Tensor] = None, out_norms=(), keep: int = -1) -> L.ChainOp:
+    """One ``dmme_chain_op`` (see include/dmme_b200.h).  ``src0 = None``: the operand the previous op kept in shared
+    memory (``c0`` channels).  The returned struct only holds raw pointers: the caller keeps the tensors alive."""
+    o = L.ChainOp()
+    o.src0, o.c0 = (ptr(src0), src0.shape[3]) if src0 is not None else (None, int(c0))
+    o.src1, o.c1 = (ptr(src1), src1.shape[3]) if src1 is not None else (None, 0)
+    o.res0, o.rc0 = (ptr(res0), res0.shape[3]) if res0 is not None else (None, 0)
+    o.res1, o.rc1 = (ptr(res1), res1.shape[3]) if res1 is not None else (None, 0)
+    o.weight, o.bias = ptr(weight), ptr(bias)
+    if temb is not None:
+        if temb.dim() != 2 or temb.dtype != torch.float32:
+            raise ValueError("temb must be a 2-D fp32 view")
+        o.temb, o.temb_rows, o.temb_ld = ptr(temb), temb.shape[0], temb.stride(0)
+    o.addend, o.out, o.stats = ptr(addend), ptr(out), ptr(stats)
+    for k in range(2):
+        o.out_norm[k] = out_norms[k] if k < len(out_norms) else L.OutNorm()
+    o.keep = int(keep)
+    return o
+
+
+def conv_chain_supported(n: int, h: int, w: int, cout: int) -> bool:
+    return bool(L.load().dmme_conv_chain_supported(n, h, w, cout))
+
+
+def conv_chain(chain, n: int, h: int, w: int) -> None:
+    """Run a list of ``chain_op`` back to back in one persistent launch (csrc/conv_chain.cu)."""
+    arr = (L.ChainOp * len(chain))(*chain)
+    L.check(L.load().dmme_conv_chain_fwd(arr, len(chain), n, h, w, L.stream_ptr()), "conv_chain_fwd")
+
+
 # ---------------------------------------------------------------------------------------------
 # GroupNorm / attention / timestep embedding
 # ---------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMME_ABI_VERSION 4
+#define DMME_ABI_VERSION 5
 #define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
@@ -203,6 +203,41 @@ int dmme_conv2d_fuses_sampler(const dmme_conv_desc* desc);
 long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* desc);
 /* A/B switch: 0 = never split K, 1 = default (by the cost model), 2 = wherever the split-K kernel supports the shape */
 void dmme_set_conv_splitk_mode(int mode);
+
+/* chain of 3x3 convolutions (low-resolution ResBlocks) in one launch ------------------------ */
+/*
+ * One conv of a chain:  out = conv3x3( cat(src0, src1) ) + conv1x1( cat(res0, res1) ) + bias + temb[n or 0][:] + addend,
+ * 256 output channels, stride 1, 4x4 or 8x8 maps, bf16 NHWC.  src0 / src1 are ALREADY NORMALISED operands
+ * (norm_act_drop_conv models/ddpm.py:25-35 applies GroupNorm + SiLU before the conv): tensors in global memory, or -- src0 ==
+ * NULL -- the operand the previous op of the chain left in shared memory (its out_norm[keep]).  res0 / res1 / addend are raw
+ * tensors (ResBlock.residual models/ddpm.py:109,131) and may be `out` of an earlier op of the same chain.  The epilogue
+ * writes the raw output (`out`, optional), its GroupNorm micro-group statistics (`stats`, optional, the format of
+ * dmme_conv_desc.stats) and the GroupNorm(+SiLU) of up to two consumers (dmme_out_norm; `.out` may be NULL for the kept one).
+ */
+typedef struct dmme_chain_op {
+  const void* src0; const void* src1; int c0, c1;
+  const void* res0; const void* res1; int rc0, rc1;
+  const void* weight;                 /* packed by dmme_pack_conv_weight(DMME_CONV_TC): bf16 [256][9 (c0 + c1) + rc0 + rc1] */
+  const float* bias;
+  const float* temb; int temb_rows, temb_ld;
+  const void* addend;
+  void* out;
+  long long* stats;
+  dmme_out_norm out_norm[2];
+  int keep;                           /* index of the out_norm kept in shared memory as the next op's src0, -1: none */
+} dmme_chain_op;
+/*
+ * Runs ops[0..nops) back to back in ONE persistent kernel (csrc/conv_chain.cu): every CTA owns whole images for the length
+ * of the chain, so the GroupNorm between two convs is finished in the epilogue and its result stays in shared memory as
+ * the next conv's tensor-core operand; only the weights stream.  Replaces the per-conv launches (split-K GEMM + finishing
+ * pass, or conv + GroupNorm) of consecutive ResBlocks at the 8x8 / 4x4 levels (UNet.forward models/ddpm.py:295-313).
+ * nops <= 16; n images of h x w (4x4 or 8x8).
+ */
+int dmme_conv_chain_fwd(const dmme_chain_op* ops, int nops, int n, int h, int w, void* stream);
+/* 1 when dmme_conv_chain_fwd takes maps of this size with this many output channels */
+int dmme_conv_chain_supported(int n, int h, int w, int cout);
+/* A/B switch: images per CTA of the chain kernel (0 = cost model) */
+void dmme_set_conv_chain_ipc(int ipc);
 
 /* GroupNorm (+ scale/shift) (+ SiLU) (+ channel dropout mask) -------------------------------- */
 /*

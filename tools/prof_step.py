@@ -61,11 +61,13 @@ def main():
             return out
         return timed
 
-    def conv_sig(desc, weight, bias, out, temb=None, addend=None, out2=None, out3=None, stats=None, gn_ab=None, gn_silu=True):
+    def conv_sig(desc, weight, bias, out, temb=None, addend=None, out2=None, out3=None, stats=None, gn_ab=None, gn_silu=True,
+                 splitk_ws=None, out_norms=None, sampler=None):
         ho, wo = ops.conv_out_hw(desc)
         return (f"conv {desc.ksize}x{desc.ksize} s{desc.stride} {desc.c0 + desc.c1}->{desc.cout} @{desc.h_in}"
                 + (f" +res{desc.rc0 + desc.rc1}" if desc.rc0 + desc.rc1 else "") + (" +add" if addend is not None else "")
-                + (" qkv" if out2 is not None else "") + (" +gn" if gn_ab is not None else ""))
+                + (" qkv" if out2 is not None else "") + (" +gn" if gn_ab is not None else "")
+                + (f" splitk+{len(out_norms or [])}norms" if splitk_ws is not None else "") + (" +sampler" if sampler is not None else ""))
 
     def gn_sig(src0, src1, *a, **k):
         c = src0.shape[3] + (src1.shape[3] if src1 is not None else 0)
