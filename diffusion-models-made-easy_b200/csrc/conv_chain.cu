@@ -16,6 +16,15 @@
 // descriptors.  The conv is computed transposed: D^T[256 cout][positions] = W X^T as two M = 128 accumulators of N =
 // n_mma <= 256 columns each (the whole TMEM); TMEM lane = output channel.
 //
+// MEASURED NEGATIVE RESULT (DESIGN.md "chain kernel"; profiles/r2_chain_*): parity-green, 127 -> 86 launches per step, but
+// SLOWER than the per-conv launches at every batch (256: 3.77 -> 4.13 ms, 32: 1.17 -> 1.63 ms per step).  An SM that owns
+// whole images must ingest ALL the weights of every conv, and with N = 100..208 positions per weight tile the SS-mode MMA
+// is bound by the shared-memory port: per 16 KB tile, 16 KB of TMA writes + 16 KB of A-operand reads + 14 KB of B reads =
+// 46 KB / 128 B/clk = 360 clocks against 224 clocks of math (clock64 timeline, tools/trace_chain.py: a tile every 400-540
+// clocks whatever the ring depth and the number of issuing threads).  The split-K path spreads one conv over all SMs with
+// N = 256 tiles and wins despite its two launches per conv.  Built only with -DDMME_EXPERIMENTAL; the entry points stay in
+// the ABI and answer "unsupported" otherwise.
+//
 // Warp roles: 0 weight-tile TMA producer, 1 activation-chunk TMA producer (inputs that come from global memory: the
 // chain's first operand, the skip half of a concat, the raw input of a fused 1x1 residual conv), 2 MMA issuer / TMEM
 // owner, 4..11 epilogue (TMEM lane quarter = warp % 4, accumulator = (warp - 4) / 4).
@@ -28,15 +37,17 @@
 #include "ptx_sm100.cuh"
 #include "tmap.cuh"
 
+#ifdef DMME_EXPERIMENTAL
 namespace dmme {
 
 constexpr int kChainMaxOps = 16;
 constexpr int kChainCout = 256;
-constexpr int kChainWStages = 3;
+constexpr int kChainMaxWStages = 12;  // weight ring: as many 16 KB stages as fit beside the activation chunks
 constexpr int kChainSlots = 2;
 constexpr int kChainWTile = 128 * 128;  // [128 cout][64 k] bf16
 constexpr int kChainThreads = 384;
 constexpr int kChainEpiWarp0 = 4;
+constexpr int kChainIssuers = 8;  // weight-tile TMA issuing threads
 constexpr int kChainEpiThreads = 256;
 constexpr int kChainSmemMax = 227 * 1024 - 512;  // dynamic shared memory the kernel may ask for (static barriers beside it)
 
@@ -67,14 +78,23 @@ struct ChainParams {
   int n_mma;   // MMA N: ipc * PP rounded up to a multiple of 16
   int rows;    // position rows per chunk buffer = n_mma + 2 * slack
   int slack;   // WP + 1 rows in front of position 0 (the taps reach that far back)
+  int wstages; // weight-ring stages: a 16 KB tile takes ~2000 clocks from request to landing, so the stream's rate is
+               // (stages x 16 KB) / latency -- three stages gave 18 B/clk, far below the MMAs' appetite
+  long long* trace;  // debugging: clock64 timestamps of CTA 0, [role][1024] (dmme_debug_set_chain_trace), or null
   ChainOp op[kChainMaxOps];
 };
+
+// roles: 0 weight producer issued tile i, 1 MMA warp saw tile i landed, 2 epilogue of op i starts, 3 ends, 4 chunk producer
+// issued streamed chunk i, 5 MMA warp saw streamed chunk i
+__device__ __forceinline__ void chain_trace(long long* trace, int role, int idx) {
+  if (trace && blockIdx.x == 0 && idx < 1024) trace[role * 1024 + idx] = clock64();
+}
 
 template <int W>
 __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int WP = W + 2, PP = WP * WP, HW = W * W;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t w_full[kChainWStages], w_empty[kChainWStages];
+  __shared__ __align__(8) uint64_t w_full[kChainMaxWStages], w_empty[kChainMaxWStages];
   __shared__ __align__(8) uint64_t s_full[kChainSlots], s_empty[kChainSlots];
   __shared__ __align__(8) uint64_t acc_full, epi_done;
   __shared__ uint32_t tmem_slot;
@@ -83,6 +103,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* wring = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int chunk_bytes = p.rows * 128;
+  const int kChainWStages = p.wstages;
   uint8_t* resident = wring + kChainWStages * kChainWTile;  // 4 chunks: the 256-channel operand an epilogue leaves
   uint8_t* slots = resident + 4 * chunk_bytes;              // ring for chunks loaded from global memory
 
@@ -96,6 +117,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   if (warp == 0 && lane == 0) {
     for (int k = 0; k < p.nops; ++k) tma_prefetch_desc(&p.op[k].w);
   }
+  // (warp 3's issuing lanes share the descriptors warp 0 prefetched)
   if (warp == 1 && lane == 0) {
     for (int k = 0; k < p.nops; ++k)
       for (int j = 0; j < 4; ++j)
@@ -115,31 +137,46 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   const uint32_t tmem_base = tmem_slot;
   pdl_trigger();  // after the TMEM allocation (see common.cuh)
 
-  if (warp == 0) {
-    // =========================== weight-tile producer ===========================
-    if (lane == 0) {
-      int wit = 0;
+  if (warp == 0 || warp == 3) {
+    // =========================== weight-tile producers ===========================
+    // One thread needs ~400 clocks per TMA issue (measured: tools/trace_chain.py), i.e. 16 KB / 400 clk = 40 B/clk -- half of
+    // what the MMAs consume at N = 112.  kChainIssuers threads (four lanes of two warps) therefore take the tiles of an op
+    // round-robin; the lanes of a warp run the same instruction stream, so their issues overlap.
+    // No more issuers than ring stages: a thread whose next tile lies two ring generations ahead of the slowest consumer
+    // would pass the parity wait of the stage's `empty` barrier one generation too early.
+    const int issuers = kChainIssuers < kChainWStages ? kChainIssuers : kChainWStages;
+    const int me = (warp == 0 ? 0 : kChainIssuers / 2) + lane;
+    if (lane < kChainIssuers / 2 && me < issuers) {
+      int wit0 = 0;
       pdl_wait();  // the packed weights may come from a pack kernel launched just before
       for (int g = blockIdx.x; g < p.groups; g += gridDim.x) {
         for (int k = 0; k < p.nops; ++k) {
           const ChainOp& op = p.op[k];
           const int cchunks = op.chunks[0] + op.chunks[1];
-          for (int j = 0; j < 4; ++j) {
-            for (int c = 0; c < op.chunks[j]; ++c) {
-              const int ntaps = j < 2 ? 9 : 1;
-              // packed K order: tap-major conv part [tap][cat(src0, src1)], then the residual channels
-              const int kb0 = j == 0 ? c : j == 1 ? op.chunks[0] + c : 9 * cchunks + (j == 3 ? op.chunks[2] : 0) + c;
-              for (int tap = 0; tap < ntaps; ++tap) {
-                const int kcol = (kb0 + tap * cchunks) * 64;
-                for (int mt = 0; mt < 2; ++mt, ++wit) {
-                  const int s = wit % kChainWStages;
-                  mbar_wait(&w_empty[s], ((wit / kChainWStages) & 1) ^ 1);
-                  mbar_expect_tx(&w_full[s], kChainWTile);
-                  tma_load_2d(wring + s * kChainWTile, &op.w, &w_full[s], kcol, mt * 128);
-                }
-              }
+          const int conv_tiles = 18 * cchunks;
+          const int ntiles = conv_tiles + 2 * (op.chunks[2] + op.chunks[3]);
+          // tile order (the MMA warp's): chunk-major, then tap, then the two 128-channel accumulators
+          // thread `me` owns the tiles whose GLOBAL index is me mod issuers (also across op boundaries: two consecutive
+          // tiles of a thread are never more than one ring length apart, see above)
+          for (int idx = (me - wit0 % issuers + issuers) % issuers; idx < ntiles; idx += issuers) {
+            int kcol, mt;
+            if (idx < conv_tiles) {
+              const int c = idx / 18, rem = idx - c * 18;
+              mt = rem & 1;
+              kcol = (c + (rem >> 1) * cchunks) * 64;  // packed K order: tap-major [tap][cat(src0, src1)]
+            } else {
+              const int r = idx - conv_tiles;
+              mt = r & 1;
+              kcol = (9 * cchunks + (r >> 1)) * 64;    // then the residual channels
             }
+            const int wit = wit0 + idx;
+            const int s = wit % kChainWStages;
+            mbar_wait(&w_empty[s], ((wit / kChainWStages) & 1) ^ 1);
+            if (me == 0) chain_trace(p.trace, 0, wit);
+            mbar_expect_tx(&w_full[s], kChainWTile);
+            tma_load_2d(wring + s * kChainWTile, &op.w, &w_full[s], kcol, mt * 128);
           }
+          wit0 += ntiles;
         }
       }
     }
@@ -159,6 +196,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
             for (int c = 0; c < op.chunks[j]; ++c, ++sit) {
               const int s = sit % kChainSlots;
               mbar_wait(&s_empty[s], ((sit / kChainSlots) & 1) ^ 1);
+              chain_trace(p.trace, 4, sit);
               mbar_expect_tx(&s_full[s], static_cast<uint32_t>(p.ipc) * PP * 128);
               asm volatile(
                   "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -175,6 +213,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     // =========================== MMA issuer ===========================
     const uint32_t idesc = umma_idesc_bf16(128, p.n_mma);
     int wit = 0, sit = 0, opc = 0;
+    int ws = 0;
+    uint32_t wph = 0;
     for (int g = blockIdx.x; g < p.groups; g += gridDim.x) {
       for (int k = 0; k < p.nops; ++k, ++opc) {
         const ChainOp& op = p.op[k];
@@ -192,6 +232,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
               s = sit % kChainSlots;
               mbar_wait(&s_full[s], (sit / kChainSlots) & 1);
               tc_fence_after();
+              if (lane == 0) chain_trace(p.trace, 5, sit);
               x0_addr = smem_u32(slots + s * chunk_bytes) + static_cast<uint32_t>(p.slack) * 128u;
             } else {
               x0_addr = smem_u32(resident + c * chunk_bytes) + static_cast<uint32_t>(p.slack) * 128u;
@@ -200,9 +241,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
               const int d = ntaps == 9 ? (tap / 3 - 1) * WP + (tap % 3 - 1) : 0;
               const uint64_t xdesc = umma_desc_sw128(x0_addr + static_cast<uint32_t>(d * 128));
               for (int mt = 0; mt < 2; ++mt, ++wit) {
-                const int ws = wit % kChainWStages;
-                mbar_wait(&w_full[ws], (wit / kChainWStages) & 1);
+                mbar_wait(&w_full[ws], wph);
                 tc_fence_after();
+                if (lane == 0) chain_trace(p.trace, 1, wit);
                 if (elect_one()) {
                   const uint64_t wdesc = umma_desc_sw128(smem_u32(wring + ws * kChainWTile));
                   const uint32_t dtm = tmem_base + static_cast<uint32_t>(mt * 256);
@@ -212,6 +253,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
                   umma_commit(&w_empty[ws]);
                 }
                 __syncwarp();
+                if (++ws == kChainWStages) { ws = 0; wph ^= 1u; }
               }
               first = false;
             }
@@ -244,6 +286,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         const float bias_c = op.bias ? __ldg(op.bias + ch) : 0.f;
         mbar_wait(&acc_full, opc & 1);
         tc_fence_after();
+        if (threadIdx.x == kChainEpiWarp0 * 32) chain_trace(p.trace, 2, opc);
         for (int i = 0; i < p.ipc; ++i) {
           const int n = g * p.ipc + i;
           if (n >= p.n) break;
@@ -252,11 +295,23 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           const long long img = static_cast<long long>(n) * HW * kChainCout + ch;
           uint32_t rfp[HW / 2];  // the stored (rounded) outputs of this channel, two bf16 per register
           float s1 = 0.f, s2 = 0.f;
+          // every accumulator row of the image is requested before the first is used (one TMEM round trip per image, not
+          // one per row: the per-op epilogue took 15k clocks with a wait per row)
+          uint32_t v[HW];
+#pragma unroll
+          for (int y = 0; y < W; ++y) {
+            const uint32_t taddr = tbase + static_cast<uint32_t>(i * PP + (y + 1) * WP + 1);
+            if constexpr (W == 8) tmem_ld8(taddr, reinterpret_cast<uint32_t(&)[8]>(v[y * W]));
+            else tmem_ld4(taddr, reinterpret_cast<uint32_t(&)[4]>(v[y * W]));
+          }
+          tmem_ld_wait();
 #pragma unroll
           for (int y = 0; y < W; ++y) {
             float av[W];
             if (op.addend) {
-              // may be a raw output an earlier op of this very launch stored: read at L2
+              // may be a raw output an earlier op of this very launch stored: read at L2.  (The engine folds identity
+              // residuals into the GEMM instead -- [W | I] weights, the raw input as 1x1 chunks -- so that no epilogue
+              // waits for global loads.)
 #pragma unroll
               for (int x = 0; x < W; ++x)
                 av[x] = __bfloat162float(__ldcg(op.addend + img + (y * W + x) * kChainCout));
@@ -264,15 +319,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
 #pragma unroll
               for (int x = 0; x < W; ++x) av[x] = 0.f;
             }
-            uint32_t v[W];
-            const uint32_t taddr = tbase + static_cast<uint32_t>(i * PP + (y + 1) * WP + 1);
-            if constexpr (W == 8) tmem_ld8(taddr, v);
-            else tmem_ld4(taddr, v);
-            tmem_ld_wait();
 #pragma unroll
             for (int x = 0; x < W; x += 2) {
-              const __nv_bfloat16 r0 = __float2bfloat16_rn(__uint_as_float(v[x]) + add + av[x]);
-              const __nv_bfloat16 r1 = __float2bfloat16_rn(__uint_as_float(v[x + 1]) + add + av[x + 1]);
+              const __nv_bfloat16 r0 = __float2bfloat16_rn(__uint_as_float(v[y * W + x]) + add + av[x]);
+              const __nv_bfloat16 r1 = __float2bfloat16_rn(__uint_as_float(v[y * W + x + 1]) + add + av[x + 1]);
               if (op.out) {
                 op.out[img + (y * W + x) * kChainCout] = r0;
                 op.out[img + (y * W + x + 1) * kChainCout] = r1;
@@ -340,6 +390,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
         tc_fence_before();
+        if (threadIdx.x == kChainEpiWarp0 * 32) chain_trace(p.trace, 3, opc);
         mbar_arrive(&epi_done);
       }
     }
@@ -353,6 +404,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   }
 }
 
+static int chain_wstages(int rows) {
+  const int room = (kChainSmemMax - 1024 - (4 + kChainSlots) * rows * 128) / kChainWTile;
+  return room > kChainMaxWStages ? kChainMaxWStages : room;
+}
+
 static int chain_geometry(int n, int w, int sms, int* ipc_out, int* n_mma_out, int* rows_out, int* smem_out) {
   const int wp = w + 2, pp = wp * wp, slack = wp + 1;
   long long best = -1;
@@ -360,13 +416,15 @@ static int chain_geometry(int n, int w, int sms, int* ipc_out, int* n_mma_out, i
     const int n_mma = ((ipc * pp + 15) / 16) * 16;
     if (n_mma > 256) break;
     const int rows = n_mma + 2 * slack;
-    const int smem = 1024 + kChainWStages * kChainWTile + (4 + kChainSlots) * rows * 128;
-    if (smem > kChainSmemMax) break;
+    const int stages = chain_wstages(rows);
+    if (stages < 2) break;
+    const int smem = 1024 + stages * kChainWTile + (4 + kChainSlots) * rows * 128;
     const int groups = (n + ipc - 1) / ipc;
     const long long waves = (groups + sms - 1) / sms;
-    // per weight tile a CTA spends max(four MMAs of N columns: 2 N clocks, the tile's 16 KB at the ~50 B/clk a streaming SM
-    // ingests); the epilogue grows with the images
-    const long long per_tile = 2 * n_mma > 330 ? 2 * n_mma : 330;
+    // per weight tile a CTA spends max(four MMAs of N columns: 2 N clocks, the tile's share of the ring's round trip: ~2000
+    // clocks / stages); the epilogue grows with the images
+    const long long feed = 2000 / stages;
+    const long long per_tile = 2 * n_mma > feed ? 2 * n_mma : feed;
     const long long cost = waves * (per_tile + 16 * ipc);
     if (best < 0 || cost < best) {
       best = cost;
@@ -376,7 +434,8 @@ static int chain_geometry(int n, int w, int sms, int* ipc_out, int* n_mma_out, i
   return best < 0 ? -1 : 0;
 }
 
-static int g_chain_ipc = 0;  // A/B: force the images per CTA (0 = cost model)
+static int g_chain_ipc = 0;
+static long long* g_chain_trace = nullptr;  // A/B: force the images per CTA (0 = cost model)
 
 template <int W>
 static int launch_chain(const ChainParams& p, int grid, int smem, cudaStream_t stream) {
@@ -395,10 +454,22 @@ static int launch_chain(const ChainParams& p, int grid, int smem, cudaStream_t s
 }
 
 }  // namespace dmme
+#endif  // DMME_EXPERIMENTAL
 
 using namespace dmme;
 
+#ifndef DMME_EXPERIMENTAL
+extern "C" void dmme_set_conv_chain_ipc(int) {}
+extern "C" void dmme_debug_set_chain_trace(long long*) {}
+extern "C" int dmme_conv_chain_supported(int, int, int, int) { return 0; }
+extern "C" int dmme_conv_chain_fwd(const dmme_chain_op*, int, int, int, int, void*) {
+  set_error("conv_chain: built only with -DDMME_EXPERIMENTAL (measured slower than the per-conv launches, DESIGN.md)");
+  return DMME_E_UNSUPPORTED;
+}
+#else
 extern "C" void dmme_set_conv_chain_ipc(int ipc) { g_chain_ipc = ipc; }
+// debugging: int64[6 * 1024] device buffer receiving CTA 0's per-role timestamps (tools/trace_chain.py), null = off
+extern "C" void dmme_debug_set_chain_trace(long long* buf) { g_chain_trace = buf; }
 
 extern "C" int dmme_conv_chain_supported(int n, int h, int w, int cout) {
   return n > 0 && h == w && (w == 4 || w == 8) && cout == kChainCout ? 1 : 0;
@@ -420,10 +491,12 @@ extern "C" int dmme_conv_chain_fwd(const dmme_chain_op* ops, int nops, int n, in
     p.ipc = g_chain_ipc;
     p.n_mma = ((p.ipc * pp + 15) / 16) * 16;
     p.rows = p.n_mma + 2 * (wp + 1);
-    smem = 1024 + kChainWStages * kChainWTile + (4 + kChainSlots) * p.rows * 128;
-    DMME_REQUIRE(p.n_mma <= 256 && smem <= kChainSmemMax, DMME_E_SHAPE, "conv_chain: forced ipc %d does not fit", p.ipc);
+    DMME_REQUIRE(p.n_mma <= 256 && chain_wstages(p.rows) >= 2, DMME_E_SHAPE, "conv_chain: forced ipc %d does not fit", p.ipc);
+    smem = 1024 + chain_wstages(p.rows) * kChainWTile + (4 + kChainSlots) * p.rows * 128;
   }
   p.slack = w + 3;
+  p.wstages = chain_wstages(p.rows);
+  p.trace = g_chain_trace;
   p.groups = (n + p.ipc - 1) / p.ipc;
   for (int k = 0; k < nops; ++k) {
     const dmme_chain_op& o = ops[k];
@@ -481,3 +554,4 @@ extern "C" int dmme_conv_chain_fwd(const dmme_chain_op* ops, int nops, int n, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return w == 8 ? launch_chain<8>(p, grid, smem, st) : launch_chain<4>(p, grid, smem, st);
 }
+#endif  // DMME_EXPERIMENTAL

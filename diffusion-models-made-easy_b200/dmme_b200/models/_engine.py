@@ -77,6 +77,7 @@ class Engine:
         # consecutive ResBlocks of the 8x8 / 4x4 levels in one persistent launch (csrc/conv_chain.cu); DMME_CHAIN=0: per-conv
         # launches as at the higher resolutions
         self.use_chain = os.environ.get("DMME_CHAIN", "1") != "0"
+        self.chain_max_hw = int(os.environ.get("DMME_CHAIN_MAX_HW", "8"))  # A/B: 4 = only the 4x4 level
         self._layers: Optional[List[Tuple[str, nn.Module, str, str]]] = None
         self.sampler_applied = False
 
@@ -425,7 +426,7 @@ class Engine:
             return 0
         n, hh, ww, c_in = h.shape
         cout = ops.CHAIN_COUT
-        if not ops.conv_chain_supported(n, hh, ww, cout):
+        if hh > self.chain_max_hw or not ops.conv_chain_supported(n, hh, ww, cout):
             return 0
         run, pops, pushed = 0, 0, False
         while i + run < len(seq) and run < ops.CHAIN_MAX_OPS // 2:
@@ -518,8 +519,10 @@ class Engine:
             if stats is None:
                 self._stats.pop(out.data_ptr(), None)
             if isinstance(blk.residual, nn.Identity):
-                kw = dict(addend=x_raw)
-                w2, b2 = self.packed_weight(conv2, None, True), conv2.bias.detach()
+                # h + x (models/ddpm.py:131) inside the GEMM: [W | I] weights, the raw input as 1x1 chunks (bf16 x 1.0
+                # accumulates exactly in fp32) -- the chunk loads overlap the MMAs, an epilogue addend read would not
+                kw = dict(res0=x_raw)
+                w2, b2 = self.packed_weight_identity(conv2), conv2.bias.detach()
             else:
                 kw = dict(res0=x_raw, res1=x1)
                 w2, b2 = self.packed_weight(conv2, blk.residual, True), self.fused_bias(conv2, blk.residual)

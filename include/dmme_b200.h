@@ -238,6 +238,11 @@ int dmme_conv_chain_fwd(const dmme_chain_op* ops, int nops, int n, int h, int w,
 int dmme_conv_chain_supported(int n, int h, int w, int cout);
 /* A/B switch: images per CTA of the chain kernel (0 = cost model) */
 void dmme_set_conv_chain_ipc(int ipc);
+/* debugging: int64[6 * 1024] device buffer receiving CTA 0's per-role clock64 timestamps (tools/trace_chain.py) */
+void dmme_debug_set_chain_trace(long long* buf);
+/* NOTE: the chain kernel is a measured negative result (slower than the per-conv launches at every batch): it
+ * is compiled only with -DDMME_EXPERIMENTAL (`make EXPERIMENTAL=1`); in the shipped build dmme_conv_chain_supported
+ * answers 0 and dmme_conv_chain_fwd returns DMME_E_UNSUPPORTED. */
 
 /* GroupNorm (+ scale/shift) (+ SiLU) (+ channel dropout mask) -------------------------------- */
 /*

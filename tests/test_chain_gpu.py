@@ -103,6 +103,8 @@ def reference(t, n, hw, iddpm):
 @pytest.mark.parametrize("iddpm", [False, True])
 def test_conv_chain_two_blocks(hw, n, ipc, iddpm):
     ops, L = _ops()
+    if not L.load().dmme_has_experimental():
+        pytest.skip("chain kernel is compiled only with -DDMME_EXPERIMENTAL (measured slower, DESIGN.md)")
     if iddpm and n > 20:
         pytest.skip("flavour covered at the small sizes")
     t = make_case(n, hw, seed=hw * 1000 + n)
