@@ -138,6 +138,103 @@ __global__ void __launch_bounds__(kFinishWarps * 32) splitk_finish_kernel(const 
   }
 }
 
+// 4x4 maps (hw <= 16): one WARP owns one (image, 32-channel slab) -- lane = channel, every pixel of the image in that lane's
+// registers -- so the per-channel sums need neither shared memory nor a block barrier, and a CTA of eight warps finishes
+// eight slabs.  (The block-per-slab kernel above runs 512 threads for 512 outputs behind two __syncthreads: 2048 CTAs and
+// 21 us per launch at batch 256 for 4 MB of partial tiles per slice.)  Same summation order as splitk_finish_kernel<1>
+// (slices in fours, pixels 0..hw-1, group channels in ascending order): identical bits.
+constexpr int kFinishSmallWarps = 8;
+static int g_finish_small = 1;  // A/B (tests: bit-equality with the block-per-slab kernel): 0 = never take the warp-per-slab kernel
+__global__ void __launch_bounds__(kFinishSmallWarps * 32) splitk_finish_small_kernel(const SplitFinishParams p) {
+  constexpr int HW = 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slabs = p.cout >> 5;
+  const int unit = blockIdx.x * kFinishSmallWarps + warp;
+  pdl_trigger();
+  pdl_wait();  // the partial tiles come from the split-K GEMM launched just before
+  if (unit >= p.n * slabs) return;
+  const int n = unit / slabs;
+  const int c = (unit - n * slabs) * 32 + lane;
+  float add = p.bias ? __ldg(p.bias + c) : 0.f;
+  if (p.temb) add += __ldg(p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : n) * p.temb_ld + c);
+  const long long img0 = static_cast<long long>(n) * p.hw;
+
+  float rf[HW];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int b = 0; b < HW; b += 4) {
+    // four pixels x every K slice requested before the first value is used
+    float a[4][kMaxSplit], ad[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int px = b + i;
+      const long long o = (img0 + px) * p.cout + c;
+#pragma unroll
+      for (int j = 0; j < kMaxSplit; ++j) a[i][j] = (px < p.hw && j < p.split) ? __ldg(p.partial + o + j * p.split_stride) : 0.f;
+      ad[i] = (px < p.hw && p.addend) ? __bfloat162float(p.addend[o]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int px = b + i;
+      rf[px] = 0.f;
+      if (px < p.hw) {
+        float v = add;
+#pragma unroll
+        for (int j = 0; j < kMaxSplit; j += 4) v += (a[i][j] + a[i][j + 1]) + (a[i][j + 2] + a[i][j + 3]);
+        v += ad[i];
+        const __nv_bfloat16 r = __float2bfloat16_rn(v);
+        p.out[(img0 + px) * p.cout + c] = r;
+        rf[px] = __bfloat162float(r);
+        s1 += rf[px];
+        s2 = fmaf(rf[px], rf[px], s2);
+      }
+    }
+  }
+  if (p.stats) {
+    float m1 = s1, m2 = s2;
+    m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+    if ((lane & 3) == 0) {
+      const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
+      unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats) +
+                               (static_cast<long long>(n) * (p.cout >> 2) + (c >> 2)) * 2;
+      atomicAdd(st, static_cast<unsigned long long>(__float2ll_rn(m1 * kFix)));
+      atomicAdd(st + 1, static_cast<unsigned long long>(__float2ll_rn(m2 * kFix)));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const NormOut& q = p.no[k];
+    if (q.out == nullptr) continue;  // uniform
+    const int g0 = (lane / q.cpg) * q.cpg;
+    float t1 = 0.f, t2 = 0.f;
+    for (int j = 0; j < q.cpg; ++j) {  // ascending channel order, as the shared-memory version
+      t1 += __shfl_sync(0xffffffffu, s1, g0 + j);
+      t2 += __shfl_sync(0xffffffffu, s2, g0 + j);
+    }
+    const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * q.cpg);
+    const float mean = t1 * inv_cnt;
+    const float var = fmaxf(t2 * inv_cnt - mean * mean, 0.f);
+    const float rs = rsqrtf(var + q.eps);
+    const float ga = q.gamma ? __ldg(q.gamma + c) : 1.f, be = q.beta ? __ldg(q.beta + c) : 0.f;
+    float aa = rs * ga, bb = be - mean * rs * ga;
+    if (q.scale) {
+      const long long r = static_cast<long long>(q.ss_rows == 1 ? 0 : n) * q.ss_ld;
+      const float sc = 1.f + __ldg(q.scale + r + c), sh = __ldg(q.shift + r + c);
+      aa *= sc;
+      bb = bb * sc + sh;
+    }
+#pragma unroll
+    for (int px = 0; px < HW; ++px) {
+      if (px < p.hw) {
+        float y = fmaf(rf[px], aa, bb);
+        if (q.silu) y = silu_f(y);
+        q.out[(img0 + px) * p.cout + c] = __float2bfloat16_rn(y);
+      }
+    }
+  }
+}
+
 int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream) {
   SplitFinishParams p;
   memset(&p, 0, sizeof(p));
@@ -164,10 +261,17 @@ int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream) 
   DMME_REQUIRE(split >= 2 && split <= kMaxSplit && p.hw <= 256, DMME_E_SHAPE, "conv split-K finish: split %d / %d pixels per image", split, p.hw);
   const dim3 grid(d.n * (d.cout / 32)), block(kFinishWarps * 32);
   cudaError_t e;
-  if (p.hw <= 16) e = launch_pdl(splitk_finish_kernel<1>, grid, block, 0, stream, p);
+  // measured (tools/sweep_step.py, DDPM step): 3.73 -> 3.68 ms at batch 256, but 2.37 -> 2.42 ms at batch 128 -- with fewer
+  // than ~2000 slabs the warps' four sequential load batches are exposed; g_finish_small == 2 forces the kernel (tests)
+  if (p.hw <= 16 && (g_finish_small == 2 || (g_finish_small == 1 && d.n * (d.cout / 32) >= 2048)))
+    e = launch_pdl(splitk_finish_small_kernel, dim3(ceil_div(d.n * (d.cout / 32), kFinishSmallWarps)), dim3(kFinishSmallWarps * 32), 0, stream, p);
+  else if (p.hw <= 16) e = launch_pdl(splitk_finish_kernel<1>, grid, block, 0, stream, p);
   else if (p.hw <= 64) e = launch_pdl(splitk_finish_kernel<4>, grid, block, 0, stream, p);
   else e = launch_pdl(splitk_finish_kernel<16>, grid, block, 0, stream, p);
   return check_launch_err(e, "splitk_finish_kernel");
 }
 
 }  // namespace dmme
+
+// A/B switch: 0 = 4x4 maps take the block-per-slab finishing kernel too, 1 = warp-per-slab kernel (default)
+extern "C" void dmme_set_splitk_finish_small(int mode) { dmme::g_finish_small = mode; }

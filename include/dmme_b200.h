@@ -203,6 +203,10 @@ int dmme_conv2d_fuses_sampler(const dmme_conv_desc* desc);
 long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* desc);
 /* A/B switch: 0 = never split K, 1 = default (by the cost model), 2 = wherever the split-K kernel supports the shape */
 void dmme_set_conv_splitk_mode(int mode);
+/* A/B switch: 0 = the finishing pass of a split-K conv on 4x4 maps takes the block-per-slab kernel of the larger maps,
+ * 1 = its warp-per-slab kernel where there are at least 2048 (image, 32-channel slab) units (default; same bits),
+ * 2 = the warp-per-slab kernel always */
+void dmme_set_splitk_finish_small(int mode);
 
 /* chain of 3x3 convolutions (low-resolution ResBlocks) in one launch ------------------------ */
 /*

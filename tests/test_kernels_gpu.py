@@ -1039,6 +1039,38 @@ def test_conv_splitk_with_output_norms(cfg, splitk_everywhere):
         assert e < 6e-3, f"fused output norm (cpg {cpg}, silu {silu}) rel-L2 {e}"
 
 
+@pytest.mark.parametrize("n,cin,cpg,addend", [(256, 256, 8, False), (37, 512, 16, True), (3, 256, 4, True)])
+def test_splitk_finish_small_bit_equal(n, cin, cpg, addend, splitk_everywhere):
+    """4x4 maps: the warp-per-slab finishing kernel writes the same bits as the block-per-slab kernel (same summation
+    order): raw output, statistics, and both consumers' GroupNorm outputs"""
+    ops, L = _ops()
+    lib = L.load()
+    g = torch.Generator().manual_seed(97)
+    cout, h = 256, 4
+    x = torch.randn(n, h, h, cin, generator=g).to(torch.bfloat16).to(DEV)
+    wp = ops.pack_conv_weight((torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(DEV), None, True)
+    bias, gamma, beta = (torch.randn(cout, generator=g).to(DEV) for _ in range(3))
+    temb = torch.randn(n, cout, generator=g).to(DEV)
+    ad = torch.randn(n, h, h, cout, generator=g).to(torch.bfloat16).to(DEV) if addend else None
+    res = []
+    for mode in (0, 2):
+        lib.dmme_set_splitk_finish_small(mode)
+        try:
+            d = ops.make_conv_desc(x, None, cout, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+            ws = torch.empty(ops.conv_splitk_workspace(d) // 4, dtype=torch.float32, device=DEV)
+            out = torch.empty((n, h, h, cout), dtype=torch.bfloat16, device=DEV)
+            y0, y1 = torch.empty_like(out), torch.empty_like(out)
+            st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+            ops.conv2d_launch(d, wp, bias, out, temb, ad, stats=st, splitk_ws=ws,
+                              out_norms=[ops.out_norm(y0, gamma, beta, cpg, True), ops.out_norm(y1, beta, gamma, 32, False)])
+            torch.cuda.synchronize()
+            res.append((out, st, y0, y1))
+        finally:
+            lib.dmme_set_splitk_finish_small(1)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 def test_conv_splitk_default_plan_matches_unsplit():
     """the cost model's own choice at the strong-scaling shard batches: wherever it splits, the result equals the unsplit
     kernels' (same operands, fp32 accumulation in a different order) and out_norm is refused without the workspace"""
