@@ -163,7 +163,7 @@ def load() -> C.CDLL:
     lib.dmme_attention_fwd_train.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, f, i, vp, i, vp, vp, vp]
     lib.dmme_temb_bwd_workspace.argtypes = [i, i, i]
     lib.dmme_temb_bwd_workspace.restype = ll
-    lib.dmme_temb_bwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, ll, vp]
+    lib.dmme_temb_bwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, vp]
     lib.dmme_gemm_strided.argtypes = [vp, i, ll, ll, ll, ll, vp, i, ll, ll, ll, ll, vp, i, ll, ll, ll, ll,
                                       i, i, i, i, i, f, i, vp]
     lib.dmme_add.argtypes = [vp, vp, vp, ll, i, vp]

@@ -321,6 +321,7 @@ class TrainEngine(Engine):
         if c.dim() != 1 or c.numel() not in (1, x.shape[0]):
             raise ValueError(f"timestep tensor must have shape (1,) or (N,), got {tuple(c.shape)}")
         dev = x.device
+        self._act_dtype = act_dtype
         self.tape.clear()
         self.pending.clear()
         self.param_grads.clear()
@@ -383,7 +384,8 @@ class TrainEngine(Engine):
         wsz = ops.temb_bwd_workspace(c.numel(), half, emb.shape[1])
         wsb = self._buf("temb.bwd_ws", (wsz // 4,), torch.float32, dev)
         ops.temb_bwd(c, cond[0].embeddings, cond[1].weight.detach(), cond[1].bias.detach(), cond[3].weight.detach(),
-                     cond[3].bias.detach(), hidden, emb, wcat, self._d_all, dw1, db1, dw2, db2, dwcat, dbcat, wsb)
+                     cond[3].bias.detach(), hidden, emb, wcat, self._d_all, dw1, db1, dw2, db2, dwcat, dbcat, wsb,
+                     bf16_mma=self._act_dtype == torch.bfloat16 and not self.force_generic)
         _, _, offs = self.temb_tables()
         for _, blk in self.resblocks():
             o, width = offs[id(blk)]

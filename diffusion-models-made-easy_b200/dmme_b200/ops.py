@@ -453,13 +453,14 @@ def temb_bwd_workspace(rows: int, half: int, emb_dim: int) -> int:
 
 def temb_bwd(t: Tensor, freq: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, hidden: Tensor, emb: Tensor,
              wcat: Tensor, d_all: Tensor, dw1: Tensor, db1: Tensor, dw2: Tensor, db2: Tensor, dwcat: Tensor, dbcat: Tensor,
-             workspace: Tensor) -> None:
+             workspace: Tensor, bf16_mma: bool = False) -> None:
+    """``bf16_mma``: the two large products run on the tensor cores with bf16-rounded operands (bf16 training mode)."""
     L.require_cuda(t, freq, w1, b1, w2, b2, hidden, emb, wcat, d_all, dw1, db1, dw2, db2, dwcat, dbcat, workspace)
     rows, emb_dim = emb.shape
     L.check(L.load().dmme_temb_bwd(ptr(t), rows, ptr(freq), freq.numel(), ptr(w1), ptr(b1), ptr(w2), ptr(b2), emb_dim,
                                    ptr(hidden), ptr(emb), ptr(wcat), wcat.shape[0], ptr(d_all), ptr(dw1), ptr(db1), ptr(dw2),
                                    ptr(db2), ptr(dwcat), ptr(dbcat), ptr(workspace),
-                                   workspace.numel() * workspace.element_size(), L.stream_ptr()), "temb_bwd")
+                                   workspace.numel() * workspace.element_size(), int(bf16_mma), L.stream_ptr()), "temb_bwd")
 
 
 def gemm_strided(a: Tensor, a_str, b: Tensor, b_str, c: Tensor, c_str, m: int, n: int, k: int, outer: int = 1,

@@ -385,7 +385,9 @@ long long dmme_temb_bwd_workspace(int rows, int half, int emb_dim);
 int dmme_temb_bwd(const int64_t* t, int rows, const float* freq, int half, const float* w1, const float* b1,
                   const float* w2, const float* b2, int emb_dim, const float* hidden, const float* emb,
                   const float* wcat, int total, const float* d_all, float* dw1, float* db1, float* dw2, float* db2,
-                  float* dwcat, float* dbcat, void* workspace, long long workspace_bytes, void* stream);
+                  float* dwcat, float* dbcat, void* workspace, long long workspace_bytes, int bf16_mma, void* stream);
+/* bf16_mma = 1 (bf16 training mode): the two products over the batched projection run on the tensor cores with operands
+ * rounded to bf16 (fp32 accumulation); 0: fp32 FFMA throughout */
 
 /* C[b](i,j) = alpha * sum_k A[b](i,k) B[b](k,j) (+ C when accumulate); b = bo*heads + h; element strides per operand
  * (outer batch, head, row, column); dtypes DMME_BF16 / DMME_F32.  CUDA-core product used by the attention and

@@ -412,8 +412,9 @@ def test_attention_fwd_train_bf16_keeps_softmax(n, c, heads, L_):
 # ---------------------------------------------------------------------------------------------
 # conditioning MLP backward
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,pos,emb,total", [(5, 128, 512, 300), (3, 4, 8, 20)])
-def test_temb_bwd(rows, pos, emb, total):
+@pytest.mark.parametrize("rows,pos,emb,total,mma", [(5, 128, 512, 300, False), (3, 4, 8, 20, False), (128, 128, 512, 3000, True),
+                                                    (7, 128, 512, 300, True)])
+def test_temb_bwd(rows, pos, emb, total, mma):
     ops, L = _ops()
     half = pos // 2
     freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).unsqueeze(0)
@@ -434,9 +435,11 @@ def test_temb_bwd(rows, pos, emb, total):
     D = lambda x: x.detach().to(DEV).contiguous()
     outs = [torch.empty_like(D(p)) for p in (w1, b1, w2, b2, wc, bc)]
     ws = torch.empty(ops.temb_bwd_workspace(rows, half, emb) // 4, device=DEV)
-    ops.temb_bwd(t.to(DEV), freq.to(DEV), D(w1), D(b1), D(w2), D(b2), D(hid), D(em), D(wc), g.to(DEV), *outs, ws)
+    ops.temb_bwd(t.to(DEV), freq.to(DEV), D(w1), D(b1), D(w2), D(b2), D(hid), D(em), D(wc), g.to(DEV), *outs, ws, bf16_mma=mma)
+    # bf16_mma (bf16 training mode): the two products over the batched projection round their operands to bf16 (2^-9 per
+    # element, fp32 accumulation)
     for got, p in zip(outs, (w1, b1, w2, b2, wc, bc)):
-        assert rel_l2(got.cpu(), p.grad) < 1e-4
+        assert rel_l2(got.cpu(), p.grad) < (6e-3 if mma else 1e-4)
 
 
 # ---------------------------------------------------------------------------------------------
