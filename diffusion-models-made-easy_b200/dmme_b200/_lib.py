@@ -31,7 +31,7 @@ EXPORTS = (
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
     "dmme_denorm", "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
     "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
-    "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
+    "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_bwd_fused", "dmme_attention_bwd_fused_supported", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
     "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_dilate2x_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
 
@@ -160,6 +160,8 @@ def load() -> C.CDLL:
     lib.dmme_attention_bwd_workspace.argtypes = [i, i, i, i]
     lib.dmme_attention_bwd_workspace.restype = ll
     lib.dmme_attention_bwd.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, f, i, vp, vp, vp, vp, i, vp, vp, ll, vp]
+    lib.dmme_attention_bwd_fused_supported.argtypes = [i, i, i, i]
+    lib.dmme_attention_bwd_fused.argtypes = [vp, vp, vp, vp, i, i, i, i, f, i, i, vp]
     lib.dmme_attention_fwd_train.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, f, i, vp, i, vp, vp, vp]
     lib.dmme_temb_bwd_workspace.argtypes = [i, i, i]
     lib.dmme_temb_bwd_workspace.restype = ll

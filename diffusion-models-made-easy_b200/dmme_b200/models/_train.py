@@ -18,6 +18,8 @@ collected per tensor and summed either inside the next kernel that can take an a
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -44,6 +46,8 @@ class TrainEngine(Engine):
         self._garena: Optional[Tensor] = None
         self._gcur = 0
         self.grad_sync = None          # None: single process; else dict(group=..., bucket_bytes=...)
+        # multi-head attention backward on the fused tcgen05 kernel where it applies (DMME_FUSED_ATTN_BWD=0: strided products)
+        self.fused_attn_bwd = os.environ.get("DMME_FUSED_ATTN_BWD", "1") != "0"
         self.want_input_grad = False   # set per call when the image tensor requires grad
         self.input_grad: Optional[Tensor] = None
         self.last_buckets = []
@@ -265,16 +269,28 @@ class TrainEngine(Engine):
             nh, dh, swap = heads, c // heads, True
             hs = 3 * dh
             q, k, v = flat, flat[dh:], flat[2 * dh:]
-        # strided products with the softmax matrix kept for the backward pass
-        p_saved = self._buf(name + ".attn_p", (n * nh, seq, seq), torch.float32, dev)
-        o_tmp = self.ws.get("train.attn_otmp", (n * nh * seq * dh,), torch.float32, dev)
-        ops.attention_fwd_train(q, k, v, n, nh, seq, dh, att.scale, seq * 3 * c, 3 * c, hs, swap, ao, p_saved, o_tmp)
+        fused = (heads is not None and not self.force_generic and self.fused_attn_bwd
+                 and ops.attention_bwd_fused_supported(nh, seq, dh, x.dtype))
+        if fused:
+            # fused tcgen05 backward (csrc/attention_bwd_tc.cu) recomputes the softmax from q and k: the forward is the
+            # inference kernel, nothing but its output is kept
+            ops.attention(q, k, v, n, nh, seq, dh, att.scale, seq * 3 * c, 3 * c, hs, False, 0, swap, ao)
+            p_saved = None
+        else:
+            # strided products with the softmax matrix kept for the backward pass
+            p_saved = self._buf(name + ".attn_p", (n * nh, seq, seq), torch.float32, dev)
+            o_tmp = self.ws.get("train.attn_otmp", (n * nh * seq * dh,), torch.float32, dev)
+            ops.attention_fwd_train(q, k, v, n, nh, seq, dh, att.scale, seq * 3 * c, 3 * c, hs, swap, ao, p_saved, o_tmp)
 
         def backward() -> None:
             g = self._grad_of(ao)
             if g is None:
                 return
             dqkv = self._like(name + ".dqkv", qkv)
+            if fused:
+                ops.attention_bwd_fused(qkv, ao, g.contiguous(), dqkv, n, nh, seq, dh, att.scale, swap)
+                self._contribute(qkv, dqkv)
+                return
             dflat = dqkv.view(-1)
             if heads is None:
                 dq, dk, dv = dflat, dflat[c:], dflat[2 * c:]

@@ -437,6 +437,20 @@ def attention_bwd(q: Tensor, k: Tensor, v: Tensor, n: int, heads: int, seq: int,
                                         workspace.numel() * workspace.element_size(), L.stream_ptr()), "attention_bwd")
 
 
+def attention_bwd_fused_supported(heads: int, seq: int, dh: int, dtype: torch.dtype) -> bool:
+    return bool(L.load().dmme_attention_bwd_fused_supported(heads, seq, dh, L.act_code(dtype)))
+
+
+def attention_bwd_fused(qkv: Tensor, out: Tensor, dout: Tensor, dqkv: Tensor, n: int, heads: int, seq: int, dh: int,
+                        scale: float, head_batch_swap: bool) -> Tensor:
+    """dqkv = gradient of the packed ``[n][L][heads][q | k | v][dh]`` tensor given the forward output and its gradient
+    (csrc/attention_bwd_tc.cu: fused tcgen05 kernel, softmax recomputed, no L x L matrix in global memory)."""
+    L.require_cuda(qkv, out, dout, dqkv)
+    L.check(L.load().dmme_attention_bwd_fused(ptr(qkv), ptr(out), ptr(dout), ptr(dqkv), n, heads, seq, dh, float(scale),
+                                              int(head_batch_swap), L.act_code(qkv.dtype), L.stream_ptr()), "attention_bwd_fused")
+    return dqkv
+
+
 def attention_fwd_train(q: Tensor, k: Tensor, v: Tensor, n: int, heads: int, seq: int, dh: int, scale: float,
                         batch_stride: int, row_stride: int, head_stride: int, head_batch_swap: bool, out: Tensor,
                         p_out: Tensor, o_tmp: Tensor) -> Tensor:

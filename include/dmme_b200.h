@@ -379,6 +379,17 @@ int dmme_attention_fwd_train(const void* q, const void* k, const void* v, long l
                              int head_stride, int n, int heads, int L, int dh, float scale, int head_batch_swap,
                              void* out, int act_dtype, float* p_out, float* o_tmp, void* stream);
 
+/*
+ * Fused tcgen05 backward of the multi-head attention core (MultiHeadAttention.forward_attention models/iddpm.py:36-59) for
+ * the packed qkv layout [n][L][heads][q | k | v][dh] with dh = 64 and L = 256 or 64, bf16: one CTA per (image, head) -- two
+ * images per CTA at L = 64 -- recomputes the softmax from Q and K, so neither the forward's softmax matrix nor any other
+ * L x L matrix touches global memory.  out / dout: the forward output and its gradient, [n][L][heads * dh] at the
+ * "(b head) -> (head b)" position when head_batch_swap; dqkv: gradient of the packed tensor (every element written).
+ */
+int dmme_attention_bwd_fused_supported(int heads, int L, int dh, int act_dtype);
+int dmme_attention_bwd_fused(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int heads, int L, int dh,
+                             float scale, int head_batch_swap, int act_dtype, void* stream);
+
 /* Backward of dmme_temb_mlp_fwd + dmme_temb_proj_fwd.  hidden/emb: the forward's scratch / emb_out;
  * d_all [rows][total]: gradient of the batched projection output.  All parameter gradients are written. */
 long long dmme_temb_bwd_workspace(int rows, int half, int emb_dim);

@@ -386,6 +386,43 @@ def test_attention_bwd(n, c, heads, L_, swap):
     assert rel_l2(dqkv2.cpu(), qkv.grad) < 1e-4
 
 
+@pytest.mark.parametrize("n,heads,L_,swap", [(3, 4, 256, True), (2, 1, 256, False), (5, 4, 64, True), (4, 2, 64, False), (1, 4, 64, True),
+                                              (128, 4, 256, True)])
+def test_attention_bwd_fused(n, heads, L_, swap):
+    """fused tcgen05 attention backward (csrc/attention_bwd_tc.cu) against autograd through fp32 attention on the SAME
+    bf16-rounded q, k, v and output gradient: what differs is the bf16 rounding of P and dS inside the kernel (2^-9 relative
+    per element) and of the stored gradients -- rel-L2 <= 1.5e-2 per gradient"""
+    ops, L = _ops()
+    dh = 64
+    c = heads * dh
+    nn_ = min(n, 6)  # the reference is computed for the first images only (the batch-128 case checks the grid / regrouping)
+    qkv = (_rand(n, L_, 3 * c, seed=11) * 0.7).to(torch.bfloat16).float().requires_grad_()
+    scale = c ** -0.5
+    t = qkv.reshape(n, L_, heads, 3, dh).permute(3, 0, 2, 1, 4).reshape(3, n * heads, L_, dh)
+    o = torch.softmax(t[0] @ (t[1] * scale).transpose(1, 2), dim=2) @ t[2]
+    if swap:
+        out = o.reshape(heads, n, L_, dh).permute(1, 2, 0, 3).reshape(n, L_, c)
+    else:
+        out = o.reshape(n, heads, L_, dh).permute(0, 2, 1, 3).reshape(n, L_, c)
+    g = _rand(*out.shape, seed=12).to(torch.bfloat16).float()
+    out.backward(g)
+    qd = qkv.detach().to(torch.bfloat16).to(DEV)
+    od = torch.empty(n, L_, c, dtype=torch.bfloat16, device=DEV)
+    flat = qd.view(-1)
+    ops.attention(flat, flat[dh:], flat[2 * dh:], n, heads, L_, dh, scale, L_ * 3 * c, 3 * c, 3 * dh, False, 0, swap, od)
+    assert rel_l2(od.float().cpu()[:nn_], out.detach()[:nn_]) < 8e-3
+    dqkv = torch.full_like(qd, float("nan"))
+    assert ops.attention_bwd_fused_supported(heads, L_, dh, torch.bfloat16)
+    ops.attention_bwd_fused(qd, od, g.to(torch.bfloat16).to(DEV), dqkv, n, heads, L_, dh, scale, swap)
+    torch.cuda.synchronize()
+    got = dqkv.float().cpu().reshape(n, L_, heads, 3, dh)
+    want = qkv.grad.reshape(n, L_, heads, 3, dh)
+    assert torch.isfinite(got).all()
+    for j, name in enumerate(("dq", "dk", "dv")):
+        e = rel_l2(got[..., j, :], want[..., j, :])
+        assert e < 1.5e-2, f"{name}: rel-L2 {e}"
+
+
 @pytest.mark.parametrize("n,c,heads,L_", [(3, 256, 4, 256), (2, 128, 4, 256), (5, 256, 4, 64), (1, 64, 1, 256), (2, 128, 4, 64)])
 def test_attention_fwd_train_bf16_keeps_softmax(n, c, heads, L_):
     """bf16 training forward of the multi-head layout (tcgen05 kernels at 256 tokens and at 64 tokens with 64-channel heads,
