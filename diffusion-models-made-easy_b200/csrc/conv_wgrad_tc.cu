@@ -204,7 +204,13 @@ static int wg_block_n(const dmme_conv_desc& d) {
   return (d.c0 % 128 == 0 && d.c1 % 128 == 0 && d.rc0 % 128 == 0 && d.rc1 % 128 == 0) ? 128 : 64;
 }
 
-// slices of the pixel axis: enough CTAs for ~3 waves, at least 4 chunks per slice
+// Slices of the pixel axis.  Measured (IDDPM training step, batch 128, tools/prof_train.py --graph): slicing for 3 / 2 / 1
+// waves of CTAs = 21.7 / 20.1 / 18.8 ms, exactly one wave rounded DOWN (148 / items slices) 17.6-18.3 ms, half a wave 18.7:
+// every slice costs a prologue, a 196 KB partial tile written and re-read by the reduction, and a tail -- so the fewest
+// slices that still give every SM a CTA win.  0 = that default; > 0: that many waves; < 0: 1 / |value| of a wave (A/B).
+static int g_wgrad_waves = 0;
+
+// slices of the pixel axis (see g_wgrad_waves), at least 4 chunks per slice
 void conv_wgrad_tc_geometry(const dmme_conv_desc& d, int& items, int& chunks_total, int& chunks_per_slice, int& slices) {
   const int nb = wg_block_n(d);
   const int rows = d.ksize == 3 ? 3 : 1;
@@ -214,7 +220,7 @@ void conv_wgrad_tc_geometry(const dmme_conv_desc& d, int& items, int& chunks_tot
   const int bh = d.h_in < kWgChunk / bw ? d.h_in : kWgChunk / bw;
   const int bni = kWgChunk / (bw * bh);
   chunks_total = (d.w_in / bw) * (d.h_in / bh) * ceil_div(d.n, bni);
-  int want = ceil_div(148 * 3, items);
+  int want = g_wgrad_waves > 0 ? ceil_div(148 * g_wgrad_waves, items) : g_wgrad_waves == 0 ? 148 / items : 148 / (items * -g_wgrad_waves);
   if (want < 1) want = 1;
   int max_slices = chunks_total / 4;
   if (max_slices < 1) max_slices = 1;
@@ -279,3 +285,6 @@ int conv_wgrad_tc_partials(const dmme_conv_desc& d, const void* grad_out, float*
 }
 
 }  // namespace dmme
+
+// A/B switch: waves of CTAs the tcgen05 weight-gradient kernel slices the pixel axis for (default 0 = one wave, rounded down)
+extern "C" void dmme_set_wgrad_waves(int waves) { dmme::g_wgrad_waves = waves; }

@@ -31,7 +31,7 @@ EXPORTS = (
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
     "dmme_denorm", "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
     "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
-    "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_bwd_fused", "dmme_attention_bwd_fused_supported", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
+    "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_bwd_fused", "dmme_attention_bwd_fused_supported", "dmme_set_wgrad_waves", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
     "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_dilate2x_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
 
@@ -190,6 +190,11 @@ def load() -> C.CDLL:
     mode = os.environ.get("DMME_SPLITK_MODE")  # A/B measurements only: 0 = never split K
     if mode:
         lib.dmme_set_conv_splitk_mode(int(mode))
+    mode = os.environ.get("DMME_WGRAD_WAVES")  # A/B measurements only
+    if mode:
+        lib.dmme_set_wgrad_waves.argtypes = [i]
+        lib.dmme_set_wgrad_waves.restype = None
+        lib.dmme_set_wgrad_waves(int(mode))
     mode = os.environ.get("DMME_FINISH_SMALL")  # A/B measurements only: 0 = block-per-slab split-K finishing kernel at 4x4
     if mode:
         lib.dmme_set_splitk_finish_small(int(mode))

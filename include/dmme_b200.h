@@ -386,6 +386,8 @@ int dmme_attention_fwd_train(const void* q, const void* k, const void* v, long l
  * L x L matrix touches global memory.  out / dout: the forward output and its gradient, [n][L][heads * dh] at the
  * "(b head) -> (head b)" position when head_batch_swap; dqkv: gradient of the packed tensor (every element written).
  */
+/* A/B switch: waves of CTAs the tcgen05 weight-gradient kernel slices the pixel axis for (0 = exactly one wave, rounded down: the default; n > 0: n waves) */
+void dmme_set_wgrad_waves(int waves);
 int dmme_attention_bwd_fused_supported(int heads, int L, int dh, int act_dtype);
 int dmme_attention_bwd_fused(const void* qkv, const void* out, const void* dout, void* dqkv, int n, int heads, int L, int dh,
                              float scale, int head_batch_swap, int act_dtype, void* stream);
