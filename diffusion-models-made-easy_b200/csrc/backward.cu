@@ -587,15 +587,27 @@ static bool conv_out_wgrad_supported(const dmme_conv_desc& d) {
 }
 
 // partial [slices][cout][kp] -> dW OIHW [cout][cin][taps], dWres [cout][rc], dbias [cout]
+// img_sums (tensor-core path): per-image pixel sums of grad_out [n_img][cout]; the bias gradient is their column sum, taken
+// here by the thread of the bias column (in image order, as colsum_kernel did in a launch of its own: 75 launches per step)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slices, int cout, int kp, int cin, int taps, int rc,
-                                    float* __restrict__ dw, float* __restrict__ dwres, float* __restrict__ dbias) {
+                                    float* __restrict__ dw, float* __restrict__ dwres, float* __restrict__ dbias,
+                                    const float* __restrict__ img_sums = nullptr, int n_img = 0) {
   const long long total = static_cast<long long>(cout) * kp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < slices; ++z) s += partial[z * total + i];
     const int co = static_cast<int>(i / kp), k = static_cast<int>(i - static_cast<long long>(co) * kp);
     const int kconv = taps * cin;
+    float s = 0.f;
+    if (k >= kconv + rc && img_sums != nullptr) {
+      if (dbias) {
+#pragma unroll 8
+        for (int r = 0; r < n_img; ++r) s += img_sums[static_cast<long long>(r) * cout + co];
+        dbias[co] = s;
+      }
+      continue;
+    }
+#pragma unroll 4
+    for (int z = 0; z < slices; ++z) s += partial[z * total + i];
     if (k < kconv) {
       const int tap = k / cin, ci = k - tap * cin;
       dw[(static_cast<long long>(co) * cin + ci) * taps + tap] = s;
@@ -1297,17 +1309,15 @@ extern "C" int dmme_conv2d_wgrad(const dmme_conv_desc* d, const void* grad_out, 
     int rc = conv_wgrad_tc_partials(*d, grad_out, partial, tslices, st);
     if (rc) return rc;
     const long long total = static_cast<long long>(d->cout) * kp;
-    wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(partial, tslices, d->cout, kp, d->c0 + d->c1, d->ksize * d->ksize,
-                                                            d->rc0 + d->rc1, dweight, dweight_res, nullptr);
-    if ((rc = check_launch("wgrad_reduce_kernel"))) return rc;
+    float* img_sums = partial + static_cast<long long>(tslices) * d->cout * kp;
     if (dbias) {
-      float* img_sums = partial + static_cast<long long>(tslices) * d->cout * kp;
       dim3 grid(ceil_div(d->cout, 32), d->n), block(32, 8);
       pixel_sum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(grad_out), ho * wo, d->cout, img_sums, d->cout);
       if ((rc = check_launch("pixel_sum_kernel"))) return rc;
-      colsum_kernel<<<ceil_div(d->cout, 128), 128, 0, st>>>(img_sums, d->n, d->cout, d->cout, dbias, 0);
-      if ((rc = check_launch("colsum_kernel"))) return rc;
     }
+    wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(partial, tslices, d->cout, kp, d->c0 + d->c1, d->ksize * d->ksize,
+                                                            d->rc0 + d->rc1, dweight, dweight_res, dbias, img_sums, d->n);
+    if ((rc = check_launch("wgrad_reduce_kernel"))) return rc;
     return 0;
   }
   WgradParams p;
