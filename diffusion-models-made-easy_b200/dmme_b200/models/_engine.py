@@ -74,6 +74,8 @@ class Engine:
         # sampler update applied by the output conv's epilogue (eps stays in registers); sampler_applied reports whether the
         # last forward did it (the callers run the stand-alone update kernel otherwise)
         self.fuse_sampler = os.environ.get("DMME_FUSE_SAMPLER", "1") != "0"
+        # single-head 256-token x 256-channel attention blocks as one launch (DMME_FUSE_ATTN=0: norm | qkv | core | proj launches)
+        self.fuse_attn = os.environ.get("DMME_FUSE_ATTN", "1") != "0"
         # consecutive ResBlocks of the 8x8 / 4x4 levels in one persistent launch (csrc/conv_chain.cu); DMME_CHAIN=0: per-conv
         # launches as at the higher resolutions
         self.use_chain = os.environ.get("DMME_CHAIN", "1") != "0"
@@ -360,10 +362,23 @@ class Engine:
     def attention_block(self, name: str, att: nn.Module, x: Tensor) -> Tensor:
         n, h, w, c = x.shape
         seq = h * w
+        heads = getattr(att, "num_heads", None)
+        st = self._stats.get(x.data_ptr())
+        if (self.fuse_attn and heads is None and st is not None and not self.force_generic and c % att.norm.num_groups == 0
+                and (c // att.norm.num_groups) % 4 == 0 and ops.attention_block_supported(1, seq, c, x.dtype)):
+            # the whole block in one launch (csrc/attention_block.cu): norm, qkv, softmax(q k^T) v, proj and + x
+            norm = att.norm
+            ab = ops.groupnorm_coeff(st, None, c, 0, n, seq, norm.num_groups, norm.weight.detach(), norm.bias.detach(), None, None,
+                                     norm.eps, out=self.ws.get("scratch.attn_ab", (n, c, 2), torch.float32, x.device))
+            out = self.ws.get(name + ".attn", (n, h, w, c), x.dtype, x.device)
+            stats = self._stats_for(out, n, c)
+            if stats is None:
+                self._stats.pop(out.data_ptr(), None)
+            return ops.attention_block(x, ab, self.packed_weight(att.qkv_proj, None, True), att.qkv_proj.bias.detach(),
+                                       self.packed_weight(att.proj, None, True), att.proj.bias.detach(), att.scale, out, stats)
         a = self._normed.get((x.data_ptr(), id(att.norm)))
         if a is None:
             a = self.gn("scratch.attn_norm", att.norm, x, None, silu=False)
-        heads = getattr(att, "num_heads", None)
         ao = self.ws.get("scratch.attn_out", (n, h, w, c), x.dtype, x.device)
         if heads is None:
             # single head; scale on K in the reference (models/ddpm.py:58) == scale on the scores

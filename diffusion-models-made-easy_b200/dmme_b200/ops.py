@@ -297,6 +297,25 @@ def attention(q: Tensor, k: Tensor, v: Tensor, n: int, heads: int, seq: int, dh:
     return out
 
 
+def attention_block_supported(heads: int, seq: int, c: int, dtype: torch.dtype) -> bool:
+    """True when ``attention_block`` (the one-launch attention block) takes this shape."""
+    return bool(L.load().dmme_attention_block_supported(heads, seq, c, L.act_code(dtype)))
+
+
+def attention_block(x: Tensor, gn_ab: Tensor, wqkv: Tensor, bias_qkv: Tensor, wproj: Tensor, bias_proj: Tensor, scale: float,
+                    out: Optional[Tensor] = None, stats: Optional[Tensor] = None) -> Tensor:
+    """``x + proj(attention(qkv_proj(GroupNorm(x))))`` (Attention.forward, models/ddpm.py:54-75) in one launch.
+    x: NHWC bf16 [n, h, w, c]; gn_ab: ``groupnorm_coeff`` of the block's norm; wqkv / wproj: ``pack_conv_weight`` of the two
+    1x1 convs; stats: optional zeroed int64 micro-group sums of the output."""
+    L.require_cuda(x, gn_ab, wqkv, bias_qkv, wproj, bias_proj, out, stats)
+    n, h, w, c = x.shape
+    y = _empty((n, h, w, c), x.dtype, x.device, out)
+    L.check(L.load().dmme_attention_block_fwd(ptr(x), ptr(gn_ab), ptr(wqkv), ptr(bias_qkv), ptr(wproj), ptr(bias_proj), n, 1,
+                                              h * w, c, float(scale), ptr(y), ptr(stats), L.act_code(x.dtype), L.stream_ptr()),
+            "attention_block_fwd")
+    return y
+
+
 def temb_mlp(t: Tensor, freq: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor,
              out: Optional[Tensor] = None, scratch: Optional[Tensor] = None) -> Tensor:
     L.require_cuda(t, freq, w1, b1, w2, b2)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMME_ABI_VERSION 5
+#define DMME_ABI_VERSION 6
 #define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
@@ -283,6 +283,21 @@ int dmme_attention_fwd(const void* q, const void* k, const void* v, long long ba
  * dense [n][L][dh] q/k and transposed v) instead of the generic CUDA-core kernel */
 int dmme_attention_uses_tc(long long batch_stride, int row_stride, int v_transposed, long long v_batch_stride,
                            int heads, int L, int dh, int head_batch_swap, int act_dtype);
+
+/*
+ * The whole attention block of Attention.forward (models/ddpm.py:54-75) in one launch:
+ *   out = x + proj( softmax(scale * q k^T) v ),  [q | k | v] = qkv_proj(GroupNorm(x))
+ * x / out: NHWC act_dtype [n][L][c]; gn_ab: the (a, b) pairs of the block's GroupNorm from dmme_groupnorm_coeff
+ * ([n][c][2], no SiLU); wqkv [3c][c] / wproj [c][c]: the 1x1 conv weights packed by dmme_pack_conv_weight (bf16, K
+ * contiguous); bias_qkv [3c], bias_proj [c] fp32; stats: optional micro-group sums of `out` (as dmme_conv_desc.stats).
+ * Nothing between x and out is written to global memory.  Supported (ask first): bf16, heads = 1, L = 256, c = 256 -- the
+ * 16x16 attention sites of the default DDPM UNet (configs/ddpm/cifar10.yaml); other shapes take the qkv conv +
+ * dmme_attention_fwd + proj conv path.
+ */
+int dmme_attention_block_supported(int heads, int L, int c, int act_dtype);
+int dmme_attention_block_fwd(const void* x, const float* gn_ab, const void* wqkv, const float* bias_qkv,
+                             const void* wproj, const float* bias_proj, int n, int heads, int L, int c, float scale,
+                             void* out, long long* stats, int act_dtype, void* stream);
 
 /* timestep embedding ----------------------------------------------------------------------- */
 /*

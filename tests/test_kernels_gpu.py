@@ -615,6 +615,64 @@ def test_attention_tc(n, c):
     assert rel_l2(out.float().cpu(), gen.float().cpu()) < 6e-3
 
 
+def _stats_of(x_nhwc):
+    """int64 micro-group sums (2^-20 fixed point) of a stored NHWC tensor, as a producing conv's epilogue leaves them"""
+    n, h, w, c = x_nhwc.shape
+    v = x_nhwc.double().reshape(n, h * w, c // 4, 4)
+    s1, s2 = v.sum((1, 3)), (v * v).sum((1, 3))
+    return (torch.stack([s1, s2], dim=-1) * 2 ** 20).round().to(torch.int64).reshape(-1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 75, 150, 256])
+def test_attention_block_fused(n):
+    """The one-launch attention block (norm | qkv | softmax(q k^T) v | proj | + x, models/ddpm.py:54-75) against the fp32
+    computation of the module on the same bf16-rounded input and weights.  n = 75 / 150 / 256: some / all clusters take
+    two, three or four images (74 clusters of two CTAs)."""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(7 + n)
+    c, hgt, groups = 256, 16, 32
+    seq = hgt * hgt
+    assert ops.attention_block_supported(1, seq, c, torch.bfloat16)
+    # per-image and per-channel offsets / gains so that the norm matters
+    x = torch.randn(n, c, hgt, hgt, generator=g) * (0.5 + torch.rand(n, c, 1, 1, generator=g)) + torch.randn(n, c, 1, 1, generator=g)
+    x = bf16_round(x)
+    gamma, beta = 1 + 0.3 * torch.randn(c, generator=g), 0.3 * torch.randn(c, generator=g)
+    wqkv = bf16_round(torch.randn(3 * c, c, 1, 1, generator=g) * (2.0 / math.sqrt(c)))
+    bqkv = torch.randn(3 * c, generator=g) * 0.5
+    wproj = bf16_round(torch.randn(c, c, 1, 1, generator=g) / math.sqrt(c))
+    bproj = torch.randn(c, generator=g) * 0.5
+    scale = c ** -0.5
+
+    hn = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+    qkv = F.conv2d(hn, wqkv, bqkv)
+    q, k, v = (t.reshape(n, c, seq).transpose(1, 2) for t in qkv.chunk(3, dim=1))
+    att = torch.bmm(F.softmax(torch.bmm(q, k.transpose(1, 2) * scale), dim=2), v)  # [n, L, c]
+    att = att.transpose(1, 2).reshape(n, c, hgt, hgt)
+    want = x + F.conv2d(att, wproj, bproj)
+
+    xd = to_nhwc(x, torch.bfloat16).to(DEV)
+    st = _stats_of(xd.cpu().float()).to(DEV)
+    ab = ops.groupnorm_coeff(st, None, c, 0, n, seq, groups, gamma.to(DEV), beta.to(DEV), None, None, 1e-5)
+    out_stats = torch.zeros(n * (c // 4) * 2, dtype=torch.int64, device=DEV)
+    out = ops.attention_block(xd, ab, ops.pack_conv_weight(wqkv.to(DEV), None, True), bqkv.to(DEV),
+                              ops.pack_conv_weight(wproj.to(DEV), None, True), bproj.to(DEV), scale, stats=out_stats)
+    torch.cuda.synchronize()
+    got = to_nchw(out.cpu())
+    err = rel_l2(got, want)
+    # the attention branch alone (the residual x dominates the output norm)
+    err_branch = rel_l2(got - x, want - x)
+    assert err < 6e-3, err
+    assert err_branch < 1.5e-2, err_branch  # h, q, k, v, P and O are each rounded to bf16 once
+    # every image separately: a wrong image -> cluster assignment would hide in the aggregate
+    per = ((got - want).flatten(1).norm(dim=1) / want.flatten(1).norm(dim=1)).max()
+    assert per < 8e-3, per
+    # statistics of the stored output
+    sums = out_stats.cpu().view(n, c // 4, 2).double() / 2 ** 20
+    yo = out.cpu().double().reshape(n, seq, c // 4, 4)
+    assert torch.allclose(sums[..., 0], yo.sum((1, 3)), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(sums[..., 1], (yo * yo).sum((1, 3)), rtol=1e-5, atol=1e-2)
+
+
 @pytest.mark.parametrize("n,c,heads,L_", [(3, 32, 4, 64), (2, 128, 4, 256), (4, 16, 4, 16)])
 def test_attention_multi_head_iddpm_regrouping(n, c, heads, L_):
     """models/iddpm.py:36-47 including the (b head) -> (head b) output regrouping."""

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""clock64 timeline of the one-launch attention block (csrc/attention_block.cu), leader CTA of cluster 0: when the worker
+warps enter / leave each phase and when the MMA thread's waits complete.  usage: python tools/trace_attn_block.py [batch]"""
+import ctypes as C
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "diffusion-models-made-easy_b200"))
+import torch  # noqa: E402
+
+from dmme_b200 import _lib as L  # noqa: E402
+from dmme_b200 import ops  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+dev, c, seq = "cuda", 256, 256
+g = torch.Generator(device=dev).manual_seed(0)
+x = torch.randn(n, 16, 16, c, device=dev, generator=g).bfloat16()
+ab = torch.stack([1 + 0.1 * torch.randn(n, c, device=dev, generator=g), 0.1 * torch.randn(n, c, device=dev, generator=g)], dim=-1).contiguous()
+wqkv = ops.pack_conv_weight(torch.randn(3 * c, c, 1, 1, device=dev, generator=g) / math.sqrt(c), None, True)
+wproj = ops.pack_conv_weight(torch.randn(c, c, 1, 1, device=dev, generator=g) / math.sqrt(c), None, True)
+bqkv, bproj = torch.randn(3 * c, device=dev, generator=g), torch.randn(c, device=dev, generator=g)
+out = torch.empty_like(x)
+st = torch.zeros(n * c // 4 * 2, dtype=torch.int64, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+trace = torch.zeros(2 * 256, dtype=torch.int64, device=dev)
+lib = L.load()
+lib.dmme_debug_set_attn_block_trace.argtypes = [C.c_void_p]
+lib.dmme_debug_set_attn_block_trace.restype = None
+for rep in range(3):
+    if len(sys.argv) > 2:
+        flush.fill_(rep)
+    trace.zero_()
+    lib.dmme_debug_set_attn_block_trace(trace.data_ptr())
+    ops.attention_block(x, ab, wqkv, bqkv, wproj, bproj, c ** -0.5, out, st)
+    torch.cuda.synchronize()
+lib.dmme_debug_set_attn_block_trace(None)
+t = trace.cpu().view(2, 256)
+WN = ["x landed", "H done", "Q ready", "Q drained", "K ready", "K drained", "V ready", "V drained", "S ready", "P done",
+      "O ready", "O drained", "D ready", "out stored"]
+MN = ["H+Wq -> Q GEMM", "Wk -> K GEMM", "Q drained -> V GEMM", "Wv kb0", "Wv kb1", "Wv kb2", "Wv kb3", "K drained -> S GEMM",
+      "P ready -> PV GEMM", "O drained+Wp -> proj GEMM"]
+ev = []
+for i in range(256):
+    if int(t[0, i]):
+        ev.append((int(t[0, i]), f"worker img{i // 14} {WN[i % 14]}"))
+    if int(t[1, i]):
+        ev.append((int(t[1, i]), f"   mma img{i // 10} {MN[i % 10]}"))
+ev.sort()
+t0 = ev[0][0]
+prev = t0
+for v, name in ev:
+    print(f"{v - t0:8d} clk (+{v - prev:6d})  {name}")
+    prev = v
