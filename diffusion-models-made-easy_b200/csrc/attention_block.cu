@@ -23,8 +23,9 @@
 //   R3: Wk slab -> K -> O (bf16)     -> next image's Wk (from "out^T complete")
 //   ring: the four k-blocks of the Wv slab
 // TMEM per CTA: T0 = columns [0, 256): Q, V^T, O;  T1 = [256, 512): K, S, out^T.
-// Warps: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2..9 = 256 workers (GroupNorm transform, the four accumulator
-// drains, softmax, output epilogue).  Worker phases of the two CTAs are joined on the leader's mbarriers (remote arrives).
+// Warps: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2..9 = 256 workers (the four accumulator drains, softmax,
+// output epilogue), 10..13 = GroupNorm transform of the NEXT image's tile.  Worker phases of the two CTAs are joined on the
+// leader's mbarriers (remote arrives); P V and the projection start on the 64-wide k-blocks the workers have finished.
 #include <cuda.h>
 #include <string.h>
 
@@ -50,7 +51,8 @@ struct AttnBlockParams {
 };
 
 static long long* g_ab_trace = nullptr;
-// role 0: worker warp 2 lane 0 (14 events per image), role 1: MMA thread (10 events per image)
+// role 0: worker warp 2 lane 0 (14 events per image), role 1: MMA thread (10 events per image), role 2: inside the Q drain
+// and the output epilogue (16 per image)
 __device__ __forceinline__ void ab_trace(long long* trace, int role, int idx) {
   if (trace != nullptr && blockIdx.x == 0 && idx < 256) trace[role * 256 + idx] = clock64();
 }
@@ -59,13 +61,17 @@ constexpr int kAbC = 256, kAbL = 256;
 constexpr int kAbBlk = 128 * 128;          // one [128 rows][64 bf16] block
 constexpr int kAbRegion = 4 * kAbBlk;      // 64 KB
 constexpr int kAbWorkers = 256;
-constexpr int kAbThreads = 64 + kAbWorkers;
+constexpr int kAbXform = 64;               // GroupNorm transform warps (run one image ahead of the workers)
+constexpr int kAbThreads = 64 + kAbWorkers + kAbXform;
 constexpr int kAbSmem = 3 * kAbRegion + 2 * kAbBlk + 1024;
 
 enum {
   AB_X_FULL = 0, AB_H_READY, AB_WQ_FULL, AB_WK_FULL, AB_WP_FULL, AB_WV_FULL0, AB_WV_FULL1, AB_WV_EMPTY0, AB_WV_EMPTY1,
-  AB_Q_DONE, AB_K_DONE, AB_V_DONE, AB_S_DONE, AB_O_DONE, AB_D_DONE, AB_QS_READY, AB_KS_READY, AB_PV_READY, AB_OS_READY,
-  AB_NBARS
+  AB_Q_DONE, AB_K_DONE, AB_V_DONE, AB_S_DONE, AB_O_DONE, AB_D_DONE,
+  AB_QS_READY, AB_KS_READY, AB_EPI_DONE,  // joined by the 2 x 256 workers
+  AB_PV_READY0,                           // + key block: P block and V^T block written (2 x 128 workers of that half each)
+  AB_OS_READY0 = AB_PV_READY0 + 4,        // + channel block of O
+  AB_NBARS = AB_OS_READY0 + 4
 };
 
 // wait on a barrier that threads of the peer CTA arrive on (release.cluster): acquire at cluster scope
@@ -89,41 +95,68 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+__device__ __forceinline__ void ab_store_chunk(uint8_t* prow, int c, int row, const float (&f)[32]) {
+  uint8_t* pc = prow + (c >> 6) * kAbBlk;
+  const int u0 = (c & 63) >> 3;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    uint4 o;
+    o.x = pack_bf16x2(f[8 * jj + 0], f[8 * jj + 1]);
+    o.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
+    o.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
+    o.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
+    *reinterpret_cast<uint4*>(pc + (((u0 + jj) ^ (row & 7)) << 4)) = o;
+  }
+}
+
 // TMEM [this warp's 32 lanes][128 columns from c_lo] fp32 -> bf16 rows of a region (four [128][64] SWIZZLE_128B blocks).
-// MODE 0: + colbias[column]; 1: + lv; 2: * lv
+// MODE 1: + lv; 2: * lv; 3: as is.  bar_a / bar_b (shared::cluster addresses, 0 = none): arrived on after the first / second 64-column
+// block has been written (a consumer MMA may start on that k-block while the other is still being drained).
 template <int MODE>
-__device__ __forceinline__ void ab_drain(uint32_t tmem, int c_lo, int row, uint8_t* region, const float* __restrict__ colbias,
-                                         float lv) {
+__device__ __forceinline__ void ab_drain(uint32_t tmem, int c_lo, int row, uint8_t* region, float lv, uint32_t bar_a,
+                                         uint32_t bar_b) {
   uint8_t* prow = region + row * 128;
 #pragma unroll 1
-  for (int c = c_lo; c < c_lo + 128; c += 32) {
+  for (int i = 0; i < 4; ++i) {
+    const int c = c_lo + 32 * i;
+    uint32_t v[32];
+    tmem_ld32(tmem + c, v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      f[j] = MODE == 1 ? __uint_as_float(v[j]) + lv : (MODE == 2 ? __uint_as_float(v[j]) * lv : __uint_as_float(v[j]));
+    ab_store_chunk(prow, c, row, f);
+    if ((i & 1) && bar_a != 0u) {
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive_cluster(i == 1 ? bar_a : bar_b);
+    }
+  }
+}
+
+// the same with a per-COLUMN bias (Q) read from shared memory (broadcast 16-byte loads).  The first version fetched the bias
+// with global loads inside the loop: the 228 KB shared-memory carve-out leaves next to no L1, every chunk paid an L2 round
+// trip and the drain took 3 k clocks instead of 1 k.
+__device__ __forceinline__ void ab_drain_colbias(uint32_t tmem, int c_lo, int row, uint8_t* region, const float* sbias,
+                                                 long long* trace, int tbase) {
+  uint8_t* prow = region + row * 128;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const int c = c_lo + 32 * i;
     uint32_t v[32];
     tmem_ld32(tmem + c, v);
     float f[32];
-    if (MODE == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(colbias + c) + j);
-        f[4 * j + 0] = b4.x; f[4 * j + 1] = b4.y; f[4 * j + 2] = b4.z; f[4 * j + 3] = b4.w;
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + 4 * j);
+      f[4 * j + 0] = b4.x; f[4 * j + 1] = b4.y; f[4 * j + 2] = b4.z; f[4 * j + 3] = b4.w;
     }
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float a = __uint_as_float(v[j]);
-      f[j] = MODE == 0 ? a + f[j] : (MODE == 1 ? a + lv : a * lv);
-    }
-    uint8_t* pc = prow + (c >> 6) * kAbBlk;
-    const int u0 = (c & 63) >> 3;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      uint4 o;
-      o.x = pack_bf16x2(f[8 * jj + 0], f[8 * jj + 1]);
-      o.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
-      o.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
-      o.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
-      *reinterpret_cast<uint4*>(pc + (((u0 + jj) ^ (row & 7)) << 4)) = o;
-    }
+    for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+    ab_store_chunk(prow, c, row, f);
+    if (tbase >= 0) ab_trace(trace, 2, tbase + i);
   }
 }
 
@@ -131,7 +164,7 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[AB_NBARS];
   __shared__ uint32_t tmem_slot;
-  __shared__ float row_part[2][128];
+  __shared__ __align__(16) float row_part[2][128];  // softmax row exchange; between images: the 256 Q biases
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -145,8 +178,8 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < AB_NBARS; ++i) {
-      const bool joined = i == AB_H_READY || i >= AB_QS_READY;
-      mbar_init(&bars[i], joined ? 2 * kAbWorkers : 1);
+      const int count = i == AB_H_READY ? 2 * kAbXform : (i >= AB_PV_READY0 ? kAbWorkers : (i >= AB_QS_READY ? 2 * kAbWorkers : 1));
+      mbar_init(&bars[i], count);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -216,6 +249,12 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
           for (int k = 0; k < 4; ++k) umma_bf16_2sm(tm, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
       };
+      // one k-block of a product whose operand blocks are delivered in the order 0, 2, 1, 3 (see the workers)
+      auto gemm_kb = [&](uint32_t tm, const uint8_t* A, const uint8_t* B, int kb, bool first) {
+        const uint64_t ad = umma_desc_sw128(smem_u32(A + kb * kAbBlk)), bd = umma_desc_sw128(smem_u32(B + kb * kAbBlk));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_2sm(tm, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+      };
       int it = 0, wv_it = 0;
       for (int img = cid; img < p.n; img += ncl, ++it) {
         const uint32_t ph = it & 1;
@@ -223,9 +262,10 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
         mbar_wait(&bars[AB_WQ_FULL], ph);
         tc_fence_after();
         ab_trace(p.trace, 1, it * 10 + 0);
-        gemm(T0, R1, R2);  // Q = H Wq^T
+        gemm(T0, R1, R2);  // Q = H Wq^T  (T0: the previous image's O was drained before its projection was issued)
         umma_commit_2sm(&bars[AB_Q_DONE], 3);
         mbar_wait(&bars[AB_WK_FULL], ph);
+        if (it > 0) mbar_wait_cluster(&bars[AB_EPI_DONE], ph ^ 1);  // T1: the previous image's output has been read
         tc_fence_after();
         ab_trace(p.trace, 1, it * 10 + 1);
         gemm(T1, R1, R3);  // K = H Wk^T
@@ -249,18 +289,82 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
         ab_trace(p.trace, 1, it * 10 + 7);
         gemm(T1, R2, R3);  // S = Q K^T
         umma_commit_2sm(&bars[AB_S_DONE], 3);
-        mbar_wait_cluster(&bars[AB_PV_READY], ph);  // T0 drained (V^T in R1), S read, P in R2
+        // O = P V, key blocks in the order the two worker halves deliver them.  Blocks 0 and 2 together also say that every
+        // worker has drained V^T out of T0.
+        mbar_wait_cluster(&bars[AB_PV_READY0 + 0], ph);
+        mbar_wait_cluster(&bars[AB_PV_READY0 + 2], ph);
         tc_fence_after();
         ab_trace(p.trace, 1, it * 10 + 8);
-        gemm(T0, R2, R1);  // O = P V
+        gemm_kb(T0, R2, R1, 0, true);
+        gemm_kb(T0, R2, R1, 2, false);
+        mbar_wait_cluster(&bars[AB_PV_READY0 + 1], ph);
+        mbar_wait_cluster(&bars[AB_PV_READY0 + 3], ph);
+        tc_fence_after();
+        gemm_kb(T0, R2, R1, 1, false);
+        gemm_kb(T0, R2, R1, 3, false);
         umma_commit_2sm(&bars[AB_O_DONE], 3);
-        mbar_wait_cluster(&bars[AB_OS_READY], ph);  // T0 drained, O in R3
+        // out^T = Wp O^T, channel blocks of O as they are drained (T1: S was read before the last P blocks were signalled)
         mbar_wait(&bars[AB_WP_FULL], ph);
+        mbar_wait_cluster(&bars[AB_OS_READY0 + 0], ph);
+        mbar_wait_cluster(&bars[AB_OS_READY0 + 2], ph);
         tc_fence_after();
         ab_trace(p.trace, 1, it * 10 + 9);
-        gemm(T1, R2, R3);  // out^T = Wp O^T
+        gemm_kb(T1, R2, R3, 0, true);
+        gemm_kb(T1, R2, R3, 2, false);
+        mbar_wait_cluster(&bars[AB_OS_READY0 + 1], ph);
+        mbar_wait_cluster(&bars[AB_OS_READY0 + 3], ph);
+        tc_fence_after();
+        gemm_kb(T1, R2, R3, 1, false);
+        gemm_kb(T1, R2, R3, 3, false);
         umma_commit_2sm(&bars[AB_D_DONE], 3);
       }
+    }
+  } else if (warp >= 2 + kAbWorkers / 32) {
+    // =========================== GroupNorm transform warps ===========================
+    // x tile -> H in place, one image ahead of the workers (the tile of image i + 1 lands once P V of image i is complete and
+    // H is not needed before the workers have stored image i: two warps are enough and leave the shared-memory port to the
+    // drains): thread = one 16-byte unit column (8 channels, their (a, b) in registers) x every 2nd token row
+    const int t2 = static_cast<int>(threadIdx.x) - (64 + kAbWorkers);
+    const int cu = t2 & 31, kb = cu >> 3, u = cu & 7, r0 = t2 >> 5;
+    const uint32_t bar_h = mapa_u32(&bars[AB_H_READY], 0);
+    pdl_wait();
+    int it = 0;
+    for (int img = cid; img < p.n; img += ncl, ++it) {
+      const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + (static_cast<long long>(img) * kAbC + kb * 64 + u * 8) * 2);
+      float a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t4 = __ldg(abp + j);
+        a[2 * j] = t4.x; b[2 * j] = t4.y; a[2 * j + 1] = t4.z; b[2 * j + 1] = t4.w;
+      }
+      mbar_wait(&bars[AB_X_FULL], it & 1);
+      if (t2 == 0) ab_trace(p.trace, 0, it * 14 + 0);
+      uint8_t* blk = R1 + kb * kAbBlk;
+#pragma unroll 2
+      for (int jb = 0; jb < 128 / (kAbXform / 32); jb += 4) {
+        uint4 v[4];
+        uint8_t* addr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = r0 + (kAbXform / 32) * (jb + j);
+          addr[j] = blk + r * 128 + ((u ^ (r & 7)) << 4);
+          v[j] = *reinterpret_cast<const uint4*>(addr[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float lo, hi;
+            unpack_bf16x2(w[e], lo, hi);
+            w[e] = pack_bf16x2(fmaf(a[2 * e], lo, b[2 * e]), fmaf(a[2 * e + 1], hi, b[2 * e + 1]));
+          }
+          *reinterpret_cast<uint4*>(addr[j]) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive_cluster(bar_h);
+      if (t2 == 0) ab_trace(p.trace, 0, it * 14 + 1);
     }
   } else {
     // =========================== workers ===========================
@@ -269,67 +373,38 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
     const int row = wq * 32 + lane;      // TMEM lane = tile row
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     const int c_lo = half * 128;
-    const int tid = static_cast<int>(threadIdx.x) - 64;
-    const uint32_t bar_h = mapa_u32(&bars[AB_H_READY], 0), bar_qs = mapa_u32(&bars[AB_QS_READY], 0),
-                   bar_ks = mapa_u32(&bars[AB_KS_READY], 0), bar_pv = mapa_u32(&bars[AB_PV_READY], 0),
-                   bar_os = mapa_u32(&bars[AB_OS_READY], 0);
+    const uint32_t bar_qs = mapa_u32(&bars[AB_QS_READY], 0), bar_ks = mapa_u32(&bars[AB_KS_READY], 0),
+                   bar_epi = mapa_u32(&bars[AB_EPI_DONE], 0),
+                   bar_pv = mapa_u32(&bars[AB_PV_READY0 + 2 * half], 0),  // this half's two key blocks: + 0, + 8 bytes
+                   bar_os = mapa_u32(&bars[AB_OS_READY0 + 2 * half], 0);
     const int och = static_cast<int>(rank) * 128 + row;  // this thread's channel where lanes are channels (V^T, out^T)
+    const int chp = och & ~1, odd = lane & 1;            // the channel pair it stores after the epilogue's lane exchange
     const float kFix = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
     pdl_wait();
     const float bias_v = __ldg(p.bias_qkv + 2 * kAbC + och);
-    const float bias_o = __ldg(p.bias_proj + och);
+    const float bias_lo = __ldg(p.bias_proj + chp), bias_hi = __ldg(p.bias_proj + chp + 1);
+    float* sbias = &row_part[0][0];
+    const int wt = static_cast<int>(threadIdx.x) - 64;
+    const float bias_q = __ldg(p.bias_qkv + wt);  // staged in row_part for every image's Q drain (the softmax reuses it)
     int it = 0;
     for (int img = cid; img < p.n; img += ncl, ++it) {
       const uint32_t ph = it & 1;
-      // ---- GroupNorm of the x tile, in place: thread = one 16-byte unit column (8 channels) x every 8th token row ----
-      {
-        const int cu = tid & 31, kb = cu >> 3, u = cu & 7, r0 = tid >> 5;
-        const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + (static_cast<long long>(img) * kAbC + kb * 64 + u * 8) * 2);
-        float a[8], b[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 t4 = __ldg(abp + j);
-          a[2 * j] = t4.x; b[2 * j] = t4.y; a[2 * j + 1] = t4.z; b[2 * j + 1] = t4.w;
-        }
-        mbar_wait(&bars[AB_X_FULL], ph);
-        if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 0);
-        uint8_t* base = R1 + kb * kAbBlk + ((u ^ r0) << 4) + r0 * 128;  // rows r0 + 8 j: (row & 7) == r0
-#pragma unroll
-        for (int jb = 0; jb < 16; jb += 4) {
-          uint4 v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(base + (jb + j) * 1024);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float lo, hi;
-              unpack_bf16x2(w[e], lo, hi);
-              w[e] = pack_bf16x2(fmaf(a[2 * e], lo, b[2 * e]), fmaf(a[2 * e + 1], hi, b[2 * e + 1]));
-            }
-            *reinterpret_cast<uint4*>(base + (jb + j) * 1024) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
-        fence_proxy_async();
-        tc_fence_before();  // orders the previous image's last tcgen05.ld before the arrive that lets K overwrite T1
-        mbar_arrive_cluster(bar_h);
-        if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 1);
-      }
+      sbias[wt] = bias_q;
+      asm volatile("bar.sync 1, %0;" ::"n"(kAbWorkers) : "memory");
       // ---- Q: T0 -> R2 ----
       mbar_wait(&bars[AB_Q_DONE], ph);
       tc_fence_after();
-      if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 2);
-      ab_drain<0>(T0 + lane_off, c_lo, row, R2, p.bias_qkv, 0.f);
+      if (warp == 2 && lane == 0) ab_trace(p.trace, 2, it * 16 + 0);
+      ab_drain_colbias(T0 + lane_off, c_lo, row, R2, sbias, p.trace, (warp == 2 && lane == 0) ? it * 16 + 1 : -1);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive_cluster(bar_qs);
       if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 3);
-      // ---- K: T1 -> R3 ----
+      // ---- K: T1 -> R3.  The K bias is left out: it adds (q_i + b_q) . b_k to every score of row i, which the softmax over
+      // the keys cancels exactly (the reference adds it and rounds K + b_k; this is the same function of the inputs) ----
       mbar_wait(&bars[AB_K_DONE], ph);
       tc_fence_after();
-      if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 4);
-      ab_drain<0>(T1 + lane_off, c_lo, row, R3, p.bias_qkv + kAbC, 0.f);
+      ab_drain<3>(T1 + lane_off, c_lo, row, R3, 0.f, 0u, 0u);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive_cluster(bar_ks);
@@ -338,7 +413,7 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
       mbar_wait(&bars[AB_V_DONE], ph);
       tc_fence_after();
       if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 6);
-      ab_drain<1>(T0 + lane_off, c_lo, row, R1, nullptr, bias_v);
+      ab_drain<1>(T0 + lane_off, c_lo, row, R1, bias_v, 0u, 0u);
       // ---- softmax of this query row (two threads per row, half of the keys each): T1 -> P in R2 ----
       if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 7);
       mbar_wait(&bars[AB_S_DONE], ph);
@@ -363,7 +438,8 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
         const float mxs = mx * sl;
         uint8_t* prow = R2 + row * 128;
 #pragma unroll 1
-        for (int c = c_lo; c < c_lo + 128; c += 32) {
+        for (int i = 0; i < 4; ++i) {
+          const int c = c_lo + 32 * i;
           uint32_t v[32];
           tmem_ld32(T1 + lane_off + c, v);
           tmem_ld_wait();
@@ -373,76 +449,72 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
             e[j] = exp2f(fmaf(__uint_as_float(v[j]), sl, -mxs));
             sum += e[j];
           }
-          uint8_t* pc = prow + (c >> 6) * kAbBlk;
-          const int u0 = (c & 63) >> 3;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            uint4 o;
-            o.x = pack_bf16x2(e[8 * jj + 0], e[8 * jj + 1]);
-            o.y = pack_bf16x2(e[8 * jj + 2], e[8 * jj + 3]);
-            o.z = pack_bf16x2(e[8 * jj + 4], e[8 * jj + 5]);
-            o.w = pack_bf16x2(e[8 * jj + 6], e[8 * jj + 7]);
-            *reinterpret_cast<uint4*>(pc + (((u0 + jj) ^ (row & 7)) << 4)) = o;
+          ab_store_chunk(prow, c, row, e);
+          if (i & 1) {
+            // a 64-key block of P (and, since the V^T drain above, of V^T) is complete: its P V k-block may be issued
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive_cluster(bar_pv + (i == 1 ? 0u : 8u));
           }
         }
       }
       row_part[half][row] = sum;
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive_cluster(bar_pv);
       if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 9);
       asm volatile("bar.sync 1, %0;" ::"n"(kAbWorkers) : "memory");
       sum = row_part[0][row] + row_part[1][row];
       asm volatile("bar.sync 1, %0;" ::"n"(kAbWorkers) : "memory");  // both halves have read before the next image's maxima land
-      // ---- O / rowsum: T0 -> R3 ----
+      // ---- O / rowsum: T0 -> R3, signalled per 64-channel block ----
       mbar_wait(&bars[AB_O_DONE], ph);
       tc_fence_after();
       if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 10);
-      ab_drain<2>(T0 + lane_off, c_lo, row, R3, nullptr, 1.0f / sum);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive_cluster(bar_os);
+      ab_drain<2>(T0 + lane_off, c_lo, row, R3, 1.0f / sum, bar_os, bar_os + 8u);
       if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 11);
-      // ---- out^T: T1 (lane = channel, column = token) + bias + x -> global, statistics of the stored values ----
+      // ---- out^T: T1 (lane = channel, column = token) + bias + x -> global, statistics of the stored values.  Neighbouring
+      // lanes exchange every second value so that a thread stores a channel PAIR of one token (4-byte accesses, half as many
+      // of them: the 2-byte version spent 6 k clocks per tile in the load / store unit) ----
       {
-        const long long ibase = static_cast<long long>(img) * (kAbL * kAbC) + och;
-        const __nv_bfloat16* __restrict__ xr = p.xres + ibase;
-        __nv_bfloat16* __restrict__ op = p.out + ibase;
-        float av[32];
+        const long long ibase = static_cast<long long>(img) * (kAbL * kAbC) + chp;
+        const uint32_t* __restrict__ xr = reinterpret_cast<const uint32_t*>(p.xres + ibase) + odd * (kAbC / 2);
+        uint32_t* __restrict__ op = reinterpret_cast<uint32_t*>(p.out + ibase) + odd * (kAbC / 2);
+        // all of the residual is requested before the projection is awaited: one chunk of look-ahead left an L2 round trip
+        // per chunk exposed (5 - 6 k clocks per tile)
+        uint32_t av[64];
+        if (warp == 2 && lane == 0) ab_trace(p.trace, 2, it * 16 + 5);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) av[i] = __bfloat162float(__ldg(xr + (c_lo + i) * kAbC));
+        for (int i = 0; i < 64; ++i) av[i] = __ldg(xr + (c_lo + 2 * i) * (kAbC / 2));
+        if (warp == 2 && lane == 0) ab_trace(p.trace, 2, it * 16 + 6);
         mbar_wait(&bars[AB_D_DONE], ph);
         tc_fence_after();
         if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 12);
         float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int tok0 = c_lo + ci * 32;
           uint32_t v[32];
           tmem_ld32(T1 + lane_off + tok0, v);
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = av[i];
-          if (ci + 1 < 4) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) av[i] = __bfloat162float(__ldg(xr + (tok0 + 32 + i) * kAbC));
-          }
           tmem_ld_wait();
           float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint32_t u = pack_bf16x2(f[i] + (__uint_as_float(v[i]) + bias_o), f[i + 1] + (__uint_as_float(v[i + 1]) + bias_o));
-            op[(tok0 + i) * kAbC] = __ushort_as_bfloat16(static_cast<unsigned short>(u & 0xffffu));
-            op[(tok0 + i + 1) * kAbC] = __ushort_as_bfloat16(static_cast<unsigned short>(u >> 16));
+          for (int i = 0; i < 16; ++i) {
+            // even lanes take token tok0 + 2 i, odd lanes token tok0 + 2 i + 1, both channels of the pair
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? v[2 * i] : v[2 * i + 1], 1);
+            const float dlo = __uint_as_float(odd ? recv : v[2 * i]), dhi = __uint_as_float(odd ? v[2 * i + 1] : recv);
+            float xl, xh;
+            unpack_bf16x2(av[ci * 16 + i], xl, xh);
+            const uint32_t uo = pack_bf16x2(xl + (dlo + bias_lo), xh + (dhi + bias_hi));
+            op[(tok0 + 2 * i) * (kAbC / 2)] = uo;
             float lo, hi;
-            unpack_bf16x2(u, lo, hi);
-            p1[(i >> 1) & 3] += lo + hi;
-            p2[(i >> 1) & 3] = fmaf(lo, lo, p2[(i >> 1) & 3]);
-            p2[((i >> 1) + 2) & 3] = fmaf(hi, hi, p2[((i >> 1) + 2) & 3]);
+            unpack_bf16x2(uo, lo, hi);
+            p1[i & 3] += lo + hi;
+            p2[i & 3] = fmaf(lo, lo, p2[i & 3]);
+            p2[(i + 2) & 3] = fmaf(hi, hi, p2[(i + 2) & 3]);
           }
           s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
           s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+          if (warp == 2 && lane == 0) ab_trace(p.trace, 2, it * 16 + 8 + ci);
         }
+        tc_fence_before();
+        mbar_arrive_cluster(bar_epi);  // T1 may be overwritten by the next image's K
         if (warp == 2 && lane == 0) ab_trace(p.trace, 0, it * 14 + 13);
         if (p.stats) {
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);

@@ -24,7 +24,7 @@ bqkv, bproj = torch.randn(3 * c, device=dev, generator=g), torch.randn(c, device
 out = torch.empty_like(x)
 st = torch.zeros(n * c // 4 * 2, dtype=torch.int64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-trace = torch.zeros(2 * 256, dtype=torch.int64, device=dev)
+trace = torch.zeros(3 * 256, dtype=torch.int64, device=dev)
 lib = L.load()
 lib.dmme_debug_set_attn_block_trace.argtypes = [C.c_void_p]
 lib.dmme_debug_set_attn_block_trace.restype = None
@@ -36,17 +36,21 @@ for rep in range(3):
     ops.attention_block(x, ab, wqkv, bqkv, wproj, bproj, c ** -0.5, out, st)
     torch.cuda.synchronize()
 lib.dmme_debug_set_attn_block_trace(None)
-t = trace.cpu().view(2, 256)
+t = trace.cpu().view(3, 256)
 WN = ["x landed", "H done", "Q ready", "Q drained", "K ready", "K drained", "V ready", "V drained", "S ready", "P done",
       "O ready", "O drained", "D ready", "out stored"]
 MN = ["H+Wq -> Q GEMM", "Wk -> K GEMM", "Q drained -> V GEMM", "Wv kb0", "Wv kb1", "Wv kb2", "Wv kb3", "K drained -> S GEMM",
       "P ready -> PV GEMM", "O drained+Wp -> proj GEMM"]
+DN = ["Q ready", "Q chunk 0", "Q chunk 1", "Q chunk 2", "Q chunk 3", "epilogue: issue residual loads", "loads issued", "D ready",
+      "out chunk 0", "out chunk 1", "out chunk 2", "out chunk 3", "", "", "", ""]
 ev = []
 for i in range(256):
     if int(t[0, i]):
         ev.append((int(t[0, i]), f"worker img{i // 14} {WN[i % 14]}"))
     if int(t[1, i]):
         ev.append((int(t[1, i]), f"   mma img{i // 10} {MN[i % 10]}"))
+    if int(t[2, i]):
+        ev.append((int(t[2, i]), f"      .. img{i // 16} {DN[i % 16]}"))
 ev.sort()
 t0 = ev[0][0]
 prev = t0
