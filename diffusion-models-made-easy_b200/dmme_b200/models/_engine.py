@@ -359,13 +359,18 @@ class Engine:
                              mask, norm.eps, out, st0, st1)
 
     # -- blocks ------------------------------------------------------------------------------
+    def attention_fused(self, att: nn.Module, seq: int, c: int, dtype: torch.dtype) -> bool:
+        """True when the block runs as the one-launch kernel (csrc/attention_block.cu) given its producer's statistics."""
+        return (self.fuse_attn and not self.force_generic and getattr(att, "num_heads", None) is None
+                and c % att.norm.num_groups == 0 and (c // att.norm.num_groups) % 4 == 0
+                and ops.attention_block_supported(1, seq, c, dtype))
+
     def attention_block(self, name: str, att: nn.Module, x: Tensor) -> Tensor:
         n, h, w, c = x.shape
         seq = h * w
         heads = getattr(att, "num_heads", None)
         st = self._stats.get(x.data_ptr())
-        if (self.fuse_attn and heads is None and st is not None and not self.force_generic and c % att.norm.num_groups == 0
-                and (c // att.norm.num_groups) % 4 == 0 and ops.attention_block_supported(1, seq, c, x.dtype)):
+        if st is not None and self.attention_fused(att, seq, c, x.dtype):
             # the whole block in one launch (csrc/attention_block.cu): norm, qkv, softmax(q k^T) v, proj and + x
             norm = att.norm
             ab = ops.groupnorm_coeff(st, None, c, 0, n, seq, norm.num_groups, norm.weight.detach(), norm.bias.detach(), None, None,
@@ -403,6 +408,10 @@ class Engine:
         out_name = name + (".pre" if has_attn else "")
         res_kw = dict(addend=x0) if isinstance(blk.residual, nn.Identity) else dict(res=blk.residual, res0=x0, res1=x1)
         res_kw["consumers"] = self.consumers().get(out_name)
+        if has_attn and res_kw["consumers"] and x0.dtype == torch.bfloat16 and \
+                self.attention_fused(blk.attention, x0.shape[1] * x0.shape[2], conv2.weight.shape[0], x0.dtype):
+            # the one-launch attention block applies its own norm: the producer's finishing pass need not write it
+            res_kw["consumers"] = [c for c in res_kw["consumers"] if c[0] is not blk.attention.norm]
         if self.flavour == "ddpm":
             c_mid = blk.conv1[2].weight.shape[0]
             h1 = self.norm_conv("scratch.h1", blk.conv1[0], x0, x1, blk.conv1[2], gn_name="scratch.a1", temb=cond,

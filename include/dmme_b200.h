@@ -290,9 +290,10 @@ int dmme_attention_uses_tc(long long batch_stride, int row_stride, int v_transpo
  * x / out: NHWC act_dtype [n][L][c]; gn_ab: the (a, b) pairs of the block's GroupNorm from dmme_groupnorm_coeff
  * ([n][c][2], no SiLU); wqkv [3c][c] / wproj [c][c]: the 1x1 conv weights packed by dmme_pack_conv_weight (bf16, K
  * contiguous); bias_qkv [3c], bias_proj [c] fp32; stats: optional micro-group sums of `out` (as dmme_conv_desc.stats).
- * Nothing between x and out is written to global memory.  Supported (ask first): bf16, heads = 1, L = 256, c = 256 -- the
- * 16x16 attention sites of the default DDPM UNet (configs/ddpm/cifar10.yaml); other shapes take the qkv conv +
- * dmme_attention_fwd + proj conv path.
+ * Nothing between x and out is written to global memory.  Supported (ask first): bf16, heads = 1, and L = 256 with c = 256
+ * or 128 (the five 16x16 sites of the default DDPM UNet, configs/ddpm/cifar10.yaml: a cluster of two CTAs per image) or
+ * L = 16 with c = 256 (its 4x4 middle block: eight images per CTA); other shapes take the qkv conv + dmme_attention_fwd +
+ * proj conv path.
  */
 int dmme_attention_block_supported(int heads, int L, int c, int act_dtype);
 int dmme_attention_block_fwd(const void* x, const float* gn_ab, const void* wqkv, const float* bias_qkv,

@@ -623,14 +623,17 @@ def _stats_of(x_nhwc):
     return (torch.stack([s1, s2], dim=-1) * 2 ** 20).round().to(torch.int64).reshape(-1)
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 75, 150, 256])
-def test_attention_block_fused(n):
+@pytest.mark.parametrize("n,hgt,c", [(1, 16, 256), (2, 16, 256), (5, 16, 256), (75, 16, 256), (150, 16, 256), (256, 16, 256),
+                                     (1, 4, 256), (5, 4, 256), (8, 4, 256), (37, 4, 256), (256, 4, 256),
+                                     (1, 16, 128), (3, 16, 128), (80, 16, 128), (256, 16, 128)])
+def test_attention_block_fused(n, hgt, c):
     """The one-launch attention block (norm | qkv | softmax(q k^T) v | proj | + x, models/ddpm.py:54-75) against the fp32
-    computation of the module on the same bf16-rounded input and weights.  n = 75 / 150 / 256: some / all clusters take
-    two, three or four images (74 clusters of two CTAs)."""
+    computation of the module on the same bf16-rounded input and weights.  16x16: n = 75 / 150 / 256: some / all clusters
+    take two, three or four images (74 clusters of two CTAs); c = 128: the V^T and projection products run with duplicated
+    weight rows.  4x4: eight images per CTA, n = 1 / 5 / 37: a ragged last group."""
     ops, L = _ops()
-    g = torch.Generator().manual_seed(7 + n)
-    c, hgt, groups = 256, 16, 32
+    g = torch.Generator().manual_seed(7 + n + hgt + c)
+    groups = 32
     seq = hgt * hgt
     assert ops.attention_block_supported(1, seq, c, torch.bfloat16)
     # per-image and per-channel offsets / gains so that the norm matters

@@ -17,17 +17,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--hw", type=int, default=16, help="16: the 16x16 sites, 4: the 4x4 middle block")
+    ap.add_argument("--c", type=int, default=256, help="channels of the site (256 or 128 at 16x16)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     torch.manual_seed(0)
     unet = m_ddpm.UNet().eval().to(dev)
     eng = unet.engine
     blk = next(m for _, m in eng.resblocks() if not isinstance(m.attention, torch.nn.Identity)
-               and m.conv1[2].weight.shape[0] == 256)
+               and m.conv1[2].weight.shape[0] == args.c)
     att = blk.attention
     n = args.batch
-    x = (torch.randn(n, 16, 16, 256, device=dev) * 1.5).to(torch.bfloat16)
-    v = x.double().reshape(n, 256, 64, 4)
+    x = (torch.randn(n, args.hw, args.hw, args.c, device=dev) * 1.5).to(torch.bfloat16)
+    v = x.double().reshape(n, args.hw * args.hw, args.c // 4, 4)
     st = (torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], dim=-1) * 2 ** 20).round().to(torch.int64).reshape(-1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     outs = {}

@@ -14,9 +14,10 @@ from dmme_b200 import _lib as L  # noqa: E402
 from dmme_b200 import ops  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-dev, c, seq = "cuda", 256, 256
+hw = int(sys.argv[3]) if len(sys.argv) > 3 else 16   # 4: the 16-token kernel (events are numbered, see attention_block.cu)
+dev, c, seq = "cuda", 256, hw * hw
 g = torch.Generator(device=dev).manual_seed(0)
-x = torch.randn(n, 16, 16, c, device=dev, generator=g).bfloat16()
+x = torch.randn(n, hw, hw, c, device=dev, generator=g).bfloat16()
 ab = torch.stack([1 + 0.1 * torch.randn(n, c, device=dev, generator=g), 0.1 * torch.randn(n, c, device=dev, generator=g)], dim=-1).contiguous()
 wqkv = ops.pack_conv_weight(torch.randn(3 * c, c, 1, 1, device=dev, generator=g) / math.sqrt(c), None, True)
 wproj = ops.pack_conv_weight(torch.randn(c, c, 1, 1, device=dev, generator=g) / math.sqrt(c), None, True)
@@ -37,6 +38,15 @@ for rep in range(3):
     torch.cuda.synchronize()
 lib.dmme_debug_set_attn_block_trace(None)
 t = trace.cpu().view(3, 256)
+if hw == 4:
+    W16 = ["start", "x landed", "H done", "K product done", "Q, K drained", "V^T done", "V^T drained", "S done", "P written",
+           "O done", "O drained", "out^T done", "stored"]
+    M16 = ["H ready", "Q issued", "K issued", "Q, K drained -> V, S", "V issued", "P ready -> P V", "O drained -> proj", "proj issued"]
+    ev = [(int(t[0, i]), "worker " + W16[i]) for i in range(13) if int(t[0, i])] + [(int(t[1, i]), "   mma " + M16[i]) for i in range(8) if int(t[1, i])]
+    ev.sort()
+    for v, name in ev:
+        print(f"{v - ev[0][0]:8d} clk  {name}")
+    sys.exit(0)
 WN = ["x landed", "H done", "Q ready", "Q drained", "K ready", "K drained", "V ready", "V drained", "S ready", "P done",
       "O ready", "O drained", "D ready", "out stored"]
 MN = ["H+Wq -> Q GEMM", "Wk -> K GEMM", "Q drained -> V GEMM", "Wv kb0", "Wv kb1", "Wv kb2", "Wv kb3", "K drained -> S GEMM",
