@@ -18,7 +18,7 @@ Rank 0 prints ONE JSON line:
   parity                  rel-L2 of the timed configuration's UNet output against the CPU oracle (16 images of this shard)
   train                   BASELINE config #4: graph-captured IDDPM hybrid-loss training step, batch 128 per GPU, bf16,
                           FusedAdamEMA, gradient all-reduce (NCCL, captured in the graph) when N > 1
-  cpu_baseline            the unmodified reference (baseline/_ref) -- or the oracle port when it is not installed -- on the
+  cpu_baseline (N = 1)    the unmodified reference (baseline/_ref) -- or the oracle port when it is not installed -- on the
                           host cores
 `--impl reference` times the reference's own CPU implementation of the step (same metric / config keys).
 """
@@ -569,7 +569,8 @@ def run_gpu(args):
         run.reset()
         parity = parity_check(model, run.x, dev)
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the contract: rank 0 at N = 1 only (at N > 1 the other ranks' host threads
+            # spin in the closing barrier and the CPU timing would measure that contention)
             rate_mean, _, cores, times, kind = cpu_step_rate(16, 5, 2)
             cpu = {"value": rate_mean / TIMESTEPS, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": f"{len(times)} timed DDPM.sampling_step calls of "
