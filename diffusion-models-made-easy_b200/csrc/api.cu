@@ -26,6 +26,7 @@ bool conv_out_supported(const dmme_conv_desc& d);
 int conv_small_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_halo_supported(const dmme_conv_desc& d);
 bool conv_halo_preferred(const dmme_conv_desc& d);
+bool conv_tct_epilogue_norm(const dmme_conv_desc& d);
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_out_tc_supported(const dmme_conv_desc& d);
 long long conv_splitk_workspace(const dmme_conv_desc& d);
@@ -84,6 +85,10 @@ extern "C" int dmme_conv2d_fuses_sampler(const dmme_conv_desc* d) {
   return d && d->kernel == DMME_CONV_AUTO && !conv_tc_supported(*d) && conv_out_tc_supported(*d) ? 1 : 0;
 }
 
+extern "C" int dmme_conv2d_epilogue_norm(const dmme_conv_desc* d) {
+  return d && takes_conv_tc(*d) && conv_tct_epilogue_norm(*d) ? 1 : 0;
+}
+
 extern "C" long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* d) {
   if (!d || !takes_conv_tc(*d)) return 0;
   return conv_splitk_workspace(*d);
@@ -93,8 +98,11 @@ extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
   DMME_REQUIRE(d != nullptr, DMME_E_BADARG, "conv2d_fwd: null descriptor");
   DMME_REQUIRE(d->gn_ab == nullptr || runs_halo_rows(*d), DMME_E_UNSUPPORTED,
                "conv2d_fwd: a fused GroupNorm (gn_ab) needs the halo kernel; ask dmme_conv2d_fuses_gn");
-  DMME_REQUIRE((d->out_norm[0].out == nullptr && d->out_norm[1].out == nullptr) || (takes_conv_tc(*d) && d->splitk_ws != nullptr),
-               DMME_E_UNSUPPORTED, "conv2d_fwd: out_norm needs the split-K path; ask dmme_conv2d_splitk_workspace");
+  DMME_REQUIRE((d->out_norm[0].out == nullptr && d->out_norm[1].out == nullptr) ||
+                   (takes_conv_tc(*d) && (d->splitk_ws != nullptr || conv_tct_epilogue_norm(*d))),
+               DMME_E_UNSUPPORTED,
+               "conv2d_fwd: out_norm needs the split-K path (ask dmme_conv2d_splitk_workspace) or the transposed kernel on an "
+               "8x8 map (ask dmme_conv2d_epilogue_norm)");
   DMME_REQUIRE(d->sampler == nullptr || d->sampler->kind == DMME_SAMPLER_NONE || dmme_conv2d_fuses_sampler(d), DMME_E_UNSUPPORTED,
                "conv2d_fwd: a fused sampler update needs the tcgen05 output-conv kernel; ask dmme_conv2d_fuses_sampler");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -383,6 +383,15 @@ struct ConvTctExtra {
   int split;
   float* partial;
   long long split_stride;  // elements between two K slices = total_pix * cout
+  // NORM kernels (8x8 maps: an image = two 32-pixel chunks of one warp, a GroupNorm group = cpg lanes of it): the
+  // GroupNorm(+SiLU) of the stored tensor for up to two consumers, written by the epilogue (dmme_conv_desc.out_norm)
+  struct Norm {
+    __nv_bfloat16* out;
+    const float* gamma; const float* beta;
+    const float* scale; const float* shift;
+    int ss_rows, ss_ld, cpg, silu;
+    float eps;
+  } no[2];
 };
 
 // trace slots of CTA 0: [role][event index]; role 0 = producer (issue time per k-block), 1 = MMA (operands landed per
@@ -410,7 +419,7 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int idx) {
 template <bool WS>
 __host__ __device__ constexpr int tct_epi_warps() { return 8; }
 
-template <bool WS, int CMOD, bool PAIR, bool SPLIT = false>
+template <bool WS, int CMOD, bool PAIR, bool SPLIT = false, bool NORM = false>
 __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
                                                                                   const ConvTctExtra x) {
   extern __shared__ uint8_t smem_raw[];
@@ -629,6 +638,17 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
       const int pix_begin = mt * NP + half * ppw;
       float s1 = 0.f, s2 = 0.f, bt = bias_c;
       int cur_n = -1;
+      // NORM: the first chunk of the image in flight (packed stored values) and the consumers' affine terms of this channel
+      uint32_t kept[16];
+      float ng[2] = {1.f, 1.f}, nb[2] = {0.f, 0.f};
+      if constexpr (NORM) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (x.no[k].out == nullptr) continue;
+          if (x.no[k].gamma) ng[k] = __ldg(x.no[k].gamma + ch);
+          if (x.no[k].beta) nb[k] = __ldg(x.no[k].beta + ch);
+        }
+      }
 
       auto flush_stats = [&]() {  // warp-uniform call: per-image sums of this lane's channel -> micro-group atomics
         if (p.stats && cur_n >= 0) {
@@ -748,6 +768,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
             // four independent partial sums per statistic: one serial chain of 64 dependent FADD / FFMA per chunk
             // left the two warps of a scheduler nothing to issue
             float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t cur[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               // packed conversion (F2FP, FMA pipe) instead of two F2F (quarter-rate conversion pipe)
@@ -758,6 +779,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
 #else
               if (u == 0x12345678u) op[i * cmod] = __ushort_as_bfloat16(static_cast<unsigned short>(u & 0xffffu));
 #endif
+              if constexpr (NORM) cur[i >> 1] = u;
               float lo, hi;
               unpack_bf16x2(u, lo, hi);
               p1[(i >> 1) & 3] += lo + hi;
@@ -766,6 +788,48 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
             }
             s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
             s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+            if constexpr (NORM) {
+              // 8x8 maps: chunks 2 j, 2 j + 1 of this warp are one image.  After the second, s1 / s2 are the image's sums of
+              // this channel's STORED values; a GroupNorm group is cpg neighbouring lanes, so the consumers' norm(+SiLU) of
+              // the image is finished here (what a stand-alone GroupNorm launch did: 10 launches of the 8x8 level)
+              if ((ci & 1) == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) kept[i] = cur[i];
+              } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  const ConvTctExtra::Norm& q = x.no[k];
+                  if (q.out == nullptr) continue;  // uniform
+                  float t1 = s1, t2 = s2;
+                  for (int o = 1; o < q.cpg; o <<= 1) {
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+                  }
+                  const float inv_cnt = 1.0f / (64.0f * q.cpg);
+                  const float mean = t1 * inv_cnt;
+                  const float var = fmaxf(t2 * inv_cnt - mean * mean, 0.f);
+                  const float rs = rsqrtf(var + q.eps);
+                  float aa = rs * ng[k], bb = nb[k] - mean * rs * ng[k];
+                  if (q.scale) {
+                    const long long r = static_cast<long long>(q.ss_rows == 1 ? 0 : cur_n) * q.ss_ld;
+                    const float sc = 1.f + __ldg(q.scale + r + ch), sh = __ldg(q.shift + r + ch);
+                    aa *= sc;
+                    bb = bb * sc + sh;
+                  }
+                  __nv_bfloat16* yp = q.out + static_cast<long long>(pix0 - 32) * cmod + chm;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    float lo, hi;
+                    unpack_bf16x2(i < 16 ? kept[i & 15] : cur[i & 15], lo, hi);
+                    float y0 = fmaf(lo, aa, bb), y1 = fmaf(hi, aa, bb);
+                    if (q.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+                    const uint32_t yu = pack_bf16x2(y0, y1);
+                    yp[(2 * i) * cmod] = __ushort_as_bfloat16(static_cast<unsigned short>(yu & 0xffffu));
+                    yp[(2 * i + 1) * cmod] = __ushort_as_bfloat16(static_cast<unsigned short>(yu >> 16));
+                  }
+                }
+              }
+            }
             continue;
           }
 #pragma unroll
@@ -983,6 +1047,16 @@ static SplitPlan splitk_plan(const dmme_conv_desc& d) {
   return best;
 }
 
+// The unsplit transposed kernel can finish the consumers' GroupNorm(+SiLU) in its epilogue on 8x8 maps with 128 / 256 output
+// channels: a warp's pixel range is whole images (two 32-pixel chunks each), the channel stride is a compile-time constant.
+bool conv_tct_epilogue_norm(const dmme_conv_desc& d) {
+  if (!conv_tc_supported(d) || d.ksize != 3 || d.upsample || d.out_layout != DMME_OUT_NHWC) return false;
+  if (d.cout != 128 && d.cout != 256) return false;
+  const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
+  if (ho * wo != 64) return false;
+  return tct_tile_pixels(d) != 0;
+}
+
 long long conv_splitk_workspace(const dmme_conv_desc& d) {
   const SplitPlan plan = splitk_plan(d);
   if (plan.split <= 1) return 0;
@@ -992,12 +1066,12 @@ long long conv_splitk_workspace(const dmme_conv_desc& d) {
 
 int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream);  // conv_splitk.cu
 
-template <bool WS, int CMOD, bool PAIR = false, bool SPLIT = false>
+template <bool WS, int CMOD, bool PAIR = false, bool SPLIT = false, bool NORM = false>
 static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
   static DeviceOnce once_;
   bool& configured = once_.here();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD, PAIR, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tct_kernel<WS, CMOD, PAIR, SPLIT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) {
       set_error("conv_tct: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1013,8 +1087,8 @@ static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cud
   }
   int grid = total < g_sm_count_tc ? total : g_sm_count_tc;
   if (WS) grid -= grid % p.n_tiles;
-  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD, PAIR, SPLIT>, dim3(grid), dim3((2 + tct_epi_warps<WS>()) * 32), smem, stream, p, x);
-  return check_launch_err(e, SPLIT ? "conv_tct_kernel (split-K)" : "conv_tct_kernel");
+  cudaError_t e = launch_pdl(conv_tct_kernel<WS, CMOD, PAIR, SPLIT, NORM>, dim3(grid), dim3((2 + tct_epi_warps<WS>()) * 32), smem, stream, p, x);
+  return check_launch_err(e, SPLIT ? "conv_tct_kernel (split-K)" : (NORM ? "conv_tct_kernel (epilogue norm)" : "conv_tct_kernel"));
 }
 
 int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
@@ -1029,8 +1103,10 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     if (plan.split > 1 && d.splitk_ws_bytes < static_cast<long long>(plan.split) * d.n * ho * wo * d.cout * 4) plan = SplitPlan{0, 1};
   }
   const bool has_out_norm = d.out_norm[0].out != nullptr || d.out_norm[1].out != nullptr;
-  DMME_REQUIRE(!has_out_norm || plan.split > 1, DMME_E_UNSUPPORTED,
-               "conv_tc: out_norm needs the split-K path (ask dmme_conv2d_splitk_workspace and pass splitk_ws)");
+  const bool epi_norm = has_out_norm && plan.split <= 1 && conv_tct_epilogue_norm(d);
+  DMME_REQUIRE(!has_out_norm || plan.split > 1 || epi_norm, DMME_E_UNSUPPORTED,
+               "conv_tc: out_norm needs the split-K path (ask dmme_conv2d_splitk_workspace and pass splitk_ws) or an 8x8 map "
+               "on the transposed kernel (ask dmme_conv2d_epilogue_norm)");
   const int np = plan.split > 1 ? plan.np : tct_tile_pixels(d);
   const int tile_px = np ? np : 128;
   p.bw = wo < tile_px ? wo : tile_px;
@@ -1085,6 +1161,7 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     x.log2_w = 0;
     while ((1 << x.log2_w) < wo) ++x.log2_w;
     x.split = 1; x.partial = nullptr; x.split_stride = 0;
+    memset(x.no, 0, sizeof(x.no));
     const int budget = 226 * 1024 - 1024;
     if (plan.split > 1) {
       x.split = plan.split;
@@ -1127,6 +1204,22 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     x.stages = stages > kTctMaxStages ? kTctMaxStages : stages;
     const int smem = x.stages * x.stage_bytes + (ws ? static_cast<int>(slab) : 0) + 1024;
     const int cmod = d.out_layout == DMME_OUT_QKV ? d.cout / 3 : d.cout;
+    if (epi_norm) {
+      for (int k = 0; k < 2; ++k) {
+        const dmme_out_norm& sn = d.out_norm[k];
+        if (sn.out == nullptr) continue;
+        DMME_REQUIRE(sn.cpg >= 1 && sn.cpg <= 32 && 32 % sn.cpg == 0, DMME_E_SHAPE,
+                     "conv_tct: out_norm channels per group must divide 32 (got %d)", sn.cpg);
+        DMME_REQUIRE(sn.out != d.out, DMME_E_BADARG, "conv_tct: out_norm[%d].out aliases out", k);
+        DMME_REQUIRE(sn.scale == nullptr || sn.shift != nullptr, DMME_E_BADARG, "conv_tct: out_norm scale without shift");
+        x.no[k].out = static_cast<__nv_bfloat16*>(sn.out);
+        x.no[k].gamma = sn.gamma; x.no[k].beta = sn.beta; x.no[k].scale = sn.scale; x.no[k].shift = sn.shift;
+        x.no[k].ss_rows = sn.ss_rows; x.no[k].ss_ld = sn.ss_ld; x.no[k].cpg = sn.cpg; x.no[k].silu = sn.silu; x.no[k].eps = sn.eps;
+      }
+      DMME_REQUIRE(!ws, DMME_E_UNSUPPORTED, "conv_tct: epilogue norm on a weight-stationary launch");
+      return cmod == 128 ? launch_conv_tct<false, 128, false, false, true>(p, x, smem, stream)
+                         : launch_conv_tct<false, 256, false, false, true>(p, x, smem, stream);
+    }
     if (cmod == 128) return ws ? launch_conv_tct<true, 128>(p, x, smem, stream) : launch_conv_tct<false, 128>(p, x, smem, stream);
     if (cmod == 256) return ws ? launch_conv_tct<true, 256>(p, x, smem, stream) : launch_conv_tct<false, 256>(p, x, smem, stream);
     // the IDDPM multi-head qkv projection writes one NHWC tensor of 3C channels (models/iddpm.py:38-39)

@@ -71,6 +71,10 @@ class Engine:
         self._normed: Dict[Tuple[int, int], Tensor] = {}
         self._consumers: Optional[Dict[str, List[Tuple]]] = None
         self.fuse_out_norm = os.environ.get("DMME_FUSE_OUT_NORM", "1") != "0"
+        # 8x8 maps: the unsplit transposed conv can finish its consumers' norms in its own epilogue (csrc/conv_tc.cu, NORM).
+        # Measured no faster than conv + stand-alone GroupNorm (3.38 vs 3.34 ms per step at batch 256, equal at 128: that
+        # epilogue is store-request bound and the norm doubles its stores), so it is opt-in: DMME_EPI_NORM=1
+        self.epi_norm = os.environ.get("DMME_EPI_NORM", "0") == "1"
         # sampler update applied by the output conv's epilogue (eps stays in registers); sampler_applied reports whether the
         # last forward did it (the callers run the stand-alone update kernel otherwise)
         self.fuse_sampler = os.environ.get("DMME_FUSE_SAMPLER", "1") != "0"
@@ -282,8 +286,11 @@ class Engine:
         if stats is None:
             self._stats.pop(out.data_ptr(), None)  # the buffer may be a reused scratch with stale statistics
         ws_bytes = ops.conv_splitk_workspace(d) if (gn_ab is None and act_dtype == torch.bfloat16 and not self.force_generic) else 0
-        if ws_bytes:
-            if self._splitk_ws is None or self._splitk_ws.device != dev or self._splitk_ws.numel() * 4 < ws_bytes:
+        # 8x8 maps on the unsplit transposed kernel: the conv's own epilogue finishes the consumers' norms (opt-in, see __init__)
+        epi_norm = (not ws_bytes and self.epi_norm and gn_ab is None and act_dtype == torch.bfloat16 and not self.force_generic
+                    and self.fuse_out_norm and bool(consumers) and stats is not None and ops.conv_epilogue_norm(d))
+        if ws_bytes or epi_norm:
+            if ws_bytes and (self._splitk_ws is None or self._splitk_ws.device != dev or self._splitk_ws.numel() * 4 < ws_bytes):
                 self._splitk_ws = torch.empty(max(ws_bytes // 4, 1 << 22), dtype=torch.float32, device=dev)
             norms = []
             for k, spec in enumerate((consumers or [])[:2] if self.fuse_out_norm else []):
@@ -296,7 +303,8 @@ class Engine:
                 norms.append(ops.out_norm(y, norm.weight.detach()[off:off + cout], norm.bias.detach()[off:off + cout], cpg,
                                           silu, norm.eps, scale, shift))
                 self._normed[(out.data_ptr(), id(norm))] = y
-            ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats, splitk_ws=self._splitk_ws, out_norms=norms)
+            ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats, splitk_ws=self._splitk_ws if ws_bytes else None,
+                              out_norms=norms)
             return out
         ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats, gn_ab=gn_ab, gn_silu=gn_silu)
         return out

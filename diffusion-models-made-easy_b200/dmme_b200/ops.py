@@ -173,6 +173,12 @@ def sampler_epilogue(kind: int, x: Tensor, t: Tensor, alpha_bar: Tensor, beta: O
     return s
 
 
+def conv_epilogue_norm(desc: L.ConvDesc) -> bool:
+    """True when the unsplit kernel that would run ``desc`` honours ``conv2d_launch(out_norms=)`` itself (8x8 maps on the
+    transposed tcgen05 kernel: the epilogue warps hold whole images)."""
+    return bool(L.load().dmme_conv2d_epilogue_norm(C.byref(desc)))
+
+
 def conv_splitk_workspace(desc: L.ConvDesc) -> int:
     """Bytes of fp32 workspace with which ``conv2d_launch(splitk_ws=)`` runs ``desc`` split-K (0: it would not split).
     Only the split-K path honours ``out_norms=``."""

@@ -201,6 +201,10 @@ int dmme_conv2d_fuses_sampler(const dmme_conv_desc* desc);
  * (enough work units without splitting, or a shape / layout the split-K kernel does not take).  desc->out_norm[] is only
  * honoured on the split-K path. */
 long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* desc);
+/* 1 when the kernel that runs `desc` WITHOUT a split-K workspace honours out_norm[] too: 3x3 convs on 8x8 maps with 128 /
+ * 256 output channels on the transposed tcgen05 kernel, whose epilogue warps hold whole images (an image = two 32-pixel
+ * chunks of one warp, a GroupNorm group = neighbouring lanes) and finish the consumers' GroupNorm(+SiLU) themselves */
+int dmme_conv2d_epilogue_norm(const dmme_conv_desc* desc);
 /* A/B switch: 0 = never split K, 1 = default (by the cost model), 2 = wherever the split-K kernel supports the shape */
 void dmme_set_conv_splitk_mode(int mode);
 /* A/B switch: 0 = the finishing pass of a split-K conv on 4x4 maps takes the block-per-slab kernel of the larger maps,

@@ -1034,6 +1034,27 @@ SPLITK_CASES = [
 def test_conv_splitk_with_output_norms(cfg, splitk_everywhere):
     """split-K tcgen05 conv (K slices as work units, fp32 partial tiles) + finishing pass == fp32 conv on the same bf16
     operands; raw output, its GroupNorm statistics, and the fused GroupNorm(+SiLU) outputs for up to two consumers"""
+    _conv_out_norms_case(cfg, split=True)
+
+
+EPI_NORM_CASES = [
+    dict(n=256, cin=256, cout=256, h=8, temb="bcast", norms=[(8, True)]),                          # the timed batch: 256-pixel tiles
+    dict(n=256, cin=512, cin1=256, cout=256, h=8, res=True, temb="bcast", norms=[(16, True), (8, False)]),  # up path, two consumers
+    dict(n=128, cin=256, cout=256, h=8, addend=True, norms=[(8, True), (16, True)]),               # 128-pixel tiles
+    dict(n=203, cin=128, cout=128, h=8, norms=[(4, True)], scale_shift=True, temb="rows"),         # ragged batch, IDDPM scale / shift
+    dict(n=128, cin=256, cout=256, h=16, stride=2, norms=[(8, True), (16, True)]),                 # stride-2 down-sampling conv 16 -> 8
+    dict(n=230, cin=256, cout=128, h=8, norms=[(32, True)]),                                       # one group per warp
+]
+
+
+@pytest.mark.parametrize("cfg", EPI_NORM_CASES)
+def test_conv_tct_epilogue_norm(cfg):
+    """8x8 maps on the UNSPLIT transposed tcgen05 conv: the conv's own epilogue (whole images per warp, a GroupNorm group =
+    neighbouring lanes) writes the raw output, its statistics and the consumers' GroupNorm(+SiLU)"""
+    _conv_out_norms_case(cfg, split=False)
+
+
+def _conv_out_norms_case(cfg, split):
     ops, L = _ops()
     g = torch.Generator().manual_seed(91)
     n, cin, cout, h = (cfg[s] for s in ("n", "cin", "cout", "h"))
@@ -1065,9 +1086,13 @@ def test_conv_splitk_with_output_norms(cfg, splitk_everywhere):
         want = want + ad
         addend = to_nhwc(ad, torch.bfloat16).to(DEV)
     d = ops.make_conv_desc(s0, s1, cout, 3, stride, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
-    ws_bytes = ops.conv_splitk_workspace(d)
-    assert ws_bytes > 0, "the forced split-K mode must accept this shape"
-    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=DEV)
+    if split:
+        ws_bytes = ops.conv_splitk_workspace(d)
+        assert ws_bytes > 0, "the forced split-K mode must accept this shape"
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=DEV)
+    else:
+        assert ops.conv_epilogue_norm(d), "the unsplit transposed kernel must take this shape with its epilogue norm"
+        ws = None
     wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
     out = torch.empty((n, ho, ho, cout), dtype=torch.bfloat16, device=DEV)
     st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
