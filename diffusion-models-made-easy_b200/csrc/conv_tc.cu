@@ -419,7 +419,14 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int idx) {
 template <bool WS>
 __host__ __device__ constexpr int tct_epi_warps() { return 8; }
 
-template <bool WS, int CMOD, bool PAIR, bool SPLIT = false, bool NORM = false>
+// CLUSTER (with SPLIT, 4x4 maps): the `split` K slices of a tile are the CTAs of ONE thread-block cluster (grid = units, one
+//       unit per CTA, cluster rank = K slice).  Instead of storing fp32 partial tiles for a finishing launch, the slices are
+//       reduce-scattered through distributed shared memory: CTA r owns pixels [r NP/split, (r + 1) NP/split) of the tile
+//       (whole 16-pixel images), every other CTA writes its partial values of those pixels into r's (dead) TMA ring, and r
+//       finishes them -- slice sum in the finishing pass's order, bias / temb / addend, bf16 store, statistics, the
+//       consumers' GroupNorm(+SiLU) -- exactly as conv_splitk.cu does (same bits).  One launch instead of two and no partial
+//       tiles in global memory.
+template <bool WS, int CMOD, bool PAIR, bool SPLIT = false, bool NORM = false, bool CLUSTER = false>
 __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
                                                                                   const ConvTctExtra x) {
   extern __shared__ uint8_t smem_raw[];
@@ -566,6 +573,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
         }
       }
     }
+    if constexpr (CLUSTER) { cluster_sync_all(); cluster_sync_all(); }  // the epilogue warps' exchange barriers (below)
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0 && rank == 0) {
@@ -600,6 +608,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
         else umma_commit(&acc_full[stage]);
       }
     }
+    if constexpr (CLUSTER) { cluster_sync_all(); cluster_sync_all(); }
   } else {
     // =========================== epilogue: thread = output channel ===========================
     // Eight warps share one accumulator, so the epilogue is bound by instruction issue: the common case (a chunk of
@@ -692,7 +701,125 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
       tc_fence_after();
       if (warp == 2 && lane == 0) trace_ev(x.trace, 2, 2 * t_it);
 
-      if constexpr (SPLIT) {
+      if constexpr (CLUSTER) {
+        const int S = nsplit;
+        const int crank = static_cast<int>(cluster_ctarank());  // == ks: the K slice this CTA accumulated
+        const int own = NP / S;                                  // pixels of the tile this CTA finishes (whole images)
+        float* recv = reinterpret_cast<float*>(ring);            // [(S - 1) senders][own pixels][128 channels] fp32
+        const int cl = q * 32 + lane;                            // channel inside the 128-channel tile
+        const uint32_t tacc = tmem_base + lane_off + static_cast<uint32_t>(stage * kAccCols);
+        cluster_sync_all();  // every CTA's accumulator is complete: every TMA ring of the cluster is dead
+        // ---- send: this warp's lane quarter x its half of the columns, chunk by chunk to the owner of the chunk ----
+#pragma unroll 1
+        for (int ci = 0; ci < nchunks; ++ci) {
+          const int col0 = half * ppw + ci * 32;
+          const int r = col0 / own;  // own is a multiple of 32: a chunk has one owner
+          if (r == crank) continue;
+          uint32_t v[32];
+          tmem_ld32(tacc + static_cast<uint32_t>(col0), v);
+          tmem_ld_wait();
+          const int slot = crank < r ? crank : crank - 1;
+          const uint32_t dst = mapa_u32(recv, static_cast<uint32_t>(r)) +
+                               static_cast<uint32_t>(((slot * own + (col0 - r * own)) * 128 + cl) * 4);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(dst + static_cast<uint32_t>(i * 512)), "r"(v[i]) : "memory");
+        }
+        cluster_sync_all();  // release / acquire: the other slices' values of this CTA's pixels have landed
+        // ---- finish: thread = channel, half h takes images [h, h + 1) * own / 32 of this CTA's pixels; the arithmetic and
+        // its order are splitk_finish_small_kernel's (conv_splitk.cu) ----
+        const int ppt = own >> 1;  // pixels per thread: 16 * images
+        const float kFixc = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
+#pragma unroll 1
+        for (int ib = 0; ib < ppt; ib += 16) {
+          const int lcol = half * ppt + ib;                 // first pixel of the image inside this CTA's range
+          const int pix = mt * NP + crank * own + lcol;     // global pixel index
+          if (pix >= total_pix) break;
+          const int n = pix >> 4;
+          float add = p.bias ? __ldg(p.bias + ch) : 0.f;
+          if (p.temb) add += __ldg(p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : n) * p.temb_ld + ch);
+          float vsum[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vsum[i] = add;
+#pragma unroll 1
+          for (int j0 = 0; j0 < S; j0 += 4) {  // slices in fours, as the finishing pass sums them
+            float a4[4][16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j0 + jj;
+              if (j >= S) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a4[jj][i] = 0.f;
+              } else if (j == crank) {
+                uint32_t t16[16];
+                tmem_ld16(tacc + static_cast<uint32_t>(crank * own + lcol), t16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a4[jj][i] = __uint_as_float(t16[i]);
+              } else {
+                const float* rp = recv + ((j < crank ? j : j - 1) * own + lcol) * 128 + cl;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a4[jj][i] = rp[i * 128];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vsum[i] += (a4[0][i] + a4[1][i]) + (a4[2][i] + a4[3][i]);
+          }
+          float rf[16];
+          float t1s = 0.f, t2s = 0.f;
+          __nv_bfloat16* orow = p.out + static_cast<long long>(pix) * p.cout + ch;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float ad = p.addend ? __bfloat162float(p.addend[static_cast<long long>(pix + i) * p.cout + ch]) : 0.f;
+            const __nv_bfloat16 rb = __float2bfloat16_rn(vsum[i] + ad);
+            orow[static_cast<long long>(i) * p.cout] = rb;
+            rf[i] = __bfloat162float(rb);
+            t1s += rf[i];
+            t2s = fmaf(rf[i], rf[i], t2s);
+          }
+          if (p.stats) {
+            float m1 = t1s, m2 = t2s;
+            m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+            m1 += __shfl_xor_sync(0xffffffffu, m1, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+            if ((lane & 3) == 0) {
+              unsigned long long* st = reinterpret_cast<unsigned long long*>(p.stats) +
+                                       (static_cast<long long>(n) * (p.cout >> 2) + (ch >> 2)) * 2;
+              atomicAdd(st, static_cast<unsigned long long>(__float2ll_rn(m1 * kFixc)));
+              atomicAdd(st + 1, static_cast<unsigned long long>(__float2ll_rn(m2 * kFixc)));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const ConvTctExtra::Norm& qn = x.no[k];
+            if (qn.out == nullptr) continue;  // uniform
+            const int g0 = (lane / qn.cpg) * qn.cpg;
+            float g1 = 0.f, g2 = 0.f;
+            for (int j = 0; j < qn.cpg; ++j) {  // ascending channel order, as the finishing pass
+              g1 += __shfl_sync(0xffffffffu, t1s, g0 + j);
+              g2 += __shfl_sync(0xffffffffu, t2s, g0 + j);
+            }
+            const float inv_cnt = 1.0f / (16.0f * qn.cpg);
+            const float mean = g1 * inv_cnt;
+            const float var = fmaxf(g2 * inv_cnt - mean * mean, 0.f);
+            const float rs = rsqrtf(var + qn.eps);
+            const float ga = qn.gamma ? __ldg(qn.gamma + ch) : 1.f, be = qn.beta ? __ldg(qn.beta + ch) : 0.f;
+            float aa = rs * ga, bb = be - mean * rs * ga;
+            if (qn.scale) {
+              const long long rr = static_cast<long long>(qn.ss_rows == 1 ? 0 : n) * qn.ss_ld;
+              const float sc = 1.f + __ldg(qn.scale + rr + ch), sh = __ldg(qn.shift + rr + ch);
+              aa *= sc;
+              bb = bb * sc + sh;
+            }
+            __nv_bfloat16* yrow = qn.out + static_cast<long long>(pix) * p.cout + ch;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float y = fmaf(rf[i], aa, bb);
+              if (qn.silu) y = silu_f(y);
+              yrow[static_cast<long long>(i) * p.cout] = __float2bfloat16_rn(y);
+            }
+          }
+        }
+      } else if constexpr (SPLIT) {
         // fp32 partial tile of this K slice: thread = channel, a warp stores 128 contiguous bytes per pixel
         float* __restrict__ pp = x.partial + ks * x.split_stride + ch;
 #pragma unroll 1
@@ -1009,7 +1136,20 @@ static int tct_tile_pixels(const dmme_conv_desc& d) {
 // 19 us for 36 k-blocks whether 16 or 128 CTAs run).  Splitting K makes every (tile, K slice) a work unit; a finishing
 // pass sums the slices and -- because it sees whole images -- also applies the consumers' GroupNorm(+SiLU).
 static int g_splitk_mode = 1;
+static int g_splitk_cluster = 1;  // 1: 4x4 maps reduce the K slices inside a thread-block cluster (one launch); 0: partial tiles + finishing pass
 struct SplitPlan { int np, split; };
+
+// cluster split-K: 4x4 maps (an image = 16 pixels), 2 / 4 / 8 slices, every CTA finishing at least two images.  The plan is
+// NOT bent towards these shapes: restricting the slice counts to 2 / 4 / 8 measured slower at the small per-GPU batches
+// (batch 128: 2.42 vs 2.23 ms per step, batch 32: 1.19 vs 1.13 -- the cost model prefers 9 - 16 slices of 128-pixel tiles
+// there), so the in-cluster reduction is taken where the plan already has such a shape (batch 256: 4 slices of 256 pixels)
+static bool splitk_cluster_ok(const dmme_conv_desc& d, const SplitPlan& plan) {
+  if (!g_splitk_cluster || plan.split < 2) return false;
+  const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
+  if (ho * wo != 16) return false;
+  if (plan.split != 2 && plan.split != 4 && plan.split != 8) return false;
+  return (plan.np / plan.split) % 32 == 0;
+}
 
 static SplitPlan splitk_plan(const dmme_conv_desc& d) {
   SplitPlan none{0, 1};
@@ -1065,6 +1205,38 @@ long long conv_splitk_workspace(const dmme_conv_desc& d) {
 }
 
 int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream);  // conv_splitk.cu
+
+// split-K with the slices of a tile as one thread-block cluster (see conv_tct_kernel, CLUSTER): grid = units
+static int launch_conv_tct_cluster(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
+  auto kern = conv_tct_kernel<false, 0, false, true, false, true>;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv_tct (cluster split-K): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * x.split;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(total);
+  cfg.blockDim = dim3((2 + tct_epi_warps<false>()) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = x.split;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, x);
+  return check_launch_err(e, "conv_tct_kernel (cluster split-K)");
+}
 
 template <bool WS, int CMOD, bool PAIR = false, bool SPLIT = false, bool NORM = false>
 static int launch_conv_tct(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
@@ -1172,6 +1344,23 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
       const int st = budget / x.stage_bytes;
       x.stages = st > kTctMaxStages ? kTctMaxStages : st;
       const int smem_s = x.stages * x.stage_bytes + 1024;
+      if (splitk_cluster_ok(d, plan) &&
+          static_cast<long long>(plan.split - 1) * (np / plan.split) * 512 <= static_cast<long long>(x.stages) * x.stage_bytes) {
+        // the slices meet inside a cluster: the finishing pass's terms stay with the kernel
+        p.bias = d.bias; p.temb = d.temb; p.addend = static_cast<const __nv_bfloat16*>(d.addend); p.stats = d.stats;
+        for (int k = 0; k < 2; ++k) {
+          const dmme_out_norm& sn = d.out_norm[k];
+          if (sn.out == nullptr) continue;
+          DMME_REQUIRE(sn.cpg >= 1 && sn.cpg <= 32 && 32 % sn.cpg == 0, DMME_E_SHAPE,
+                       "conv_tct: out_norm channels per group must divide 32 (got %d)", sn.cpg);
+          DMME_REQUIRE(sn.out != d.out, DMME_E_BADARG, "conv_tct: out_norm[%d].out aliases out", k);
+          DMME_REQUIRE(sn.scale == nullptr || sn.shift != nullptr, DMME_E_BADARG, "conv_tct: out_norm scale without shift");
+          x.no[k].out = static_cast<__nv_bfloat16*>(sn.out);
+          x.no[k].gamma = sn.gamma; x.no[k].beta = sn.beta; x.no[k].scale = sn.scale; x.no[k].shift = sn.shift;
+          x.no[k].ss_rows = sn.ss_rows; x.no[k].ss_ld = sn.ss_ld; x.no[k].cpg = sn.cpg; x.no[k].silu = sn.silu; x.no[k].eps = sn.eps;
+        }
+        return launch_conv_tct_cluster(p, x, smem_s, stream);
+      }
       if ((rc = launch_conv_tct<false, 0, false, true>(p, x, smem_s, stream))) return rc;
       return conv_splitk_finish(d, plan.split, stream);
     }
@@ -1264,6 +1453,8 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
 extern "C" void dmme_set_conv_tct_mode(int mode) { dmme::g_tct_mode = mode; }
 // A/B measurement switch: 0 = never split K, 1 = default (cost model), 2 = wherever supported (tests)
 extern "C" void dmme_set_conv_splitk_mode(int mode) { dmme::g_splitk_mode = mode; }
+// A/B and test switch: 1 (default) = 4x4 maps reduce their K slices inside a thread-block cluster, 0 = partial tiles + finishing pass
+extern "C" void dmme_set_conv_splitk_cluster(int mode) { dmme::g_splitk_cluster = mode; }
 extern "C" int dmme_get_conv_tct_mode(void) { return dmme::g_tct_mode; }
 // debugging: device buffer of 3 x 512 int64 that CTA 0 of the transposed kernel fills with clock64 timestamps
 extern "C" void dmme_debug_set_conv_trace(long long* buf) { dmme::g_conv_trace = buf; }

@@ -25,7 +25,7 @@ CONV_AUTO, CONV_GENERIC, CONV_TC, CONV_HALO = 0, 1, 2, 3
 EXPORTS = (
     "dmme_abi_version", "dmme_has_experimental", "dmme_last_error", "dmme_launch_count", "dmme_reset_launch_count",
     "dmme_pack_conv_weight", "dmme_nchw_to_nhwc", "dmme_nhwc_to_nchw", "dmme_upsample2x_nhwc",
-    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_conv2d_splitk_workspace", "dmme_conv2d_epilogue_norm", "dmme_conv2d_fuses_sampler", "dmme_set_conv_splitk_mode", "dmme_set_splitk_finish_small", "dmme_conv_chain_fwd", "dmme_conv_chain_supported", "dmme_set_conv_chain_ipc", "dmme_debug_set_chain_trace", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc", "dmme_attention_block_fwd", "dmme_attention_block_supported",
+    "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_conv2d_splitk_workspace", "dmme_conv2d_epilogue_norm", "dmme_conv2d_fuses_sampler", "dmme_set_conv_splitk_mode", "dmme_set_splitk_finish_small", "dmme_set_conv_splitk_cluster", "dmme_conv_chain_fwd", "dmme_conv_chain_supported", "dmme_set_conv_chain_ipc", "dmme_debug_set_chain_trace", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc", "dmme_attention_block_fwd", "dmme_attention_block_supported",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode", "dmme_set_conv_halo_multicast",
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
@@ -127,6 +127,8 @@ def load() -> C.CDLL:
     lib.dmme_set_conv_splitk_mode.restype = None
     lib.dmme_set_splitk_finish_small.argtypes = [i]
     lib.dmme_set_splitk_finish_small.restype = None
+    lib.dmme_set_conv_splitk_cluster.argtypes = [i]
+    lib.dmme_set_conv_splitk_cluster.restype = None
     lib.dmme_conv_chain_fwd.argtypes = [C.POINTER(ChainOp), i, i, i, i, vp]
     lib.dmme_conv_chain_supported.argtypes = [i, i, i, i]
     lib.dmme_set_conv_chain_ipc.argtypes = [i]

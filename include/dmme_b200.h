@@ -211,6 +211,10 @@ void dmme_set_conv_splitk_mode(int mode);
  * 1 = its warp-per-slab kernel where there are at least 2048 (image, 32-channel slab) units (default; same bits),
  * 2 = the warp-per-slab kernel always */
 void dmme_set_splitk_finish_small(int mode);
+/* A/B and test switch: 1 (default) = split-K convs on 4x4 maps reduce their K slices inside a thread-block cluster through
+ * distributed shared memory and finish in the same launch (same bits as GEMM + finishing pass); 0 = partial tiles in the
+ * workspace + finishing pass */
+void dmme_set_conv_splitk_cluster(int mode);
 
 /* chain of 3x3 convolutions (low-resolution ResBlocks) in one launch ------------------------ */
 /*

@@ -1141,6 +1141,7 @@ def test_splitk_finish_small_bit_equal(n, cin, cpg, addend, splitk_everywhere):
     res = []
     for mode in (0, 2):
         lib.dmme_set_splitk_finish_small(mode)
+        lib.dmme_set_conv_splitk_cluster(0)  # the two finishing kernels, not the in-cluster reduction
         try:
             d = ops.make_conv_desc(x, None, cout, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
             ws = torch.empty(ops.conv_splitk_workspace(d) // 4, dtype=torch.float32, device=DEV)
@@ -1153,7 +1154,52 @@ def test_splitk_finish_small_bit_equal(n, cin, cpg, addend, splitk_everywhere):
             res.append((out, st, y0, y1))
         finally:
             lib.dmme_set_splitk_finish_small(1)
+            lib.dmme_set_conv_splitk_cluster(1)
     for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,cin,cin1,cpg,addend,res", [(256, 256, 0, 8, False, False), (256, 512, 256, 16, True, True),
+                                                      (37, 512, 256, 16, True, False), (3, 256, 0, 4, True, False),
+                                                      (32, 256, 0, 8, False, True), (128, 512, 256, 8, False, False)])
+def test_conv_splitk_cluster_bit_equal(n, cin, cin1, cpg, addend, res, splitk_everywhere):
+    """4x4 maps: the K slices reduced inside a thread-block cluster through distributed shared memory and finished by the
+    same launch write the same bits as split-K GEMM + finishing pass (same slice order): raw output, statistics, both
+    consumers' GroupNorm outputs.  Concat inputs, fused 1x1 residual, ragged batches."""
+    ops, L = _ops()
+    lib = L.load()
+    g = torch.Generator().manual_seed(101 + n)
+    cout, h = 256, 4
+    c0 = cin - cin1
+    xa = torch.randn(n, h, h, cin, generator=g).to(torch.bfloat16)
+    s0 = xa[..., :c0].contiguous().to(DEV)
+    s1 = xa[..., c0:].contiguous().to(DEV) if cin1 else None
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(DEV)
+    wres = (torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin)).to(DEV) if res else None
+    wp = ops.pack_conv_weight(w, wres, True)
+    bias, gamma, beta = (torch.randn(cout, generator=g).to(DEV) for _ in range(3))
+    temb = torch.randn(n, cout, generator=g).to(DEV)
+    ad = torch.randn(n, h, h, cout, generator=g).to(torch.bfloat16).to(DEV) if addend else None
+    outs = []
+    for cluster in (1, 0):
+        lib.dmme_set_conv_splitk_cluster(cluster)
+        lib.dmme_set_splitk_finish_small(2)
+        try:
+            d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, s0 if res else None, s1 if res else None, False, L.OUT_NHWC,
+                                   torch.bfloat16, L.CONV_AUTO)
+            ws = torch.empty(ops.conv_splitk_workspace(d) // 4, dtype=torch.float32, device=DEV)
+            out = torch.full((n, h, h, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            y0, y1 = torch.full_like(out, float("nan")), torch.full_like(out, float("nan"))
+            st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+            ops.conv2d_launch(d, wp, bias, out, temb, ad, stats=st, splitk_ws=ws,
+                              out_norms=[ops.out_norm(y0, gamma, beta, cpg, True), ops.out_norm(y1, beta, gamma, 32, False)])
+            torch.cuda.synchronize()
+            outs.append((out, st, y0, y1))
+        finally:
+            lib.dmme_set_conv_splitk_cluster(1)
+            lib.dmme_set_splitk_finish_small(1)
+    assert not torch.isnan(outs[0][0].float()).any()
+    for a, b in zip(*outs):
         assert torch.equal(a, b)
 
 
@@ -1183,7 +1229,11 @@ def test_conv_splitk_default_plan_matches_unsplit():
         torch.cuda.synchronize()
         assert rel_l2(b.float().cpu(), a.float().cpu()) < 3e-3
     assert split_seen >= 3
-    y = torch.empty_like(a)
-    d3 = ops.make_conv_desc(x, None, c, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+    # out_norm without a kernel that honours it (a 16x16 map: neither split-K nor the 8x8 epilogue norm) is refused
+    x16 = torch.randn(8, 16, 16, c, generator=g).to(torch.bfloat16).to(DEV)
+    a16 = torch.empty((8, 16, 16, c), dtype=torch.bfloat16, device=DEV)
+    y = torch.empty_like(a16)
+    d3 = ops.make_conv_desc(x16, None, c, 3, 1, False, None, None, False, L.OUT_NHWC, torch.bfloat16, L.CONV_AUTO)
+    assert not ops.conv_splitk_workspace(d3) and not ops.conv_epilogue_norm(d3)
     with pytest.raises(RuntimeError, match="split-K"):
-        ops.conv2d_launch(d3, wp, bias, a, out_norms=[ops.out_norm(y, bias, bias, 8, True)])
+        ops.conv2d_launch(d3, wp, bias, a16, out_norms=[ops.out_norm(y, bias, bias, 8, True)])
