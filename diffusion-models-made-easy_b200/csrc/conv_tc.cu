@@ -709,30 +709,31 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
         const int cl = q * 32 + lane;                            // channel inside the 128-channel tile
         const uint32_t tacc = tmem_base + lane_off + static_cast<uint32_t>(stage * kAccCols);
         cluster_sync_all();  // every CTA's accumulator is complete: every TMA ring of the cluster is dead
-        // ---- send: this warp's lane quarter x its half of the columns, chunk by chunk to the owner of the chunk ----
+        // ---- send: this warp's lane quarter x its half of the columns, image by image (16 columns) to the image's owner ----
 #pragma unroll 1
-        for (int ci = 0; ci < nchunks; ++ci) {
-          const int col0 = half * ppw + ci * 32;
-          const int r = col0 / own;  // own is a multiple of 32: a chunk has one owner
+        for (int ci = 0; ci < 2 * nchunks; ++ci) {
+          const int col0 = half * ppw + ci * 16;
+          const int r = col0 / own;  // own is a multiple of 16: an image has one owner
           if (r == crank) continue;
-          uint32_t v[32];
-          tmem_ld32(tacc + static_cast<uint32_t>(col0), v);
+          uint32_t v[16];
+          tmem_ld16(tacc + static_cast<uint32_t>(col0), v);
           tmem_ld_wait();
           const int slot = crank < r ? crank : crank - 1;
           const uint32_t dst = mapa_u32(recv, static_cast<uint32_t>(r)) +
                                static_cast<uint32_t>(((slot * own + (col0 - r * own)) * 128 + cl) * 4);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
+          for (int i = 0; i < 16; ++i)
             asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(dst + static_cast<uint32_t>(i * 512)), "r"(v[i]) : "memory");
         }
         cluster_sync_all();  // release / acquire: the other slices' values of this CTA's pixels have landed
         // ---- finish: thread = channel, half h takes images [h, h + 1) * own / 32 of this CTA's pixels; the arithmetic and
         // its order are splitk_finish_small_kernel's (conv_splitk.cu) ----
-        const int ppt = own >> 1;  // pixels per thread: 16 * images
+        // pixels per thread: 16 * images; a CTA that owns a single image leaves it to the first half of the warps
+        const int ppt = own >= 32 ? own >> 1 : (half == 0 ? own : 0);
         const float kFixc = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
 #pragma unroll 1
         for (int ib = 0; ib < ppt; ib += 16) {
-          const int lcol = half * ppt + ib;                 // first pixel of the image inside this CTA's range
+          const int lcol = (own >= 32 ? half * ppt : 0) + ib;  // first pixel of the image inside this CTA's range
           const int pix = mt * NP + crank * own + lcol;     // global pixel index
           if (pix >= total_pix) break;
           const int n = pix >> 4;
@@ -1136,7 +1137,9 @@ static int tct_tile_pixels(const dmme_conv_desc& d) {
 // 19 us for 36 k-blocks whether 16 or 128 CTAs run).  Splitting K makes every (tile, K slice) a work unit; a finishing
 // pass sums the slices and -- because it sees whole images -- also applies the consumers' GroupNorm(+SiLU).
 static int g_splitk_mode = 1;
-static int g_splitk_cluster = 1;  // 1: 4x4 maps reduce the K slices inside a thread-block cluster (one launch); 0: partial tiles + finishing pass
+// 1: 4x4 maps reduce the K slices inside a thread-block cluster (one launch) where the plan has 2 / 4 / 8 slices; 0: partial
+// tiles + finishing pass; A/B and tests: 2 = plan restricted to the cluster shapes, 3 = that plan WITHOUT the cluster
+static int g_splitk_cluster = 1;
 struct SplitPlan { int np, split; };
 
 // cluster split-K: 4x4 maps (an image = 16 pixels), 2 / 4 / 8 slices, every CTA finishing at least two images.  The plan is
@@ -1144,11 +1147,11 @@ struct SplitPlan { int np, split; };
 // (batch 128: 2.42 vs 2.23 ms per step, batch 32: 1.19 vs 1.13 -- the cost model prefers 9 - 16 slices of 128-pixel tiles
 // there), so the in-cluster reduction is taken where the plan already has such a shape (batch 256: 4 slices of 256 pixels)
 static bool splitk_cluster_ok(const dmme_conv_desc& d, const SplitPlan& plan) {
-  if (!g_splitk_cluster || plan.split < 2) return false;
+  if (!(g_splitk_cluster == 1 || g_splitk_cluster == 2) || plan.split < 2) return false;
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
   if (ho * wo != 16) return false;
   if (plan.split != 2 && plan.split != 4 && plan.split != 8) return false;
-  return (plan.np / plan.split) % 32 == 0;
+  return (plan.np / plan.split) % 16 == 0;
 }
 
 static SplitPlan splitk_plan(const dmme_conv_desc& d) {
@@ -1177,6 +1180,8 @@ static SplitPlan splitk_plan(const dmme_conv_desc& d) {
     if (np == 256 && wo > 256) continue;
     const long long base_units = ceil_div_ll(total_pix, np) * n_tiles;
     for (int split = 2; split <= 16 && 2 * split <= nkb; ++split) {
+      // A/B (dmme_set_conv_splitk_cluster(2)): only the shapes the in-cluster reduction takes
+      if (g_splitk_cluster >= 2 && ho * wo == 16 && !((split == 2 || split == 4 || split == 8) && (np / split) % 16 == 0)) continue;
       const long long units = base_units * split;
       if (units > 2 * sm) break;
       const double gemm = static_cast<double>(ceil_div_ll(units, sm)) * unit_clocks(ceil_div(nkb, split), np * 128 + 16384);

@@ -200,6 +200,9 @@ def load() -> C.CDLL:
         lib.dmme_set_wgrad_waves.argtypes = [i]
         lib.dmme_set_wgrad_waves.restype = None
         lib.dmme_set_wgrad_waves(int(mode))
+    mode = os.environ.get("DMME_SPLITK_CLUSTER")  # A/B measurements only: 0 = GEMM + finishing pass at 4x4, 2 = bend the plan
+    if mode:
+        lib.dmme_set_conv_splitk_cluster(int(mode))
     mode = os.environ.get("DMME_FINISH_SMALL")  # A/B measurements only: 0 = block-per-slab split-K finishing kernel at 4x4
     if mode:
         lib.dmme_set_splitk_finish_small(int(mode))

@@ -1162,7 +1162,8 @@ def test_splitk_finish_small_bit_equal(n, cin, cpg, addend, splitk_everywhere):
 @pytest.mark.parametrize("n,cin,cin1,cpg,addend,res", [(256, 256, 0, 8, False, False), (256, 512, 256, 16, True, True),
                                                       (37, 512, 256, 16, True, False), (3, 256, 0, 4, True, False),
                                                       (32, 256, 0, 8, False, True), (128, 512, 256, 8, False, False)])
-def test_conv_splitk_cluster_bit_equal(n, cin, cin1, cpg, addend, res, splitk_everywhere):
+@pytest.mark.parametrize("bend", [1, 2])
+def test_conv_splitk_cluster_bit_equal(n, cin, cin1, cpg, addend, res, bend, splitk_everywhere):
     """4x4 maps: the K slices reduced inside a thread-block cluster through distributed shared memory and finished by the
     same launch write the same bits as split-K GEMM + finishing pass (same slice order): raw output, statistics, both
     consumers' GroupNorm outputs.  Concat inputs, fused 1x1 residual, ragged batches."""
@@ -1181,7 +1182,9 @@ def test_conv_splitk_cluster_bit_equal(n, cin, cin1, cpg, addend, res, splitk_ev
     temb = torch.randn(n, cout, generator=g).to(DEV)
     ad = torch.randn(n, h, h, cout, generator=g).to(torch.bfloat16).to(DEV) if addend else None
     outs = []
-    for cluster in (1, 0):
+    # bend = 2: the plan restricted to the shapes the cluster reduction takes (also CTAs that own a single image); the
+    # reference run needs the same plan without the cluster: switch value 3
+    for cluster in ((1, 0) if bend == 1 else (2, 3)):
         lib.dmme_set_conv_splitk_cluster(cluster)
         lib.dmme_set_splitk_finish_small(2)
         try:
