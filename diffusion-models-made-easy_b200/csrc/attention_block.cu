@@ -42,7 +42,10 @@ struct AttnBlockParams {
   CUtensorMap wproj;  // [C][C] bf16, box [64][128]
   int n;
   float scale_log2e;
-  const float* gn_ab;         // [n][C][2]
+  const float* gn_ab;         // [n][C][2], or null: coefficients from stats_in / gamma / beta in the kernel
+  const long long* stats_in;  // micro-group sums of x written by its producer ([n][C/4][2])
+  const float* gamma; const float* beta;
+  int cpg; float eps;
   const float* bias_qkv;      // [768]
   const float* bias_proj;     // [256]
   const __nv_bfloat16* xres;  // the raw x again (residual), [n][256][256]
@@ -100,6 +103,45 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       printf("dmme: cluster mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }
+  }
+}
+
+// (a, b) of y = a x + b for channels c0 .. c0 + 7 of image img: from the coefficient tensor of dmme_groupnorm_coeff, or --
+// saving that launch -- from the producer's fixed-point micro-group sums with gn_coefficients' arithmetic (groupnorm.cu: one
+// source, no scale / shift; same bits).  cpg is a multiple of 4.
+__device__ __forceinline__ void ab_coeff8(const float* gn_ab, const long long* stats_in, const float* gamma, const float* beta,
+                                          int cpg, float eps, int hw, int C, int img, int c0, float (&a)[8], float (&b)[8]) {
+  if (gn_ab != nullptr) {
+    const float4* abp = reinterpret_cast<const float4*>(gn_ab + (static_cast<long long>(img) * C + c0) * 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t4 = __ldg(abp + j);
+      a[2 * j] = t4.x; b[2 * j] = t4.y; a[2 * j + 1] = t4.z; b[2 * j + 1] = t4.w;
+    }
+    return;
+  }
+  const float inv_cnt = 1.0f / (static_cast<float>(hw) * cpg);
+  const double unfix = 1.0 / static_cast<double>(1 << DMME_STATS_FRAC_BITS);
+  float mean = 0.f, rs = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    if (e == 0 || c % cpg == 0) {
+      const int g0 = (c / cpg) * cpg;
+      long long s1 = 0, s2 = 0;
+      for (int cc = g0; cc < g0 + cpg; cc += 4) {
+        const long long* st = stats_in + (static_cast<long long>(img) * (C >> 2) + (cc >> 2)) * 2;
+        s1 += st[0];
+        s2 += st[1];
+      }
+      mean = static_cast<float>(static_cast<double>(s1) * unfix) * inv_cnt;
+      const float ex2 = static_cast<float>(static_cast<double>(s2) * unfix) * inv_cnt;
+      const float var = fmaxf(ex2 - mean * mean, 0.f);
+      rs = rsqrtf(var + eps);
+    }
+    const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+    a[e] = rs * ga;
+    b[e] = be - mean * rs * ga;
   }
 }
 
@@ -361,13 +403,8 @@ __global__ void __launch_bounds__(kAbThreads, 1) attn_block_kernel(const __grid_
     pdl_wait();
     int it = 0;
     for (int img = cid; img < p.n; img += ncl, ++it) {
-      const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + (static_cast<long long>(img) * C + kb * 64 + u * 8) * 2);
       float a[8], b[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 t4 = __ldg(abp + j);
-        a[2 * j] = t4.x; b[2 * j] = t4.y; a[2 * j + 1] = t4.z; b[2 * j + 1] = t4.w;
-      }
+      ab_coeff8(p.gn_ab, p.stats_in, p.gamma, p.beta, p.cpg, p.eps, kAbL, C, img, kb * 64 + u * 8, a, b);
       mbar_wait(&bars[AB_X_FULL], it & 1);
       if (t2 == 0) ab_trace(p.trace, 0, it * 14 + 0);
       uint8_t* blk = R1 + kb * kAbBlk;
@@ -596,6 +633,9 @@ struct AttnBlock16Params {
   int n;
   float scale_log2e;
   const float* gn_ab;
+  const long long* stats_in;
+  const float* gamma; const float* beta;
+  int cpg; float eps;
   const float* bias_qkv;
   const float* bias_proj;
   const __nv_bfloat16* xres;
@@ -753,14 +793,7 @@ __global__ void __launch_bounds__(kA16Threads, 1) attn_block16_kernel(const __gr
       const int gi = wt >> 5, cu = wt & 31, kb = cu >> 3, u = cu & 7;
       float a[8], b[8];
       const bool valid = img0 + gi < p.n;
-      if (valid) {
-        const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + (static_cast<long long>(img0 + gi) * kAbC + kb * 64 + u * 8) * 2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 t4 = __ldg(abp + j);
-          a[2 * j] = t4.x; b[2 * j] = t4.y; a[2 * j + 1] = t4.z; b[2 * j + 1] = t4.w;
-        }
-      }
+      if (valid) ab_coeff8(p.gn_ab, p.stats_in, p.gamma, p.beta, p.cpg, p.eps, 16, kAbC, img0 + gi, kb * 64 + u * 8, a, b);
       mbar_wait(&bars[B16_X_FULL], 0);
       if (wt == 0) ab_trace(p.trace, 0, 1);
       if (valid) {
@@ -952,7 +985,9 @@ bool attn_block_supported(int act_dtype, int heads, int L, int c) {
   return act_dtype == DMME_BF16 && heads == 1 && ((L == kAbL && (c == 256 || c == 128)) || (L == 16 && c == kAbC));
 }
 
-static int attn_block16_forward(const void* x, const float* gn_ab, const void* wqkv, const float* bias_qkv, const void* wproj,
+struct AbNorm { const float* gn_ab; const long long* stats_in; const float* gamma; const float* beta; int cpg; float eps; };
+
+static int attn_block16_forward(const void* x, const AbNorm& nm, const void* wqkv, const float* bias_qkv, const void* wproj,
                                 const float* bias_proj, int n, float scale, void* out, long long* stats, cudaStream_t stream) {
   AttnBlock16Params p;
   memset(&p, 0, sizeof(p));
@@ -967,7 +1002,7 @@ static int attn_block16_forward(const void* x, const float* gn_ab, const void* w
   if ((rc = encode_map(&p.wproj, wproj, 2, dims, strides, box))) return rc;
   p.n = n;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.gn_ab = gn_ab;
+  p.gn_ab = nm.gn_ab; p.stats_in = nm.stats_in; p.gamma = nm.gamma; p.beta = nm.beta; p.cpg = nm.cpg; p.eps = nm.eps;
   p.bias_qkv = bias_qkv;
   p.bias_proj = bias_proj;
   p.xres = static_cast<const __nv_bfloat16*>(x);
@@ -1000,9 +1035,9 @@ static int attn_block_launch(const AttnBlockParams& p, int n, cudaStream_t strea
   return check_launch_err(e, "attn_block_kernel");
 }
 
-int attn_block_forward(const void* x, const float* gn_ab, const void* wqkv, const float* bias_qkv, const void* wproj,
+int attn_block_forward(const void* x, const AbNorm& nm, const void* wqkv, const float* bias_qkv, const void* wproj,
                        const float* bias_proj, int n, int L, int c, float scale, void* out, long long* stats, cudaStream_t stream) {
-  if (L == 16) return attn_block16_forward(x, gn_ab, wqkv, bias_qkv, wproj, bias_proj, n, scale, out, stats, stream);
+  if (L == 16) return attn_block16_forward(x, nm, wqkv, bias_qkv, wproj, bias_proj, n, scale, out, stats, stream);
   AttnBlockParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -1023,7 +1058,7 @@ int attn_block_forward(const void* x, const float* gn_ab, const void* wqkv, cons
   }
   p.n = n;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.gn_ab = gn_ab;
+  p.gn_ab = nm.gn_ab; p.stats_in = nm.stats_in; p.gamma = nm.gamma; p.beta = nm.beta; p.cpg = nm.cpg; p.eps = nm.eps;
   p.bias_qkv = bias_qkv;
   p.bias_proj = bias_proj;
   p.xres = static_cast<const __nv_bfloat16*>(x);
@@ -1041,16 +1076,22 @@ extern "C" int dmme_attention_block_supported(int heads, int L, int c, int act_d
   return dmme::attn_block_supported(act_dtype, heads, L, c) ? 1 : 0;
 }
 
-extern "C" int dmme_attention_block_fwd(const void* x, const float* gn_ab, const void* wqkv, const float* bias_qkv,
+extern "C" int dmme_attention_block_fwd(const void* x, const float* gn_ab, const long long* stats_in, const float* gamma,
+                                        const float* beta, int groups, float eps, const void* wqkv, const float* bias_qkv,
                                         const void* wproj, const float* bias_proj, int n, int heads, int L, int c, float scale,
                                         void* out, long long* stats, int act_dtype, void* stream) {
-  DMME_REQUIRE(x && gn_ab && wqkv && bias_qkv && wproj && bias_proj && out && n > 0, DMME_E_BADARG,
+  DMME_REQUIRE(x && wqkv && bias_qkv && wproj && bias_proj && out && n > 0, DMME_E_BADARG,
                "dmme_attention_block_fwd: null pointer or empty batch");
+  DMME_REQUIRE(gn_ab != nullptr || stats_in != nullptr, DMME_E_BADARG,
+               "dmme_attention_block_fwd: the block's GroupNorm needs gn_ab or the producer's statistics (stats_in)");
   DMME_REQUIRE(dmme::attn_block_supported(act_dtype, heads, L, c), DMME_E_SHAPE,
                "dmme_attention_block_fwd: only bf16, one head, 256 tokens x 256 / 128 channels or 16 tokens x 256 channels (got heads=%d L=%d c=%d)", heads, L, c);
+  DMME_REQUIRE(gn_ab != nullptr || (groups > 0 && c % groups == 0 && (c / groups) % 4 == 0), DMME_E_SHAPE,
+               "dmme_attention_block_fwd: in-kernel GroupNorm coefficients need channels per group to be a multiple of 4");
   DMME_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wqkv) | reinterpret_cast<uintptr_t>(wproj) |
                  reinterpret_cast<uintptr_t>(gn_ab) | reinterpret_cast<uintptr_t>(bias_qkv)) & 15u) == 0,
                DMME_E_BADARG, "dmme_attention_block_fwd: x / weights / gn_ab / bias_qkv must be 16-byte aligned");
-  return dmme::attn_block_forward(x, gn_ab, wqkv, bias_qkv, wproj, bias_proj, n, L, c, scale, out, stats,
+  dmme::AbNorm nm{gn_ab, stats_in, gamma, beta, groups > 0 ? c / groups : 0, eps};
+  return dmme::attn_block_forward(x, nm, wqkv, bias_qkv, wproj, bias_proj, n, L, c, scale, out, stats,
                                   static_cast<cudaStream_t>(stream));
 }

@@ -136,7 +136,7 @@ def load() -> C.CDLL:
     lib.dmme_attention_fwd.argtypes = [vp, vp, vp, ll, i, i, i, ll, i, i, i, i, f, i, vp, i, i, vp]
     lib.dmme_attention_uses_tc.argtypes = [ll, i, i, ll, i, i, i, i, i]
     lib.dmme_attention_block_supported.argtypes = [i, i, i, i]
-    lib.dmme_attention_block_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, f, vp, vp, i, vp]
+    lib.dmme_attention_block_fwd.argtypes = [vp, vp, vp, vp, vp, i, f, vp, vp, vp, vp, i, i, i, i, f, vp, vp, i, vp]
     lib.dmme_temb_mlp_fwd.argtypes = [vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, vp]
     lib.dmme_temb_proj_fwd.argtypes = [vp, i, i, vp, vp, i, vp, vp]
     lib.dmme_ddpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, ll, ull, ull, vp]

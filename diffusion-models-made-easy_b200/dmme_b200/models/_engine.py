@@ -80,6 +80,10 @@ class Engine:
         self.fuse_sampler = os.environ.get("DMME_FUSE_SAMPLER", "1") != "0"
         # single-head 256-token x 256-channel attention blocks as one launch (DMME_FUSE_ATTN=0: norm | qkv | core | proj launches)
         self.fuse_attn = os.environ.get("DMME_FUSE_ATTN", "1") != "0"
+        # the block kernels can form their GroupNorm coefficients themselves from the producer's statistics (six launches fewer
+        # per step, same bits); measured within noise of the coefficient launch it replaces (3.33 vs 3.25 - 3.31 ms at batch
+        # 256, +0.01 ms at the smaller batches: the dependent loads sit in front of the first tile's norm), so opt-in
+        self.attn_coeff_in_kernel = os.environ.get("DMME_ATTN_COEFF_IN_KERNEL", "0") == "1"
         # consecutive ResBlocks of the 8x8 / 4x4 levels in one persistent launch (csrc/conv_chain.cu); DMME_CHAIN=0: per-conv
         # launches as at the higher resolutions
         self.use_chain = os.environ.get("DMME_CHAIN", "1") != "0"
@@ -381,14 +385,18 @@ class Engine:
         if st is not None and self.attention_fused(att, seq, c, x.dtype):
             # the whole block in one launch (csrc/attention_block.cu): norm, qkv, softmax(q k^T) v, proj and + x
             norm = att.norm
-            ab = ops.groupnorm_coeff(st, None, c, 0, n, seq, norm.num_groups, norm.weight.detach(), norm.bias.detach(), None, None,
-                                     norm.eps, out=self.ws.get("scratch.attn_ab", (n, c, 2), torch.float32, x.device))
             out = self.ws.get(name + ".attn", (n, h, w, c), x.dtype, x.device)
             stats = self._stats_for(out, n, c)
             if stats is None:
                 self._stats.pop(out.data_ptr(), None)
-            return ops.attention_block(x, ab, self.packed_weight(att.qkv_proj, None, True), att.qkv_proj.bias.detach(),
-                                       self.packed_weight(att.proj, None, True), att.proj.bias.detach(), att.scale, out, stats)
+            wq, wp = self.packed_weight(att.qkv_proj, None, True), self.packed_weight(att.proj, None, True)
+            if self.attn_coeff_in_kernel:
+                return ops.attention_block(x, None, wq, att.qkv_proj.bias.detach(), wp, att.proj.bias.detach(), att.scale, out,
+                                           stats, stats_in=st, gamma=norm.weight.detach(), beta=norm.bias.detach(),
+                                           groups=norm.num_groups, eps=norm.eps)
+            ab = ops.groupnorm_coeff(st, None, c, 0, n, seq, norm.num_groups, norm.weight.detach(), norm.bias.detach(), None, None,
+                                     norm.eps, out=self.ws.get("scratch.attn_ab", (n, c, 2), torch.float32, x.device))
+            return ops.attention_block(x, ab, wq, att.qkv_proj.bias.detach(), wp, att.proj.bias.detach(), att.scale, out, stats)
         a = self._normed.get((x.data_ptr(), id(att.norm)))
         if a is None:
             a = self.gn("scratch.attn_norm", att.norm, x, None, silu=False)

@@ -308,16 +308,20 @@ def attention_block_supported(heads: int, seq: int, c: int, dtype: torch.dtype) 
     return bool(L.load().dmme_attention_block_supported(heads, seq, c, L.act_code(dtype)))
 
 
-def attention_block(x: Tensor, gn_ab: Tensor, wqkv: Tensor, bias_qkv: Tensor, wproj: Tensor, bias_proj: Tensor, scale: float,
-                    out: Optional[Tensor] = None, stats: Optional[Tensor] = None) -> Tensor:
+def attention_block(x: Tensor, gn_ab: Optional[Tensor], wqkv: Tensor, bias_qkv: Tensor, wproj: Tensor, bias_proj: Tensor,
+                    scale: float, out: Optional[Tensor] = None, stats: Optional[Tensor] = None, *,
+                    stats_in: Optional[Tensor] = None, gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None,
+                    groups: int = 0, eps: float = 1e-5) -> Tensor:
     """``x + proj(attention(qkv_proj(GroupNorm(x))))`` (Attention.forward, models/ddpm.py:54-75) in one launch.
-    x: NHWC bf16 [n, h, w, c]; gn_ab: ``groupnorm_coeff`` of the block's norm; wqkv / wproj: ``pack_conv_weight`` of the two
-    1x1 convs; stats: optional zeroed int64 micro-group sums of the output."""
-    L.require_cuda(x, gn_ab, wqkv, bias_qkv, wproj, bias_proj, out, stats)
+    x: NHWC bf16 [n, h, w, c]; the block's norm either as ``gn_ab`` (``groupnorm_coeff``) or, with ``gn_ab=None``, as the
+    producer's statistics ``stats_in`` + ``gamma`` / ``beta`` / ``groups`` / ``eps`` (the kernel forms the coefficients);
+    wqkv / wproj: ``pack_conv_weight`` of the two 1x1 convs; stats: optional zeroed int64 micro-group sums of the output."""
+    L.require_cuda(x, gn_ab, wqkv, bias_qkv, wproj, bias_proj, out, stats, stats_in, gamma, beta)
     n, h, w, c = x.shape
     y = _empty((n, h, w, c), x.dtype, x.device, out)
-    L.check(L.load().dmme_attention_block_fwd(ptr(x), ptr(gn_ab), ptr(wqkv), ptr(bias_qkv), ptr(wproj), ptr(bias_proj), n, 1,
-                                              h * w, c, float(scale), ptr(y), ptr(stats), L.act_code(x.dtype), L.stream_ptr()),
+    L.check(L.load().dmme_attention_block_fwd(ptr(x), ptr(gn_ab), ptr(stats_in), ptr(gamma), ptr(beta), int(groups), float(eps),
+                                              ptr(wqkv), ptr(bias_qkv), ptr(wproj), ptr(bias_proj), n, 1, h * w, c,
+                                              float(scale), ptr(y), ptr(stats), L.act_code(x.dtype), L.stream_ptr()),
             "attention_block_fwd")
     return y
 

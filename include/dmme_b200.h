@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMME_ABI_VERSION 6
+#define DMME_ABI_VERSION 7
 #define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
@@ -296,7 +296,7 @@ int dmme_attention_uses_tc(long long batch_stride, int row_stride, int v_transpo
  * The whole attention block of Attention.forward (models/ddpm.py:54-75) in one launch:
  *   out = x + proj( softmax(scale * q k^T) v ),  [q | k | v] = qkv_proj(GroupNorm(x))
  * x / out: NHWC act_dtype [n][L][c]; gn_ab: the (a, b) pairs of the block's GroupNorm from dmme_groupnorm_coeff
- * ([n][c][2], no SiLU); wqkv [3c][c] / wproj [c][c]: the 1x1 conv weights packed by dmme_pack_conv_weight (bf16, K
+ * ([n][c][2], no SiLU) -- or NULL with stats_in, see below; wqkv [3c][c] / wproj [c][c]: the 1x1 conv weights packed by dmme_pack_conv_weight (bf16, K
  * contiguous); bias_qkv [3c], bias_proj [c] fp32; stats: optional micro-group sums of `out` (as dmme_conv_desc.stats).
  * Nothing between x and out is written to global memory.  Supported (ask first): bf16, heads = 1, and L = 256 with c = 256
  * or 128 (the five 16x16 sites of the default DDPM UNet, configs/ddpm/cifar10.yaml: a cluster of two CTAs per image) or
@@ -304,9 +304,13 @@ int dmme_attention_uses_tc(long long batch_stride, int row_stride, int v_transpo
  * proj conv path.
  */
 int dmme_attention_block_supported(int heads, int L, int c, int act_dtype);
-int dmme_attention_block_fwd(const void* x, const float* gn_ab, const void* wqkv, const float* bias_qkv,
+int dmme_attention_block_fwd(const void* x, const float* gn_ab, const long long* stats_in, const float* gamma,
+                             const float* beta, int groups, float eps, const void* wqkv, const float* bias_qkv,
                              const void* wproj, const float* bias_proj, int n, int heads, int L, int c, float scale,
                              void* out, long long* stats, int act_dtype, void* stream);
+/* The block's GroupNorm: either gn_ab (coefficient pairs from dmme_groupnorm_coeff) or, with gn_ab = NULL, stats_in (the
+ * micro-group sums its producer wrote, dmme_conv_desc.stats) + gamma / beta / groups / eps: the kernel then forms the
+ * coefficients itself (same arithmetic, same bits) and the coefficient launch disappears. */
 
 /* timestep embedding ----------------------------------------------------------------------- */
 /*

@@ -659,7 +659,12 @@ def test_attention_block_fused(n, hgt, c):
     out_stats = torch.zeros(n * (c // 4) * 2, dtype=torch.int64, device=DEV)
     out = ops.attention_block(xd, ab, ops.pack_conv_weight(wqkv.to(DEV), None, True), bqkv.to(DEV),
                               ops.pack_conv_weight(wproj.to(DEV), None, True), bproj.to(DEV), scale, stats=out_stats)
+    # the same with the coefficients formed inside the kernel from the producer's statistics: identical bits
+    out2 = ops.attention_block(xd, None, ops.pack_conv_weight(wqkv.to(DEV), None, True), bqkv.to(DEV),
+                               ops.pack_conv_weight(wproj.to(DEV), None, True), bproj.to(DEV), scale,
+                               stats_in=st, gamma=gamma.to(DEV), beta=beta.to(DEV), groups=groups, eps=1e-5)
     torch.cuda.synchronize()
+    assert torch.equal(out, out2)
     got = to_nchw(out.cpu())
     err = rel_l2(got, want)
     # the attention branch alone (the residual x dominates the output norm)
