@@ -14,7 +14,7 @@ def main():
     ni, ui, gi = hdr.index("Kernel Name"), hdr.index("Metric Unit"), hdr.index("Grid Size")
     data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
     marks = [i for i, r in enumerate(data) if "add_i64_kernel" in r[ni]]
-    seg = data[marks[-2] + 1:marks[-1] + 1]
+    seg = data[marks[-2] + 1:marks[-1] + 1] if len(marks) >= 2 else data  # tools/one_step.py lists exactly one step
     d = collections.defaultdict(lambda: [0, 0.0])
     for r in seg:
         v = float(r[-1].replace(",", ""))
@@ -26,7 +26,8 @@ def main():
         d[key][1] += v
     tot = sum(v[1] for v in d.values())
     print("# one DDPM sampling step (temb -> UNet forward -> DDPM update in the output conv's epilogue), default UNet, batch 256,")
-    print("# bf16, one B200; ncu --metrics gpu__time_duration.sum --clock-control none of bench.py (last graph replay)")
+    print("# bf16, one B200; ncu --metrics gpu__time_duration.sum --clock-control none of bench.py (last graph replay) or of")
+    print("# tools/one_step.py with --profile-from-start off (exactly one replay)")
     print("# per-launch times are cold-cache and serialised: compare SHARES" +
           (f"; the graph-replayed step measures {sys.argv[2]} ms (bench.py)" if len(sys.argv) > 2 else ""))
     print(f"step total us {tot:.1f}   launches {len(seg)}")
