@@ -529,17 +529,21 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
 // memory, every activation value is loaded once (coalesced, 2 B) and feeds 9 taps x cout FMAs against broadcast
 // shared-memory reads; the CTA writes its [cout][kp] partial (slice = image) for wgrad_reduce_kernel.
 //   dW[co][ci][r][s] = sum over input pixels (y, x) of a[y][x][ci] * g[co][y - r + 1][x - s + 1]
+constexpr int kOutWgradRowSplit = 4;  // CTAs per image (row bands): 128 CTAs of four warps left the SMs at 6 % occupancy
 template <int COUT>
 __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const WgradParams p) {
   extern __shared__ float gs[];  // [COUT][h + 2][w + 4]: zero halo, rows padded to a multiple of 4 floats
   const int h = p.h_in, w = p.w_in, ws = w + 4, plane = (h + 2) * ws;
   const int n = blockIdx.x;
+  const int band = blockIdx.y, bands = gridDim.y;  // input rows [y_lo, y_hi) of the image
+  const int y_lo = band * h / bands, y_hi = (band + 1) * h / bands;
   const int ci = threadIdx.x;  // blockDim.x == c0
   for (int i = threadIdx.x; i < COUT * plane; i += blockDim.x) gs[i] = 0.f;
   __syncthreads();
   const float* g = static_cast<const float*>(p.g) + static_cast<long long>(n) * COUT * h * w;
   for (int i = threadIdx.x; i < COUT * h * w; i += blockDim.x) {
     const int co = i / (h * w), rem = i - co * h * w, y = rem / w, x = rem - y * w;
+    if (y + 2 < y_lo || y > y_hi) continue;  // only the output rows this band's taps reach
     gs[co * plane + (y + 1) * ws + x + 1] = g[i];
   }
   __syncthreads();
@@ -549,9 +553,20 @@ __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const WgradParams p
 #pragma unroll
     for (int co = 0; co < COUT; ++co) acc[t][co] = 0.f;
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(p.src0) + static_cast<long long>(n) * h * w * p.c0 + ci;
-  for (int y = 0; y < h; ++y) {
-    for (int x = 0; x < w; ++x) {
-      const float av = __bfloat162float(a[static_cast<long long>(y * w + x) * p.c0]);
+  // the activation values of kAhead pixels are requested before the first is used: one load per pixel with its use right
+  // behind it left a DRAM / L2 round trip per pixel exposed (714 us per launch)
+  constexpr int kAhead = 16;
+  const int p_lo = y_lo * w, p_hi = y_hi * w;
+  for (int p0 = p_lo; p0 < p_hi; p0 += kAhead) {
+    float avs[kAhead];
+#pragma unroll
+    for (int i = 0; i < kAhead; ++i)
+      avs[i] = p0 + i < p_hi ? __bfloat162float(a[static_cast<long long>(p0 + i) * p.c0]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < kAhead; ++i) {
+      if (p0 + i >= p_hi) break;
+      const int y = (p0 + i) / w, x = (p0 + i) - y * w;
+      const float av = avs[i];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         // output row y - r + 1 -> halo row y - r + 2; output columns x - s + 1 -> halo columns x + 2 - s, s = 0..2
@@ -566,16 +581,18 @@ __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const WgradParams p
       }
     }
   }
-  float* part = p.partial + static_cast<long long>(n) * COUT * p.kp;
+  float* part = p.partial + (static_cast<long long>(n) * bands + band) * COUT * p.kp;  // slice = (image, band)
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int co = 0; co < COUT; ++co) part[static_cast<long long>(co) * p.kp + t * p.c0 + ci] = acc[t][co];
-  // bias column k = 9 c0: sum of grad_out over the image
+  // bias column k = 9 c0: sum of grad_out over the image (first band; the others contribute zero)
   if (threadIdx.x < COUT) {
     float t = 0.f;
-    const float* gp = g + static_cast<long long>(threadIdx.x) * h * w;
-    for (int i = 0; i < h * w; ++i) t += gp[i];
+    if (band == 0) {
+      const float* gp = g + static_cast<long long>(threadIdx.x) * h * w;
+      for (int i = 0; i < h * w; ++i) t += gp[i];
+    }
     part[static_cast<long long>(threadIdx.x) * p.kp + 9 * p.c0] = t;
   }
 }
@@ -1285,7 +1302,8 @@ extern "C" long long dmme_conv2d_wgrad_workspace(const dmme_conv_desc* d) {
     // partials + the per-image pixel sums of grad_out for the bias gradient
     return (static_cast<long long>(tslices) * d->cout * kp + static_cast<long long>(d->n) * d->cout) * sizeof(float);
   }
-  if (conv_out_wgrad_supported(*d)) slices = slices > d->n ? slices : d->n;  // one slice per image
+  if (conv_out_wgrad_supported(*d))  // one slice per (image, row band)
+    slices = slices > d->n * kOutWgradRowSplit ? slices : d->n * kOutWgradRowSplit;
   return static_cast<long long>(slices) * d->cout * kp * sizeof(float);
 }
 
@@ -1330,12 +1348,14 @@ extern "C" int dmme_conv2d_wgrad(const dmme_conv_desc* d, const void* grad_out, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (conv_out_wgrad_supported(*d)) {
     const int smem = d->cout * (d->h_in + 2) * (d->w_in + 4) * static_cast<int>(sizeof(float));
-    if (d->cout == 3) conv_out_wgrad_kernel<3><<<d->n, d->c0, smem, st>>>(p);
-    else conv_out_wgrad_kernel<6><<<d->n, d->c0, smem, st>>>(p);
+    const int bands = d->h_in >= kOutWgradRowSplit ? kOutWgradRowSplit : 1;
+    const dim3 ogrid(d->n, bands);
+    if (d->cout == 3) conv_out_wgrad_kernel<3><<<ogrid, d->c0, smem, st>>>(p);
+    else conv_out_wgrad_kernel<6><<<ogrid, d->c0, smem, st>>>(p);
     int rc = check_launch("conv_out_wgrad_kernel");
     if (rc) return rc;
     const long long total = static_cast<long long>(d->cout) * kp;
-    wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(p.partial, d->n, d->cout, kp, d->c0, 9, 0, dweight, nullptr, dbias);
+    wgrad_reduce_kernel<<<grid_1d(total, 256), 256, 0, st>>>(p.partial, d->n * bands, d->cout, kp, d->c0, 9, 0, dweight, nullptr, dbias);
     return check_launch("wgrad_reduce_kernel");
   }
   dim3 grid(ceil_div(kp, SG_N), ceil_div(d->cout, SG_M), slices);
