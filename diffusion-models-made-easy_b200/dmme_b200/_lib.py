@@ -30,10 +30,21 @@ EXPORTS = (
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode", "dmme_set_conv_halo_multicast",
     "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
     "dmme_denorm", "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
-    "dmme_pack_conv_weight_dgrad", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
+    "dmme_pack_conv_weight_dgrad", "dmme_pack_block_elems", "dmme_pack_conv_weights_batch", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
     "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_bwd_fused", "dmme_attention_bwd_fused_supported", "dmme_set_wgrad_waves", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
     "dmme_gemm_strided", "dmme_add", "dmme_pixel_sum", "dmme_pool2x_sum_nhwc", "dmme_dilate2x_nhwc", "dmme_colsum_f32", "dmme_mse_loss", "dmme_iddpm_loss",
 )
+
+
+class PackItem(C.Structure):
+    """Mirror of ``struct dmme_pack_item``."""
+
+    _fields_ = [
+        ("w", C.c_void_p), ("wres", C.c_void_p), ("packed", C.c_void_p),
+        ("cout", C.c_int), ("cin", C.c_int), ("ksize", C.c_int), ("rc", C.c_int),
+        ("dgrad", C.c_int), ("ci_off", C.c_int), ("ci_cnt", C.c_int), ("reserved", C.c_int),
+        ("first_block", C.c_longlong),
+    ]
 
 
 class OutNorm(C.Structure):
@@ -122,6 +133,8 @@ def load() -> C.CDLL:
     lib.dmme_conv2d_fuses_sampler.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_conv2d_splitk_workspace.argtypes = [C.POINTER(ConvDesc)]
     lib.dmme_conv2d_epilogue_norm.argtypes = [C.POINTER(ConvDesc)]
+    lib.dmme_pack_block_elems.argtypes = []
+    lib.dmme_pack_conv_weights_batch.argtypes = [vp, i, ll, vp]
     lib.dmme_conv2d_splitk_workspace.restype = ll
     lib.dmme_set_conv_splitk_mode.argtypes = [i]
     lib.dmme_set_conv_splitk_mode.restype = None

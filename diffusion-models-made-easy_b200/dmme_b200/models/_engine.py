@@ -51,6 +51,10 @@ class Engine:
         self.flavour = flavour  # "ddpm" | "iddpm"
         self.ws = Workspace()
         self._packed: Dict[Tuple, Tuple[Tuple, Tensor]] = {}
+        # (weight, residual weight, dgrad, ci_off, ci_cnt) of every tensor-core weight pack, for pack_batch(); the keys whose
+        # cache entries a batched launch refreshes in place
+        self._pack_specs: Dict[Tuple, Tuple] = {}
+        self._batched_packs: set = set()
         self._blocks: Optional[List[Tuple[str, nn.Module]]] = None
         self.force_generic = False  # debugging / fp32 mode: never take the tcgen05 path
         # True while a training step is captured into a CUDA graph: weight-derived buffers are rebuilt on every call, so
@@ -96,9 +100,27 @@ class Engine:
         hit = self._packed.get(key)
         if hit is not None and hit[0] == versions and not self.always_repack:
             return hit[1]
+        if hit is not None and self.always_repack and key in self._batched_packs:
+            return hit[1]  # refreshed in place by the batched pack launch at the head of the captured step
         val = build()
         self._packed[key] = (versions, val)
         return val
+
+    def pack_batch(self) -> Optional["ops.PackBatch"]:
+        """One-launch refresh of every bf16 tensor-core weight pack made so far (``packed_weight`` / ``_dgrad_weight`` with
+        ``tc``), writing into the cached buffers; while ``always_repack`` is set those entries are then served from the cache.
+        The graph-captured training step calls it at the head of the captured region."""
+        entries, keys = [], []
+        for key, (w, wres, dgrad, off, cnt) in self._pack_specs.items():
+            hit = self._packed.get(key)
+            if hit is None or hit[1].dtype != torch.bfloat16:
+                continue
+            entries.append((w.detach(), wres.detach() if wres is not None else None, hit[1], dgrad, off, cnt))
+            keys.append(key)
+        if not entries:
+            return None
+        self._batched_packs = set(keys)
+        return ops.PackBatch(entries, entries[0][2].device)
 
     @staticmethod
     def _ver(*params: Optional[Tensor]) -> Tuple:
@@ -107,8 +129,10 @@ class Engine:
 
     def packed_weight(self, conv: nn.Conv2d, res: Optional[nn.Conv2d], tc: bool) -> Tensor:
         wr = res.weight if res is not None else None
-        return self._cached(("w", id(conv), tc), self._ver(conv.weight, wr),
-                            lambda: ops.pack_conv_weight(conv.weight, wr, tc))
+        key = ("w", id(conv), tc)
+        if tc and conv.weight.dtype == torch.float32 and (wr is None or wr.dtype == torch.float32):
+            self._pack_specs[key] = (conv.weight, wr, 0, 0, 0)
+        return self._cached(key, self._ver(conv.weight, wr), lambda: ops.pack_conv_weight(conv.weight, wr, tc))
 
     def packed_weight_identity(self, conv: nn.Conv2d) -> Tensor:
         """[W | I]: the conv weight with an identity 1x1 residual block appended, so that ``conv(a) + x`` runs as extra

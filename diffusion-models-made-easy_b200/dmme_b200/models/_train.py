@@ -98,8 +98,10 @@ class TrainEngine(Engine):
 
     # -- convolution ---------------------------------------------------------------------------
     def _dgrad_weight(self, conv: nn.Conv2d, off: int, cnt: int, tc: bool) -> Tensor:
-        return self._cached(("wd", id(conv), off, cnt, tc), self._ver(conv.weight),
-                            lambda: ops.pack_conv_weight_dgrad(conv.weight, off, cnt, tc))
+        key = ("wd", id(conv), off, cnt, tc)
+        if tc and conv.weight.dtype == torch.float32:
+            self._pack_specs[key] = (conv.weight, None, 1, off, cnt)
+        return self._cached(key, self._ver(conv.weight), lambda: ops.pack_conv_weight_dgrad(conv.weight, off, cnt, tc))
 
     def conv(self, name: str, src0: Tensor, src1: Optional[Tensor], conv: nn.Conv2d, *, stride: int = 1,
              upsample: bool = False, res: Optional[nn.Conv2d] = None, res0: Optional[Tensor] = None,

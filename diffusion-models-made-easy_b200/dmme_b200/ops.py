@@ -47,6 +47,32 @@ def pack_conv_weight(w: Tensor, w_res: Optional[Tensor] = None, tc: bool = True)
     return packed
 
 
+class PackBatch:
+    """Device table of ``dmme_pack_item`` entries: every bf16 tensor-core weight pack of a model as ONE launch."""
+
+    def __init__(self, entries, device) -> None:
+        # entries: [(w, wres | None, packed, dgrad, ci_off, ci_cnt)]; the tensors are kept alive here (raw pointers in the table)
+        per = int(L.load().dmme_pack_block_elems())
+        self.tensors = entries
+        items = (L.PackItem * len(entries))()
+        blocks = 0
+        for k, (w, wres, packed, dgrad, off, cnt) in enumerate(entries):
+            cout, cin, ks, _ = w.shape
+            it = items[k]
+            it.w, it.wres, it.packed = ptr(w), ptr(wres), ptr(packed)
+            it.cout, it.cin, it.ksize, it.rc = cout, cin, ks, (wres.shape[1] if wres is not None else 0)
+            it.dgrad, it.ci_off, it.ci_cnt, it.reserved = int(dgrad), int(off), int(cnt), 0
+            it.first_block = blocks
+            elems = packed.numel()
+            blocks += (elems + per - 1) // per
+        self.n, self.blocks = len(entries), blocks
+        raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
+        self.table = raw.to(device)
+
+    def launch(self) -> None:
+        L.check(L.load().dmme_pack_conv_weights_batch(ptr(self.table), self.n, self.blocks, L.stream_ptr()), "pack_conv_weights_batch")
+
+
 def pack_upsample_phase_weight(w: Tensor) -> Tensor:
     """Weights of ``nearest x2 -> conv3x3`` (UpSample, models/ddpm.py:150-173) collapsed onto the low-resolution grid:
     bf16 ``[4 phases][cout][4 taps x cin]`` for ``make_conv_desc(upsample=3)``.  Phase (a, b) is the parity of the output

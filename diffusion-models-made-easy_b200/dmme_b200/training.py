@@ -12,6 +12,7 @@ backward kernels and all-reduces concurrently on the captured stream fork, with 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -35,6 +36,8 @@ class GraphedTrainingStep:
         self._x: Optional[Tensor] = None
         self._loss: Optional[Tensor] = None
         self._grads = []  # (parameter, gradient buffer inside the graph's private pool) of the captured backward
+        self._pack = None  # ops.PackBatch replayed at the head of the graph (keeps its table and tensors alive)
+        self.batch_packs = os.environ.get("DMME_BATCH_PACKS", "1") != "0"
 
     def _params(self):
         return [p for p in self.diffusion.parameters() if p.requires_grad]
@@ -57,14 +60,20 @@ class GraphedTrainingStep:
         self._graph = torch.cuda.CUDAGraph()
         eng = self.diffusion.model.train_engine
         eng.always_repack = True  # the bf16 weight packing must be replayed too: the weights change between replays
+        # ... as ONE launch at the head of the graph for every tensor-core pack the warm-up made (172 pack launches, 0.9 ms of
+        # the step, when each conv re-packs its own); the few other derived buffers still rebuild in place in the graph
+        self._pack = eng.pack_batch() if self.batch_packs else None
         try:
             # thread-local capture mode with collectives inside: NCCL's watchdog thread polls CUDA events concurrently, which
             # the default (global) mode would treat as a capture violation
             with torch.cuda.graph(self._graph, capture_error_mode="thread_local" if synced else "global"):
+                if self._pack is not None:
+                    self._pack.launch()
                 self._loss = self.diffusion.training_step(self._x)
                 self._loss.backward()
         finally:
             eng.always_repack = False
+            eng._batched_packs = set()
         self._grads = [(p, p.grad) for p in self._params() if p.grad is not None]
 
     def __call__(self, x_0: Tensor) -> Tensor:

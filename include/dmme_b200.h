@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMME_ABI_VERSION 7
+#define DMME_ABI_VERSION 8
 #define DMME_STATS_FRAC_BITS 20
 
 enum { DMME_BF16 = 0, DMME_F32 = 1 };
@@ -369,6 +369,24 @@ int dmme_philox_normal(float* out, long long numel, unsigned long long seed, uns
  * Stride-2 convs (models/ddpm.py:147) additionally set desc.upsample = 2 on the grad_out source. */
 int dmme_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin, int ksize, int ci_off, int ci_cnt,
                                 void* packed, int kernel, void* stream);
+
+/*
+ * All tensor-core (bf16, [rows][K]) weight packs of a model in one launch: items_dev is a DEVICE array of n_items entries,
+ * each the arguments of one dmme_pack_conv_weight (dgrad = 0) or dmme_pack_conv_weight_dgrad (dgrad = 1) call with
+ * kernel = DMME_CONV_TC; first_block = the sum of ceil(elements / dmme_pack_block_elems()) over the preceding entries,
+ * total_blocks = that sum over all entries.  Same values as the per-weight calls.  Used by the graph-captured training step,
+ * which re-packs every weight after each optimizer step.
+ */
+typedef struct dmme_pack_item {
+  const float* w;        /* OIHW fp32 */
+  const float* wres;     /* optional fused 1x1 residual weight [cout][rc] (dgrad = 0) */
+  void* packed;          /* bf16 destination */
+  int cout, cin, ksize, rc;
+  int dgrad, ci_off, ci_cnt, reserved;
+  long long first_block;
+} dmme_pack_item;
+int dmme_pack_block_elems(void);
+int dmme_pack_conv_weights_batch(const dmme_pack_item* items_dev, int n_items, long long total_blocks, void* stream);
 
 /* Weight, fused-residual-weight and bias gradients of the forward call described by `fwd` (sources and geometry;
  * its weight/out fields are ignored).  grad_out: NHWC act dtype [n][ho][wo][cout] (NCHW fp32 when fwd->out_layout

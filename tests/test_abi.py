@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dmme_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.dmme_abi_version() == 7
+    assert lib.dmme_abi_version() == 8
 
 
 def test_argument_errors_are_reported_not_fatal():
