@@ -84,6 +84,7 @@ class Engine:
         self.fuse_sampler = os.environ.get("DMME_FUSE_SAMPLER", "1") != "0"
         # single-head 256-token x 256-channel attention blocks as one launch (DMME_FUSE_ATTN=0: norm | qkv | core | proj launches)
         self.fuse_attn = os.environ.get("DMME_FUSE_ATTN", "1") != "0"
+        self.attn16_min_batch = int(os.environ.get("DMME_ATTN16_MIN_BATCH", "128"))
         # the block kernels can form their GroupNorm coefficients themselves from the producer's statistics (six launches fewer
         # per step, same bits); measured within noise of the coefficient launch it replaces (3.33 vs 3.25 - 3.31 ms at batch
         # 256, +0.01 ms at the smaller batches: the dependent loads sit in front of the first tile's norm), so opt-in
@@ -395,8 +396,13 @@ class Engine:
                              mask, norm.eps, out, st0, st1)
 
     # -- blocks ------------------------------------------------------------------------------
-    def attention_fused(self, att: nn.Module, seq: int, c: int, dtype: torch.dtype) -> bool:
+    def attention_fused(self, att: nn.Module, seq: int, c: int, dtype: torch.dtype, n: int = 1 << 30) -> bool:
         """True when the block runs as the one-launch kernel (csrc/attention_block.cu) given its producer's statistics."""
+        if seq == 16 and n < self.attn16_min_batch:
+            # the 16-token kernel takes eight images per CTA and ~20 us per CTA whatever the batch (weight streaming and
+            # phase latencies): below ~128 images the four small launches it replaces are faster (batch 64: 1.488 vs 1.502 ms
+            # per step, batch 32: 1.135 vs 1.150)
+            return False
         return (self.fuse_attn and not self.force_generic and getattr(att, "num_heads", None) is None
                 and c % att.norm.num_groups == 0 and (c // att.norm.num_groups) % 4 == 0
                 and ops.attention_block_supported(1, seq, c, dtype))
@@ -406,7 +412,7 @@ class Engine:
         seq = h * w
         heads = getattr(att, "num_heads", None)
         st = self._stats.get(x.data_ptr())
-        if st is not None and self.attention_fused(att, seq, c, x.dtype):
+        if st is not None and self.attention_fused(att, seq, c, x.dtype, n):
             # the whole block in one launch (csrc/attention_block.cu): norm, qkv, softmax(q k^T) v, proj and + x
             norm = att.norm
             out = self.ws.get(name + ".attn", (n, h, w, c), x.dtype, x.device)
@@ -449,7 +455,7 @@ class Engine:
         res_kw = dict(addend=x0) if isinstance(blk.residual, nn.Identity) else dict(res=blk.residual, res0=x0, res1=x1)
         res_kw["consumers"] = self.consumers().get(out_name)
         if has_attn and res_kw["consumers"] and x0.dtype == torch.bfloat16 and \
-                self.attention_fused(blk.attention, x0.shape[1] * x0.shape[2], conv2.weight.shape[0], x0.dtype):
+                self.attention_fused(blk.attention, x0.shape[1] * x0.shape[2], conv2.weight.shape[0], x0.dtype, x0.shape[0]):
             # the one-launch attention block applies its own norm: the producer's finishing pass need not write it
             res_kw["consumers"] = [c for c in res_kw["consumers"] if c[0] is not blk.attention.norm]
         if self.flavour == "ddpm":
