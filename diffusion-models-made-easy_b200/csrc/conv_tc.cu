@@ -1141,6 +1141,7 @@ static int g_splitk_mode = 1;
 // tiles + finishing pass; A/B and tests: 2 = plan restricted to the cluster shapes, 3 = that plan WITHOUT the cluster
 static int g_splitk_cluster = 1;
 struct SplitPlan { int np, split; };
+static int g_splitk_force_np = 0, g_splitk_force_split = 0;  // A/B (dmme_debug_force_splitk_4x4)
 
 // cluster split-K: 4x4 maps (an image = 16 pixels), 2 / 4 / 8 slices, every CTA finishing at least two images.  The plan is
 // NOT bent towards these shapes: restricting the slice counts to 2 / 4 / 8 measured slower at the small per-GPU batches
@@ -1172,6 +1173,17 @@ static SplitPlan splitk_plan(const dmme_conv_desc& d) {
     const int np0 = tct_tile_pixels(d);
     if (np0) base_cost = static_cast<double>(ceil_div_ll(ceil_div_ll(total_pix, np0) * n_tiles, sm)) * unit_clocks(nkb, np0 * 128 + 16384);
     else base_cost = static_cast<double>(ceil_div_ll(ceil_div_ll(total_pix, 128) * (d.cout / 64), sm)) * unit_clocks(nkb, 24576);
+  }
+  if (ho * wo == 16 && g_splitk_force_np > 0 && g_splitk_force_split > 1 && 2 * g_splitk_force_split <= nkb)
+    return SplitPlan{g_splitk_force_np, g_splitk_force_split};  // A/B: a fixed shape for the 4x4 maps
+  if (g_splitk_cluster <= 1 && ho * wo == 16 && nkb >= 8) {  // (mode 0 keeps the plan and only executes it as GEMM + finishing pass)
+    // 4x4 maps: four slices as one cluster of four whenever that is about one wave of CTAs (batch 256: 256-pixel tiles,
+    // batch 128: 128-pixel tiles -- measured 2.20 vs 2.25 ms per step there against the cost model's nine slices + finishing
+    // pass; two or eight slices, and four at other batches, measured slower: tools/sweep_step.py with DMME_SPLITK_FORCE_4X4)
+    for (int np = 256; np >= 128; np >>= 1) {
+      const long long units = ceil_div_ll(total_pix, np) * n_tiles * 4;
+      if (units >= 100 && units <= sm) return SplitPlan{np, 4};
+    }
   }
   SplitPlan best = none;
   double best_cost = 0.8 * base_cost + 6000.0;  // + the stand-alone GroupNorm launch the finishing pass replaces
@@ -1460,6 +1472,8 @@ extern "C" void dmme_set_conv_tct_mode(int mode) { dmme::g_tct_mode = mode; }
 extern "C" void dmme_set_conv_splitk_mode(int mode) { dmme::g_splitk_mode = mode; }
 // A/B and test switch: 1 (default) = 4x4 maps reduce their K slices inside a thread-block cluster, 0 = partial tiles + finishing pass
 extern "C" void dmme_set_conv_splitk_cluster(int mode) { dmme::g_splitk_cluster = mode; }
+// A/B measurements only: a fixed (tile pixels, slices) plan for split-K on 4x4 maps (0, 0 = the cost model's)
+extern "C" void dmme_debug_force_splitk_4x4(int np, int split) { dmme::g_splitk_force_np = np; dmme::g_splitk_force_split = split; }
 extern "C" int dmme_get_conv_tct_mode(void) { return dmme::g_tct_mode; }
 // debugging: device buffer of 3 x 512 int64 that CTA 0 of the transposed kernel fills with clock64 timestamps
 extern "C" void dmme_debug_set_conv_trace(long long* buf) { dmme::g_conv_trace = buf; }

@@ -216,6 +216,11 @@ def load() -> C.CDLL:
     mode = os.environ.get("DMME_SPLITK_CLUSTER")  # A/B measurements only: 0 = GEMM + finishing pass at 4x4, 2 = bend the plan
     if mode:
         lib.dmme_set_conv_splitk_cluster(int(mode))
+    mode = os.environ.get("DMME_SPLITK_FORCE_4X4")  # A/B measurements only: "np,split" for split-K on 4x4 maps
+    if mode:
+        lib.dmme_debug_force_splitk_4x4.argtypes = [i, i]
+        lib.dmme_debug_force_splitk_4x4.restype = None
+        lib.dmme_debug_force_splitk_4x4(*[int(v) for v in mode.split(",")])
     mode = os.environ.get("DMME_FINISH_SMALL")  # A/B measurements only: 0 = block-per-slab split-K finishing kernel at 4x4
     if mode:
         lib.dmme_set_splitk_finish_small(int(mode))
