@@ -426,7 +426,9 @@ __host__ __device__ constexpr int tct_epi_warps() { return 8; }
 //       finishes them -- slice sum in the finishing pass's order, bias / temb / addend, bf16 store, statistics, the
 //       consumers' GroupNorm(+SiLU) -- exactly as conv_splitk.cu does (same bits).  One launch instead of two and no partial
 //       tiles in global memory.
-template <bool WS, int CMOD, bool PAIR, bool SPLIT = false, bool NORM = false, bool CLUSTER = false>
+//       CLPX: pixels per image of the maps it handles (16: 4x4, 64: 8x8 -- there only raw output and slice order are
+//       bit-equal to the two-launch path, the statistics are summed by one thread per (image, channel) instead of 16 warps).
+template <bool WS, int CMOD, bool PAIR, bool SPLIT = false, bool NORM = false, bool CLUSTER = false, int CLPX = 16>
 __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_kernel(const __grid_constant__ ConvTcParams p,
                                                                                   const ConvTctExtra x) {
   extern __shared__ uint8_t smem_raw[];
@@ -728,55 +730,62 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
         cluster_sync_all();  // release / acquire: the other slices' values of this CTA's pixels have landed
         // ---- finish: thread = channel, half h takes images [h, h + 1) * own / 32 of this CTA's pixels; the arithmetic and
         // its order are splitk_finish_small_kernel's (conv_splitk.cu) ----
-        // pixels per thread: 16 * images; a CTA that owns a single image leaves it to the first half of the warps
-        const int ppt = own >= 32 ? own >> 1 : (half == 0 ? own : 0);
+        // pixels per thread: whole images; a CTA whose pixels do not split into two sets of whole images leaves them to the
+        // first half of the warps
+        const bool both = (own >> 1) % CLPX == 0;
+        const int ppt = both ? own >> 1 : (half == 0 ? own : 0);
         const float kFixc = static_cast<float>(1 << DMME_STATS_FRAC_BITS);
 #pragma unroll 1
-        for (int ib = 0; ib < ppt; ib += 16) {
-          const int lcol = (own >= 32 ? half * ppt : 0) + ib;  // first pixel of the image inside this CTA's range
-          const int pix = mt * NP + crank * own + lcol;     // global pixel index
+        for (int ib = 0; ib < ppt; ib += CLPX) {
+          const int lcol0 = (both ? half * ppt : 0) + ib;   // first pixel of the image inside this CTA's range
+          const int pix = mt * NP + crank * own + lcol0;    // global pixel index
           if (pix >= total_pix) break;
-          const int n = pix >> 4;
+          const int n = pix / CLPX;
           float add = p.bias ? __ldg(p.bias + ch) : 0.f;
           if (p.temb) add += __ldg(p.temb + static_cast<long long>(p.temb_rows == 1 ? 0 : n) * p.temb_ld + ch);
-          float vsum[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) vsum[i] = add;
-#pragma unroll 1
-          for (int j0 = 0; j0 < S; j0 += 4) {  // slices in fours, as the finishing pass sums them
-            float a4[4][16];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j0 + jj;
-              if (j >= S) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) a4[jj][i] = 0.f;
-              } else if (j == crank) {
-                uint32_t t16[16];
-                tmem_ld16(tacc + static_cast<uint32_t>(crank * own + lcol), t16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) a4[jj][i] = __uint_as_float(t16[i]);
-              } else {
-                const float* rp = recv + ((j < crank ? j : j - 1) * own + lcol) * 128 + cl;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) a4[jj][i] = rp[i * 128];
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) vsum[i] += (a4[0][i] + a4[1][i]) + (a4[2][i] + a4[3][i]);
-          }
-          float rf[16];
+          float rf[CLPX];
           float t1s = 0.f, t2s = 0.f;
           __nv_bfloat16* orow = p.out + static_cast<long long>(pix) * p.cout + ch;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float ad = p.addend ? __bfloat162float(p.addend[static_cast<long long>(pix + i) * p.cout + ch]) : 0.f;
-            const __nv_bfloat16 rb = __float2bfloat16_rn(vsum[i] + ad);
-            orow[static_cast<long long>(i) * p.cout] = rb;
-            rf[i] = __bfloat162float(rb);
-            t1s += rf[i];
-            t2s = fmaf(rf[i], rf[i], t2s);
+          for (int sb = 0; sb < CLPX / 16; ++sb) {
+            const int lcol = lcol0 + 16 * sb;
+            float vsum[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vsum[i] = add;
+#pragma unroll 1
+            for (int j0 = 0; j0 < S; j0 += 4) {  // slices in fours, as the finishing pass sums them
+              float a4[4][16];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j0 + jj;
+                if (j >= S) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) a4[jj][i] = 0.f;
+                } else if (j == crank) {
+                  uint32_t t16[16];
+                  tmem_ld16(tacc + static_cast<uint32_t>(crank * own + lcol), t16);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) a4[jj][i] = __uint_as_float(t16[i]);
+                } else {
+                  const float* rp = recv + ((j < crank ? j : j - 1) * own + lcol) * 128 + cl;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) a4[jj][i] = rp[i * 128];
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) vsum[i] += (a4[0][i] + a4[1][i]) + (a4[2][i] + a4[3][i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int pi = 16 * sb + i;
+              const float ad = p.addend ? __bfloat162float(p.addend[static_cast<long long>(pix + pi) * p.cout + ch]) : 0.f;
+              const __nv_bfloat16 rb = __float2bfloat16_rn(vsum[i] + ad);
+              orow[static_cast<long long>(pi) * p.cout] = rb;
+              rf[pi] = __bfloat162float(rb);
+              t1s += rf[pi];
+              t2s = fmaf(rf[pi], rf[pi], t2s);
+            }
           }
           if (p.stats) {
             float m1 = t1s, m2 = t2s;
@@ -799,7 +808,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
               g1 += __shfl_sync(0xffffffffu, t1s, g0 + j);
               g2 += __shfl_sync(0xffffffffu, t2s, g0 + j);
             }
-            const float inv_cnt = 1.0f / (16.0f * qn.cpg);
+            const float inv_cnt = 1.0f / (static_cast<float>(CLPX) * qn.cpg);
             const float mean = g1 * inv_cnt;
             const float var = fmaxf(g2 * inv_cnt - mean * mean, 0.f);
             const float rs = rsqrtf(var + qn.eps);
@@ -813,7 +822,7 @@ __global__ void __launch_bounds__((2 + tct_epi_warps<WS>()) * 32, 1) conv_tct_ke
             }
             __nv_bfloat16* yrow = qn.out + static_cast<long long>(pix) * p.cout + ch;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < CLPX; ++i) {
               float y = fmaf(rf[i], aa, bb);
               if (qn.silu) y = silu_f(y);
               yrow[static_cast<long long>(i) * p.cout] = __float2bfloat16_rn(y);
@@ -1143,16 +1152,17 @@ static int g_splitk_cluster = 1;
 struct SplitPlan { int np, split; };
 static int g_splitk_force_np = 0, g_splitk_force_split = 0;  // A/B (dmme_debug_force_splitk_4x4)
 
-// cluster split-K: 4x4 maps (an image = 16 pixels), 2 / 4 / 8 slices, every CTA finishing at least two images.  The plan is
-// NOT bent towards these shapes: restricting the slice counts to 2 / 4 / 8 measured slower at the small per-GPU batches
+// cluster split-K: 4x4 and 8x8 maps, 2 / 4 / 8 slices, every CTA finishing whole images (8x8: the cost model's own plans at
+// 128 / 64 images per GPU are such shapes: 2.20 -> 2.04 and 1.48 -> 1.45 ms per step).  The plan is NOT bent towards these
+// shapes beyond the one-wave rule in splitk_plan: restricting the slice counts to 2 / 4 / 8 measured slower at the small per-GPU batches
 // (batch 128: 2.42 vs 2.23 ms per step, batch 32: 1.19 vs 1.13 -- the cost model prefers 9 - 16 slices of 128-pixel tiles
 // there), so the in-cluster reduction is taken where the plan already has such a shape (batch 256: 4 slices of 256 pixels)
 static bool splitk_cluster_ok(const dmme_conv_desc& d, const SplitPlan& plan) {
   if (!(g_splitk_cluster == 1 || g_splitk_cluster == 2) || plan.split < 2) return false;
   const int ho = d.h_in / d.stride, wo = d.w_in / d.stride;
-  if (ho * wo != 16) return false;
+  if (ho * wo != 16 && ho * wo != 64) return false;
   if (plan.split != 2 && plan.split != 4 && plan.split != 8) return false;
-  return (plan.np / plan.split) % 16 == 0;
+  return (plan.np / plan.split) % (ho * wo) == 0;  // every CTA finishes whole images
 }
 
 static SplitPlan splitk_plan(const dmme_conv_desc& d) {
@@ -1174,8 +1184,8 @@ static SplitPlan splitk_plan(const dmme_conv_desc& d) {
     if (np0) base_cost = static_cast<double>(ceil_div_ll(ceil_div_ll(total_pix, np0) * n_tiles, sm)) * unit_clocks(nkb, np0 * 128 + 16384);
     else base_cost = static_cast<double>(ceil_div_ll(ceil_div_ll(total_pix, 128) * (d.cout / 64), sm)) * unit_clocks(nkb, 24576);
   }
-  if (ho * wo == 16 && g_splitk_force_np > 0 && g_splitk_force_split > 1 && 2 * g_splitk_force_split <= nkb)
-    return SplitPlan{g_splitk_force_np, g_splitk_force_split};  // A/B: a fixed shape for the 4x4 maps
+  if ((ho * wo == 16 || ho * wo == 64) && g_splitk_force_np > 0 && g_splitk_force_split > 1 && 2 * g_splitk_force_split <= nkb)
+    return SplitPlan{g_splitk_force_np, g_splitk_force_split};  // A/B and tests: a fixed shape for the 4x4 / 8x8 maps
   if (g_splitk_cluster <= 1 && ho * wo == 16 && nkb >= 8) {  // (mode 0 keeps the plan and only executes it as GEMM + finishing pass)
     // 4x4 maps: four slices as one cluster of four whenever that is about one wave of CTAs (batch 256: 256-pixel tiles,
     // batch 128: 128-pixel tiles -- measured 2.20 vs 2.25 ms per step there against the cost model's nine slices + finishing
@@ -1224,8 +1234,9 @@ long long conv_splitk_workspace(const dmme_conv_desc& d) {
 int conv_splitk_finish(const dmme_conv_desc& d, int split, cudaStream_t stream);  // conv_splitk.cu
 
 // split-K with the slices of a tile as one thread-block cluster (see conv_tct_kernel, CLUSTER): grid = units
+template <int CLPX>
 static int launch_conv_tct_cluster(ConvTcParams& p, const ConvTctExtra& x, int smem, cudaStream_t stream) {
-  auto kern = conv_tct_kernel<false, 0, false, true, false, true>;
+  auto kern = conv_tct_kernel<false, 0, false, true, false, true, CLPX>;
   static DeviceOnce once_;
   bool& configured = once_.here();
   if (!configured) {
@@ -1376,7 +1387,7 @@ int conv_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
           x.no[k].gamma = sn.gamma; x.no[k].beta = sn.beta; x.no[k].scale = sn.scale; x.no[k].shift = sn.shift;
           x.no[k].ss_rows = sn.ss_rows; x.no[k].ss_ld = sn.ss_ld; x.no[k].cpg = sn.cpg; x.no[k].silu = sn.silu; x.no[k].eps = sn.eps;
         }
-        return launch_conv_tct_cluster(p, x, smem_s, stream);
+        return ho * wo == 16 ? launch_conv_tct_cluster<16>(p, x, smem_s, stream) : launch_conv_tct_cluster<64>(p, x, smem_s, stream);
       }
       if ((rc = launch_conv_tct<false, 0, false, true>(p, x, smem_s, stream))) return rc;
       return conv_splitk_finish(d, plan.split, stream);

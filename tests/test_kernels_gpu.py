@@ -1211,6 +1211,55 @@ def test_conv_splitk_cluster_bit_equal(n, cin, cin1, cpg, addend, res, bend, spl
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("n,cin,cin1,cpg,addend,res,shape", [(64, 256, 0, 8, False, False, (256, 4)), (64, 512, 256, 16, True, True, (256, 4)),
+                                                            (37, 256, 0, 8, True, False, (256, 4)), (32, 256, 0, 4, False, False, (256, 2)),
+                                                            (50, 512, 256, 8, False, True, (128, 2))])
+def test_conv_splitk_cluster_8x8(n, cin, cin1, cpg, addend, res, shape):
+    """8x8 maps: the in-cluster reduction (one image per CTA, or more) against split-K GEMM + finishing pass with the same
+    plan: the raw output is bit-equal (same slice order), statistics and the consumers' norms agree to fp32 summation order"""
+    ops, L = _ops()
+    lib = L.load()
+    import ctypes as C
+    lib.dmme_debug_force_splitk_4x4.argtypes = [C.c_int, C.c_int]
+    lib.dmme_debug_force_splitk_4x4.restype = None
+    g = torch.Generator().manual_seed(211 + n)
+    cout, h = 256, 8
+    c0 = cin - cin1
+    xa = torch.randn(n, h, h, cin, generator=g).to(torch.bfloat16)
+    s0 = xa[..., :c0].contiguous().to(DEV)
+    s1 = xa[..., c0:].contiguous().to(DEV) if cin1 else None
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(DEV)
+    wres = (torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin)).to(DEV) if res else None
+    wp = ops.pack_conv_weight(w, wres, True)
+    bias, gamma, beta = (torch.randn(cout, generator=g).to(DEV) for _ in range(3))
+    temb = torch.randn(n, cout, generator=g).to(DEV)
+    ad = torch.randn(n, h, h, cout, generator=g).to(torch.bfloat16).to(DEV) if addend else None
+    outs = []
+    lib.dmme_debug_force_splitk_4x4(*shape)
+    try:
+        for cluster in (1, 0):
+            lib.dmme_set_conv_splitk_cluster(cluster)
+            d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, s0 if res else None, s1 if res else None, False, L.OUT_NHWC,
+                                   torch.bfloat16, L.CONV_AUTO)
+            ws = torch.empty(ops.conv_splitk_workspace(d) // 4, dtype=torch.float32, device=DEV)
+            out = torch.full((n, h, h, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            y0, y1 = torch.full_like(out, float("nan")), torch.full_like(out, float("nan"))
+            st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+            ops.conv2d_launch(d, wp, bias, out, temb, ad, stats=st, splitk_ws=ws,
+                              out_norms=[ops.out_norm(y0, gamma, beta, cpg, True), ops.out_norm(y1, beta, gamma, 32, False)])
+            torch.cuda.synchronize()
+            outs.append((out, st, y0, y1))
+    finally:
+        lib.dmme_set_conv_splitk_cluster(1)
+        lib.dmme_debug_force_splitk_4x4(0, 0)
+    (oa, sa, ya0, ya1), (ob, sb, yb0, yb1) = outs
+    assert not torch.isnan(oa.float()).any() and not torch.isnan(ya0.float()).any() and not torch.isnan(ya1.float()).any()
+    assert torch.equal(oa, ob)
+    assert torch.allclose(sa.double() / 2 ** 20, sb.double() / 2 ** 20, rtol=1e-5, atol=1e-2)
+    assert rel_l2(ya0.float().cpu(), yb0.float().cpu()) < 2e-3
+    assert rel_l2(ya1.float().cpu(), yb1.float().cpu()) < 2e-3
+
+
 def test_conv_splitk_default_plan_matches_unsplit():
     """the cost model's own choice at the strong-scaling shard batches: wherever it splits, the result equals the unsplit
     kernels' (same operands, fp32 accumulation in a different order) and out_norm is refused without the workspace"""
