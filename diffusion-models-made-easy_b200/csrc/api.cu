@@ -29,6 +29,7 @@ bool conv_halo_preferred(const dmme_conv_desc& d);
 bool conv_tct_epilogue_norm(const dmme_conv_desc& d);
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_out_tc_supported(const dmme_conv_desc& d);
+bool conv_out_dx_supported(const dmme_conv_desc& d);
 long long conv_splitk_workspace(const dmme_conv_desc& d);
 int conv_out_tc_forward(const dmme_conv_desc& d, cudaStream_t stream);
 
@@ -73,7 +74,12 @@ static bool runs_halo_rows(const dmme_conv_desc& d) {
   return halo && d.w_in >= 16;
 }
 
-extern "C" int dmme_conv2d_fuses_gn(const dmme_conv_desc* d) { return d && runs_halo_rows(*d) ? 1 : 0; }
+// ... and so has the output conv's row-tile kernel (32x32 maps)
+static bool runs_out_dx(const dmme_conv_desc& d) {
+  return d.kernel == DMME_CONV_AUTO && !conv_tc_supported(d) && conv_out_dx_supported(d) && d.c1 == 0;
+}
+
+extern "C" int dmme_conv2d_fuses_gn(const dmme_conv_desc* d) { return d && (runs_halo_rows(*d) || runs_out_dx(*d)) ? 1 : 0; }
 
 // split-K is a choice of the AUTO / TC dispatch below 16x16-and-up halo territory: the same conditions as the dispatch
 static bool takes_conv_tc(const dmme_conv_desc& d) {
@@ -96,8 +102,8 @@ extern "C" long long dmme_conv2d_splitk_workspace(const dmme_conv_desc* d) {
 
 extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
   DMME_REQUIRE(d != nullptr, DMME_E_BADARG, "conv2d_fwd: null descriptor");
-  DMME_REQUIRE(d->gn_ab == nullptr || runs_halo_rows(*d), DMME_E_UNSUPPORTED,
-               "conv2d_fwd: a fused GroupNorm (gn_ab) needs the halo kernel; ask dmme_conv2d_fuses_gn");
+  DMME_REQUIRE(d->gn_ab == nullptr || runs_halo_rows(*d) || runs_out_dx(*d), DMME_E_UNSUPPORTED,
+               "conv2d_fwd: a fused GroupNorm (gn_ab) needs the halo kernel or the 32x32 output conv; ask dmme_conv2d_fuses_gn");
   DMME_REQUIRE((d->out_norm[0].out == nullptr && d->out_norm[1].out == nullptr) ||
                    (takes_conv_tc(*d) && (d->splitk_ws != nullptr || conv_tct_epilogue_norm(*d))),
                DMME_E_UNSUPPORTED,

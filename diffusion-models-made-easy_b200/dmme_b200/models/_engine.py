@@ -298,10 +298,10 @@ class Engine:
             out = self.ws.get(name, (d.n, cout, ho, wo), torch.float32, dev)
             if sampler is not None and self.fuse_sampler and temb is None and addend is None and ops.conv_fuses_sampler(d):
                 d.out = None  # eps is consumed in the epilogue and never written
-                ops.conv2d_launch(d, w, b, None, sampler=sampler)
+                ops.conv2d_launch(d, w, b, None, sampler=sampler, gn_ab=gn_ab, gn_silu=gn_silu)
                 self.sampler_applied = True
                 return out
-            ops.conv2d_launch(d, w, b, out, temb, addend)
+            ops.conv2d_launch(d, w, b, out, temb, addend, gn_ab=gn_ab, gn_silu=gn_silu)
             return out
         if out_layout == L.OUT_QKV:
             c = cout // 3
@@ -365,7 +365,7 @@ class Engine:
                 and (x1 is None or st1 is not None) and cpg % 4 == 0 and c0 % cpg == 0):
             cout, ks = conv.weight.shape[0], conv.weight.shape[2]
             probe = ops.make_conv_desc(x0, x1, cout, ks, 1, False, conv_kw.get("res0"), conv_kw.get("res1"), False,
-                                       L.OUT_NHWC, x0.dtype, L.CONV_AUTO)
+                                       conv_kw.get("out_layout", L.OUT_NHWC), x0.dtype, L.CONV_AUTO)
             if ops.conv_fuses_gn(probe):
                 n, h, w, _ = x0.shape
                 ab = ops.groupnorm_coeff(st0, st1, c0, c1, n, h * w, norm.num_groups, norm.weight.detach(),
@@ -678,5 +678,6 @@ class Engine:
             if sec == "down":
                 skips.append(h)
             i += 1
-        a = self.gn("scratch.out_norm", u.output_conv[0], h, None, silu=True)
-        return self.conv("output_conv", a, None, u.output_conv[2], out_layout=L.OUT_NCHW_F32, sampler=sampler)
+        # GroupNorm + SiLU inside the output conv on 32x32 maps (csrc/conv_out_tc.cu), its own pass otherwise
+        return self.norm_conv("output_conv", u.output_conv[0], h, None, u.output_conv[2], gn_name="scratch.out_norm",
+                              out_layout=L.OUT_NCHW_F32, sampler=sampler)

@@ -209,6 +209,66 @@ def test_conv_out_tc(n, h, cin, cout):
     assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 1e-5
 
 
+@pytest.mark.parametrize("n,cin,cout", [(3, 128, 3), (150, 128, 6), (1, 256, 8)])
+def test_conv_out_tc_per_tap_kernel_32x32(n, cin, cout):
+    """the per-tap tcgen05 output conv stays covered on 32x32 maps (mode 2), where the row-tile kernel is the default"""
+    _, L = _ops()
+    lib = L.load()
+    lib.dmme_set_conv_out_tc_mode(2)
+    try:
+        g = torch.Generator().manual_seed(34)
+        x = bf16_round(torch.randn(n, cin, 32, 32, generator=g))
+        w = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+        b = torch.randn(cout, generator=g)
+        got, tc = run_conv(x, w, b, dtype=torch.bfloat16, out_layout=L.OUT_NCHW_F32)
+        assert tc
+        assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 1e-5
+    finally:
+        lib.dmme_set_conv_out_tc_mode(1)
+
+
+@pytest.mark.parametrize("n,cin,cout,silu", [(3, 128, 3, True), (149, 128, 3, True), (300, 128, 6, True), (5, 256, 6, False),
+                                             (2, 128, 1, True)])
+def test_conv_out_fused_groupnorm(n, cin, cout, silu):
+    """models/ddpm.py:277 (GroupNorm -> SiLU -> Conv) in ONE launch on 32x32 maps: the norm applied to the operand tile
+    inside the output conv == gn_apply followed by the same conv, bit for bit; both against the fp32 reference"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(35)
+    h = 32
+    # producer: a conv that writes the tensor and its statistics
+    x = bf16_round(torch.randn(n, 64, h, h, generator=g))
+    w = bf16_round(torch.randn(cin, 64, 3, 3, generator=g) / 8)
+    b = torch.randn(cin, generator=g) * 2
+    d = ops.make_conv_desc(to_nhwc(x, torch.bfloat16).to(DEV), None, cin, 3, 1, False, None, None, False, L.OUT_NHWC,
+                           torch.bfloat16, L.CONV_AUTO)
+    src = torch.empty((n, h, h, cin), dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(n * (cin // 4) * 2, dtype=torch.int64, device=DEV)
+    ops.conv2d_launch(d, ops.pack_conv_weight(w.to(DEV), None, True), b.to(DEV), src, stats=st)
+    gamma, beta = torch.randn(cin, generator=g).to(DEV), torch.randn(cin, generator=g).to(DEV)
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    bias = torch.randn(cout, generator=g)
+    wp = ops.pack_conv_weight(wt.to(DEV), None, True)
+
+    a = ops.groupnorm(src, None, 32, gamma, beta, silu, stats0=st)
+    d = ops.make_conv_desc(a, None, cout, 3, 1, False, None, None, False, L.OUT_NCHW_F32, torch.bfloat16, L.CONV_AUTO)
+    want = torch.empty((n, cout, h, h), dtype=torch.float32, device=DEV)
+    ops.conv2d_launch(d, wp, bias.to(DEV), want)
+
+    d = ops.make_conv_desc(src, None, cout, 3, 1, False, None, None, False, L.OUT_NCHW_F32, torch.bfloat16, L.CONV_AUTO)
+    assert ops.conv_fuses_gn(d)
+    ab = ops.groupnorm_coeff(st, None, cin, 0, n, h * h, 32, gamma, beta)
+    got = torch.full((n, cout, h, h), float("nan"), dtype=torch.float32, device=DEV)
+    ops.conv2d_launch(d, wp, bias.to(DEV), got, gn_ab=ab, gn_silu=silu)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    ref = F.conv2d(to_nchw(a.cpu()).float(), wt, bias, padding=1)
+    assert rel_l2(got.cpu(), ref) < 1e-5
+    # smaller maps keep the norm as its own pass
+    d16 = ops.make_conv_desc(src[:, :16, :16].contiguous(), None, cout, 3, 1, False, None, None, False, L.OUT_NCHW_F32,
+                             torch.bfloat16, L.CONV_AUTO)
+    assert not ops.conv_fuses_gn(d16)
+
+
 # ---------------------------------------------------------------------------------------------
 # tcgen05 convolution
 # ---------------------------------------------------------------------------------------------
