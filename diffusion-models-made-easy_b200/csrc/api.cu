@@ -28,6 +28,8 @@ bool conv_halo_supported(const dmme_conv_desc& d);
 bool conv_halo_preferred(const dmme_conv_desc& d);
 bool conv_tct_epilogue_norm(const dmme_conv_desc& d);
 int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream);
+bool conv_in_tc_supported(const dmme_conv_desc& d);
+int conv_in_tc_forward(const dmme_conv_desc& d, cudaStream_t stream);
 bool conv_out_tc_supported(const dmme_conv_desc& d);
 bool conv_out_dx_supported(const dmme_conv_desc& d);
 long long conv_splitk_workspace(const dmme_conv_desc& d);
@@ -122,6 +124,7 @@ extern "C" int dmme_conv2d_fwd(const dmme_conv_desc* d, void* stream) {
     case DMME_CONV_AUTO:
       if (conv_tc_supported(*d)) return conv_halo_preferred(*d) ? conv_halo_forward(*d, st) : conv_tc_forward(*d, st);
       if (conv_out_tc_supported(*d)) return conv_out_tc_forward(*d, st);
+      if (conv_in_tc_supported(*d)) return conv_in_tc_forward(*d, st);
       if (conv_in_supported(*d) || conv_out_supported(*d)) return conv_small_forward(*d, st);
       return conv_generic_forward(*d, st);
     default:

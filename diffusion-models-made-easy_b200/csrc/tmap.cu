@@ -47,14 +47,26 @@ struct MapKeyHash {
   }
 };
 
+static int encode_map_kind(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, bool f32_plain);
+
 int encode_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box) {
+               const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_map_kind(out, ptr, rank, dims, strides_bytes, box, false);
+}
+int encode_map_f32(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_map_kind(out, ptr, rank, dims, strides_bytes, box, true);
+}
+
+static int encode_map_kind(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, bool f32_plain) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr;
-  key.rank = rank;
+  key.rank = rank | (f32_plain ? 0x100u : 0u);
   for (uint32_t i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
   for (uint32_t i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
   {
@@ -65,8 +77,9 @@ int encode_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t*
   EncodeTiledFn enc = get_encoder();
   DMME_REQUIRE(enc != nullptr, DMME_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(out, f32_plain ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                   const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32_plain ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DMME_REQUIRE(r == CUDA_SUCCESS, DMME_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   {

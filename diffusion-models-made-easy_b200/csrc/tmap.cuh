@@ -8,4 +8,7 @@ namespace dmme {
 // dims/box innermost first; strides_bytes has rank-1 entries (dims 1..rank-1).
 int encode_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box);
+// fp32 tiled map without swizzle (zero OOB fill): the image patches of the input conv
+int encode_map_f32(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
 }  // namespace dmme

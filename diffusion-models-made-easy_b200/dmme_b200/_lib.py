@@ -28,7 +28,7 @@ EXPORTS = (
     "dmme_conv2d_fwd", "dmme_conv2d_uses_tc", "dmme_conv2d_writes_stats", "dmme_conv2d_fuses_gn", "dmme_conv2d_splitk_workspace", "dmme_conv2d_epilogue_norm", "dmme_conv2d_fuses_sampler", "dmme_set_conv_splitk_mode", "dmme_set_splitk_finish_small", "dmme_set_conv_splitk_cluster", "dmme_conv_chain_fwd", "dmme_conv_chain_supported", "dmme_set_conv_chain_ipc", "dmme_debug_set_chain_trace", "dmme_groupnorm_coeff", "dmme_groupnorm_fwd", "dmme_attention_fwd", "dmme_attention_uses_tc", "dmme_attention_block_fwd", "dmme_attention_block_supported",
     "dmme_temb_mlp_fwd", "dmme_temb_proj_fwd", "dmme_ddpm_step", "dmme_ddim_step", "dmme_iddpm_step",
     "dmme_gather_i64", "dmme_add_i64", "dmme_philox_normal", "dmme_set_conv_halo_mode", "dmme_get_conv_halo_mode", "dmme_set_conv_halo_multicast",
-    "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
+    "dmme_set_conv_tct_mode", "dmme_get_conv_tct_mode", "dmme_set_conv_out_tc_mode", "dmme_set_conv_in_tc_mode", "dmme_set_conv_pair_mode", "dmme_set_attn_mma_mode",
     "dmme_denorm", "dmme_optim_table_entry_bytes", "dmme_optim_chunk", "dmme_adam_ema_step",
     "dmme_pack_conv_weight_dgrad", "dmme_pack_block_elems", "dmme_pack_conv_weights_batch", "dmme_conv2d_wgrad_workspace", "dmme_conv2d_wgrad", "dmme_conv2d_wgrad_uses_tc", "dmme_groupnorm_bwd",
     "dmme_attention_bwd_workspace", "dmme_attention_bwd", "dmme_attention_bwd_fused", "dmme_attention_bwd_fused_supported", "dmme_set_wgrad_waves", "dmme_attention_fwd_train", "dmme_temb_bwd_workspace", "dmme_temb_bwd",
@@ -163,6 +163,7 @@ def load() -> C.CDLL:
     lib.dmme_set_conv_halo_multicast.restype = None
     lib.dmme_set_conv_tct_mode.argtypes = [i]
     lib.dmme_set_conv_out_tc_mode.argtypes = [i]
+    lib.dmme_set_conv_in_tc_mode.argtypes = [i]
     lib.dmme_set_conv_pair_mode.argtypes = [i]
     lib.dmme_set_attn_mma_mode.argtypes = [i]
     lib.dmme_denorm.argtypes = [vp, vp, vp, ll, vp]
@@ -196,6 +197,7 @@ def load() -> C.CDLL:
     lib.dmme_set_conv_halo_mode.restype = None
     lib.dmme_set_conv_tct_mode.restype = None
     lib.dmme_set_conv_out_tc_mode.restype = None
+    lib.dmme_set_conv_in_tc_mode.restype = None
     lib.dmme_set_conv_pair_mode.restype = None
     lib.dmme_set_attn_mma_mode.restype = None
     for name in EXPORTS:
@@ -242,6 +244,9 @@ def load() -> C.CDLL:
     mode = os.environ.get("DMME_OUT_TC_MODE")  # A/B measurements only: 0 = output conv on the FFMA kernel
     if mode:
         lib.dmme_set_conv_out_tc_mode(int(mode))
+    mode = os.environ.get("DMME_IN_TC_MODE")  # A/B measurements only: 0 = input conv on the FFMA kernel
+    if mode:
+        lib.dmme_set_conv_in_tc_mode(int(mode))
     _lib = lib
     return lib
 

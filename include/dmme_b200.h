@@ -169,8 +169,12 @@ int dmme_get_conv_tct_mode(void);
 void dmme_set_conv_pair_mode(int mode);
 /* A/B switch: 0 = multi-head attention (models/iddpm.py:16-59) stays on the CUDA-core kernel, 1 = mma.sync kernel */
 void dmme_set_attn_mma_mode(int mode);
-/* A/B switch: 0 = the output conv (models/ddpm.py:277) stays on the FFMA kernel, 1 = tcgen05 (default) */
+/* A/B switch: 0 = the output conv (models/ddpm.py:277) stays on the FFMA kernel, 1 = tcgen05 (default; on 32x32 maps the
+ * row-tile kernel that also applies desc->gn_ab), 2 = tcgen05 per-tap kernel on every size */
 void dmme_set_conv_out_tc_mode(int mode);
+/* A/B switch: 0 = the input conv (models/ddpm.py:219) stays on the FFMA kernel, 1 = tcgen05 on 32x32 images from 64
+ * images up (default), 2 = at every batch size */
+void dmme_set_conv_in_tc_mode(int mode);
 
 /* weights ---------------------------------------------------------------------------------- */
 /*

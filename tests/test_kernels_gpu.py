@@ -158,10 +158,46 @@ def test_conv_in_image_to_nhwc_bf16(n, h, cout):
     assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 4e-3
 
 
-def test_conv_in_writes_groupnorm_stats():
+@pytest.mark.parametrize("n", [1, 37, 300])
+def test_conv_in_tc_32x32(n):
+    """input_conv on tcgen05 (operand rows [hi | lo] built from the fp32 image, bf16 weights): against the fp32 conv on
+    bf16-rounded weights, and against the FFMA kernel it replaces (fp32 weights) within the weight rounding"""
     ops, L = _ops()
+    lib = L.load()
+    g = torch.Generator().manual_seed(36)
+    x = torch.randn(n, 3, 32, 32, generator=g) * 1.7
+    w = torch.randn(128, 3, 3, 3, generator=g) / 5
+    b = torch.randn(128, generator=g)
+    lib.dmme_set_conv_in_tc_mode(2)  # the default takes it from 64 images up
+    try:
+        got, tc = run_conv(x, w, b, dtype=torch.bfloat16, in_nchw=True)
+    finally:
+        lib.dmme_set_conv_in_tc_mode(1)
+    assert not tc  # fp32 [K][cout] weights, like the FFMA kernel
+    want = F.conv2d(x, bf16_round(w), b, padding=1)
+    assert rel_l2(got, want) < 2.5e-3  # bf16 rounding of the stored output
+    assert (got - bf16_round(want)).abs().max() <= 2 * bf16_round(want).abs().max() * 2 ** -8
+    lib.dmme_set_conv_in_tc_mode(0)
+    try:
+        ffma, _ = run_conv(x, w, b, dtype=torch.bfloat16, in_nchw=True)
+    finally:
+        lib.dmme_set_conv_in_tc_mode(1)
+    assert rel_l2(got, ffma) < 4e-3
+
+
+@pytest.mark.parametrize("n,tc_mode", [(3, 2), (3, 0), (200, 1)])
+def test_conv_in_writes_groupnorm_stats(n, tc_mode):
+    ops, L = _ops()
+    L.load().dmme_set_conv_in_tc_mode(tc_mode)
+    try:
+        _conv_in_stats_case(ops, L, n)
+    finally:
+        L.load().dmme_set_conv_in_tc_mode(1)
+
+
+def _conv_in_stats_case(ops, L, n):
     g = torch.Generator().manual_seed(33)
-    n, h, cout = 3, 32, 128
+    h, cout = 32, 128
     x = torch.randn(n, 3, h, h, generator=g)
     w = torch.randn(cout, 3, 3, 3, generator=g) / 5
     b = torch.randn(cout, generator=g)
