@@ -440,6 +440,15 @@ __global__ void __launch_bounds__(kDxThreads, 1) conv_out_dx_kernel(const __grid
     int u_it = half;
     for (int u = blockIdx.x + half * gridDim.x; u < p.units; u += 2 * gridDim.x, u_it += 2) {
       const int img = u >> 3, yy = (u & 7) * 4 + q;
+      // x_t is fetched before the accumulator is awaited: the step's traffic has pushed it out of L2 and the DRAM round
+      // trip would otherwise sit between the accumulator and the store
+      const long long e0 = (static_cast<long long>(img) * img_c * kDxW + yy) * kDxW + lane;
+      float xin[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.samp_kind != DMME_SAMPLER_NONE) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < img_c) xin[c] = p.x[e0 + c * plane];
+      }
       mbar_wait(&acc_full[half], (u_it >> 1) & 1);
       tc_fence_after();
       uint32_t v[NLD];
@@ -471,7 +480,6 @@ __global__ void __launch_bounds__(kDxThreads, 1) conv_out_dx_kernel(const __grid
         // element e of x_t (NCHW); its noise is lane e % 4 of Philox group e / 4, exactly what the stand-alone kernels
         // draw.  The four lanes of a quad share the groups of their row: lane j draws the group of channel j once and
         // the normals are handed round with shuffles.
-        const long long e0 = (static_cast<long long>(img) * img_c * kDxW + yy) * kDxW + lane;
         float zc[4] = {0.f, 0.f, 0.f, 0.f};
         if (need_z && !p.noise) {  // warp-uniform
           const int j = lane & 3;
@@ -495,7 +503,7 @@ __global__ void __launch_bounds__(kDxThreads, 1) conv_out_dx_kernel(const __grid
         for (int c = 0; c < 4; ++c) {
           if (c < img_c) {
             const long long e = e0 + c * plane;
-            const float xi = p.x[e];
+            const float xi = xin[c];
             float z = zc[c];
             if (p.noise && p.samp_kind != DMME_SAMPLER_DDIM) z = p.noise[e];  // t == 1: drawn and discarded, like the reference
             float r;
