@@ -562,21 +562,30 @@ __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const WgradParams p
 #pragma unroll
     for (int i = 0; i < kAhead; ++i)
       avs[i] = p0 + i < p_hi ? __bfloat162float(a[static_cast<long long>(p0 + i) * p.c0]) : 0.f;
+    // four pixels of a row share one six-column window of grad_out per (tap row, channel): two vector reads feed twelve
+    // FMAs (one broadcast read per FMA, the first version, was shared-memory bound); w % 4 == 0, so a group of four never
+    // leaves its row, and every accumulator still meets the pixels in ascending order (same bits)
 #pragma unroll
-    for (int i = 0; i < kAhead; ++i) {
-      if (p0 + i >= p_hi) break;
-      const int y = (p0 + i) / w, x = (p0 + i) - y * w;
-      const float av = avs[i];
+    for (int gq = 0; gq < kAhead / 4; ++gq) {
+      const int pp = p0 + 4 * gq;
+      if (pp >= p_hi) break;
+      const int y = pp / w, x = pp - y * w;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        // output row y - r + 1 -> halo row y - r + 2; output columns x - s + 1 -> halo columns x + 2 - s, s = 0..2
+        // output row y - r + 1 -> halo row y - r + 2; pixel x + i, tap s -> halo column x + i + 2 - s
         const float* row = gs + (y - r + 2) * ws + x;
 #pragma unroll
         for (int co = 0; co < COUT; ++co) {
-          const float g2 = row[co * plane + 2], g1 = row[co * plane + 1], g0 = row[co * plane];
-          acc[r * 3 + 0][co] = fmaf(av, g2, acc[r * 3 + 0][co]);
-          acc[r * 3 + 1][co] = fmaf(av, g1, acc[r * 3 + 1][co]);
-          acc[r * 3 + 2][co] = fmaf(av, g0, acc[r * 3 + 2][co]);
+          const float4 g03 = *reinterpret_cast<const float4*>(row + co * plane);
+          const float2 g45 = *reinterpret_cast<const float2*>(row + co * plane + 4);
+          const float gw[6] = {g03.x, g03.y, g03.z, g03.w, g45.x, g45.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float av = avs[4 * gq + i];
+            acc[r * 3 + 0][co] = fmaf(av, gw[i + 2], acc[r * 3 + 0][co]);
+            acc[r * 3 + 1][co] = fmaf(av, gw[i + 1], acc[r * 3 + 1][co]);
+            acc[r * 3 + 2][co] = fmaf(av, gw[i], acc[r * 3 + 2][co]);
+          }
         }
       }
     }
@@ -600,7 +609,8 @@ __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const WgradParams p
 static bool conv_out_wgrad_supported(const dmme_conv_desc& d) {
   return d.kernel != DMME_CONV_GENERIC && d.act_dtype == DMME_BF16 && d.out_layout == DMME_OUT_NCHW_F32 &&
          d.in_layout == DMME_IN_NHWC && d.ksize == 3 && d.stride == 1 && !d.upsample && d.c1 == 0 && d.rc0 + d.rc1 == 0 &&
-         (d.cout == 3 || d.cout == 6) && d.c0 >= 32 && d.c0 <= 256 && d.c0 % 32 == 0 && d.h_in <= 32 && d.w_in <= 32;
+         (d.cout == 3 || d.cout == 6) && d.c0 >= 32 && d.c0 <= 256 && d.c0 % 32 == 0 && d.h_in <= 32 && d.w_in <= 32 &&
+         d.w_in % 4 == 0;
 }
 
 // partial [slices][cout][kp] -> dW OIHW [cout][cin][taps], dWres [cout][rc], dbias [cout]
