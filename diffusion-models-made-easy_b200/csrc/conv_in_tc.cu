@@ -10,6 +10,10 @@
 // thread).  The FFMA kernel this replaces (conv_small.cu: conv_in_rows_kernel) is instruction-issue bound at 69 us for
 // batch 256; here the tensor-core time is negligible and the kernel is paced by its epilogue stores.
 //
+// CIN = 6 is the same problem met in training: the data gradient of the IDDPM output conv (models/ddpm.py:277) is a 3x3
+// conv of the 6-channel fp32 NCHW image-space gradient into 128 channels.  Its 54 taps fill a K = 64 block on their own,
+// so hi and lo are two operand tiles (eight MMAs per unit) against the one weight tile [ w(54) | 0 ].
+//
 // Warps: 0 = TMA producer (zero-padded fp32 patches: rows -1 / 32 and columns -1 / 32 are out of bounds = zero fill),
 // 1 = MMA issuer / TMEM owner, 2..9 = epilogue, 10..17 = operand builders (thread = one position x 8 taps).
 #include <cuda.h>
@@ -20,11 +24,9 @@
 
 namespace dmme {
 
-bool conv_in_supported(const dmme_conv_desc& d);
-
 struct ConvInTcParams {
-  CUtensorMap x;        // image NCHW fp32 as (w, h, c, n): box (40, 6, 3, 1) at (-4, 4 t - 1, 0, image)
-  const float* weight;  // fp32 [27][128], k = tap * 3 + ci (dmme_pack_conv_weight, DMME_CONV_GENERIC)
+  CUtensorMap x;        // image NCHW fp32 as (w, h, c, n): box (40, 6, CIN, 1) at (-4, 4 t - 1, 0, image)
+  const float* weight;  // fp32 [9 CIN][128], k = tap * CIN + ci (dmme_pack_conv_weight, DMME_CONV_GENERIC)
   const float* bias;
   __nv_bfloat16* out;   // NHWC
   long long* stats;
@@ -35,15 +37,24 @@ constexpr int kInW = 32;
 constexpr int kInCout = 128;
 constexpr int kInPatchX0 = 4;                        // patch column of image column 0 (TMA: 16-byte aligned box start)
 constexpr int kInPatchCols = 40;                     // image columns -4 .. 35
-constexpr int kInPatchFloats = 3 * 6 * kInPatchCols;
-constexpr int kInPatchSlot = 3072;                   // >= kInPatchFloats * 4, multiple of 128
 constexpr int kInPatchStages = 4;
 constexpr int kInBTile = 128 * 128;                  // [128 positions][64 k] bf16
 constexpr int kInBStages = 3;
+template <int CIN> struct InGeom {
+  static constexpr int kTaps = 9 * CIN;                        // 27: hi and lo halves of one tile; 54: a tile each
+  static constexpr int kTiles = CIN == 3 ? 1 : 2;
+  static constexpr int kGroups = CIN == 3 ? 4 : 8;             // 8-tap groups of a position
+  static constexpr int kPatchFloats = CIN * 6 * kInPatchCols;
+  static constexpr int kPatchSlot = (kPatchFloats * 4 + 1023) / 1024 * 1024;
+  static constexpr int kSmem = kInCout * 128 + kInBStages * kTiles * kInBTile + kInPatchStages * kPatchSlot + 1024;
+};
 constexpr int kInEpiWarps = 8, kInBuildWarps = 8;
 constexpr int kInThreads = (2 + kInEpiWarps + kInBuildWarps) * 32;
 
+template <int CIN>
 __global__ void __launch_bounds__(kInThreads, 1) conv_in_tc_kernel(const __grid_constant__ ConvInTcParams p) {
+  using G = InGeom<CIN>;
+  constexpr int kStage = G::kTiles * kInBTile;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t patch_full[kInPatchStages], patch_empty[kInPatchStages];
   __shared__ __align__(8) uint64_t b_ready[kInBStages], b_empty[kInBStages];
@@ -55,7 +66,7 @@ __global__ void __launch_bounds__(kInThreads, 1) conv_in_tc_kernel(const __grid_
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* wbuf = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // [128 channels][64 k] bf16, SWIZZLE_128B
   uint8_t* bbuf = wbuf + kInCout * 128;
-  uint8_t* pbuf = bbuf + kInBStages * kInBTile;
+  uint8_t* pbuf = bbuf + kInBStages * kStage;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kInPatchStages; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], kInBuildWarps * 32); }
@@ -85,9 +96,9 @@ __global__ void __launch_bounds__(kInThreads, 1) conv_in_tc_kernel(const __grid_
       for (int u = u_begin; u < u_end; ++u, ++it) {
         const int s = it % kInPatchStages;
         mbar_wait(&patch_empty[s], ((it / kInPatchStages) & 1) ^ 1);
-        mbar_expect_tx(&patch_full[s], kInPatchFloats * 4);
+        mbar_expect_tx(&patch_full[s], G::kPatchFloats * 4);
         // the innermost start coordinate must be a multiple of 16 bytes: the box starts at image column -4
-        tma_load_4d(pbuf + s * kInPatchSlot, &p.x, &patch_full[s], -kInPatchX0, (u & 7) * 4 - 1, 0, u >> 3);
+        tma_load_4d(pbuf + s * G::kPatchSlot, &p.x, &patch_full[s], -kInPatchX0, (u & 7) * 4 - 1, 0, u >> 3);
       }
     }
   } else if (warp == 1) {
@@ -104,9 +115,12 @@ __global__ void __launch_bounds__(kInThreads, 1) conv_in_tc_kernel(const __grid_
         mbar_wait(&b_ready[bs], (it / kInBStages) & 1);
         tc_fence_after();
         const uint32_t dtm = tmem_base + stage * 128;
-        const uint64_t xdesc = umma_desc_sw128(smem_u32(bbuf + bs * kInBTile));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+        for (int tl = 0; tl < G::kTiles; ++tl) {  // CIN = 6: the hi tile, then the lo tile, against the same weight tile
+          const uint64_t xdesc = umma_desc_sw128(smem_u32(bbuf + bs * kStage + tl * kInBTile));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(dtm, wdesc + 2 * k, xdesc + 2 * k, idesc, (tl | k) != 0 ? 1u : 0u);
+        }
         umma_commit(&b_empty[bs]);
         umma_commit(&acc_full[stage]);
       }
@@ -115,43 +129,44 @@ __global__ void __launch_bounds__(kInThreads, 1) conv_in_tc_kernel(const __grid_
     // =========================== operand builders ===========================
     const int bt = threadIdx.x - (2 + kInEpiWarps) * 32;  // 0..255
     pdl_wait();
-    // weight rows [ w(27) | 0 | w(27) | 0 ]: unit u and unit u + 4 of a row hold taps [8 (u & 3), +8)
-    for (int idx = bt; idx < kInCout * 4; idx += kInBuildWarps * 32) {
-      const int co = idx >> 2, g = idx & 3;
+    // weight rows: CIN = 3 [ w(27) | 0 | w(27) | 0 ] (unit g and unit g + 4 hold taps [8 g, +8)), CIN = 6 [ w(54) | 0 ]
+    for (int idx = bt; idx < kInCout * G::kGroups; idx += kInBuildWarps * 32) {
+      const int co = idx / G::kGroups, g = idx % G::kGroups;
       float wv[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = g * 8 + e;
-        wv[e] = k < 27 ? __ldg(p.weight + k * kInCout + co) : 0.f;
+        wv[e] = k < G::kTaps ? __ldg(p.weight + k * kInCout + co) : 0.f;
       }
       uint4 o;
       o.x = pack_bf16x2(wv[0], wv[1]); o.y = pack_bf16x2(wv[2], wv[3]);
       o.z = pack_bf16x2(wv[4], wv[5]); o.w = pack_bf16x2(wv[6], wv[7]);
       uint8_t* row = wbuf + co * 128;
       *reinterpret_cast<uint4*>(row + ((g ^ (co & 7)) << 4)) = o;
-      *reinterpret_cast<uint4*>(row + (((g + 4) ^ (co & 7)) << 4)) = o;
+      if (CIN == 3) *reinterpret_cast<uint4*>(row + (((g + 4) ^ (co & 7)) << 4)) = o;
     }
     fence_proxy_async();
     mbar_arrive(&w_ready);
     // this thread's taps: k = 8 g + e -> (ci, dy, dx) -> offset inside the patch [3][6][40] of position (row 0, x = 0)
-    const int g = bt & 3;
+    const int g = bt % G::kGroups;
     int koff[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = g * 8 + e;
-      const int tap = k / 3, ci = k - tap * 3, dy = tap / 3, dx = tap - dy * 3;
-      koff[e] = k < 27 ? ci * (6 * kInPatchCols) + dy * kInPatchCols + dx : -1;
+      const int tap = k / CIN, ci = k - tap * CIN, dy = tap / 3, dx = tap - dy * 3;
+      koff[e] = k < G::kTaps ? ci * (6 * kInPatchCols) + dy * kInPatchCols + dx : -1;
     }
+    constexpr int kPosStep = kInBuildWarps * 32 / G::kGroups;  // positions covered by one pass of the builder threads
     int it = 0;
     for (int u = u_begin; u < u_end; ++u, ++it) {
       const int s = it % kInPatchStages, bs = it % kInBStages;
       mbar_wait(&patch_full[s], (it / kInPatchStages) & 1);
       mbar_wait(&b_empty[bs], ((it / kInBStages) & 1) ^ 1);
-      const float* patch = reinterpret_cast<const float*>(pbuf + s * kInPatchSlot);
-      uint8_t* tile = bbuf + bs * kInBTile;
+      const float* patch = reinterpret_cast<const float*>(pbuf + s * G::kPatchSlot);
+      uint8_t* tile = bbuf + bs * kStage;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int pos = (bt >> 2) + 64 * j;           // position inside the unit: row pos / 32, column pos % 32
+      for (int j = 0; j < 128 / kPosStep; ++j) {
+        const int pos = bt / G::kGroups + kPosStep * j;  // position inside the unit: row pos / 32, column pos % 32
         const int base = (pos >> 5) * kInPatchCols + (pos & 31) + kInPatchX0 - 1;  // tap dx = 0 reads image column x - 1
         float v[8];
 #pragma unroll
@@ -166,7 +181,8 @@ __global__ void __launch_bounds__(kInThreads, 1) conv_in_tc_kernel(const __grid_
         lo.z = pack_bf16x2(v[4] - r[4], v[5] - r[5]); lo.w = pack_bf16x2(v[6] - r[6], v[7] - r[7]);
         uint8_t* row = tile + pos * 128;
         *reinterpret_cast<uint4*>(row + ((g ^ (pos & 7)) << 4)) = hi;
-        *reinterpret_cast<uint4*>(row + (((g + 4) ^ (pos & 7)) << 4)) = lo;
+        if (CIN == 3) *reinterpret_cast<uint4*>(row + (((g + 4) ^ (pos & 7)) << 4)) = lo;
+        else *reinterpret_cast<uint4*>(row + kInBTile + ((g ^ (pos & 7)) << 4)) = lo;
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the MMA's async-proxy reads
       mbar_arrive(&b_ready[bs]);
@@ -243,8 +259,27 @@ static int g_in_tc_mode = 1;  // 0 = the input conv stays on the FFMA kernel, 1 
 constexpr int kInTcMinBatch = 64;
 
 bool conv_in_tc_supported(const dmme_conv_desc& d) {
-  return g_in_tc_mode != 0 && conv_in_supported(d) && d.cout == kInCout && d.w_in == kInW && d.h_in == kInW &&
+  const bool plain = d.ksize == 3 && d.stride == 1 && !d.upsample && d.c1 == 0 && d.rc0 == 0 && d.rc1 == 0 && !d.temb &&
+                     !d.addend && d.act_dtype == DMME_BF16 && d.in_layout == DMME_IN_NCHW_F32 && d.out_layout == DMME_OUT_NHWC;
+  return g_in_tc_mode != 0 && plain && (d.c0 == 3 || d.c0 == 6) && d.cout == kInCout && d.w_in == kInW && d.h_in == kInW &&
          d.n >= (g_in_tc_mode == 2 ? 1 : kInTcMinBatch) && d.n <= (1 << 24);
+}
+
+template <int CIN>
+static int launch_in_tc(const ConvInTcParams& p, int grid, cudaStream_t stream) {
+  constexpr int smem = InGeom<CIN>::kSmem;
+  static DeviceOnce once_;
+  bool& configured = once_.here();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_in_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("conv_in_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  cudaError_t e = launch_pdl(conv_in_tc_kernel<CIN>, dim3(grid), dim3(kInThreads), smem, stream, p);
+  return check_launch_err(e, "conv_in_tc_kernel");
 }
 
 int conv_in_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
@@ -259,27 +294,15 @@ int conv_in_tc_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   p.n = d.n;
   p.units = d.n * (kInW / 4);
   {
-    uint64_t dims[4] = {(uint64_t)kInW, (uint64_t)kInW, 3, (uint64_t)d.n};
-    uint64_t strides[3] = {(uint64_t)kInW * 4, (uint64_t)kInW * kInW * 4, (uint64_t)3 * kInW * kInW * 4};
-    uint32_t box[4] = {(uint32_t)kInPatchCols, 6u, 3u, 1u};
+    uint64_t dims[4] = {(uint64_t)kInW, (uint64_t)kInW, (uint64_t)d.c0, (uint64_t)d.n};
+    uint64_t strides[3] = {(uint64_t)kInW * 4, (uint64_t)kInW * kInW * 4, (uint64_t)d.c0 * kInW * kInW * 4};
+    uint32_t box[4] = {(uint32_t)kInPatchCols, 6u, (uint32_t)d.c0, 1u};
     int rc = encode_map_f32(&p.x, d.src0, 4, dims, strides, box);
     if (rc) return rc;
   }
-  const int smem = kInCout * 128 + kInBStages * kInBTile + kInPatchStages * kInPatchSlot + 1024;
-  static DeviceOnce once_;
-  bool& configured = once_.here();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("conv_in_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
   const int sm_count = device_sm_count();
   const int grid = p.units < sm_count ? p.units : sm_count;
-  cudaError_t e = launch_pdl(conv_in_tc_kernel, dim3(grid), dim3(kInThreads), smem, stream, p);
-  return check_launch_err(e, "conv_in_tc_kernel");
+  return d.c0 == 3 ? launch_in_tc<3>(p, grid, stream) : launch_in_tc<6>(p, grid, stream);
 }
 
 }  // namespace dmme

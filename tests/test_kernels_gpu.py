@@ -158,15 +158,16 @@ def test_conv_in_image_to_nhwc_bf16(n, h, cout):
     assert rel_l2(got, F.conv2d(x, w, b, padding=1)) < 4e-3
 
 
-@pytest.mark.parametrize("n", [1, 37, 300])
-def test_conv_in_tc_32x32(n):
+@pytest.mark.parametrize("n,cin", [(1, 3), (37, 3), (300, 3), (2, 6), (131, 6)])
+def test_conv_in_tc_32x32(n, cin):
     """input_conv on tcgen05 (operand rows [hi | lo] built from the fp32 image, bf16 weights): against the fp32 conv on
     bf16-rounded weights, and against the FFMA kernel it replaces (fp32 weights) within the weight rounding"""
     ops, L = _ops()
     lib = L.load()
     g = torch.Generator().manual_seed(36)
-    x = torch.randn(n, 3, 32, 32, generator=g) * 1.7
-    w = torch.randn(128, 3, 3, 3, generator=g) / 5
+    # cin = 6: the data gradient of the IDDPM output conv (a 6-channel fp32 NCHW image-space gradient into 128 channels)
+    x = torch.randn(n, cin, 32, 32, generator=g) * 1.7
+    w = torch.randn(128, cin, 3, 3, generator=g) / 5
     b = torch.randn(128, generator=g)
     lib.dmme_set_conv_in_tc_mode(2)  # the default takes it from 64 images up
     try:
