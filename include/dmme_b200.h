@@ -130,8 +130,9 @@ typedef struct dmme_conv_desc {
   const float* gn_ab;                 /* optional fused GroupNorm(+SiLU) of the conv INPUT (norm_act_drop_conv,
                                          models/ddpm.py:25-35): interleaved (a, b) fp32 pairs [n][c0 + c1][2] from
                                          dmme_groupnorm_coeff; the kernel convolves [silu](a * x + b) with zero padding
-                                         applied after the activation, as the reference does.  Halo kernel only: ask
-                                         dmme_conv2d_fuses_gn first */
+                                         applied after the activation, as the reference does.  Halo kernel (16x16 and
+                                         32x32 ResBlock convs) and the 32x32 output conv only: ask dmme_conv2d_fuses_gn
+                                         first */
   int gn_silu;                        /* 1: SiLU after the fused norm */
   void* splitk_ws;                    /* optional fp32 workspace of dmme_conv2d_splitk_workspace(desc) bytes.  With it, a
                                          3x3 conv whose grid would leave most SMs idle (the 4x4 / 8x8 levels, small
