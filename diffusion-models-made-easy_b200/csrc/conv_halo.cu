@@ -98,7 +98,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
-  constexpr int WP = W + 2;
+  // Row tiles (16x16 / 32x32 maps) use the SHARED-PADDING layout: one zero column per image row (x = -1) and one zero row
+  // per image (y = -1).  With a row pitch of W + 1 that column is at once the left padding of its row and the right padding
+  // of the row before it, the row the top padding of its image and the bottom padding of the image before it (the row
+  // after the last image is out of bounds = zero-filled like every other padding position): 17 x 17 instead of 18 x 18
+  // positions per 16x16 image, 15 instead of 14 rows per 256-column tile.  Tap shifts stay d = (r-1) * pitch + (s-1).
+  // Whole-image tiles (8x8 / 4x4) keep private padding on all four sides: their halo rows are never loaded.
+  constexpr bool kShared = W >= 16;
+  constexpr int WP = kShared ? W + 1 : W + 2;  // row pitch in positions
+  constexpr int HP = kShared ? W + 1 : W + 2;  // stack rows per image (square maps)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* abuf = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -126,6 +134,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     for (int s = 0; s < kHaloBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kHaloEpiWarps * 32); }
     fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (kShared && warp == 1) {
+    // shared padding: tap (+1, +1) of the last pixel of the tile's last row reads the position AFTER the last halo row (the
+    // padding column of the row below it).  No load ever writes that position: zero it once in every stage.
+    *reinterpret_cast<uint4*>(abuf + (lane >> 3) * kHaloASlot + 128 + nr * kRowBytes + (lane & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
   }
   if (warp == kWarpProdA && lane == 0) {
@@ -161,8 +175,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int pr0 = mt * p.rt - 1;  // first halo row (padded-row index, may be -1)
         // three of four tiles lie inside one padded image: ONE box of rt + 2 rows (rows -1 / h and everything past the batch
         // are out of bounds = zero-filled) instead of a box per row -- the issuing thread needs ~300 clocks per box
-        const int ni0 = (pr0 < 0 ? 0 : pr0) / (p.h + 2);
-        const bool one_img = p.imgs_per_tile == 0 && (pr0 + nr - 1) / (p.h + 2) == ni0;
+        // (shared padding: the tile's last halo row may be the next image's padding row = row h of this image)
+        const int ni0 = (pr0 < 0 ? 0 : pr0) / HP;
+        const int pr_last = pr0 + nr - 1 - (kShared ? 1 : 0);
+        const bool one_img = p.imgs_per_tile == 0 && (pr_last < 0 ? 0 : pr_last) / HP == ni0;
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           int which, cc;
           const HaloChunk hc = halo_chunk_of(p.order[ck]);
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if (one_img) {
             if (second) { mbar_arrive(&a_full[as]); continue; }
             mbar_expect_tx(&a_full[as], nr * kRowBytes);
-            tma_load_5d(abuf + as * kHaloASlot + 128, &p.at[which], &a_full[as], cc, -1, 0, pr0 - ni0 * (p.h + 2) - 1, ni0);
+            tma_load_5d(abuf + as * kHaloASlot + 128, &p.at[which], &a_full[as], cc, -1, 0, pr0 - ni0 * HP - 1, ni0);
             continue;
           }
           // tiles spanning two images: a box per padded row, split between the producers.  The single-tap chunks of a fused
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const int pr = pr0 + i;
             int ni, yy;
             if (pr < 0) { ni = -1; yy = 0; }             // before the first image: whole row out of bounds -> zeros
-            else { ni = pr / (p.h + 2); yy = pr - ni * (p.h + 2) - 1; }  // yy = -1 or h: padding row -> zeros
+            else { ni = pr / HP; yy = pr - ni * HP - 1; }  // yy = -1 or h: padding row -> zeros
             tma_load_5d(dst + i * kRowBytes, &p.a[which], &a_full[as], cc, -1, 0, yy, ni);
           }
         }
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int mt = item_mt(u);
         const int pr0 = mt * p.rt - 1;
         // first image the tile touches; it touches at most n_lo + 1 too (clamped: a pair's odd tile may lie past the batch)
-        const int n_lo = min((pr0 < 0 ? 0 : pr0) / (p.h + 2), p.n - 1);
+        const int n_lo = min((pr0 < 0 ? 0 : pr0) / HP, p.n - 1);
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           const int as = a_it % kHaloAStages;
           const HaloChunk hc = halo_chunk_of(p.order[ck]);
@@ -335,9 +351,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 const int r = rb + b * 4 * kHaloXfWarps;
                 const int hr = r / WP, xx = r - hr * WP;
                 const int pr = pr0 + hr;
-                const int n = pr / WP;  // square maps: h + 2 == W + 2
-                const int yy = pr - n * WP - 1;
-                const bool valid = r < rows && xx != 0 && xx != WP - 1 && pr >= 0 && pr < p.total_rows && yy >= 0 && yy < W;
+                const int n = pr / HP;
+                const int yy = pr - n * HP - 1;
+                const bool valid = r < rows && xx != 0 && xx <= W && pr >= 0 && pr < p.total_rows && yy >= 0 && yy < W;
                 sel[b] = valid ? (n != n_lo ? 2 : 1) : 0;
                 // SWIZZLE_128B: the 16-byte unit index is XORed with address bits [7, 10) of the row
                 const uint32_t phase = ((tile_addr + static_cast<uint32_t>(r) * 128u) >> 7) & 7u;
@@ -413,8 +429,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       for (int rr = half; rr < p.rt; rr += 2) {
         const int pr = mt * p.rt + rr;
         if (pr >= p.total_rows) break;
-        const int n = pr / (p.h + 2);
-        const int yy = pr - n * (p.h + 2) - 1;
+        const int n = pr / HP;
+        const int yy = pr - n * HP - 1;
         if (yy < 0 || yy >= p.h) continue;  // padding row: junk accumulator columns
         if (n != cur_n) {
           flush_stats();
@@ -547,7 +563,9 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   ConvHaloParams p;
   memset(&p, 0, sizeof(p));
   p.chunks0 = d.c0 / 64; p.chunks1 = d.c1 / 64; p.rchunks0 = d.rc0 / 64; p.rchunks1 = d.rc1 / 64;
-  p.n = d.n; p.h = d.h_in; p.wp = d.w_in + 2;
+  const bool shared_pad = d.w_in >= 16;  // row tiles: shared-padding layout (see the kernel)
+  const int hp = shared_pad ? d.h_in + 1 : d.h_in + 2;
+  p.n = d.n; p.h = d.h_in; p.wp = shared_pad ? d.w_in + 1 : d.w_in + 2;
   {
     const int cc = p.chunks0 + p.chunks1, rc = p.rchunks0 + p.rchunks1;
     DMME_REQUIRE(cc + rc <= 32, DMME_E_SHAPE, "conv_halo: more than 32 channel chunks per work unit");
@@ -559,12 +577,12 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     }
     while (r < rc) p.order[pos++] = static_cast<unsigned char>(r++);
   }
-  p.total_rows = d.n * (d.h_in + 2);
+  p.total_rows = d.n * hp;
   p.n_tiles = d.cout / kHaloBN;
   g_sm_count = device_sm_count();
-  const int img_pos = (d.h_in + 2) * p.wp;
+  const int img_pos = (d.h_in + 2) * (d.w_in + 2);
   p.imgs_per_tile = 0;
-  if (img_pos <= kHaloCols) {
+  if (!shared_pad) {
     // small resolutions: a tile is k whole padded images (2 at 8x8, 7 at 4x4), or fewer when that fills more SMs
     long long best_cost = -1;
     for (int k = kHaloCols / img_pos; k >= 1; k = k / 2) {
@@ -601,7 +619,7 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   DMME_REQUIRE(d.gn_ab == nullptr || p.imgs_per_tile == 0, DMME_E_UNSUPPORTED,
                "conv_halo: fused GroupNorm needs row tiles (16x16 and 32x32 maps)");
   // the MMA reads n_mma + (W+3) position rows past the first tile position; keep that inside the slot
-  DMME_REQUIRE((1 + (p.rt + 2) * p.wp) * 128 <= kHaloASlot && (1 + 2 * p.wp + 1 + p.n_mma) * 128 <= kHaloASlot,
+  DMME_REQUIRE((1 + (p.rt + 2) * p.wp + (shared_pad ? 1 : 0)) * 128 <= kHaloASlot && (1 + 2 * p.wp + 1 + p.n_mma) * 128 <= kHaloASlot,
                DMME_E_SHAPE, "conv_halo: halo tile does not fit its shared-memory slot");
 
   auto act_map = [&](CUtensorMap* m, const void* ptr, int c, int rows = 0) -> int {
