@@ -38,6 +38,10 @@ struct ConvHaloParams {
   int n, h, wp;
   int rt;            // padded rows per tile
   int n_mma;         // MMA N: rt * wp rounded up to a multiple of 16
+  // tail tiles (row tiles only): row tiles [0, m_big) hold rt rows, tiles [m_big, m_tiles) hold rs < rt rows.  When the
+  // equal tiles leave a last wave that occupies only some of the SMs, the rows of that wave are spread over all of them as
+  // short tiles instead (1207 tiles of 7 rows on 148 SMs = 9 rounds of 240 columns -> 8 rounds + one of 80 columns)
+  int m_big, rs, n_mma_s;
   int total_rows;    // n * (h + 2)
   int imgs_per_tile; // > 0: tiles hold whole padded images (small resolutions), one TMA box per image
   int m_tiles, n_tiles;
@@ -124,6 +128,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const int sched0 = MC ? blockIdx.x / 2 : blockIdx.x;
   const int items = MC ? ((p.m_tiles + 1) / 2) * p.n_tiles : units;
   auto item_mt = [&](int v) { return MC ? 2 * (v / p.n_tiles) + static_cast<int>(crank) : v / p.n_tiles; };
+  auto tile_row0 = [&](int mt) { return mt < p.m_big ? mt * p.rt : p.m_big * p.rt + (mt - p.m_big) * p.rs; };
+  auto tile_rt = [&](int mt) { return mt < p.m_big ? p.rt : p.rs; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHaloAStages; ++s) {
@@ -172,13 +178,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       pdl_wait();
       for (int u = sched0; u < items; u += nsched) {
         const int mt = item_mt(u);
-        const int pr0 = mt * p.rt - 1;  // first halo row (padded-row index, may be -1)
+        const int rt_u = tile_rt(mt), nr_u = rt_u + 2;
+        const bool tail = rt_u != p.rt;
+        const int pr0 = tile_row0(mt) - 1;  // first halo row (padded-row index, may be -1)
         // three of four tiles lie inside one padded image: ONE box of rt + 2 rows (rows -1 / h and everything past the batch
         // are out of bounds = zero-filled) instead of a box per row -- the issuing thread needs ~300 clocks per box
         // (shared padding: the tile's last halo row may be the next image's padding row = row h of this image)
         const int ni0 = (pr0 < 0 ? 0 : pr0) / HP;
         const int pr_last = pr0 + nr - 1 - (kShared ? 1 : 0);
-        const bool one_img = p.imgs_per_tile == 0 && (pr_last < 0 ? 0 : pr_last) / HP == ni0;
+        const bool one_img = p.imgs_per_tile == 0 && !tail && (pr_last < 0 ? 0 : pr_last) / HP == ni0;
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           int which, cc;
           const HaloChunk hc = halo_chunk_of(p.order[ck]);
@@ -212,7 +220,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           // tiles spanning two images: a box per padded row, split between the producers.  The single-tap chunks of a fused
           // 1x1 residual only read the tile's own rows: the two halo rows are not loaded (whatever the slot holds there only
           // reaches padding-position accumulator columns)
-          int i_lo = hc.is_conv ? 0 : 1, i_hi = hc.is_conv ? nr : nr - 1;
+          // (a tail tile also loads the row after its halo: that row's padding column is the position the one-time zeroing
+          // above provides for the full-height tiles)
+          int i_lo = hc.is_conv ? 0 : 1, i_hi = hc.is_conv ? nr_u + (tail ? 1 : 0) : nr_u - 1;
           const int i_cnt = i_hi - i_lo;
           i_hi = i_lo + (i_cnt * (prod + 1)) / kHaloProdA;
           i_lo = i_lo + (i_cnt * prod) / kHaloProdA;
@@ -258,10 +268,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   } else if (warp == kWarpMma) {
     // =========================== MMA issuer ===========================
     // the whole warp walks the loop (converged waits); one elected lane issues the MMAs and their commits
-    const uint32_t idesc = umma_idesc_bf16(kHaloBN, p.n_mma);  // M = 128 output channels, N = positions of the tile
+    const uint32_t idesc_big = umma_idesc_bf16(kHaloBN, p.n_mma);  // M = 128 output channels, N = positions of the tile
+    const uint32_t idesc_tail = umma_idesc_bf16(kHaloBN, p.n_mma_s);
     int a_it = 0, b_it = 0, u_it = 0;
     for (int u = sched0; u < items; u += nsched, ++u_it) {
       const int stage = u_it & 1;
+      const uint32_t idesc = item_mt(u) < p.m_big ? idesc_big : idesc_tail;
       mbar_wait(&acc_empty[stage], ((u_it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t dtm = tmem_base + stage * kHaloCols;
@@ -308,12 +320,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const int xt = threadIdx.x - kWarpXf0 * 32;  // 0..kHaloXfWarps * 32
       const int ul = xt & 7;                       // logical 16-byte unit = channels [8 ul, 8 ul + 8) of the chunk
       const int r_first = xt >> 3;                 // rows r_first, r_first + 4 * kHaloXfWarps, ...
-      const int rows = nr * WP;
       int a_it = 0;
       pdl_wait();
       for (int u = sched0; u < items; u += nsched) {
         const int mt = item_mt(u);
-        const int pr0 = mt * p.rt - 1;
+        const int pr0 = tile_row0(mt) - 1;
+        const int rows = (tile_rt(mt) + 2) * WP;
         // first image the tile touches; it touches at most n_lo + 1 too (clamped: a pair's odd tile may lie past the batch)
         const int n_lo = min((pr0 < 0 ? 0 : pr0) / HP, p.n - 1);
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
@@ -401,6 +413,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     pdl_wait();
     for (int u = sched0; u < items; u += nsched, ++u_it) {
       const int mt = item_mt(u), nt = u % p.n_tiles;
+      const int row0 = tile_row0(mt), rt_u = tile_rt(mt);
       const int ch = nt * kHaloBN + q * 32 + lane;
       const float bias_c = p.bias ? __ldg(p.bias + ch) : 0.f;
       const int stage = u_it & 1;
@@ -426,8 +439,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       tc_fence_after();
       if (threadIdx.x == 0) halo_trace(p.trace, 5, u_it);
 #pragma unroll 1
-      for (int rr = half; rr < p.rt; rr += 2) {
-        const int pr = mt * p.rt + rr;
+      for (int rr = half; rr < rt_u; rr += 2) {
+        const int pr = row0 + rr;
         if (pr >= p.total_rows) break;
         const int n = pr / HP;
         const int yy = pr - n * HP - 1;
@@ -512,7 +525,10 @@ bool conv_halo_supported(const dmme_conv_desc& d) {
 bool conv_halo_preferred(const dmme_conv_desc& d) {
   if (!conv_halo_supported(d)) return false;
   if (d.w_in < 16) return false;
-  if (d.w_in == 16 && (d.rc0 + d.rc1) > 128 && !(d.cout == 128 && d.rc0 + d.rc1 <= 256)) return false;
+  // (round 2, shared-padding row tiles: the halo kernel is ~13% faster at 16x16 and the wide-residual convs now win with
+  // their GroupNorm inside -- whole step 3.06 vs 3.11 ms at batch 256, 1.844 vs 1.866 at 128, 1.086 vs 1.099 at 32; bit 6 of the
+  // mode restores the old rule for A/B runs)
+  if ((g_halo_mode & 64) && d.w_in == 16 && (d.rc0 + d.rc1) > 128 && !(d.cout == 128 && d.rc0 + d.rc1 <= 256)) return false;
   return true;
 }
 
@@ -592,7 +608,9 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.imgs_per_tile = k; p.n_mma = n_mma; }
       if (k == 1) break;
     }
-    p.rt = p.imgs_per_tile * (d.h_in + 2);
+    p.rt = p.rs = p.imgs_per_tile * (d.h_in + 2);
+    p.m_tiles = p.m_big = (p.total_rows + p.rt - 1) / p.rt;
+    p.n_mma_s = p.n_mma;
   } else {
     // rows per tile: at most what fits 256 accumulator columns (7 rows of 34, 14 of 18); fewer rows when that fills the
     // last wave better (cost ~ waves x (MMA width + per-unit overhead; 96 columns' worth by measurement: with 48 the 32x32
@@ -602,12 +620,30 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     const int rt_max = kHaloCols / p.wp;
     for (int rt = rt_max; rt >= 1 && 2 * rt >= rt_max; --rt) {
       const int n_mma = ((rt * p.wp + 15) / 16) * 16;
-      const long long units = static_cast<long long>((p.total_rows + rt - 1) / rt) * p.n_tiles;
+      const int m_all = (p.total_rows + rt - 1) / rt;
+      const long long units = static_cast<long long>(m_all) * p.n_tiles;
       const long long cost = ((units + g_sm_count - 1) / g_sm_count) * (n_mma + 96);
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.rt = rt; p.n_mma = n_mma; }
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost; p.rt = rt; p.n_mma = n_mma; p.m_tiles = p.m_big = m_all; p.rs = rt; p.n_mma_s = n_mma;
+      }
+      // tail tiles: the full rounds as above, the rows of the partial last round as one round of short tiles
+      const long long full = units / g_sm_count;
+      if (shared_pad && (g_halo_mode & 32) == 0 && g_halo_mc == 0 && full >= 1 && units % g_sm_count != 0 && g_sm_count % p.n_tiles == 0) {
+        const int m_big = static_cast<int>(full * g_sm_count / p.n_tiles);
+        const int rows_left = p.total_rows - m_big * rt;
+        const int per_round = g_sm_count / p.n_tiles;
+        const int rs = (rows_left + per_round - 1) / per_round;
+        if (rows_left > 0 && rs < rt) {
+          const int n_mma_s = ((rs * p.wp + 15) / 16) * 16;
+          const long long cost_t = full * (n_mma + 96) + (n_mma_s + 96);
+          if (cost_t < best_cost) {
+            best_cost = cost_t; p.rt = rt; p.n_mma = n_mma; p.m_big = m_big; p.rs = rs; p.n_mma_s = n_mma_s;
+            p.m_tiles = m_big + (rows_left + rs - 1) / rs;
+          }
+        }
+      }
     }
   }
-  p.m_tiles = (p.total_rows + p.rt - 1) / p.rt;
   p.bias = d.bias; p.temb = d.temb; p.temb_rows = d.temb_rows; p.temb_ld = d.temb_ld;
   p.addend = static_cast<const __nv_bfloat16*>(d.addend);
   p.out = static_cast<__nv_bfloat16*>(d.out);
