@@ -1067,6 +1067,48 @@ def test_conv_halo_fused_groupnorm(cfg):
 
 
 @pytest.mark.parametrize("cfg", [
+    dict(n=150, c0=128, c1=0, cout=128, h=32, gn=True),             # 4 full rounds of 7-row tiles + one round of short tiles
+    dict(n=256, c0=128, c1=128, cout=128, h=32, res=True, gn=True),  # the step's dominant launch: 8 rounds + a 2-row tail
+    dict(n=128, c0=256, c1=0, cout=256, h=16, gn=True),             # two channel tiles per row tile
+    dict(n=64, c0=128, c1=0, cout=128, h=32),
+    dict(n=37, c0=256, c1=256, cout=256, h=16),
+])
+def test_conv_halo_tail_tiles(cfg):
+    """tail tiles (the rows of the partial last wave as one round of short tiles, csrc/conv_halo.cu) == equal tiles: raw
+    outputs bit for bit (same K order per output); GroupNorm statistics to the fixed-point rounding of the per-tile sums"""
+    ops, L = _ops()
+    lib = L.load()
+    g = torch.Generator().manual_seed(71)
+    n, c0, c1, cout, h = (cfg[k] for k in ("n", "c0", "c1", "cout", "h"))
+    C = c0 + c1
+    s0 = to_nhwc(bf16_round(torch.randn(n, c0, h, h, generator=g)), torch.bfloat16).to(DEV)
+    s1 = to_nhwc(bf16_round(torch.randn(n, c1, h, h, generator=g)), torch.bfloat16).to(DEV) if c1 else None
+    wt = bf16_round(torch.randn(cout, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    wres = bf16_round(torch.randn(cout, C, 1, 1, generator=g) / math.sqrt(C)) if cfg.get("res") else None
+    wp = ops.pack_conv_weight(wt.to(DEV), wres.to(DEV) if wres is not None else None, True)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    ab = torch.randn(n, C, 2, generator=g).to(DEV) if cfg.get("gn") else None
+    r0, r1 = (s0, s1) if cfg.get("res") else (None, None)
+    d = ops.make_conv_desc(s0, s1, cout, 3, 1, False, r0, r1, False, L.OUT_NHWC, torch.bfloat16, L.CONV_HALO)
+    outs = []
+    mode0 = lib.dmme_get_conv_halo_mode()
+    try:
+        for mode in (mode0 | 32, mode0 & ~32):  # bit 5: equal tiles only
+            lib.dmme_set_conv_halo_mode(mode)
+            out = torch.full((n, h, h, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            st = torch.zeros(n * (cout // 4) * 2, dtype=torch.int64, device=DEV)
+            ops.conv2d_launch(d, wp, bias, out, stats=st, gn_ab=ab)
+            torch.cuda.synchronize()
+            outs.append((out, st))
+    finally:
+        lib.dmme_set_conv_halo_mode(mode0)
+    assert torch.isfinite(outs[0][0].float()).all()
+    assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16))
+    a, b = (o[1].double() / 2 ** 20 for o in outs)
+    assert torch.allclose(a, b, rtol=1e-5, atol=2e-2)
+
+
+@pytest.mark.parametrize("cfg", [
     dict(n=5, c0=128, c1=0, cout=128, h=32),                       # odd number of row tiles: the pair's last tile is past the batch
     dict(n=37, c0=128, c1=128, cout=128, h=32, res=True, gn=True),
     dict(n=9, c0=256, c1=0, cout=256, h=16, gn=True),              # two channel tiles per row-tile pair
