@@ -130,7 +130,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -597,13 +597,33 @@ def run_gpu(args):
         }
         if sweep:
             line["strong_scaling_projection"] = {str(n): sweep["256"] * 1.0 / sweep[str(256 // n)] for n in (1, 2, 4, 8)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The JSON line goes to the process's ORIGINAL stdout; everything else written to fd 1 (NCCL prints its version banner
+    there when NCCL_DEBUG is set) has been redirected to stderr by quiet_stdout()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def quiet_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -628,7 +648,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
                os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=_JSON_OUT))  # the ranks inherit the original stdout
     run_gpu(args)
 
 
