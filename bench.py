@@ -613,6 +613,10 @@ def run_gpu(args):
                                    "the 126 MB L2: every launch streams from / to HBM), one CUDA-event pair on the launching stream",
                             "us_per_launch_event_pair_in_eager_step": gd_us_in_step,
                             "peak_source": pk["source"] + " STREAM-style copy",
+                            "note": "the GroupNorms of the 32x32 / 16x16 levels and of the output conv (most of the step's "
+                                    "GroupNorm bytes) run inside the consuming conv kernels and have no pass of their own; the "
+                                    "stand-alone launches left are 8-34 MB tensors (8x8 level), far below the 126 MB L2 and bound "
+                                    "by launch + first-load latency, not by HBM",
                             "all_groupnorm_launches": {"launches_per_step": gn_n, "bytes_per_step": gn_bytes,
                                                        "ms_per_step": gn_ms, "achieved": gn_gbs,
                                                        "frac": gn_gbs / pk["hbm_gbs"],
