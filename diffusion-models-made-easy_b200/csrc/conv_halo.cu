@@ -9,7 +9,10 @@
 // exactly as TMA does when writing, so row-granular shifts need no re-layout and the descriptor's base-offset
 // field stays 0 (setting it to (addr >> 7) & 7 gives wrong results).
 //
-// Work unit = 128 output channels x RT whole padded rows (7 rows of 34 at 32x32, 14 rows of 18 at 16x16),
+// (Row tiles -- 16x16 and 32x32 maps -- share the padding between neighbours: one zero column per row and one zero row per
+// image, pitch W+1; see kShared in the kernel.  The description here is the private-padding layout of the whole-image tiles.)
+//
+// Work unit = 128 output channels x RT whole padded rows (7 rows of 33 at 32x32, 15 rows of 17 at 16x16),
 // computed TRANSPOSED: the weight tile [128 cout][64] is the MMA's M-side operand, the pixel rows are the N side
 // (D^T = W X^T, one M=128, N<=256 instruction per 16 channels).  A 128x128 tile makes every MMA read 8 KB of shared
 // memory per 64 cycles = the SM's whole 128 B/cycle (measured 41% tensor utilisation); 128x256 needs 96 B/cycle.
