@@ -69,11 +69,11 @@ extern "C" int dmme_conv2d_writes_stats(const dmme_conv_desc* d) {
   return 0;
 }
 
-// fused GroupNorm of the input: the halo kernel's row-tile mode (16x16 / 32x32 maps) has the transform stage
+// fused GroupNorm of the input: the halo kernel's row-tile mode (8x8 / 16x16 / 32x32 maps) has the transform stage
 static bool runs_halo_rows(const dmme_conv_desc& d) {
   const bool halo = d.kernel == DMME_CONV_HALO ? conv_halo_supported(d)
                                                : (d.kernel == DMME_CONV_AUTO && conv_tc_supported(d) && conv_halo_preferred(d));
-  return halo && d.w_in >= 16;
+  return halo && d.w_in >= 8;
 }
 
 // ... and so has the output conv's row-tile kernel (32x32 maps)

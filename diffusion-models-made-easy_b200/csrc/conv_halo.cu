@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   // of the row before it, the row the top padding of its image and the bottom padding of the image before it (the row
   // after the last image is out of bounds = zero-filled like every other padding position): 17 x 17 instead of 18 x 18
   // positions per 16x16 image, 15 instead of 14 rows per 256-column tile.  Tap shifts stay d = (r-1) * pitch + (s-1).
-  // Whole-image tiles (8x8 / 4x4) keep private padding on all four sides: their halo rows are never loaded.
-  constexpr bool kShared = W >= 16;
+  // 8x8 maps take row tiles of one or two WHOLE images (9 or 18 stack rows: the fused norm keeps the coefficients of two
+  // images per tile).  Whole-image tiles (4x4) keep private padding on all four sides: their halo rows are never loaded.
+  constexpr bool kShared = W >= 8;
   constexpr int WP = kShared ? W + 1 : W + 2;  // row pitch in positions
   constexpr int HP = kShared ? W + 1 : W + 2;  // stack rows per image (square maps)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         // (shared padding: the tile's last halo row may be the next image's padding row = row h of this image)
         const int ni0 = (pr0 < 0 ? 0 : pr0) / HP;
         const int pr_last = pr0 + nr - 1 - (kShared ? 1 : 0);
-        const bool one_img = p.imgs_per_tile == 0 && !tail && (pr_last < 0 ? 0 : pr_last) / HP == ni0;
+        const bool one_img = p.imgs_per_tile == 0 && !tail && p.rt <= p.h && (pr_last < 0 ? 0 : pr_last) / HP == ni0;
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           int which, cc;
           const HaloChunk hc = halo_chunk_of(p.order[ck]);
@@ -330,7 +331,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int pr0 = tile_row0(mt) - 1;
         const int rows = (tile_rt(mt) + 2) * WP;
         // first image the tile touches; it touches at most n_lo + 1 too (clamped: a pair's odd tile may lie past the batch)
-        const int n_lo = min((pr0 < 0 ? 0 : pr0) / HP, p.n - 1);
+        // (image-aligned tiles -- 8x8 maps -- start at an image's padding row: their halo row above belongs to the image
+        // before and only feeds padding-row outputs, so the tile's two images are the ones counted from its first own row)
+        const int pr_first = (p.rt % HP) == 0 ? pr0 + 1 : pr0;
+        const int n_lo = min((pr_first < 0 ? 0 : pr_first) / HP, p.n - 1);
         for (int ck = 0; ck < nck; ++ck, ++a_it) {
           const int as = a_it % kHaloAStages;
           const HaloChunk hc = halo_chunk_of(p.order[ck]);
@@ -527,7 +531,13 @@ bool conv_halo_supported(const dmme_conv_desc& d) {
 // overhead (36% at 8x8, 56% at 4x4) cancels the gain below 16x16 (37 vs 31 us, 27 vs 23 us).
 bool conv_halo_preferred(const dmme_conv_desc& d) {
   if (!conv_halo_supported(d)) return false;
-  if (d.w_in < 16) return false;
+  // 8x8 maps (round 2: row tiles of two whole images in the shared-padding layout, GroupNorm inside) are parity-green and
+  // SLOWER than the transposed kernel + stand-alone GroupNorm (3.11-3.12 vs 3.06 ms per step at batch 256): with N = 176
+  // positions per MMA the weight tiles are 40 % of the shared-memory port bytes (a nine-tap chunk takes 4.4 k clocks for
+  // 3.2 k of MMA) and 256 units need two rounds where the transposed kernel's 128 units need one.  Bit 7 of the mode takes
+  // them anyway at large batches (A/B); explicit DMME_CONV_HALO requests always run.
+  if (d.w_in == 8 && (!(g_halo_mode & 128) || d.n < 160)) return false;
+  if (d.w_in < 8) return false;
   // (round 2, shared-padding row tiles: the halo kernel is ~13% faster at 16x16 and the wide-residual convs now win with
   // their GroupNorm inside -- whole step 3.06 vs 3.11 ms at batch 256, 1.844 vs 1.866 at 128, 1.086 vs 1.099 at 32; bit 6 of the
   // mode restores the old rule for A/B runs)
@@ -582,7 +592,7 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   ConvHaloParams p;
   memset(&p, 0, sizeof(p));
   p.chunks0 = d.c0 / 64; p.chunks1 = d.c1 / 64; p.rchunks0 = d.rc0 / 64; p.rchunks1 = d.rc1 / 64;
-  const bool shared_pad = d.w_in >= 16;  // row tiles: shared-padding layout (see the kernel)
+  const bool shared_pad = d.w_in >= 8;  // row tiles: shared-padding layout (see the kernel)
   const int hp = shared_pad ? d.h_in + 1 : d.h_in + 2;
   p.n = d.n; p.h = d.h_in; p.wp = shared_pad ? d.w_in + 1 : d.w_in + 2;
   {
@@ -620,8 +630,10 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
     // level went to 6-row tiles and lost 4%)): at batch 256 the 128-channel 16x16 convs
     // take 11 rows (419 units = 2.8 waves) instead of 14 (330 units = 2.2 waves, a third wave for a fifth of the SMs)
     long long best_cost = -1;
-    const int rt_max = kHaloCols / p.wp;
+    const bool whole_imgs = d.w_in == 8;  // 8x8: tiles of one or two whole images (hp rows each)
+    const int rt_max = whole_imgs ? 2 * hp : kHaloCols / p.wp;
     for (int rt = rt_max; rt >= 1 && 2 * rt >= rt_max; --rt) {
+      if (whole_imgs && rt % hp) continue;
       const int n_mma = ((rt * p.wp + 15) / 16) * 16;
       const int m_all = (p.total_rows + rt - 1) / rt;
       const long long units = static_cast<long long>(m_all) * p.n_tiles;
@@ -631,7 +643,7 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
       }
       // tail tiles: the full rounds as above, the rows of the partial last round as one round of short tiles
       const long long full = units / g_sm_count;
-      if (shared_pad && (g_halo_mode & 32) == 0 && g_halo_mc == 0 && full >= 1 && units % g_sm_count != 0 && g_sm_count % p.n_tiles == 0) {
+      if (shared_pad && !whole_imgs && (g_halo_mode & 32) == 0 && g_halo_mc == 0 && full >= 1 && units % g_sm_count != 0 && g_sm_count % p.n_tiles == 0) {
         const int m_big = static_cast<int>(full * g_sm_count / p.n_tiles);
         const int rows_left = p.total_rows - m_big * rt;
         const int per_round = g_sm_count / p.n_tiles;
@@ -674,10 +686,12 @@ int conv_halo_forward(const dmme_conv_desc& d, cudaStream_t stream) {
   if (d.rc0 && (rc = act_map(&p.a[2], d.res0, d.rc0))) return rc;
   if (d.rc1 && (rc = act_map(&p.a[3], d.res1, d.rc1))) return rc;
   if (p.imgs_per_tile == 0) {
-    if ((rc = act_map(&p.at[0], d.src0, d.c0, p.rt + 2))) return rc;
-    if (d.c1 && (rc = act_map(&p.at[1], d.src1, d.c1, p.rt + 2))) return rc;
-    if (d.rc0 && (rc = act_map(&p.at[2], d.res0, d.rc0, p.rt + 2))) return rc;
-    if (d.rc1 && (rc = act_map(&p.at[3], d.res1, d.rc1, p.rt + 2))) return rc;
+    // (8x8: a tile of whole images never lies inside one image's rows -1 .. h, the whole-tile box is unused there)
+    const int at_rows = p.rt + 2 <= d.h_in + 2 ? p.rt + 2 : d.h_in + 2;
+    if ((rc = act_map(&p.at[0], d.src0, d.c0, at_rows))) return rc;
+    if (d.c1 && (rc = act_map(&p.at[1], d.src1, d.c1, at_rows))) return rc;
+    if (d.rc0 && (rc = act_map(&p.at[2], d.res0, d.rc0, at_rows))) return rc;
+    if (d.rc1 && (rc = act_map(&p.at[3], d.res1, d.rc1, at_rows))) return rc;
   }
   {
     const uint64_t ktot = 9ull * (d.c0 + d.c1) + d.rc0 + d.rc1;

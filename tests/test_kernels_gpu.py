@@ -1010,6 +1010,12 @@ def test_attention_mma_multi_head(n, c, heads, L_, swap):
     dict(n=64, c0=256, c1=0, cout=256, h=16, addend=True),
     dict(n=32, c0=128, c1=128, cout=128, h=32, res=True),
     dict(n=32, c0=256, c1=0, cout=256, h=16, temb="bcast"),
+    # 8x8 maps: row tiles of two whole images in the shared-padding layout (AUTO's choice from 160 images per GPU up)
+    dict(n=256, c0=256, c1=0, cout=256, h=8, temb="bcast"),
+    dict(n=256, c0=256, c1=256, cout=256, h=8),                      # concat input of the up path
+    dict(n=5, c0=256, c1=0, cout=256, h=8, addend=True, temb="rows"),  # odd batch: the last tile holds one image
+    dict(n=200, c0=256, c1=256, cout=256, h=8, res=True),            # fused 1x1 residual over the concat (eight single-tap chunks)
+    dict(n=161, c0=128, c1=128, cout=128, h=8, silu=False),
 ])
 def test_conv_halo_fused_groupnorm(cfg):
     """GroupNorm(+SiLU) applied to the halo tile inside the conv kernel == gn_apply followed by the same conv, bit for bit
