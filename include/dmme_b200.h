@@ -157,7 +157,8 @@ void dmme_reset_launch_count(void);
 
 /* A/B switch for measurements: 0 = AUTO never picks the halo kernel, 1 = default; further bits (with bit 0 set): 16 = the
  * chunks of a fused 1x1 residual after the conv chunks instead of between them, 32 = equal row tiles only (no tail tiles),
- * 64 = the round-1 rule that keeps 16x16 convs with a wide fused residual on the transposed kernel */
+ * 64 = the round-1 rule that keeps 16x16 convs with a wide fused residual on the transposed kernel, 128 = AUTO also takes the
+ * 8x8 convs of batches >= 160 (row tiles of two whole images, GroupNorm inside: measured slower, off by default) */
 void dmme_set_conv_halo_mode(int mode);
 int dmme_get_conv_halo_mode(void);
 /* halo kernel: clusters of two CTAs share the weight stream through TMA multicast.  0 = off (default; measured slower),
