@@ -452,7 +452,7 @@ def train_bench(dev, world, rank, steps, warmup, barrier, max_over_ranks, pk):
             loss = step(x0)
         e1.record()
         barrier()
-        return max_over_ranks(e0.elapsed_time(e1) / steps), float(loss)
+        return max_over_ranks(e0.elapsed_time(e1) / steps), float(loss.detach())
 
     ms_local, loss = measure(False)
     out = {"workload": "IDDPM cosine-schedule hybrid-loss training step (BASELINE config #4): default IDDPM UNet, batch 128 per "

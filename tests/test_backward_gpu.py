@@ -551,7 +551,7 @@ def _oracle_training(flavour, sd, x0, t, z, tables, groups, masks=None, loss_typ
         vlb = O.vlb_loss(eps, var, x_t, t, x0, tables)
         loss = vlb if loss_type == "vlb" else O.ddpm_loss(x_t, qm, qs, eps) + gamma * vlb
     loss.backward()
-    return float(loss), {k: p.grad for k, p in params.items() if p.requires_grad}
+    return float(loss.detach()), {k: p.grad for k, p in params.items() if p.requires_grad}
 
 
 def _model(flavour, precision, dropout, seed=0, **kw):
