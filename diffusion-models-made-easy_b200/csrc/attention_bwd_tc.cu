@@ -63,10 +63,15 @@ __device__ __forceinline__ uint64_t bwd_desc_mn(uint32_t saddr, uint32_t lbo_byt
   return d;
 }
 
-// L256: 256 tokens per image, two query blocks and two key blocks of 128 per CTA; otherwise 64 tokens and two images per CTA
-template <bool L256>
+// L256: 256 tokens per image, two query blocks and two key blocks of 128 per CTA; otherwise 64 tokens and two images per CTA.
+// DH = 32 (the 128-channel sites, models/iddpm.py: four heads of 32 channels): the same 64-channel TMA boxes, each starting at
+// its own tensor -- [q | k], [k | v], [v | next head], [dO_h | dO_h+1] -- so every operand's first 32 elements are the head's.
+// The products that reduce over the channels (S, dP) take two K = 16 steps instead of four; the ones that produce channels
+// (dV, dK, dQ) keep N = 64 and their upper 32 accumulator columns -- products with the neighbouring tensor -- are not stored.
+template <bool L256, int DH>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdParams p) {
-  constexpr int kDh = 64;
+  constexpr int kDh = DH;
+  constexpr int kN = 64;  // channels per operand tile / accumulator block
   constexpr int NB = L256 ? 2 : 1;          // 128-row blocks of queries / keys held by the CTA
   constexpr int kRows = NB * 128;
   extern __shared__ uint8_t smem_raw[];
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         if (qb > 0) { mbar_wait(&p_ready, (n_pr++) & 1); tc_fence_after(); }
         const uint64_t ad = umma_desc_sw128(qa + qb * kBwdTile), bd = umma_desc_sw128(ka);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tm_s, ad + 2 * k, bd + 2 * k, bwd_idesc(128, kRows, 0, 0), k != 0 ? 1u : 0u);
+        for (int k = 0; k < kDh / 16; ++k) umma_bf16(tm_s, ad + 2 * k, bd + 2 * k, bwd_idesc(128, kRows, 0, 0), k != 0 ? 1u : 0u);
         umma_commit(&st_full);
         ++n_st;
       }
@@ -167,9 +172,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
           const uint64_t qd = umma_desc_sw128(qa + qb * kBwdTile), kd = umma_desc_sw128(ka + kb * kBwdTile);
           const uint64_t dod = umma_desc_sw128(doa + qb * kBwdTile), vd = umma_desc_sw128(va + kb * kBwdTile);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm_s, qd + 2 * k, kd + 2 * k, bwd_idesc(128, 128, 0, 0), k != 0 ? 1u : 0u);
+          for (int k = 0; k < kDh / 16; ++k) umma_bf16(tm_s, qd + 2 * k, kd + 2 * k, bwd_idesc(128, 128, 0, 0), k != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm_dp, dod + 2 * k, vd + 2 * k, bwd_idesc(128, 128, 0, 0), k != 0 ? 1u : 0u);
+          for (int k = 0; k < kDh / 16; ++k) umma_bf16(tm_dp, dod + 2 * k, vd + 2 * k, bwd_idesc(128, 128, 0, 0), k != 0 ? 1u : 0u);
           umma_commit(&st_full);
           ++n_st;
           mbar_wait(&p_ready, (n_pr++) & 1);
@@ -178,16 +183,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_bf16(tm_dv, bwd_desc_mn(pa + k * 2048, kBwdTile), bwd_desc_mn(doa + qb * kBwdTile + k * 2048, kBwdTile),
-                      bwd_idesc(128, kDh, 1, 1), (qb | k) != 0 ? 1u : 0u);
+                      bwd_idesc(128, kN, 1, 1), (qb | k) != 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_bf16(tm_dk, bwd_desc_mn(dsa + k * 2048, kBwdTile), bwd_desc_mn(qa + qb * kBwdTile + k * 2048, kBwdTile),
-                      bwd_idesc(128, kDh, 1, 1), (qb | k) != 0 ? 1u : 0u);
+                      bwd_idesc(128, kN, 1, 1), (qb | k) != 0 ? 1u : 0u);
           // dQ_qb += dS_t K_kb   (M = 128 queries, N = 64, reduction over the tile's 128 keys: two 64-key blocks of dS_t)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(tm_dq + qb * kDh, umma_desc_sw128(dsa + (k >> 2) * kBwdTile) + 2 * (k & 3),
-                      bwd_desc_mn(ka + kb * kBwdTile + k * 2048, kBwdTile), bwd_idesc(128, kDh, 0, 1), (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tm_dq + qb * kN, umma_desc_sw128(dsa + (k >> 2) * kBwdTile) + 2 * (k & 3),
+                      bwd_desc_mn(ka + kb * kBwdTile + k * 2048, kBwdTile), bwd_idesc(128, kN, 0, 1), (kb | k) != 0 ? 1u : 0u);
           umma_commit(&acc_done);
         }
       }
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         tmem_ld32(tm_dv + lane_off + half * 32, a);
         tmem_ld32(tm_dk + lane_off + half * 32, b);
         tmem_ld_wait();
-        if (img < p.n) {
+        if (img < p.n && half * 32 < kDh) {  // (DH = 32: columns 32..63 belong to the neighbouring tensor)
           __nv_bfloat16* base = p.dqkv + (static_cast<long long>(img) * p.L + tok) * (3 * C) + ch0 + half * 32;
           uint4* dk = reinterpret_cast<uint4*>(base + kDh);
           uint4* dv = reinterpret_cast<uint4*>(base + 2 * kDh);
@@ -365,9 +370,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       int img, tok;
       if (L256) { img = unit; tok = qb * 128 + row; } else { img = 2 * unit + (row >> 6); tok = row & 63; }
       uint32_t a[32];
-      tmem_ld32(tm_dq + qb * kDh + lane_off + half * 32, a);
+      tmem_ld32(tm_dq + qb * kN + lane_off + half * 32, a);
       tmem_ld_wait();
-      if (img < p.n) {
+      if (img < p.n && half * 32 < kDh) {
         uint4* dq = reinterpret_cast<uint4*>(p.dqkv + (static_cast<long long>(img) * p.L + tok) * (3 * C) + ch0 + half * 32);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -390,21 +395,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
 }
 
 bool attn_bwd_tc_supported(int act_dtype, int heads, int L, int dh) {
-  return act_dtype == DMME_BF16 && heads >= 1 && dh == 64 && (L == 256 || L == 64);
+  return act_dtype == DMME_BF16 && heads >= 1 && (dh == 64 || dh == 32) && (L == 256 || L == 64);
 }
 
-template <bool L256>
+template <bool L256, int DH>
 static int attn_bwd_tc_launch(const AttnBwdParams& p, int units, cudaStream_t stream) {
   constexpr int NB = L256 ? 2 : 1;
   constexpr int smem = (4 * NB + 4) * kBwdTile + 1024;
   static DeviceOnce once_;
   bool& configured = once_.here();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<L256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<L256, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
-  cudaError_t e = launch_pdl(attn_bwd_tc_kernel<L256>, dim3(p.heads, units), dim3(kBwdThreads), smem, stream, p);
+  cudaError_t e = launch_pdl(attn_bwd_tc_kernel<L256, DH>, dim3(p.heads, units), dim3(kBwdThreads), smem, stream, p);
   return check_launch_err(e, "attn_bwd_tc_kernel");
 }
 
@@ -420,7 +425,7 @@ extern "C" int dmme_attention_bwd_fused(const void* qkv, const void* out, const 
                                         int L, int dh, float scale, int head_batch_swap, int act_dtype, void* stream) {
   DMME_REQUIRE(qkv && out && dout && dqkv, DMME_E_BADARG, "attention_bwd_fused: null pointer");
   DMME_REQUIRE(n > 0 && attn_bwd_tc_supported(act_dtype, heads, L, dh), DMME_E_SHAPE,
-               "attention_bwd_fused: bf16, 64-channel heads, 256 or 64 tokens (got L = %d, dh = %d)", L, dh);
+               "attention_bwd_fused: bf16, 64- or 32-channel heads, 256 or 64 tokens (got L = %d, dh = %d)", L, dh);
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
   const int C = heads * dh;
@@ -446,5 +451,6 @@ extern "C" int dmme_attention_bwd_fused(const void* qkv, const void* out, const 
   p.dout_p = static_cast<const __nv_bfloat16*>(dout);
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return L == 256 ? attn_bwd_tc_launch<true>(p, n, st) : attn_bwd_tc_launch<false>(p, (n + 1) / 2, st);
+  if (dh == 32) return L == 256 ? attn_bwd_tc_launch<true, 32>(p, n, st) : attn_bwd_tc_launch<false, 32>(p, (n + 1) / 2, st);
+  return L == 256 ? attn_bwd_tc_launch<true, 64>(p, n, st) : attn_bwd_tc_launch<false, 64>(p, (n + 1) / 2, st);
 }

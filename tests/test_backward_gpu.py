@@ -386,14 +386,16 @@ def test_attention_bwd(n, c, heads, L_, swap):
     assert rel_l2(dqkv2.cpu(), qkv.grad) < 1e-4
 
 
-@pytest.mark.parametrize("n,heads,L_,swap", [(3, 4, 256, True), (2, 1, 256, False), (5, 4, 64, True), (4, 2, 64, False), (1, 4, 64, True),
-                                              (128, 4, 256, True)])
-def test_attention_bwd_fused(n, heads, L_, swap):
+@pytest.mark.parametrize("n,heads,L_,swap,dh", [(3, 4, 256, True, 64), (2, 1, 256, False, 64), (5, 4, 64, True, 64), (4, 2, 64, False, 64),
+                                                 (1, 4, 64, True, 64), (128, 4, 256, True, 64),
+                                                 # 32-channel heads (the 128-channel 16x16 sites of the IDDPM UNet, models/iddpm.py)
+                                                 (3, 4, 256, True, 32), (2, 2, 256, False, 32), (5, 4, 64, True, 32), (1, 1, 256, False, 32),
+                                                 (128, 4, 256, True, 32)])
+def test_attention_bwd_fused(n, heads, L_, swap, dh):
     """fused tcgen05 attention backward (csrc/attention_bwd_tc.cu) against autograd through fp32 attention on the SAME
     bf16-rounded q, k, v and output gradient: what differs is the bf16 rounding of P and dS inside the kernel (2^-9 relative
     per element) and of the stored gradients -- rel-L2 <= 1.5e-2 per gradient"""
     ops, L = _ops()
-    dh = 64
     c = heads * dh
     nn_ = min(n, 6)  # the reference is computed for the first images only (the batch-128 case checks the grid / regrouping)
     qkv = (_rand(n, L_, 3 * c, seed=11) * 0.7).to(torch.bfloat16).float().requires_grad_()
