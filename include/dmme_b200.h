@@ -435,7 +435,7 @@ int dmme_attention_fwd_train(const void* q, const void* k, const void* v, long l
 
 /*
  * Fused tcgen05 backward of the multi-head attention core (MultiHeadAttention.forward_attention models/iddpm.py:36-59) for
- * the packed qkv layout [n][L][heads][q | k | v][dh] with dh = 64 and L = 256 or 64, bf16: one CTA per (image, head) -- two
+ * the packed qkv layout [n][L][heads][q | k | v][dh] with dh = 64 or 32 and L = 256 or 64, bf16: one CTA per (image, head) -- two
  * images per CTA at L = 64 -- recomputes the softmax from Q and K, so neither the forward's softmax matrix nor any other
  * L x L matrix touches global memory.  out / dout: the forward output and its gradient, [n][L][heads * dh] at the
  * "(b head) -> (head b)" position when head_batch_swap; dqkv: gradient of the packed tensor (every element written).
