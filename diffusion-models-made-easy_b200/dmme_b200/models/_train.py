@@ -48,6 +48,8 @@ class TrainEngine(Engine):
         self.grad_sync = None          # None: single process; else dict(group=..., bucket_bytes=...)
         # multi-head attention backward on the fused tcgen05 kernel where it applies (DMME_FUSED_ATTN_BWD=0: strided products)
         self.fused_attn_bwd = os.environ.get("DMME_FUSED_ATTN_BWD", "1") != "0"
+        # split-K plans for the training convs too (DMME_SPLITK_TRAIN=0: unsplit kernels, A/B)
+        self.splitk_train = os.environ.get("DMME_SPLITK_TRAIN", "1") != "0"
         self.want_input_grad = False   # set per call when the image tensor requires grad
         self.input_grad: Optional[Tensor] = None
         self.last_buckets = []
@@ -103,6 +105,18 @@ class TrainEngine(Engine):
             self._pack_specs[key] = (conv.weight, None, 1, off, cnt)
         return self._cached(key, self._ver(conv.weight), lambda: ops.pack_conv_weight_dgrad(conv.weight, off, cnt, tc))
 
+    def _launch(self, d, w, b, out, temb=None, addend=None, stats=None) -> None:
+        """conv2d_launch with the split-K workspace where the C side's cost model splits (the 4x4 / 8x8 levels at training
+        batch sizes: a 3x3 conv over 2048 pixels is 16 tiles for 148 SMs); same plan as the sampling executor's."""
+        ws = None
+        if self.splitk_train and not self.force_generic and out is not None and out.dtype == torch.bfloat16:
+            ws_bytes = ops.conv_splitk_workspace(d)
+            if ws_bytes:
+                if self._splitk_ws is None or self._splitk_ws.device != out.device or self._splitk_ws.numel() * 4 < ws_bytes:
+                    self._splitk_ws = torch.empty(max(ws_bytes // 4, 1 << 22), dtype=torch.float32, device=out.device)
+                ws = self._splitk_ws
+        ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats, splitk_ws=ws)
+
     def conv(self, name: str, src0: Tensor, src1: Optional[Tensor], conv: nn.Conv2d, *, stride: int = 1,
              upsample: bool = False, res: Optional[nn.Conv2d] = None, res0: Optional[Tensor] = None,
              res1: Optional[Tensor] = None, temb: Optional[Tensor] = None, addend: Optional[Tensor] = None,
@@ -131,7 +145,7 @@ class TrainEngine(Engine):
         else:
             out = self._buf(name, (d.n, ho, wo, cout), act_dtype, dev)
             stats = self._stats_for(out, d.n, cout) if ops.conv_writes_stats(d) else None
-            ops.conv2d_launch(d, w, b, out, temb, addend, stats=stats)
+            self._launch(d, w, b, out, temb, addend, stats=stats)
 
         def backward() -> None:
             g = self._grad_of(out)
@@ -183,7 +197,7 @@ class TrainEngine(Engine):
             target = src0 if src_lo is None and not upsample else None
             fuse = self._take(target, 1) if target is not None else []
             gin = self._buf(name + ".gin", (d.n, hi, wi, cin), act_dtype, dev)
-            ops.conv2d_launch(dd, self._dgrad_weight(conv, 0, cin, dtc), None, gin, None, fuse[0] if fuse else None)
+            self._launch(dd, self._dgrad_weight(conv, 0, cin, dtc), None, gin, None, fuse[0] if fuse else None)
             if target is not None:
                 self._contribute(src0, gin)
             else:  # nearest x2 in front of the conv (models/ddpm.py:161): sum each 2x2 block
@@ -199,7 +213,7 @@ class TrainEngine(Engine):
                 rtc = ops.conv_uses_tc(rd)
                 fuse = self._take(r, 1)
                 gr = self._like(name + ".gres", r)
-                ops.conv2d_launch(rd, self._dgrad_weight(res, off, cnt, rtc), None, gr, None, fuse[0] if fuse else None)
+                self._launch(rd, self._dgrad_weight(res, off, cnt, rtc), None, gr, None, fuse[0] if fuse else None)
                 self._contribute(r, gr)
                 off += cnt
 
