@@ -1442,3 +1442,25 @@ def test_conv_splitk_default_plan_matches_unsplit():
     assert not ops.conv_splitk_workspace(d3) and not ops.conv_epilogue_norm(d3)
     with pytest.raises(RuntimeError, match="split-K"):
         ops.conv2d_launch(d3, wp, bias, a16, out_norms=[ops.out_norm(y, bias, bias, 8, True)])
+
+
+def test_pack_weights_batch_bit_equal():
+    """dmme_pack_conv_weights_batch (one launch for every tensor-core weight pack of a model, the head of the graph-captured
+    training step) == the per-tensor pack kernels, bit for bit: 3x3 and 1x1, fused residual rows, data-gradient slices,
+    shapes whose 2048-element blocks cut rows mid-way"""
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(5)
+    entries, want = [], []
+    for cout, cin, ks, rc, dgrad, off, cnt in [(128, 128, 3, 0, 0, 0, 0), (256, 512, 3, 512, 0, 0, 0), (128, 256, 3, 256, 0, 0, 0),
+                                               (256, 256, 3, 0, 1, 0, 256), (256, 512, 3, 0, 1, 256, 256), (128, 384, 3, 0, 1, 128, 256),
+                                               (6, 128, 3, 0, 0, 0, 0), (128, 3, 3, 0, 1, 0, 3), (768, 256, 1, 0, 0, 0, 0),
+                                               (256, 256, 1, 0, 1, 0, 256), (192, 64, 3, 64, 0, 0, 0), (64, 192, 3, 0, 1, 64, 128)]:
+        w = torch.randn(cout, cin, ks, ks, generator=g).to(DEV)
+        wres = torch.randn(cout, rc, 1, 1, generator=g).to(DEV) if rc else None
+        ref = ops.pack_conv_weight_dgrad(w, off, cnt, True) if dgrad else ops.pack_conv_weight(w, wres, True)
+        entries.append((w, wres, torch.full_like(ref, float("nan")), dgrad, off, cnt))
+        want.append(ref)
+    ops.PackBatch(entries, torch.device(DEV)).launch()
+    torch.cuda.synchronize()
+    for (w, wres, packed, dgrad, off, cnt), ref in zip(entries, want):
+        assert torch.equal(packed.view(torch.int16), ref.view(torch.int16)), (tuple(w.shape), wres is not None, dgrad, off, cnt)
